@@ -1,0 +1,3 @@
+// TEST INFRASTRUCTURE ONLY (oracle build).  See ../python.hpp.
+#include <iterator>
+#include "boost/python.hpp"
