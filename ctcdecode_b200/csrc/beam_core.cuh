@@ -1,0 +1,243 @@
+// The per-utterance CTC prefix beam-search program: ONE CTA PER UTTERANCE, beams in shared memory.
+//
+// Replaces the reference's DecoderState::next / DecoderState::decode
+// (reference ctc_beam_search_decoder.cpp:56-211), PathTrie (path_trie.cpp:38-163) and the
+// std::nth_element prune (ctc_beam_search_decoder.cpp:149-160, decoder_utils.cpp:122-132).
+// It is NOT a translation of that code.  The reference materialises beam x vocab trie nodes per
+// frame, DFS-walks the whole trie and deletes all but beam_size of them; this program relies on
+// the set-semantics of the algorithm (every float field receives at most two
+// commutative log_sum_exp contributions per frame, and unselected candidates leave no trace):
+//
+//   * the beam lives in shared-memory slot arrays (node id, last char, p_blank, p_nonblank, score);
+//   * the beam x pruned-vocab candidates are never materialised -- a candidate's score is one
+//     float add, recomputed on the fly;
+//   * only candidates that survive the cut become nodes of a per-utterance arena in global memory
+//     (parent / first_child / next_sibling / live-child count / lpc / timestep), so "timesteps"
+//     keeps the reference's arg-max-while-parent-in-beam semantics (path_trie.cpp:41-46) including
+//     dead interior nodes that are later revived (path_trie.cpp:50-56);
+//   * the top-beam_size cut is an exact radix select over 48-bit keys (ordered float score,
+//     then smaller char first == prefix_compare) with shared-memory histograms;
+//   * removal (path_trie.cpp:144-163) is a tombstone + atomic live-child count cascade.
+//
+// The source is written as barrier-separated parallel regions (CTC_PAR { ... } CTC_BARRIER();) so
+// the very same text also compiles as a sequential single-threaded emulation for CPU logic tests
+// (tests/native/emulate_cta.cpp, test infrastructure only -- the product never runs it).
+#pragma once
+#include <cfloat>
+#include <cstdint>
+
+#include "glibc_math.cuh"
+
+#if defined(CTC_EMULATE)
+#define CTC_PAR for (int tid = 0; tid < NT; ++tid)
+#define CTC_BARRIER() ((void)0)
+#define CTC_FN static inline
+#define CTC_MFN inline
+#else
+#define CTC_PAR for (int tid = (int)threadIdx.x, once_ = 1; once_; once_ = 0)
+#define CTC_BARRIER() __syncthreads()
+#define CTC_FN __device__ __forceinline__
+#define CTC_MFN __device__ __forceinline__
+#endif
+
+namespace ctc {
+
+// ---- status / flag bits reported per utterance (include/ctcdecode_b200.h mirrors these) --------
+enum : int {
+  FLAG_TIE_PRUNE = 1,   // comparator-equivalent prefixes straddled the beam cut (reference: unspecified)
+  FLAG_TIE_FINAL = 2,   // comparator-equivalent prefixes adjacent in the final order
+  FLAG_TIE_VOCAB = 4,   // equal probabilities straddled the cutoff_top_n / cutoff_prob cut
+  FLAG_ERR_ARENA = 256, // node arena exhausted (cannot happen with the documented sizing)
+};
+
+constexpr float kNInf = -FLT_MAX;  // reference NUM_FLT_INF negated (decoder_utils.h:12)
+constexpr int kStDead = -1;        // node in trie, not in beam (reference exists_ == false)
+constexpr int kStDeleted = -2;     // node removed from the trie (tombstone until unlinked)
+constexpr int kNBins = 256;
+
+// Trie node, one 32-byte sector.  chr_nchild: low 16 bits = character + 1 (root = 0), high 16 bits =
+// number of children currently in the trie (alive or dead).  state: beam slot (>= 0), kStDead or
+// kStDeleted.
+struct alignas(32) Node {
+  int parent;
+  int first_child;
+  int next_sib;
+  unsigned chr_nchild;
+  float lpc;
+  int ts;
+  int state;
+  int depth;
+};
+
+// Per-utterance persistent state (global memory; survives between chunks of a streaming decode).
+// Layout in ints: [0]=M (beam count) [1]=nnodes [2]=abs_t [3]=flags, then 7 slot arrays of K ints:
+// node, chr, bprev, nbprev, score, fchild, depth (floats stored by bit pattern).
+constexpr int kStateHeader = 4;
+CTC_HD long long state_ints(int K) { return kStateHeader + 7ll * K; }
+
+struct BeamParams {
+  const float *lp;        // [B][T][NP] pruned float32 log-probs from the prune kernel
+  const uint16_t *idx;    // [B][T][NP] character of each pruned entry, 0xFFFF = unused (sorted mode only)
+  const int *seq_lens;    // [B] or nullptr
+  int T, V, NP, K, blank;
+  int tile_frames;        // frames per staged tile
+  Node *arena;            // offline: base of B arenas
+  long long arena_stride; // nodes per utterance
+  int *state;             // offline: base of B state blocks
+  long long state_stride; // ints per utterance
+  Node *const *arena_ptrs;  // streaming: per-utterance arena (overrides arena/arena_stride)
+  int *const *state_ptrs;   // streaming: per-utterance state block
+  const int *arena_caps;    // streaming: per-utterance arena capacity (nodes)
+  int arena_cap;            // offline capacity per utterance
+  int fresh;                // 1: start from the root state instead of loading `state`
+  const unsigned char *finalize;  // [B] or nullptr (= finalize all)
+  int *out_tokens, *out_timesteps;  // [B][K][out_T]
+  float *out_scores;                // [B][K]
+  int *out_lens;                    // [B][K]
+  int *n_results;                   // [B]
+  int out_T;
+  int *flags;  // [B], OR-ed
+};
+
+// ---- shared memory carve-up (bytes) ---------------------------------------------------------------
+struct SmemLayout {
+  int tile_lp, tile_idx, mbar, rank, exptab, logtab;
+  int node, chr, bprev, nbprev, score, fchild, depth;  // persistent slot arrays [KP]
+  int bnew, nbnew, ext, snew;                          // per-frame slot temporaries [KP]
+  int mask, rmask;                                     // [KP][W] bitmasks over pruned ranks
+  int evict;                                           // [KP]
+  int sel, sel2, freel, freel2, newinfo;               // [KP] lists; newinfo [KP][6]
+  int tie, rv;                                         // [2*KP], [KP][2]
+  int hist;                                            // [2][kNBins]
+  int ctl;                                             // control words
+  int total;
+  int KP, W;
+};
+CTC_HD int align_up(int x, int a) { return (x + a - 1) / a * a; }
+CTC_HD SmemLayout make_layout(int K, int V, int NP, int tile_frames, bool sorted) {
+  SmemLayout L;
+  const int KP = align_up(K, 32);
+  const int W = (NP + 31) / 32;
+  int o = 0;
+  L.KP = KP;
+  L.W = W;
+  L.tile_lp = o;   o += 2 * tile_frames * NP * 4;
+  L.tile_idx = o;  o += sorted ? 2 * tile_frames * NP * 2 : 0;
+  o = align_up(o, 16);
+  L.mbar = o;      o += 16;
+  L.rank = o;      o += sorted ? align_up(2 * V * 2, 16) : 0;
+  L.exptab = o;    o += 32 * 8;
+  L.logtab = o;    o += 32 * 8;
+  L.node = o;      o += KP * 4;
+  L.chr = o;       o += KP * 4;
+  L.bprev = o;     o += KP * 4;
+  L.nbprev = o;    o += KP * 4;
+  L.score = o;     o += KP * 4;
+  L.fchild = o;    o += KP * 4;
+  L.depth = o;     o += KP * 4;
+  L.bnew = o;      o += KP * 4;
+  L.nbnew = o;     o += KP * 4;
+  L.ext = o;       o += KP * 4;
+  L.snew = o;      o += KP * 4;
+  L.mask = o;      o += KP * W * 4;
+  L.rmask = o;     o += KP * W * 4;
+  L.evict = o;     o += KP * 4;
+  L.sel = o;       o += KP * 4;
+  L.sel2 = o;      o += KP * 4;
+  L.freel = o;     o += KP * 4;
+  L.freel2 = o;    o += KP * 4;
+  L.newinfo = o;   o += KP * 6 * 4;
+  L.tie = o;       o += 2 * KP * 4;
+  L.rv = o;        o += KP * 2 * 4;
+  L.hist = o;      o += 2 * kNBins * 4;
+  o = align_up(o, 16);
+  L.ctl = o;       o += 32 * 4 + 16 * 8;
+  L.total = o;
+  return L;
+}
+
+// control words: 32 ints in L.ctl (followed by 16 spare 64-bit words)
+enum {
+  C_M = 0, C_NNODES, C_FLAGS, C_NSEL, C_NFREE, C_NTIE, C_NRV, C_NPAIRS, C_ABOVE, C_BIN, C_CNT, C_KMIN, C_KMAX,
+  C_SMAX
+};
+
+// ---- small helpers --------------------------------------------------------------------------------
+CTC_FN uint32_t ord_f(float x) {  // monotone float -> uint32 (larger float => larger key)
+  uint32_t u = f_bits(x);
+  return u ^ ((u >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+}
+CTC_FN float unord_f(uint32_t o) { return bits_f((o & 0x80000000u) ? (o ^ 0x80000000u) : ~o); }
+// prefix_compare as a key: score descending, then character ascending (decoder_utils.cpp:122-132)
+CTC_FN uint64_t key64(float score, int chr) {
+  return ((uint64_t)ord_f(score) << 16) | (uint64_t)(0xFFFF - (chr + 1));
+}
+
+#if defined(CTC_EMULATE)
+template <class T> static inline T atom_add(T *p, T v) { T o = *p; *p = o + v; return o; }
+static inline int atom_exch(int *p, int v) { int o = *p; *p = v; return o; }
+static inline unsigned atom_sub_u(unsigned *p, unsigned v) { unsigned o = *p; *p = o - v; return o; }
+static inline int atom_or(int *p, int v) { int o = *p; *p = o | v; return o; }
+template <class T> static inline T ld_cg(const T *p) { return *p; }
+#else
+template <class T> CTC_FN T atom_add(T *p, T v) { return atomicAdd(p, v); }
+CTC_FN int atom_exch(int *p, int v) { return atomicExch(p, v); }
+CTC_FN unsigned atom_sub_u(unsigned *p, unsigned v) { return atomicSub(p, v); }
+CTC_FN int atom_or(int *p, int v) { return atomicOr(p, v); }
+template <class T> CTC_FN T ld_cg(const T *p) { return __ldcg(p); }
+#endif
+
+// log_sum_exp<float> (reference decoder_utils.h:47-54) with the 32-entry expf / 16-entry logf tables
+// staged in shared memory (a __constant__ table indexed per thread would serialise divergent reads).
+CTC_FN float lse_smem(float x, float y, const uint64_t *exptab, const double *logtab) {
+  if (x <= -FLT_MAX) return y;
+  if (y <= -FLT_MAX) return x;
+  const float m = x > y ? x : y;
+  const float d = f_add(x > y ? y : x, -m);
+  if (!(d >= -17.0f)) return f_add(0.0f, m);  // 1.0f + expf(d) == 1.0f, logf(1.0f) == 0
+  const float s = f_add(1.0f, expf_glibc_t(d, exptab));
+  return f_add(logf_glibc_t(s, logtab), m);
+}
+
+// Everything a region needs, by value (pointers into shared memory / this utterance's global state).
+template <bool SORTED>
+struct Cta {
+  // shared
+  int *s_node, *s_chr, *s_fchild, *s_depth, *s_evict, *s_sel, *s_sel2, *s_free, *s_free2, *s_newinfo, *s_tie,
+      *s_rv, *s_hist;
+  float *s_bprev, *s_nbprev, *s_score, *s_bnew, *s_nbnew, *s_ext, *s_snew;
+  uint32_t *s_mask, *s_rmask;
+  int16_t *s_rank;  // [2][V]
+  int *s_ctl;
+  unsigned long long *s_ctl64;
+  const uint64_t *s_exptab;
+  const double *s_logtab;
+  // per frame
+  const float *lp;       // [NP]
+  const uint16_t *idx;   // [NP] (sorted mode)
+  const int16_t *rank;   // [V]  (sorted mode): rank of char in this frame's pruned list or -1
+  // global
+  Node *nodes;
+  int K, V, NP, W, blank;
+
+  CTC_MFN int chr_at(int r) const { return SORTED ? (int)idx[r] : r; }
+  CTC_MFN int rank_of(int c) const { return SORTED ? (int)rank[c] : c; }
+
+  // Score of candidate (beam slot i) + (pruned entry r); false if it is not a new-prefix candidate.
+  // (reference ctc_beam_search_decoder.cpp:108-118 with nb_cur == -inf => lse(-inf, log_p) = log_p)
+  CTC_MFN bool cand(int i, int r, float &sc, int &c) const {
+    c = chr_at(r);
+    if (c == blank) return false;
+    if ((s_mask[i * W + (r >> 5)] >> (r & 31)) & 1u) return false;  // child is itself a beam member
+    const float l = lp[r];
+    if (c == s_chr[i]) {
+      const float b = s_bprev[i];
+      sc = (b > kNInf) ? f_add(l, b) : kNInf;
+    } else {
+      sc = f_add(l, s_score[i]);
+    }
+    return true;
+  }
+};
+
+}  // namespace ctc

@@ -1,0 +1,535 @@
+// C ABI of ctcdecode_b200 (include/ctcdecode_b200.h): kernel wrappers, launch logic, workspace carve-up,
+// host-buffer entry points and the device-resident streaming state.  sm_100a only; there is no CPU path.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <algorithm>
+#include <memory>
+#include <mutex>
+
+#include "../../include/ctcdecode_b200.h"
+#include "beam_program.cuh"
+#include "plan.h"
+#include "prune_program.cuh"
+
+namespace ctc {
+
+// ---------------------------------------------------------------------------------------------------
+//  kernels
+// ---------------------------------------------------------------------------------------------------
+template <int NT, bool SORTED>
+__global__ void __launch_bounds__(NT) beam_kernel(const BeamParams p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  beam_cta_run<NT, SORTED>(p, (int)blockIdx.x, smem);
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT) finalize_kernel(const BeamParams p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  finalize_cta_run<NT>(p, (int)blockIdx.x, smem);
+}
+
+__global__ void selftest_math_kernel(int which, const float *x, const float *x2, float *y, size_t n) {
+  __shared__ uint64_t exptab[32];
+  __shared__ double logftab[32];
+  __shared__ double logtab[256];
+  for (int i = threadIdx.x; i < 32; i += blockDim.x) { exptab[i] = kExp2fTab[i]; logftab[i] = kLogfTab[i]; }
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) logtab[i] = kLogTab[i];
+  __syncthreads();
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float r;
+    if (which == 0) r = expf_glibc_t(x[i], exptab);
+    else if (which == 1) r = logf_glibc_t(x[i], logftab);
+    else if (which == 2) r = logprob_glibc_t(x[i], logtab);
+    else r = lse_smem(x[i], x2[i], exptab, logftab);
+    y[i] = r;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+//  errors
+// ---------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static int fail(int code, const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CU(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) return fail(CTCDEC_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+  } while (0)
+
+static int make_plan(const ctcdec_config *cfg, int B, int T, Plan *pl) {
+  char msg[256];
+  const int rc = make_plan_core(cfg, B, T, pl, msg, sizeof(msg));
+  if (rc) return fail(rc, "%s", msg);
+  if (const char *e = getenv("CTCDEC_NT")) {
+    const int v = atoi(e);
+    if (v == 128 || v == 256 || v == 512 || v == 1024) pl->NT = v;
+  }
+  return CTCDEC_OK;
+}
+
+template <int NT>
+static int launch_beam_nt(const BeamParams &bp, const Plan &pl, int B, cudaStream_t s) {
+  if (pl.sorted) {
+    CU(cudaFuncSetAttribute(beam_kernel<NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.L.total));
+    beam_kernel<NT, true><<<B, NT, pl.L.total, s>>>(bp);
+  } else {
+    CU(cudaFuncSetAttribute(beam_kernel<NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.L.total));
+    beam_kernel<NT, false><<<B, NT, pl.L.total, s>>>(bp);
+  }
+  CU(cudaGetLastError());
+  return CTCDEC_OK;
+}
+
+static int launch_beam(const BeamParams &bp, const Plan &pl, int B, cudaStream_t s) {
+  switch (pl.NT) {
+    case 128: return launch_beam_nt<128>(bp, pl, B, s);
+    case 256: return launch_beam_nt<256>(bp, pl, B, s);
+    case 1024: return launch_beam_nt<1024>(bp, pl, B, s);
+    default: return launch_beam_nt<512>(bp, pl, B, s);
+  }
+}
+
+static int launch_prune(const ctcdec_config *cfg, const Plan &pl, const float *probs, const int *seq_lens, int B,
+                        int T, float *lp, uint16_t *idx, int *flags, cudaStream_t s) {
+  PruneParams pp;
+  pp.probs = probs; pp.seq_lens = seq_lens; pp.B = B; pp.T = T; pp.V = cfg->vocab_size; pp.NP = pl.NP;
+  pp.blank = cfg->blank_id; pp.log_input = cfg->log_input; pp.top_n = cfg->cutoff_top_n;
+  pp.cp_active = pl.cp_active; pp.cutoff_prob = cfg->cutoff_prob; pp.P = pl.P; pp.lp = lp; pp.idx = idx;
+  pp.flags = flags;
+  const long long frames = (long long)B * T;
+  if (frames == 0) return CTCDEC_OK;
+  if (!pl.sorted) {
+    const int wpc = 8;
+    const int grid = (int)std::min<long long>((frames + wpc - 1) / wpc, 148 * 16);
+    prune_kernel<false><<<grid, wpc * 32, 2048, s>>>(pp);
+  } else {
+    int wpc = (int)std::min<size_t>(8, (200 * 1024 - 2048) / ((size_t)pl.P * 8));
+    if (wpc < 1) wpc = 1;
+    const size_t smem = 2048 + (size_t)wpc * pl.P * 8;
+    CU(cudaFuncSetAttribute(prune_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = (int)std::min<long long>((frames + wpc - 1) / wpc, 148 * 8);
+    prune_kernel<true><<<grid, wpc * 32, smem, s>>>(pp);
+  }
+  CU(cudaGetLastError());
+  return CTCDEC_OK;
+}
+
+static int launch_finalize(const BeamParams &bp, int B, cudaStream_t s) {
+  const size_t smem = (size_t)bp.K * 12 + 16;
+  if (smem > 48 * 1024)
+    CU(cudaFuncSetAttribute(finalize_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  finalize_kernel<128><<<B, 128, smem, s>>>(bp);
+  CU(cudaGetLastError());
+  return CTCDEC_OK;
+}
+
+static int check_device() {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return fail(CTCDEC_E_NO_DEVICE, "no CUDA device: %s (this library has no CPU fallback)", cudaGetErrorString(e));
+  int major = 0;
+  CU(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (major != 10) return fail(CTCDEC_E_NO_DEVICE, "device %d has compute capability %d.x; the kernels are built for sm_100a only", dev, major);
+  return CTCDEC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+//  per-device cache for the host-buffer entry points (stream + grow-only device buffers)
+// ---------------------------------------------------------------------------------------------------
+struct DevCache {
+  cudaStream_t stream = nullptr;
+  void *buf[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  size_t cap[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+};
+static DevCache g_cache[64];
+static std::mutex g_mu;
+
+static int ensure(DevCache &c, int slot, size_t bytes) {
+  if (bytes <= c.cap[slot]) return CTCDEC_OK;
+  if (c.buf[slot]) CU(cudaFree(c.buf[slot]));
+  c.buf[slot] = nullptr;
+  c.cap[slot] = 0;
+  const size_t want = bytes + bytes / 8;
+  CU(cudaMalloc(&c.buf[slot], want));
+  c.cap[slot] = want;
+  return CTCDEC_OK;
+}
+
+// streaming state object
+struct StreamState {
+  ctcdec_config cfg;
+  int device;
+  Node *arena;
+  int arena_cap;
+  int *state;
+  int frames;
+};
+
+}  // namespace ctc
+
+using namespace ctc;
+
+extern "C" {
+
+const char *ctcdec_version(void) { return "ctcdecode_b200 0.1 (sm_100a)"; }
+const char *ctcdec_last_error(void) { return g_err; }
+
+int ctcdec_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  int ok = 0;
+  for (int d = 0; d < n; ++d) {
+    int major = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10) ++ok;
+  }
+  return ok;
+}
+
+int ctcdec_workspace_bytes(const ctcdec_config *cfg, int B, int T, size_t *bytes) {
+  Plan pl;
+  int rc = make_plan(cfg, B, T, &pl);
+  if (rc) return rc;
+  if (!bytes) return fail(CTCDEC_E_INVALID, "bytes is NULL");
+  *bytes = pl.total + 256;
+  return CTCDEC_OK;
+}
+
+int ctcdec_decode_batch_device(const ctcdec_config *cfg, const float *probs, const int32_t *seq_lens, int B, int T,
+                               int32_t *tokens, int32_t *timesteps, float *scores, int32_t *lens,
+                               int32_t *n_results, int32_t *flags, void *workspace, size_t workspace_bytes,
+                               void *stream) {
+  Plan pl;
+  int rc = make_plan(cfg, B, T, &pl);
+  if (rc) return rc;
+  if ((rc = check_device())) return rc;
+  if (B == 0) return CTCDEC_OK;
+  if (!probs && T > 0) return fail(CTCDEC_E_INVALID, "probs is NULL");
+  if (!tokens || !timesteps || !scores || !lens) return fail(CTCDEC_E_INVALID, "an output pointer is NULL");
+  unsigned char *ws = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(workspace) + 255) / 256 * 256);
+  if (!workspace || ws + pl.total > reinterpret_cast<unsigned char *>(workspace) + workspace_bytes)
+    return fail(CTCDEC_E_WORKSPACE, "workspace of %zu bytes given, %zu needed", workspace_bytes, pl.total + 256);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  // n_results / flags are optional for the caller: park them at the end of the state area if absent
+  int *state = reinterpret_cast<int *>(ws + pl.off_state);
+  // flags are OR-accumulated by the prune and finalize kernels
+  int *flags_dev = flags;
+  int *nres_dev = n_results;
+  // (state_stride is padded to >= 64 ints beyond need only when K is tiny; keep explicit scratch instead)
+  static_assert(kStateHeader == 4, "state header");
+  if (!flags_dev || !nres_dev) return fail(CTCDEC_E_INVALID, "n_results and flags device buffers are required by the device entry point");
+  CU(cudaMemsetAsync(flags_dev, 0, (size_t)B * 4, s));
+
+  float *lp = reinterpret_cast<float *>(ws + pl.off_lp);
+  uint16_t *idx = pl.sorted ? reinterpret_cast<uint16_t *>(ws + pl.off_idx) : nullptr;
+  if ((rc = launch_prune(cfg, pl, probs, seq_lens, B, T, lp, idx, flags_dev, s))) return rc;
+
+  BeamParams bp;
+  memset(&bp, 0, sizeof(bp));
+  bp.lp = lp; bp.idx = idx; bp.seq_lens = seq_lens; bp.T = T; bp.V = cfg->vocab_size; bp.NP = pl.NP;
+  bp.K = cfg->beam_size; bp.blank = cfg->blank_id; bp.tile_frames = pl.F;
+  bp.arena = reinterpret_cast<Node *>(ws + pl.off_arena); bp.arena_stride = pl.arena_stride;
+  bp.state = state; bp.state_stride = pl.state_stride; bp.arena_cap = (int)pl.arena_stride; bp.fresh = 1;
+  bp.out_tokens = tokens; bp.out_timesteps = timesteps; bp.out_scores = scores; bp.out_lens = lens;
+  bp.n_results = nres_dev; bp.out_T = T; bp.flags = flags_dev;
+  if ((rc = launch_beam(bp, pl, B, s))) return rc;
+  return launch_finalize(bp, B, s);
+}
+
+int ctcdec_decode_batch_host(const ctcdec_config *cfg, const float *probs, const int32_t *seq_lens, int B, int T,
+                             int32_t *tokens, int32_t *timesteps, float *scores, int32_t *lens, int32_t *n_results,
+                             int32_t *flags, int device) {
+  Plan pl;
+  int rc = make_plan(cfg, B, T, &pl);
+  if (rc) return rc;
+  if (device < 0 || device >= 64) return fail(CTCDEC_E_INVALID, "device %d out of range", device);
+  if (cudaSetDevice(device) != cudaSuccess) return fail(CTCDEC_E_NO_DEVICE, "cudaSetDevice(%d) failed (this library has no CPU fallback)", device);
+  if ((rc = check_device())) return rc;
+  if (B == 0) return CTCDEC_OK;
+  std::lock_guard<std::mutex> lock(g_mu);
+  DevCache &c = g_cache[device];
+  if (!c.stream) CU(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+  const int V = cfg->vocab_size, K = cfg->beam_size;
+  const size_t n_probs = (size_t)B * T * V, n_out = (size_t)B * K * T, n_bk = (size_t)B * K;
+  if ((rc = ensure(c, 0, n_probs * 4 + 256))) return rc;
+  if ((rc = ensure(c, 1, (size_t)B * 4 + 256))) return rc;
+  if ((rc = ensure(c, 2, n_out * 4 + 256))) return rc;
+  if ((rc = ensure(c, 3, n_out * 4 + 256))) return rc;
+  if ((rc = ensure(c, 4, n_bk * 4 * 2 + (size_t)B * 8 + 1024))) return rc;
+  if ((rc = ensure(c, 5, pl.total + 512))) return rc;
+  float *d_probs = (float *)c.buf[0];
+  int *d_lens_in = seq_lens ? (int *)c.buf[1] : nullptr;
+  int *d_tok = (int *)c.buf[2], *d_ts = (int *)c.buf[3];
+  float *d_scores = (float *)c.buf[4];
+  int *d_lens = (int *)((char *)c.buf[4] + al256(n_bk * 4));
+  int *d_nres = (int *)((char *)d_lens + al256(n_bk * 4));
+  int *d_flags = d_nres + B;
+  cudaStream_t s = c.stream;
+  if (n_probs) CU(cudaMemcpyAsync(d_probs, probs, n_probs * 4, cudaMemcpyHostToDevice, s));
+  if (seq_lens) CU(cudaMemcpyAsync(d_lens_in, seq_lens, (size_t)B * 4, cudaMemcpyHostToDevice, s));
+  rc = ctcdec_decode_batch_device(cfg, d_probs, d_lens_in, B, T, d_tok, d_ts, d_scores, d_lens, d_nres, d_flags,
+                                  c.buf[5], c.cap[5], s);
+  if (rc) return rc;
+  // small results first: lens tell how many columns of the big tensors carry data
+  std::unique_ptr<int[]> h_nres(new int[(size_t)B * 2]);
+  CU(cudaMemcpyAsync(scores, d_scores, n_bk * 4, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(lens, d_lens, n_bk * 4, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(h_nres.get(), d_nres, (size_t)B * 8, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  // The reference leaves rows p >= n_results and columns >= len untouched; lens of untouched rows are
+  // whatever the caller put there (the reference's Python zero-fills out_seq_len), so only trust rows
+  // below n_results when sizing the column window.
+  int max_len = 0;
+  for (int b = 0; b < B; ++b) {
+    const int nr = h_nres[b];
+    for (int p = 0; p < nr && p < K; ++p) max_len = std::max(max_len, lens[(size_t)b * K + p]);
+  }
+  if (max_len > T) max_len = T;
+  if (max_len > 0) {
+    CU(cudaMemcpy2DAsync(tokens, (size_t)T * 4, d_tok, (size_t)T * 4, (size_t)max_len * 4, n_bk, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpy2DAsync(timesteps, (size_t)T * 4, d_ts, (size_t)T * 4, (size_t)max_len * 4, n_bk, cudaMemcpyDeviceToHost, s));
+  }
+  CU(cudaStreamSynchronize(s));
+  if (n_results) memcpy(n_results, h_nres.get(), (size_t)B * 4);
+  if (flags) memcpy(flags, h_nres.get() + B, (size_t)B * 4);
+  return CTCDEC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+//  streaming
+// ---------------------------------------------------------------------------------------------------
+static int state_init_device(StreamState *st) {
+  const int K = st->cfg.beam_size;
+  const long long n = state_ints(K);
+  std::unique_ptr<int[]> h(new int[n]);
+  for (long long i = 0; i < n; ++i) h[i] = 0;
+  h[0] = 1; h[1] = 1; h[2] = 0; h[3] = 0;
+  int *s = h.get() + kStateHeader;
+  const float ninf = -FLT_MAX, zero = 0.0f;
+  for (int j = 0; j < K; ++j) {
+    s[j] = 0; s[K + j] = -1;
+    memcpy(&s[2 * K + j], j == 0 ? &zero : &ninf, 4);
+    memcpy(&s[3 * K + j], &ninf, 4);
+    memcpy(&s[4 * K + j], j == 0 ? &zero : &ninf, 4);
+    s[5 * K + j] = -1; s[6 * K + j] = 0;
+  }
+  CU(cudaMemcpy(st->state, h.get(), n * 4, cudaMemcpyHostToDevice));
+  Node root;
+  root.parent = -1; root.first_child = -1; root.next_sib = -1; root.chr_nchild = 0u; root.lpc = -FLT_MAX; root.ts = 0;
+  root.state = 0; root.depth = 0;
+  CU(cudaMemcpy(st->arena, &root, sizeof(Node), cudaMemcpyHostToDevice));
+  return CTCDEC_OK;
+}
+
+int ctcdec_state_create(const ctcdec_config *cfg, int device, void **state) {
+  Plan pl;
+  int rc = make_plan(cfg, 1, 1, &pl);
+  if (rc) return rc;
+  if (!state) return fail(CTCDEC_E_INVALID, "state is NULL");
+  if (cudaSetDevice(device) != cudaSuccess) return fail(CTCDEC_E_NO_DEVICE, "cudaSetDevice(%d) failed (this library has no CPU fallback)", device);
+  if ((rc = check_device())) return rc;
+  StreamState *st = new StreamState();
+  st->cfg = *cfg; st->device = device; st->frames = 0; st->arena = nullptr; st->state = nullptr;
+  st->arena_cap = 1 + cfg->beam_size * 256;
+  if (cudaMalloc(&st->arena, (size_t)st->arena_cap * sizeof(Node)) != cudaSuccess ||
+      cudaMalloc(&st->state, (size_t)state_ints(cfg->beam_size) * 4) != cudaSuccess) {
+    if (st->arena) cudaFree(st->arena);
+    delete st;
+    return fail(CTCDEC_E_CUDA, "cudaMalloc failed for the streaming state");
+  }
+  if ((rc = state_init_device(st))) { cudaFree(st->arena); cudaFree(st->state); delete st; return rc; }
+  *state = st;
+  return CTCDEC_OK;
+}
+
+int ctcdec_state_destroy(void *state) {
+  if (!state) return CTCDEC_OK;
+  StreamState *st = static_cast<StreamState *>(state);
+  cudaSetDevice(st->device);
+  cudaFree(st->arena);
+  cudaFree(st->state);
+  delete st;
+  return CTCDEC_OK;
+}
+
+int ctcdec_state_frames(const void *state, int *frames) {
+  if (!state || !frames) return fail(CTCDEC_E_INVALID, "NULL argument");
+  *frames = static_cast<const StreamState *>(state)->frames;
+  return CTCDEC_OK;
+}
+
+int ctcdec_decode_stream_host(const float *probs, const int32_t *seq_lens, int B, int T, void *const *states,
+                              const uint8_t *is_eos, int32_t *tokens, int32_t *timesteps, int out_T, float *scores,
+                              int32_t *lens, int32_t *n_results, int32_t *flags) {
+  if (B <= 0) return B == 0 ? CTCDEC_OK : fail(CTCDEC_E_INVALID, "negative batch");
+  if (!states || !is_eos) return fail(CTCDEC_E_INVALID, "states / is_eos is NULL");
+  for (int b = 0; b < B; ++b)
+    if (!states[b]) return fail(CTCDEC_E_INVALID, "states[%d] is NULL", b);
+  StreamState *s0 = static_cast<StreamState *>(states[0]);
+  const ctcdec_config cfg = s0->cfg;
+  for (int b = 1; b < B; ++b) {
+    StreamState *sb = static_cast<StreamState *>(states[b]);
+    if (memcmp(&sb->cfg, &cfg, sizeof(cfg)) != 0 || sb->device != s0->device)
+      return fail(CTCDEC_E_UNSUPPORTED, "all states of one call must come from the same decoder configuration and device");
+    for (int a = 0; a < b; ++a)
+      if (states[a] == states[b]) return fail(CTCDEC_E_INVALID, "states[%d] and states[%d] are the same object", a, b);
+  }
+  Plan pl;
+  int rc = make_plan(&cfg, B, T, &pl);
+  if (rc) return rc;
+  const int device = s0->device;
+  if (cudaSetDevice(device) != cudaSuccess) return fail(CTCDEC_E_NO_DEVICE, "cudaSetDevice(%d) failed", device);
+  if ((rc = check_device())) return rc;
+  std::lock_guard<std::mutex> lock(g_mu);
+  DevCache &c = g_cache[device];
+  if (!c.stream) CU(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+  cudaStream_t s = c.stream;
+  const int V = cfg.vocab_size, K = cfg.beam_size;
+  bool any_eos = false;
+  int h_len_max = 0;
+  for (int b = 0; b < B; ++b) {
+    any_eos |= is_eos[b] != 0;
+    int len = seq_lens ? seq_lens[b] : T;
+    len = std::max(0, std::min(len, T));
+    StreamState *sb = static_cast<StreamState *>(states[b]);
+    // grow the arena so that 1 + K * (frames consumed after this chunk) nodes fit
+    const long long need = 1 + (long long)K * (sb->frames + len);
+    if (need > sb->arena_cap) {
+      long long cap = std::max<long long>(need, 2ll * sb->arena_cap);
+      if (cap > 0x7fffffffll / 2) return fail(CTCDEC_E_UNSUPPORTED, "stream too long for the node arena");
+      Node *na = nullptr;
+      CU(cudaMalloc(&na, (size_t)cap * sizeof(Node)));
+      const long long used = std::min<long long>(sb->arena_cap, 1 + (long long)K * sb->frames);
+      CU(cudaMemcpyAsync(na, sb->arena, (size_t)used * sizeof(Node), cudaMemcpyDeviceToDevice, s));
+      CU(cudaStreamSynchronize(s));
+      CU(cudaFree(sb->arena));
+      sb->arena = na;
+      sb->arena_cap = (int)cap;
+    }
+    h_len_max = std::max(h_len_max, sb->frames + len);
+  }
+  if (any_eos && (!tokens || !timesteps || !scores || !lens)) return fail(CTCDEC_E_INVALID, "an output pointer is NULL");
+  if (any_eos && out_T < 0) return fail(CTCDEC_E_INVALID, "out_T < 0");
+  const size_t n_probs = (size_t)B * T * V, n_bk = (size_t)B * K, n_out = any_eos ? n_bk * (size_t)out_T : 0;
+  const size_t ptr_bytes = al256((size_t)B * 8) * 2 + al256((size_t)B * 4) + al256((size_t)B);
+  if ((rc = ensure(c, 0, n_probs * 4 + 256))) return rc;
+  if ((rc = ensure(c, 1, (size_t)B * 4 + 256))) return rc;
+  if ((rc = ensure(c, 2, n_out * 4 + 256))) return rc;
+  if ((rc = ensure(c, 3, n_out * 4 + 256))) return rc;
+  if ((rc = ensure(c, 4, n_bk * 4 * 2 + (size_t)B * 8 + 1024))) return rc;
+  if ((rc = ensure(c, 5, pl.off_arena + 512))) return rc;  // only the lp / idx part of the plan is used
+  if ((rc = ensure(c, 6, ptr_bytes + 256))) return rc;
+  float *d_probs = (float *)c.buf[0];
+  int *d_lens_in = seq_lens ? (int *)c.buf[1] : nullptr;
+  int *d_tok = (int *)c.buf[2], *d_ts = (int *)c.buf[3];
+  float *d_scores = (float *)c.buf[4];
+  int *d_lens = (int *)((char *)c.buf[4] + al256(n_bk * 4));
+  int *d_nres = (int *)((char *)d_lens + al256(n_bk * 4));
+  int *d_flags = d_nres + B;
+  // pointer tables
+  std::unique_ptr<unsigned char[]> h_tab(new unsigned char[ptr_bytes]);
+  Node **h_arenas = (Node **)h_tab.get();
+  int **h_states = (int **)(h_tab.get() + al256((size_t)B * 8));
+  int *h_caps = (int *)(h_tab.get() + 2 * al256((size_t)B * 8));
+  unsigned char *h_fin = h_tab.get() + 2 * al256((size_t)B * 8) + al256((size_t)B * 4);
+  for (int b = 0; b < B; ++b) {
+    StreamState *sb = static_cast<StreamState *>(states[b]);
+    h_arenas[b] = sb->arena; h_states[b] = sb->state; h_caps[b] = sb->arena_cap; h_fin[b] = is_eos[b] ? 1 : 0;
+  }
+  unsigned char *d_tab = (unsigned char *)c.buf[6];
+  CU(cudaMemcpyAsync(d_tab, h_tab.get(), ptr_bytes, cudaMemcpyHostToDevice, s));
+  if (n_probs) CU(cudaMemcpyAsync(d_probs, probs, n_probs * 4, cudaMemcpyHostToDevice, s));
+  if (seq_lens) CU(cudaMemcpyAsync(d_lens_in, seq_lens, (size_t)B * 4, cudaMemcpyHostToDevice, s));
+  CU(cudaMemsetAsync(d_flags, 0, (size_t)B * 4, s));
+  CU(cudaMemsetAsync(d_nres, 0, (size_t)B * 4, s));
+  unsigned char *ws = (unsigned char *)c.buf[5];
+  ws = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(ws) + 255) / 256 * 256);
+  float *lp = reinterpret_cast<float *>(ws + pl.off_lp);
+  uint16_t *idx = pl.sorted ? reinterpret_cast<uint16_t *>(ws + pl.off_idx) : nullptr;
+  if (T > 0 && (rc = launch_prune(&cfg, pl, d_probs, d_lens_in, B, T, lp, idx, d_flags, s))) return rc;
+  BeamParams bp;
+  memset(&bp, 0, sizeof(bp));
+  bp.lp = lp; bp.idx = idx; bp.seq_lens = d_lens_in; bp.T = T; bp.V = V; bp.NP = pl.NP; bp.K = K;
+  bp.blank = cfg.blank_id; bp.tile_frames = pl.F;
+  bp.arena_ptrs = (Node *const *)d_tab; bp.state_ptrs = (int *const *)(d_tab + al256((size_t)B * 8));
+  bp.arena_caps = (const int *)(d_tab + 2 * al256((size_t)B * 8));
+  bp.finalize = d_tab + 2 * al256((size_t)B * 8) + al256((size_t)B * 4);
+  bp.fresh = 0;
+  bp.out_tokens = d_tok; bp.out_timesteps = d_ts; bp.out_scores = d_scores; bp.out_lens = d_lens;
+  bp.n_results = d_nres; bp.out_T = out_T; bp.flags = d_flags;
+  if (T > 0 && (rc = launch_beam(bp, pl, B, s))) return rc;
+  for (int b = 0; b < B; ++b) {
+    int len = seq_lens ? seq_lens[b] : T;
+    static_cast<StreamState *>(states[b])->frames += std::max(0, std::min(len, T));
+  }
+  if (any_eos) {
+    if ((rc = launch_finalize(bp, B, s))) return rc;
+    std::unique_ptr<int[]> h_nres(new int[(size_t)B * 2]);
+    std::unique_ptr<float[]> h_scores(new float[n_bk]);
+    std::unique_ptr<int[]> h_lens(new int[n_bk]);
+    CU(cudaMemcpyAsync(h_scores.get(), d_scores, n_bk * 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(h_lens.get(), d_lens, n_bk * 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(h_nres.get(), d_nres, (size_t)B * 8, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    int max_len = 0;
+    for (int b = 0; b < B; ++b) {
+      if (!is_eos[b]) continue;
+      for (int p = 0; p < h_nres[b] && p < K; ++p) {
+        scores[(size_t)b * K + p] = h_scores[(size_t)b * K + p];
+        lens[(size_t)b * K + p] = h_lens[(size_t)b * K + p];
+        max_len = std::max(max_len, h_lens[(size_t)b * K + p]);
+      }
+    }
+    if (max_len > out_T) return fail(CTCDEC_E_INVALID, "out_T (%d) smaller than the longest prefix (%d)", out_T, max_len);
+    if (max_len > 0) {
+      // copy per finalized stream so rows of non-eos streams stay untouched
+      for (int b = 0; b < B; ++b) {
+        if (!is_eos[b] || h_nres[b] == 0) continue;
+        const size_t off = (size_t)b * K * out_T;
+        CU(cudaMemcpy2DAsync(tokens + off, (size_t)out_T * 4, d_tok + off, (size_t)out_T * 4, (size_t)max_len * 4,
+                             (size_t)h_nres[b], cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpy2DAsync(timesteps + off, (size_t)out_T * 4, d_ts + off, (size_t)out_T * 4, (size_t)max_len * 4,
+                             (size_t)h_nres[b], cudaMemcpyDeviceToHost, s));
+      }
+    }
+    CU(cudaStreamSynchronize(s));
+    if (n_results) memcpy(n_results, h_nres.get(), (size_t)B * 4);
+    if (flags) memcpy(flags, h_nres.get() + B, (size_t)B * 4);
+  } else {
+    CU(cudaStreamSynchronize(s));
+    if (n_results) memset(n_results, 0, (size_t)B * 4);
+  }
+  return CTCDEC_OK;
+}
+
+int ctcdec_selftest_math(int which, const float *x, const float *x2, float *y, size_t n, int device) {
+  if (which < 0 || which > 3 || !x || !y || (which == 3 && !x2)) return fail(CTCDEC_E_INVALID, "bad selftest arguments");
+  if (cudaSetDevice(device) != cudaSuccess) return fail(CTCDEC_E_NO_DEVICE, "cudaSetDevice(%d) failed", device);
+  int rc = check_device();
+  if (rc) return rc;
+  if (n == 0) return CTCDEC_OK;
+  float *dx = nullptr, *dx2 = nullptr, *dy = nullptr;
+  CU(cudaMalloc(&dx, n * 4));
+  CU(cudaMalloc(&dy, n * 4));
+  if (which == 3) CU(cudaMalloc(&dx2, n * 4));
+  CU(cudaMemcpy(dx, x, n * 4, cudaMemcpyHostToDevice));
+  if (which == 3) CU(cudaMemcpy(dx2, x2, n * 4, cudaMemcpyHostToDevice));
+  selftest_math_kernel<<<148 * 8, 256>>>(which, dx, dx2, dy, n);
+  CU(cudaGetLastError());
+  CU(cudaMemcpy(y, dy, n * 4, cudaMemcpyDeviceToHost));
+  cudaFree(dx); cudaFree(dy);
+  if (dx2) cudaFree(dx2);
+  return CTCDEC_OK;
+}
+
+}  // extern "C"

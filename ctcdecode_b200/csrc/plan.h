@@ -1,0 +1,72 @@
+// Everything derived from (config, B, T): pruning mode, row padding, shared-memory layout, block size
+// and the workspace carve-up.  Shared by the CUDA library and the CPU logic-test emulation.
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+
+#include "../../include/ctcdecode_b200.h"
+#include "beam_core.cuh"
+
+namespace ctc {
+
+struct Plan {
+  bool sorted;    // the reference sorts (and possibly cuts) the vocabulary every frame
+  int cp_active;  // log(cutoff_prob) < 0
+  int n_max;      // most characters a frame can keep
+  int NP;         // row length of the pruned log-prob rows (multiple of 8, >= n_max + 2)
+  int P;          // next power of two >= V
+  int F;          // frames per staged tile
+  int NT;         // threads per CTA of the beam kernel
+  SmemLayout L;
+  size_t off_lp, off_idx, off_arena, off_state, total;
+  long long arena_stride, state_stride;
+};
+
+static inline size_t al256(size_t x) { return (x + 255) / 256 * 256; }
+
+static inline int make_plan_core(const ctcdec_config *cfg, int B, int T, Plan *pl, char *msg, size_t msglen) {
+#define PLAN_FAIL(code, ...) do { snprintf(msg, msglen, __VA_ARGS__); return code; } while (0)
+  if (!cfg) PLAN_FAIL(CTCDEC_E_INVALID, "cfg is NULL");
+  const int V = cfg->vocab_size, K = cfg->beam_size;
+  if (B < 0 || T < 0) PLAN_FAIL(CTCDEC_E_INVALID, "negative batch (%d) or time (%d)", B, T);
+  if (V < 1 || V > 65534) PLAN_FAIL(CTCDEC_E_UNSUPPORTED, "vocab_size %d outside [1, 65534]", V);
+  if (K < 1 || K > 4096) PLAN_FAIL(CTCDEC_E_UNSUPPORTED, "beam_size %d outside [1, 4096]", K);
+  if (cfg->cutoff_top_n < 0) PLAN_FAIL(CTCDEC_E_INVALID, "cutoff_top_n %d < 0", cfg->cutoff_top_n);
+  if (cfg->blank_id < 0) PLAN_FAIL(CTCDEC_E_INVALID, "blank_id %d < 0", cfg->blank_id);
+  if ((long long)K * (long long)(T > 0 ? T : 1) + 1 > 0x7fffffffll / 2)
+    PLAN_FAIL(CTCDEC_E_UNSUPPORTED, "beam_size * T too large for the node arena");
+  // reference decoder_utils.cpp:15,21: sort (and possibly cut) iff log(cutoff_prob) < 0 or top_n < V
+  const double log_cp = std::log(cfg->cutoff_prob);
+  pl->cp_active = (log_cp < 0.0) ? 1 : 0;
+  pl->sorted = pl->cp_active || cfg->cutoff_top_n < V;
+  if (!pl->sorted) pl->n_max = V;
+  else if (pl->cp_active) pl->n_max = std::min(V, std::max(1, cfg->cutoff_top_n));
+  else pl->n_max = std::min(V, cfg->cutoff_top_n);
+  pl->NP = align_up(pl->n_max + 2, 8);
+  int P = 1;
+  while (P < V) P <<= 1;
+  pl->P = P;
+  pl->F = std::max(1, std::min(32, 4096 / (pl->NP * 4)));
+  const long long grid = (long long)K * pl->n_max;
+  pl->NT = grid <= 1024 ? 128 : (grid <= 2048 ? 256 : 512);
+  pl->L = make_layout(K, V, pl->NP, pl->F, pl->sorted);
+  if (pl->L.total > 227 * 1024)
+    PLAN_FAIL(CTCDEC_E_UNSUPPORTED, "beam_size %d x pruned vocab %d needs %d bytes of shared memory (> 227 KB)", K,
+              pl->n_max, pl->L.total);
+  if (pl->sorted && 2048 + (size_t)P * 8 > 200 * 1024)
+    PLAN_FAIL(CTCDEC_E_UNSUPPORTED, "vocab_size %d too large for the in-shared-memory vocabulary sort", V);
+  pl->arena_stride = 1 + (long long)K * T;
+  pl->state_stride = (state_ints(K) + 63) / 64 * 64;
+  size_t o = 0;
+  pl->off_lp = o;     o = al256(o + (size_t)B * T * pl->NP * 4);
+  pl->off_idx = o;    o = al256(o + (pl->sorted ? (size_t)B * T * pl->NP * 2 : 0));
+  pl->off_arena = o;  o = al256(o + (size_t)B * pl->arena_stride * sizeof(Node));
+  pl->off_state = o;  o = al256(o + (size_t)B * pl->state_stride * 4);
+  pl->total = o;
+  msg[0] = 0;
+  return CTCDEC_OK;
+#undef PLAN_FAIL
+}
+
+}  // namespace ctc

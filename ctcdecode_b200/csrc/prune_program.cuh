@@ -1,0 +1,180 @@
+// Frame-parallel vocabulary prune + log pre-pass ("logprob scan"), one warp per frame.
+//
+// Replaces the reference's get_pruned_log_probs (reference decoder_utils.cpp:10-45), which the
+// reference calls once per frame inside the serial time loop (ctc_beam_search_decoder.cpp:84-85).
+// Frames are independent, so here the whole [B, T, V] tensor is scanned once at HBM bandwidth
+// before the beam kernel starts, and the beam kernel streams compact, 16-byte-aligned rows:
+//
+//   lp  row (float32[NP]) : entries 0..n-1 = log-probs of the kept characters, in the reference's
+//                           iteration order (index order if nothing is cut, else probability
+//                           descending); entries n..NP-3 = -FLT_MAX;
+//                           [NP-2] = bit pattern  n | (rank_of_blank + 1) << 16;
+//                           [NP-1] = largest non-blank kept log-prob (-FLT_MAX if none)
+//   idx row (uint16[NP])  : character of each kept entry, 0xFFFF beyond n   (sorted mode only)
+//
+// Device-only (the CPU logic tests use the mirror in tests/native/emulate_cta.cpp).
+#pragma once
+#include "beam_core.cuh"
+
+namespace ctc {
+
+struct PruneParams {
+  const float *probs;   // [B][T][V]
+  const int *seq_lens;  // [B] or nullptr
+  int B, T, V, NP, blank, log_input;
+  int top_n;            // cutoff_top_n
+  int cp_active;        // log(cutoff_prob) < 0
+  double cutoff_prob;
+  int P;                // next power of two >= V (sorted mode)
+  float *lp;            // [B][T][NP]
+  uint16_t *idx;        // [B][T][NP] (sorted mode)
+  int *flags;           // [B]
+};
+
+#if !defined(CTC_EMULATE)
+
+CTC_FN float prune_value(float x, int log_input, const double *logtab) {
+  return log_input ? x : logprob_glibc_t(x, logtab);  // reference decoder_utils.cpp:40-43
+}
+
+template <bool SORTED>
+__global__ void __launch_bounds__(256) prune_kernel(const PruneParams p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  double *logtab = reinterpret_cast<double *>(smem);  // 256 doubles
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) logtab[i] = kLogTab[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+  uint64_t *keys = reinterpret_cast<uint64_t *>(smem + 2048) + (size_t)warp * p.P;
+  const long long nframes = (long long)p.B * p.T;
+  const int V = p.V, NP = p.NP;
+  const int rblank_unsorted = (p.blank >= 0 && p.blank < V) ? p.blank : -1;
+  const unsigned ninf_ord = ord_f(kNInf);
+
+  for (long long f = (long long)blockIdx.x * wpc + warp; f < nframes; f += (long long)gridDim.x * wpc) {
+    const int b = (int)(f / p.T), t = (int)(f - (long long)b * p.T);
+    int len = p.seq_lens ? p.seq_lens[b] : p.T;
+    if (t >= len) continue;
+    const float *row = p.probs + f * V;
+    float *out = p.lp + f * NP;
+
+    if (!SORTED) {
+      unsigned mx = ninf_ord;
+      for (int r = lane; r < NP - 2; r += 32) {
+        float v = kNInf;
+        if (r < V) {
+          v = prune_value(row[r], p.log_input, logtab);
+          if (r != p.blank) { const unsigned o = ord_f(v); mx = o > mx ? o : mx; }
+        }
+        out[r] = v;
+      }
+      mx = __reduce_max_sync(0xffffffffu, mx);
+      if (lane == 0) {
+        out[NP - 2] = bits_f((uint32_t)V | ((uint32_t)(rblank_unsorted + 1) << 16));
+        out[NP - 1] = unord_f(mx);
+      }
+      continue;
+    }
+
+    // ---- sorted mode: std::sort by probability descending (decoder_utils.cpp:22-24); ties -> lower index
+    uint16_t *oidx = p.idx + f * NP;
+    for (int c = lane; c < p.P; c += 32)
+      keys[c] = c < V ? (((uint64_t)ord_f(row[c]) << 32) | (uint64_t)(0xFFFFFFFFu - (unsigned)c)) : 0ull;
+    __syncwarp();
+    for (int k = 2; k <= p.P; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int i = lane; i < p.P; i += 32) {
+          const int l = i ^ j;
+          if (l > i) {
+            const uint64_t a = keys[i], bb = keys[l];
+            const bool desc_block = (i & k) == 0;
+            if (desc_block ? (a < bb) : (a > bb)) { keys[i] = bb; keys[l] = a; }
+          }
+        }
+        __syncwarp();
+      }
+    }
+    // ---- how many entries survive (decoder_utils.cpp:25-35)
+    int n;
+    if (!p.cp_active) {
+      n = p.top_n < V ? p.top_n : V;
+    } else {
+      const int lim = V < (p.top_n > 1 ? p.top_n : 1) ? V : (p.top_n > 1 ? p.top_n : 1);
+      // cum_i = log(1 + sum_{k<=i} p_k) up to rounding; decide with a prefix sum unless a decision is
+      // within 1e-9 of the threshold, in which case lane 0 replays the reference's serial chain.
+      double carry = 0.0;
+      int first = -1;
+      bool uncertain = false;
+      for (int base = 0; base < lim && first < 0; base += 32) {
+        const int i = base + lane;
+        double pv = 0.0;
+        if (i < lim) {
+          const double v = (double)unord_f((uint32_t)(keys[i] >> 32));
+          pv = p.log_input ? exp(v) : v;
+        }
+        double s = pv;
+        for (int d = 1; d < 32; d <<= 1) {
+          const double o = __shfl_up_sync(0xffffffffu, s, d);
+          if (lane >= d) s += o;
+        }
+        s += carry;
+        const double approx = log1p(s);
+        const bool in = i < lim;
+        const bool fire = in && approx >= p.cutoff_prob;
+        const bool unc = in && fabs(approx - p.cutoff_prob) <= 1e-9 * (1.0 + fabs(p.cutoff_prob));
+        const unsigned fb = __ballot_sync(0xffffffffu, fire);
+        const unsigned ub = __ballot_sync(0xffffffffu, unc);
+        if (fb) {
+          const int fl = __ffs(fb) - 1;
+          first = base + fl;
+          if (ub & ((2u << fl) - 1u)) uncertain = true;
+        } else if (ub) {
+          uncertain = true;
+        }
+        carry = __shfl_sync(0xffffffffu, s, 31);
+      }
+      n = first >= 0 ? first + 1 : lim;
+      if (uncertain) {
+        int nn = 0;
+        if (lane == 0) {
+          double cum = 0.0;  // reference starts the log-domain accumulator at 0.0 (decoder_utils.cpp:26)
+          for (int i = 0; i < V; ++i) {
+            const double v = (double)unord_f((uint32_t)(keys[i] >> 32));
+            const double term = p.log_input ? v : log(v);
+            const double m = cum > term ? cum : term;
+            cum = (term <= -DBL_MAX) ? cum : log(exp(cum - m) + exp(term - m)) + m;
+            nn += 1;
+            if (cum >= p.cutoff_prob || nn >= p.top_n) break;
+          }
+        }
+        n = __shfl_sync(0xffffffffu, nn, 0);
+      }
+    }
+    if (lane == 0 && n > 0 && n < V && (keys[n - 1] >> 32) == (keys[n] >> 32)) atomicOr(&p.flags[b], FLAG_TIE_VOCAB);
+    // ---- emit
+    int rb = 0;
+    float first_two = kNInf;  // lp of entry `lane` for lanes 0 and 1
+    for (int r = lane; r < NP; r += 32) {
+      float v = kNInf;
+      unsigned c = 0xFFFFu;
+      if (r < n) {
+        c = 0xFFFFFFFFu - (unsigned)(keys[r] & 0xFFFFFFFFull);
+        v = prune_value(unord_f((uint32_t)(keys[r] >> 32)), p.log_input, logtab);
+        if ((int)c == p.blank) rb = r + 1;
+      }
+      if (r < 2) first_two = v;
+      if (r < NP - 2) out[r] = v;
+      oidx[r] = (uint16_t)c;
+    }
+    rb = __reduce_max_sync(0xffffffffu, rb);
+    const float l0 = __shfl_sync(0xffffffffu, first_two, 0), l1 = __shfl_sync(0xffffffffu, first_two, 1);
+    if (lane == 0) {
+      out[NP - 2] = bits_f((uint32_t)n | ((uint32_t)rb << 16));
+      out[NP - 1] = (rb == 1) ? (n > 1 ? l1 : kNInf) : (n > 0 ? l0 : kNInf);
+    }
+    __syncwarp();
+  }
+}
+
+#endif  // !CTC_EMULATE
+
+}  // namespace ctc

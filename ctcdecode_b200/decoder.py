@@ -1,0 +1,232 @@
+"""Host-side mirror of the reference's Python interface for the beam-search path.
+
+Same class names, constructor arguments, argument meaning and return tuple as the reference's
+``ctcdecode/__init__.py`` (CTCBeamDecoder :6-140, OnlineCTCBeamDecoder :143-250, DecoderState :253-272), so
+``decoder.decode(output)`` keeps working; the work itself goes through the C ABI of
+include/ctcdecode_b200.h into the sm_100a kernels.  There is no CPU fallback: without the CUDA library or
+without a B200 the calls raise.
+
+Differences from the reference, all additive:
+  * ``probs`` may live on the GPU; it is then decoded in place (the reference does ``probs.cpu()`` first,
+    __init__.py:77).  Results are CPU tensors like the reference's unless ``device_outputs=True``.
+  * ``num_processes`` is accepted and ignored: the batch is a CUDA grid (one CTA per utterance).
+  * ``decoder.last_flags`` / ``decoder.last_n_results`` expose the per-utterance tie flags and beam counts
+    of the last call (the reference has no equivalent; see include/ctcdecode_b200.h).
+  * the KenLM scorer (``model_path``) is not built yet -- constructing a decoder with one raises.
+"""
+import ctypes
+
+import torch
+
+from . import _native
+
+
+def _cfg(decoder):
+    return _native.Config(decoder._num_labels, decoder._beam_width, decoder._blank_id, decoder._log_probs,
+                          decoder._cutoff_top_n_value(), float(decoder._cutoff_prob))
+
+
+class _Base(object):
+    def _init_common(self, labels, model_path, alpha, beta, cutoff_top_n, cutoff_prob, beam_width, num_processes,
+                     blank_id, log_probs_input, device):
+        self._beam_width = int(beam_width)
+        self._scorer = None
+        self._num_processes = num_processes
+        self._labels = list(labels)
+        self._num_labels = len(self._labels)
+        self._blank_id = int(blank_id)
+        self._log_probs = 1 if log_probs_input else 0
+        self._cutoff_prob = cutoff_prob
+        self._device = device
+        self.last_flags = None
+        self.last_n_results = None
+        if model_path:
+            raise NotImplementedError(
+                "ctcdecode_b200: the KenLM scorer hook (model_path=...) is not built in this round; "
+                "only the no-LM beam search path is available (there is no CPU fallback)")
+        _native.load()
+
+    def _device_index(self, probs=None):
+        if probs is not None and probs.is_cuda:
+            return probs.device.index if probs.device.index is not None else torch.cuda.current_device()
+        if self._device is not None:
+            return torch.device(self._device).index or 0
+        return 0
+
+    def character_based(self):
+        return None
+
+    def max_order(self):
+        return None
+
+    def dict_size(self):
+        return None
+
+
+class CTCBeamDecoder(_Base):
+    """Drop-in for the reference CTCBeamDecoder (reference ctcdecode/__init__.py:6-140)."""
+
+    def __init__(self, labels, model_path=None, alpha=0, beta=0, cutoff_top_n=40, cutoff_prob=1.0, beam_width=100,
+                 num_processes=4, blank_id=0, log_probs_input=False, device=None, device_outputs=False):
+        self.cutoff_top_n = cutoff_top_n  # public attribute name kept from the reference (:39)
+        self._device_outputs = device_outputs
+        self._ws = None
+        self._init_common(labels, model_path, alpha, beta, cutoff_top_n, cutoff_prob, beam_width, num_processes,
+                          blank_id, log_probs_input, device)
+
+    def _cutoff_top_n_value(self):
+        return int(self.cutoff_top_n)
+
+    def decode(self, probs, seq_lens=None):
+        """probs: [B, T, V] float tensor (CPU or CUDA); seq_lens: optional [B] ints.
+        Returns (beam_results [B, beam, T] int32, beam_scores [B, beam] float32, timesteps [B, beam, T] int32,
+        out_lens [B, beam] int32) exactly like reference __init__.py:53-123: only [b, p, :out_lens[b, p]] of
+        beam_results / timesteps is meaningful, the rest is uninitialised."""
+        lib = _native.load()
+        if probs.dim() != 3:
+            raise ValueError("probs must be [batch, time, labels], got %s" % (tuple(probs.shape),))
+        B, T, V = probs.shape
+        if V != self._num_labels:
+            raise ValueError("probs has %d labels, decoder was built with %d" % (V, self._num_labels))
+        cfg = _cfg(self)
+        K = self._beam_width
+        if probs.is_cuda:
+            return self._decode_device(lib, cfg, probs, seq_lens, B, T, K)
+        probs = probs.float().contiguous()
+        if seq_lens is not None:
+            seq_lens = seq_lens.cpu().int().contiguous()
+        output = torch.empty(B, K, T, dtype=torch.int32)
+        timesteps = torch.empty(B, K, T, dtype=torch.int32)
+        scores = torch.empty(B, K, dtype=torch.float32)
+        out_seq_len = torch.zeros(B, K, dtype=torch.int32)
+        n_results = torch.zeros(B, dtype=torch.int32)
+        flags = torch.zeros(B, dtype=torch.int32)
+        _native.check(lib.ctcdec_decode_batch_host(
+            ctypes.byref(cfg), probs.data_ptr(), seq_lens.data_ptr() if seq_lens is not None else None, B, T,
+            output.data_ptr(), timesteps.data_ptr(), scores.data_ptr(), out_seq_len.data_ptr(),
+            n_results.data_ptr(), flags.data_ptr(), self._device_index()))
+        self.last_flags, self.last_n_results = flags, n_results
+        return output, scores, timesteps, out_seq_len
+
+    def _decode_device(self, lib, cfg, probs, seq_lens, B, T, K):
+        dev = probs.device
+        probs = probs.float().contiguous()
+        if seq_lens is not None:
+            seq_lens = seq_lens.to(device=dev, dtype=torch.int32).contiguous()
+        nbytes = ctypes.c_size_t(0)
+        _native.check(lib.ctcdec_workspace_bytes(ctypes.byref(cfg), B, T, ctypes.byref(nbytes)))
+        if self._ws is None or self._ws.numel() < nbytes.value or self._ws.device != dev:
+            self._ws = None
+            self._ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+        output = torch.empty(B, K, T, dtype=torch.int32, device=dev)
+        timesteps = torch.empty(B, K, T, dtype=torch.int32, device=dev)
+        scores = torch.empty(B, K, dtype=torch.float32, device=dev)
+        out_seq_len = torch.zeros(B, K, dtype=torch.int32, device=dev)
+        n_results = torch.zeros(B, dtype=torch.int32, device=dev)
+        flags = torch.zeros(B, dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _native.check(lib.ctcdec_decode_batch_device(
+                ctypes.byref(cfg), probs.data_ptr(), seq_lens.data_ptr() if seq_lens is not None else None, B, T,
+                output.data_ptr(), timesteps.data_ptr(), scores.data_ptr(), out_seq_len.data_ptr(),
+                n_results.data_ptr(), flags.data_ptr(), self._ws.data_ptr(), self._ws.numel(), stream))
+        self.last_flags, self.last_n_results = flags, n_results
+        if self._device_outputs:
+            return output, scores, timesteps, out_seq_len
+        # reference semantics: CPU tensors.  Only columns < max(out_lens) carry data.
+        lens_cpu = out_seq_len.cpu()
+        max_len = int(lens_cpu.max()) if lens_cpu.numel() else 0
+        out_cpu = torch.empty(B, K, T, dtype=torch.int32)
+        ts_cpu = torch.empty(B, K, T, dtype=torch.int32)
+        if max_len > 0:
+            out_cpu[:, :, :max_len] = output[:, :, :max_len].cpu()
+            ts_cpu[:, :, :max_len] = timesteps[:, :, :max_len].cpu()
+        self.last_flags, self.last_n_results = flags.cpu(), n_results.cpu()
+        return out_cpu, scores.cpu(), ts_cpu, lens_cpu
+
+    def reset_params(self, alpha, beta):
+        pass  # no scorer attached (reference __init__.py:134-136 is a no-op without one)
+
+
+class OnlineCTCBeamDecoder(_Base):
+    """Drop-in for the reference OnlineCTCBeamDecoder (reference ctcdecode/__init__.py:143-250); the per-stream
+    DecoderState (beam, trie, absolute frame counter) lives in GPU memory between chunks."""
+
+    def __init__(self, labels, model_path=None, alpha=0, beta=0, cutoff_top_n=40, cutoff_prob=1.0, beam_width=100,
+                 num_processes=4, blank_id=0, log_probs_input=False, device=None):
+        self._cutoff_top_n = cutoff_top_n  # private name kept from the reference (:175)
+        self._init_common(labels, model_path, alpha, beta, cutoff_top_n, cutoff_prob, beam_width, num_processes,
+                          blank_id, log_probs_input, device)
+
+    def _cutoff_top_n_value(self):
+        return int(self._cutoff_top_n)
+
+    def decode(self, probs, states, is_eos_s, seq_lens=None):
+        """Feeds one chunk per stream.  Returns (beam_results, beam_scores, timesteps, out_lens) like reference
+        __init__.py:189-238: beam_results / timesteps are [B, n_beams, max_len] (both [B, 0, 0] while no stream
+        has reached eos), beam_scores / out_lens are [B, beam]."""
+        lib = _native.load()
+        probs = probs.cpu().float().contiguous()
+        B, T, V = probs.shape
+        if V != self._num_labels:
+            raise ValueError("probs has %d labels, decoder was built with %d" % (V, self._num_labels))
+        if len(states) != B or len(is_eos_s) != B:
+            raise ValueError("need one state and one is_eos flag per batch item")
+        if seq_lens is not None:
+            seq_lens = seq_lens.cpu().int().contiguous()
+        K = self._beam_width
+        scores = torch.empty(B, K, dtype=torch.float32)
+        out_seq_len = torch.zeros(B, K, dtype=torch.int32)
+        n_results = torch.zeros(B, dtype=torch.int32)
+        flags = torch.zeros(B, dtype=torch.int32)
+        handles = (ctypes.c_void_p * B)(*[s.state for s in states])
+        eos = (ctypes.c_uint8 * B)(*[1 if e else 0 for e in is_eos_s])
+        any_eos = any(bool(e) for e in is_eos_s)
+        out_T = 0
+        if any_eos:
+            for b, s in enumerate(states):
+                if is_eos_s[b]:
+                    fr = ctypes.c_int(0)
+                    _native.check(lib.ctcdec_state_frames(s.state, ctypes.byref(fr)))
+                    ln = T if seq_lens is None else max(0, min(int(seq_lens[b]), T))
+                    out_T = max(out_T, fr.value + ln)
+        tokens = torch.zeros(B, K, max(out_T, 1), dtype=torch.int32)
+        timesteps = torch.zeros(B, K, max(out_T, 1), dtype=torch.int32)
+        _native.check(lib.ctcdec_decode_stream_host(
+            probs.data_ptr(), seq_lens.data_ptr() if seq_lens is not None else None, B, T, handles, eos,
+            tokens.data_ptr(), timesteps.data_ptr(), max(out_T, 1), scores.data_ptr(), out_seq_len.data_ptr(),
+            n_results.data_ptr(), flags.data_ptr()))
+        self.last_flags, self.last_n_results = flags, n_results
+        if not any_eos:
+            empty = torch.zeros(B, 0, 0, dtype=torch.int32)
+            return empty, scores, empty.clone(), out_seq_len
+        max_res = int(n_results.max())
+        max_len = int(out_seq_len.max())
+        # reference binding.cpp:181-205: tensors sized [B, max_result_size, max_output_tokens_size]
+        return (tokens[:, :max_res, :max_len].contiguous(), scores, timesteps[:, :max_res, :max_len].contiguous(),
+                out_seq_len)
+
+    def reset_state(state):  # noqa: N805 -- signature kept from the reference (:249), which lacks `self`
+        state.release()
+
+
+class DecoderState(object):
+    """One stream's decoding state (reference ctcdecode/__init__.py:253-272); device resident."""
+
+    def __init__(self, decoder):
+        lib = _native.load()
+        cfg = _cfg(decoder)
+        handle = ctypes.c_void_p()
+        _native.check(lib.ctcdec_state_create(ctypes.byref(cfg), decoder._device_index(), ctypes.byref(handle)))
+        self.state = handle.value
+
+    def release(self):
+        if getattr(self, "state", None):
+            _native.load().ctcdec_state_destroy(self.state)
+            self.state = None
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass

@@ -1,0 +1,117 @@
+/*
+ * ctcdecode_b200 -- C ABI of the B200-native CTC prefix beam-search decoder.
+ *
+ * This is the drop-in boundary for ONE path of parlance/ctcdecode: the batched beam search that the
+ * reference reaches through its pybind module `ctcdecode._ext.ctc_decode` (reference
+ * ctcdecode/src/binding.cpp:290-303).  Every entry point below names the reference interface it
+ * replaces.  Plain pointers and sizes only -- no torch / pybind types -- so the same library binds
+ * from the reference's own __init__.py (ctypes), from C++ (binding.cpp) or from anything with an FFI.
+ * INTEGRATION.md shows the reference-side stubs.
+ *
+ * Conventions
+ *   - every function returns CTCDEC_OK (0) or a negative CTCDEC_E_* code; ctcdec_last_error() gives
+ *     the message for the calling thread.  Nothing aborts the process (the reference's
+ *     VALID_CHECK -> LOG(FATAL) does, decoder_utils.h:17-23).
+ *   - tensors are dense, row-major, caller-allocated, exactly shaped like the reference's:
+ *       probs      float32 [B, T, V]          (probabilities, or log-probabilities if log_input)
+ *       seq_lens   int32   [B] or NULL         (NULL = T for every utterance; values clamped to
+ *                                               [0, T] like reference binding.cpp:64-65)
+ *       tokens     int32   [B, beam, T]        (reference `output`;  only [b, p, :lens[b,p]] written)
+ *       timesteps  int32   [B, beam, T]        (only [b, p, :lens[b,p]] written)
+ *       scores     float32 [B, beam]           (rows p < n_results[b] written)
+ *       lens       int32   [B, beam]           (reference `out_seq_len`; rows p < n_results[b] written)
+ *     plus two outputs the reference does not have (both may be NULL):
+ *       n_results  int32   [B]   how many beams utterance b produced (reference: results.size())
+ *       flags      int32   [B]   CTCDEC_FLAG_* bits; the TIE bits mark utterances where the
+ *                                reference's own result is unspecified (equal score AND equal last
+ *                                character straddling a cut -- std::nth_element / std::sort internals)
+ *   - "device" entry points take device pointers and a CUDA stream and never synchronise; "host"
+ *     entry points take host pointers, stage through pinned memory and return when results are in
+ *     the caller's buffers (what the reference's CPU-tensor API looks like to its caller).
+ */
+#ifndef CTCDECODE_B200_H_
+#define CTCDECODE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CTCDEC_OK 0
+#define CTCDEC_E_INVALID (-1)   /* bad argument (shape, range, NULL)                                  */
+#define CTCDEC_E_UNSUPPORTED (-2) /* configuration outside what the kernels implement (says which)    */
+#define CTCDEC_E_CUDA (-3)      /* a CUDA runtime call failed                                         */
+#define CTCDEC_E_WORKSPACE (-4) /* workspace too small                                                */
+#define CTCDEC_E_NO_DEVICE (-5) /* no CUDA device / wrong architecture: there is NO CPU fallback      */
+
+#define CTCDEC_FLAG_TIE_PRUNE 1
+#define CTCDEC_FLAG_TIE_FINAL 2
+#define CTCDEC_FLAG_TIE_VOCAB 4
+#define CTCDEC_FLAG_ERR_ARENA 256
+
+/* Decoder parameters: the arguments of the reference's ctc_beam_search_decoder_batch
+ * (ctc_beam_search_decoder.h:63-72) / paddle_beam_decode (binding.cpp:103-120) that shape the search.
+ * `num_processes` has no equivalent: the batch is a CUDA grid, one CTA per utterance. */
+typedef struct ctcdec_config {
+  int vocab_size;      /* V = len(labels)                                   */
+  int beam_size;       /* beam_width                                         */
+  int blank_id;        /* index of the CTC blank                             */
+  int log_input;       /* 0: probs are probabilities, 1: log-probabilities   */
+  int cutoff_top_n;    /* reference default 40                               */
+  double cutoff_prob;  /* reference default 1.0                              */
+} ctcdec_config;
+
+const char *ctcdec_version(void);
+const char *ctcdec_last_error(void);
+
+/* Number of CUDA devices usable by this library (compute capability 10.x); 0 if none. */
+int ctcdec_device_count(void);
+
+/* Bytes of device scratch ctcdec_decode_batch_device needs for a [B, T, V] batch. */
+int ctcdec_workspace_bytes(const ctcdec_config *cfg, int B, int T, size_t *bytes);
+
+/* Replaces: beam_decode / paddle_beam_decode -> ctc_beam_search_decoder_batch with ext_scorer == NULL
+ * (reference binding.cpp:35-120, ctc_beam_search_decoder.cpp:245-285).  All pointers are DEVICE
+ * pointers on the current device; work is enqueued on `stream` (a cudaStream_t) and not synchronised. */
+int ctcdec_decode_batch_device(const ctcdec_config *cfg, const float *probs, const int32_t *seq_lens, int B, int T,
+                               int32_t *tokens, int32_t *timesteps, float *scores, int32_t *lens,
+                               int32_t *n_results, int32_t *flags, void *workspace, size_t workspace_bytes,
+                               void *stream);
+
+/* Same operation with HOST buffers shaped exactly like the reference's CPU tensors
+ * (reference __init__.py:77-86); copies in and out through pinned staging on `device`. */
+int ctcdec_decode_batch_host(const ctcdec_config *cfg, const float *probs, const int32_t *seq_lens, int B, int T,
+                             int32_t *tokens, int32_t *timesteps, float *scores, int32_t *lens, int32_t *n_results,
+                             int32_t *flags, int device);
+
+/* ---- streaming (OnlineCTCBeamDecoder) ------------------------------------------------------------- */
+
+/* Replaces: paddle_get_decoder_state (binding.cpp:246-261).  The state (beam + trie + absolute frame
+ * counter, reference ctc_beam_search_decoder.h:73-124) lives in device memory of `device`. */
+int ctcdec_state_create(const ctcdec_config *cfg, int device, void **state);
+/* Replaces: paddle_release_state (binding.cpp:263-265). */
+int ctcdec_state_destroy(void *state);
+/* Frames consumed so far (reference DecoderState::abs_time_step). */
+int ctcdec_state_frames(const void *state, int *frames);
+
+/* Replaces: beam_decode_with_given_state / paddle_beam_decode_with_given_state ->
+ * ctc_beam_search_decoder_batch_with_states (binding.cpp:153-241, ctc_beam_search_decoder.cpp:288-317).
+ * probs [B, T, V] and seq_lens are HOST buffers holding the next chunk of every stream; states[b] is
+ * advanced by min(seq_lens[b], T) frames; for streams with is_eos[b] != 0 the current beams are written
+ * to tokens/timesteps [B, beam, out_T] (rows of other streams untouched), scores/lens [B, beam].
+ * out_T must be >= the longest prefix (the number of frames consumed is always enough). */
+int ctcdec_decode_stream_host(const float *probs, const int32_t *seq_lens, int B, int T, void *const *states,
+                              const uint8_t *is_eos, int32_t *tokens, int32_t *timesteps, int out_T, float *scores,
+                              int32_t *lens, int32_t *n_results, int32_t *flags);
+
+/* ---- diagnostics used by the tests (device self-check of the bit-exact libm restatements) ----------- */
+/* y[i] = f(x[i]) computed ON THE DEVICE; which: 0 expf, 1 logf, 2 float(log(double(x) + FLT_MIN)),
+ * 3 log_sum_exp(x[i], x2[i]).  Host pointers. */
+int ctcdec_selftest_math(int which, const float *x, const float *x2, float *y, size_t n, int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CTCDECODE_B200_H_ */

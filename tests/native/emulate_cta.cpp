@@ -1,0 +1,160 @@
+// TEST INFRASTRUCTURE ONLY -- single-threaded CPU emulation of the CUDA CTA program.
+//
+// ctcdecode_b200/csrc/beam_program.cuh is written as barrier-separated parallel regions; with
+// CTC_EMULATE defined each region becomes a sequential loop over the "threads", so the exact source
+// the GPU runs (beam state machine, radix select, tie handling, trie arena, removal cascade, state
+// save/restore, finalize) can be checked against the oracle on a machine without a GPU.  Warp
+// intrinsics, TMA and atomics have trivial sequential stand-ins; data races are therefore NOT
+// exercised here (compute-sanitizer on the GPU box does that).  The product never builds or loads
+// this file: python -m pytest -m "not gpu" compiles it into tests/native/_build/.
+#define CTC_EMULATE 1
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../ctcdecode_b200/csrc/beam_program.cuh"
+#include "../../ctcdecode_b200/csrc/plan.h"
+
+using namespace ctc;
+
+// Host mirror of prune_program.cuh (same row format); the vocabulary cut follows reference
+// decoder_utils.cpp:10-45 literally.
+static void prune_rows(const ctcdec_config &cfg, const Plan &pl, const float *probs, const int *seq_lens, int B, int T,
+                       float *lp, uint16_t *idx, int *flags) {
+  const int V = cfg.vocab_size, NP = pl.NP;
+  std::vector<std::pair<uint64_t, int>> keys(V);
+  for (int b = 0; b < B; ++b) {
+    int len = seq_lens ? seq_lens[b] : T;
+    for (int t = 0; t < T && t < len; ++t) {
+      const float *row = probs + ((size_t)b * T + t) * V;
+      float *out = lp + ((size_t)b * T + t) * NP;
+      if (!pl.sorted) {
+        float mx = kNInf;
+        for (int r = 0; r < NP - 2; ++r) {
+          float v = kNInf;
+          if (r < V) {
+            v = cfg.log_input ? row[r] : logprob_glibc(row[r]);
+            if (r != cfg.blank_id && ord_f(v) > ord_f(mx)) mx = v;
+          }
+          out[r] = v;
+        }
+        const int rb = cfg.blank_id < V ? cfg.blank_id : -1;
+        out[NP - 2] = bits_f((uint32_t)V | ((uint32_t)(rb + 1) << 16));
+        out[NP - 1] = mx;
+        continue;
+      }
+      uint16_t *oidx = idx + ((size_t)b * T + t) * NP;
+      for (int c = 0; c < V; ++c) keys[c] = {((uint64_t)ord_f(row[c]) << 32) | (uint64_t)(0xFFFFFFFFu - (unsigned)c), c};
+      std::sort(keys.begin(), keys.end(), [](const auto &a, const auto &b) { return a.first > b.first; });
+      int n;
+      if (!pl.cp_active) {
+        n = std::min(cfg.cutoff_top_n, V);
+      } else {
+        double cum = 0.0;
+        n = 0;
+        for (int i = 0; i < V; ++i) {
+          const double v = (double)row[keys[i].second];
+          const double term = cfg.log_input ? v : std::log(v);
+          if (!(term <= -DBL_MAX)) {
+            const double m = std::max(cum, term);
+            cum = std::log(std::exp(cum - m) + std::exp(term - m)) + m;
+          }
+          n += 1;
+          if (cum >= cfg.cutoff_prob || n >= cfg.cutoff_top_n) break;
+        }
+      }
+      if (n > 0 && n < V && (keys[n - 1].first >> 32) == (keys[n].first >> 32)) flags[b] |= FLAG_TIE_VOCAB;
+      int rb = 0;
+      for (int r = 0; r < NP; ++r) {
+        float v = kNInf;
+        unsigned c = 0xFFFFu;
+        if (r < n) {
+          c = (unsigned)keys[r].second;
+          v = cfg.log_input ? row[c] : logprob_glibc(row[c]);
+          if ((int)c == cfg.blank_id) rb = r + 1;
+        }
+        if (r < NP - 2) out[r] = v;
+        oidx[r] = (uint16_t)c;
+      }
+      out[NP - 2] = bits_f((uint32_t)n | ((uint32_t)rb << 16));
+      out[NP - 1] = (rb == 1) ? (n > 1 ? out[1] : kNInf) : (n > 0 ? out[0] : kNInf);
+    }
+  }
+}
+
+template <int NT>
+static void run_beam(const BeamParams &bp, bool sorted, int B, unsigned char *smem) {
+  for (int b = 0; b < B; ++b) {
+    if (sorted) beam_cta_run<NT, true>(bp, b, smem);
+    else beam_cta_run<NT, false>(bp, b, smem);
+  }
+}
+
+extern "C" {
+
+// Offline batch decode through the emulated CTA program.  `chunk` > 0 feeds the frames in chunks of
+// that many frames through the streaming state path (state stored to / loaded from "global" memory
+// between chunks); chunk <= 0 decodes in one go.  Returns 0 or a CTCDEC_E_* code.
+int emu_decode_batch(const float *probs, const int *seq_lens, int B, int T, int V, int K, double cutoff_prob,
+                     int cutoff_top_n, int blank, int log_input, int NT, int chunk, int *tokens, int *timesteps,
+                     float *scores, int *lens, int *n_results, int *flags) {
+  ctcdec_config cfg;
+  cfg.vocab_size = V; cfg.beam_size = K; cfg.blank_id = blank; cfg.log_input = log_input;
+  cfg.cutoff_top_n = cutoff_top_n; cfg.cutoff_prob = cutoff_prob;
+  Plan pl;
+  char msg[256];
+  int rc = make_plan_core(&cfg, B, T, &pl, msg, sizeof(msg));
+  if (rc) { fprintf(stderr, "emu: %s\n", msg); return rc; }
+  if (NT <= 0) NT = pl.NT;
+  std::vector<float> lp((size_t)B * T * pl.NP + 8, 0.f);
+  std::vector<uint16_t> idx(pl.sorted ? (size_t)B * T * pl.NP + 8 : 8, 0);
+  std::vector<Node> arena((size_t)B * pl.arena_stride);
+  std::vector<int> state((size_t)B * pl.state_stride, 0);
+  std::vector<unsigned char> smem(pl.L.total + 64);
+  for (int b = 0; b < B; ++b) flags[b] = 0;
+  prune_rows(cfg, pl, probs, seq_lens, B, T, lp.data(), idx.data(), flags);
+
+  BeamParams bp;
+  memset(&bp, 0, sizeof(bp));
+  bp.V = V; bp.NP = pl.NP; bp.K = K; bp.blank = blank; bp.tile_frames = pl.F;
+  bp.arena = arena.data(); bp.arena_stride = pl.arena_stride; bp.state = state.data();
+  bp.state_stride = pl.state_stride; bp.arena_cap = (int)pl.arena_stride;
+  bp.out_tokens = tokens; bp.out_timesteps = timesteps; bp.out_scores = scores; bp.out_lens = lens;
+  bp.n_results = n_results; bp.out_T = T; bp.flags = flags;
+
+  std::vector<int> chunk_lens(B);
+  const int step = chunk > 0 ? chunk : (T > 0 ? T : 1);
+  bool first = true;
+  for (int t0 = 0; t0 < T || first; t0 += step) {
+    const int tc = std::min(step, T - t0);
+    // a chunk view: rows [t0, t0+tc) of every utterance.  The program indexes lp as [b][T][NP] with
+    // frame offset t, so pass pointers shifted by t0 rows and keep the full stride T.
+    bp.lp = lp.data() + (size_t)t0 * pl.NP;
+    bp.idx = pl.sorted ? idx.data() + (size_t)t0 * pl.NP : nullptr;
+    bp.T = T;
+    for (int b = 0; b < B; ++b) {
+      int len = seq_lens ? seq_lens[b] : T;
+      len = std::max(0, std::min(len, T));
+      chunk_lens[b] = std::max(0, std::min(len - t0, tc));
+    }
+    bp.seq_lens = chunk_lens.data();
+    bp.fresh = first ? 1 : 0;
+    switch (NT) {
+      case 32: run_beam<32>(bp, pl.sorted, B, smem.data()); break;
+      case 64: run_beam<64>(bp, pl.sorted, B, smem.data()); break;
+      case 128: run_beam<128>(bp, pl.sorted, B, smem.data()); break;
+      case 256: run_beam<256>(bp, pl.sorted, B, smem.data()); break;
+      case 1024: run_beam<1024>(bp, pl.sorted, B, smem.data()); break;
+      default: run_beam<512>(bp, pl.sorted, B, smem.data()); break;
+    }
+    first = false;
+    if (T == 0) break;
+  }
+  std::vector<unsigned char> fsmem((size_t)K * 12 + 64);
+  for (int b = 0; b < B; ++b) finalize_cta_run<128>(bp, b, fsmem.data());
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,45 @@
+"""Shared comparison helper: bit-exact check of two decoder outputs (dicts of numpy arrays as returned by
+oracle.oracle / tests.emul / the CUDA path), honouring the reference's "unspecified" cases.
+
+Integer outputs (tokens, timesteps, lens, n_results) must be identical on [:len]; scores must be identical
+as float32 bit patterns (stronger than the 1e-4 the spec asks for).  Utterances whose tie flags are set
+by either side are skipped and counted (the reference's own result there depends on libstdc++
+introsort/introselect internals).  Beams with score == FLT_MAX are -FLT_MAX "junk" prefixes
+ whose relative order is a tie by construction.
+"""
+import numpy as np
+
+FLT_MAX = np.float32(3.4028235e38)
+
+
+def compare(ref, got, ref_ties=None, name=""):
+    B = ref["lens"].shape[0]
+    skipped, checked = 0, 0
+    for b in range(B):
+        tie = 0
+        if ref_ties is not None:
+            tie |= int(ref_ties[b])
+        if "ties" in got:
+            tie |= int(got["ties"][b]) & 7
+        if tie:
+            skipped += 1
+            continue
+        checked += 1
+        n = int(ref["n_results"][b])
+        assert int(got["n_results"][b]) == n, f"{name} utt {b}: n_results {got['n_results'][b]} != {n}"
+        rs, gs = ref["scores"][b, :n], got["scores"][b, :n]
+        junk = rs == FLT_MAX
+        assert np.array_equal(junk, gs == FLT_MAX), f"{name} utt {b}: junk beam pattern differs"
+        ok = ~junk
+        assert np.array_equal(rs[ok].view(np.int32), gs[ok].view(np.int32)), \
+            f"{name} utt {b}: scores differ\n{rs[ok][:8]}\n{gs[ok][:8]}"
+        assert np.array_equal(ref["lens"][b, :n][ok], got["lens"][b, :n][ok]), f"{name} utt {b}: lens differ"
+        for p in range(n):
+            if junk[p]:
+                continue
+            L = int(ref["lens"][b, p])
+            assert np.array_equal(ref["tokens"][b, p, :L], got["tokens"][b, p, :L]), \
+                f"{name} utt {b} beam {p}: tokens differ\n{ref['tokens'][b, p, :L]}\n{got['tokens'][b, p, :L]}"
+            assert np.array_equal(ref["timesteps"][b, p, :L], got["timesteps"][b, p, :L]), \
+                f"{name} utt {b} beam {p}: timesteps differ\n{ref['timesteps'][b, p, :L]}\n{got['timesteps'][b, p, :L]}"
+    return checked, skipped
