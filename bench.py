@@ -1,0 +1,293 @@
+#!/usr/bin/env python
+"""bench.py -- utterances/sec of the CTC beam-search hot path on BASELINE.json's config 2
+([256, T=1000, V=29] per GPU, beam 100, cutoff_top_n 40, cutoff_prob 1.0, no LM; synthetic CTC-like input).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c2|c4]
+
+One process per GPU (torchrun sets RANK / LOCAL_RANK / WORLD_SIZE); utterances are independent, so each
+rank decodes its own [256, T, V] shard and there is no data-path collective ("weak" scaling, N=8 is
+BASELINE config 3: 2048 utterances over 8 GPUs).  Rank 0 prints ONE JSON line:
+
+  value        whole-job utterances/s with inputs resident in HBM (device entry point of the C ABI), CUDA-event
+               time of K steps, max over ranks; L2 is flushed between timed steps
+  e2e          same metric through the host-buffer C-ABI call: pinned host probs -> H2D -> kernels -> D2H of the
+               results into pinned host tensors, wall clock around the call, max over ranks
+  roofline     beam-search kernel: algorithmic bytes (B*T*V*4) / its CUDA-event duration,
+               against MEASURED_PEAKS.json's HBM copy bandwidth.  The kernel is T-serial per utterance
+               (latency bound), so the fraction is tiny by construction; `scan` reports the HBM-bound
+               prune/log pre-pass the same way.
+  cpu_baseline the reference's own CPU path (oracle/_ref: unmodified reference sources, ThreadPool over all
+               host cores; falls back to the single-threaded C port if that build is absent) on a bounded
+               sample of the same batch
+
+--impl reference times only that CPU path and prints the same line shape with "impl": "reference".
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    "c2": dict(B=256, T=1000, V=29, beam=100, cutoff_top_n=40, cutoff_prob=1.0,
+               name="config2: [256 x T=1000 x V=29] per GPU, beam 100, cutoff_top_n 40, cutoff_prob 1.0, no LM"),
+    "c4": dict(B=256, T=2000, V=256, beam=200, cutoff_top_n=40, cutoff_prob=0.99,
+               name="config4: [256 x T=2000 x V=256] per GPU, beam 200, cutoff_top_n 40, cutoff_prob 0.99, no LM"),
+}
+METRIC = "utterances/sec at beam_width=100, T=1000, V=29; HBM GB/s vs roofline"
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:  # noqa: BLE001
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:  # noqa: BLE001
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def reference_cpu(probs_np, cfg, n_utts, threads):
+    """Times the reference's CPU path on the first n_utts utterances.  Returns (seconds, kind)."""
+    from oracle import oracle as orc
+    sample = probs_np[:n_utts]
+    if orc.reference_available():
+        ref = orc.Reference([str(i) for i in range(cfg["V"])])
+        t0 = time.perf_counter()
+        ref.decode(sample, beam=cfg["beam"], cutoff_prob=cfg["cutoff_prob"], cutoff_top_n=cfg["cutoff_top_n"],
+                   num_processes=threads)
+        return time.perf_counter() - t0, "reference"
+    cp = orc.CPort()
+    t0 = time.perf_counter()
+    cp.decode(sample, beam=cfg["beam"], cutoff_prob=cfg["cutoff_prob"], cutoff_top_n=cfg["cutoff_top_n"])
+    return time.perf_counter() - t0, "port"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    K, W = args.steps, max(args.warmup, 3 if args.impl == "ours" else 0)
+    B, T, V = cfg["B"], cfg["T"], cfg["V"]
+    cores = len(os.sched_getaffinity(0))
+    config = {"workload": cfg["name"], "batch_per_gpu": B, "global_batch": B * world, "T": T, "V": V,
+              "beam_width": cfg["beam"], "cutoff_top_n": cfg["cutoff_top_n"], "cutoff_prob": cfg["cutoff_prob"],
+              "parallelism": "batch-sharded x%d (no data-path collective)" % world,
+              "l2": "flushed between timed steps (256 MiB write)"}
+
+    from ctcdecode_b200.synth import ctc_like_probs
+
+    # ------------------------------------------------------------------------------------------------------
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        probs = ctc_like_probs(B, T, V, seed=0).numpy()
+        n = max(1, min(B, cores))  # one utterance per host thread per step
+        times, kind = [], "reference"
+        for i in range(W + K):
+            dt, kind = reference_cpu(probs, cfg, n, cores)
+            if i >= W:
+                times.append(dt)
+        total = sum(times)
+        val = n * K / total
+        sample = "%d of the %d utterances of the same seeded batch per step (one per host thread)" % (n, B)
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": val, "unit": "utterances/s", "n_gpus": args.gpus,
+            "steps": K, "warmup": W, "ms_per_step": 1e3 * total / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+            "cpu_baseline": {"value": val, "unit": "utterances/s", "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": val, "unit": "utterances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    # ------------------------------------------------------------------------------------------------------
+    import torch
+    import torch.distributed as dist
+    from ctcdecode_b200 import CTCBeamDecoder, _native
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _native.load()
+    probs_cpu = ctc_like_probs(B, T, V, seed=rank)  # every rank its own shard of the global batch
+    labels = [str(i) for i in range(V)]
+    dec = CTCBeamDecoder(labels, beam_width=cfg["beam"], cutoff_top_n=cfg["cutoff_top_n"],
+                         cutoff_prob=cfg["cutoff_prob"], device_outputs=True)
+    probs_dev = probs_cpu.to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    _native.check(lib.ctcdec_profile_enable(1))
+    ms3 = (ctypes.c_float * 3)()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: inputs resident in HBM ---------------------------------------------------------------------
+    for _ in range(W):
+        dec.decode(probs_dev)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    step_ms, kern_ms = [], []
+    for _ in range(K):
+        flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = dec.decode(probs_dev)
+        e1.record()
+        e1.synchronize()
+        step_ms.append(e0.elapsed_time(e1))
+        _native.check(lib.ctcdec_profile_read(ms3))
+        kern_ms.append(list(ms3))
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = sum(step_ms)
+    flags = dec.last_flags
+    n_err = int((flags & 256).sum())
+    n_tie = int(((flags & 7) != 0).sum())
+
+    # ---- e2e: host buffers through the C-ABI host entry point -------------------------------------------------
+    Kb = cfg["beam"]
+    h_probs = probs_cpu.pin_memory()
+    h_tok = torch.empty(B, Kb, T, dtype=torch.int32).pin_memory()
+    h_ts = torch.empty(B, Kb, T, dtype=torch.int32).pin_memory()
+    h_sc = torch.empty(B, Kb, dtype=torch.float32).pin_memory()
+    h_len = torch.zeros(B, Kb, dtype=torch.int32).pin_memory()
+    h_nres = torch.zeros(B, dtype=torch.int32).pin_memory()
+    h_flags = torch.zeros(B, dtype=torch.int32).pin_memory()
+    ccfg = _native.Config(V, Kb, 0, 0, cfg["cutoff_top_n"], float(cfg["cutoff_prob"]))
+
+    def host_step():
+        _native.check(lib.ctcdec_decode_batch_host(ctypes.byref(ccfg), h_probs.data_ptr(), None, B, T,
+                                                   h_tok.data_ptr(), h_ts.data_ptr(), h_sc.data_ptr(),
+                                                   h_len.data_ptr(), h_nres.data_ptr(), h_flags.data_ptr(),
+                                                   local_rank))
+
+    for _ in range(W):
+        host_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        host_step()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    max_len = int(h_len.max())
+    h2d = B * T * V * 4
+    d2h = 2 * B * Kb * max_len * 4 + 2 * B * Kb * 4 + 2 * B * 4
+    # sanity: host path and device path agree
+    same = bool(torch.equal(h_sc, out[1].cpu()) and torch.equal(h_len, out[3].cpu()))
+
+    # ---- reduce over ranks (max time) ----------------------------------------------------------------------------
+    t = torch.tensor([total_ms, e2e_s * 1e3, float(n_err), float(n_tie), 0.0 if same else 1.0], device=dev,
+                     dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max, e2e_ms_max = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    value = B * world * K / (total_ms_max / 1e3)
+    e2e_val = B * world * K / (e2e_ms_max / 1e3)
+    peak, peak_src = peaks()
+    beam_ms = statistics.mean(k[1] for k in kern_ms)
+    scan_ms = statistics.mean(k[0] for k in kern_ms)
+    fin_ms = statistics.mean(k[2] for k in kern_ms)
+    alg_bytes = B * T * V * 4
+    achieved = alg_bytes / (beam_ms * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": "utterances/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": config,
+        "e2e": {"value": e2e_val, "unit": "utterances/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_ms_max / K, "host_equals_device": same},
+        "gpu_launches": 3 * K,
+        "kernels_ms": {"prune_log_scan": scan_ms, "beam_search": beam_ms, "finalize": fin_ms,
+                       "beam_share_of_step": beam_ms * K / total_ms},
+        "roofline": {"kernel": "beam_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": alg_bytes,
+                     "ns_per_frame_per_cta": beam_ms * 1e6 / T,
+                     "note": "T-serial per utterance: latency bound, far below the HBM roofline by construction",
+                     "scan": {"kernel": "prune_kernel", "achieved": (alg_bytes + B * T * 32 * 4) / (scan_ms * 1e-3) / 1e9,
+                              "unit": "GB/s", "frac": (alg_bytes + B * T * 32 * 4) / (scan_ms * 1e-3) / 1e9 / peak}},
+        "clocks": clocks,
+        "parity": {"arena_errors": int(t[2]), "tie_flagged_utterances_max_per_rank": int(t[3])},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        # bounded sample: one utterance per host thread, repeated until ~10 s of CPU work
+        n = max(1, min(B, cores))
+        dt, kind = reference_cpu(probs_cpu.numpy(), cfg, n, cores)
+        reps, spent = 1, dt
+        while spent < 10.0 and reps < 8:
+            d2, _ = reference_cpu(probs_cpu.numpy(), cfg, n, cores)
+            spent += d2
+            reps += 1
+        line["cpu_baseline"] = {"value": n * reps / spent, "unit": "utterances/s", "cores": cores if kind == "reference" else 1,
+                                "kind": kind,
+                                "sample": "%d x the first %d utterances of the same batch (one per host thread)" % (reps, n)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

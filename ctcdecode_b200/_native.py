@@ -34,6 +34,8 @@ _SIGNATURES = {
     "ctcdec_state_frames": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_int)]),
     "ctcdec_decode_stream_host": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(_vp), _vp,
                                                  _vp, _vp, ctypes.c_int, _vp, _vp, _vp, _vp]),
+    "ctcdec_profile_enable": (ctypes.c_int, [ctypes.c_int]),
+    "ctcdec_profile_read": (ctypes.c_int, [ctypes.POINTER(ctypes.c_float)]),
     "ctcdec_selftest_math": (ctypes.c_int, [ctypes.c_int, _vp, _vp, _vp, ctypes.c_size_t, ctypes.c_int]),
 }
 EXPORTS = tuple(_SIGNATURES)

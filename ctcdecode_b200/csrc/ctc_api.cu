@@ -166,6 +166,14 @@ static int ensure(DevCache &c, int slot, size_t bytes) {
   return CTCDEC_OK;
 }
 
+// optional per-kernel timing of the device entry point (bench.py roofline leg)
+struct Profile {
+  bool on = false;
+  bool valid = false;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+};
+static thread_local Profile g_prof;
+
 // streaming state object
 struct StreamState {
   ctcdec_config cfg;
@@ -232,7 +240,15 @@ int ctcdec_decode_batch_device(const ctcdec_config *cfg, const float *probs, con
 
   float *lp = reinterpret_cast<float *>(ws + pl.off_lp);
   uint16_t *idx = pl.sorted ? reinterpret_cast<uint16_t *>(ws + pl.off_idx) : nullptr;
+  const bool prof = g_prof.on;
+  if (prof) {
+    for (int i = 0; i < 4; ++i)
+      if (!g_prof.ev[i]) CU(cudaEventCreate(&g_prof.ev[i]));
+    g_prof.valid = false;
+    CU(cudaEventRecord(g_prof.ev[0], s));
+  }
   if ((rc = launch_prune(cfg, pl, probs, seq_lens, B, T, lp, idx, flags_dev, s))) return rc;
+  if (prof) CU(cudaEventRecord(g_prof.ev[1], s));
 
   BeamParams bp;
   memset(&bp, 0, sizeof(bp));
@@ -243,7 +259,27 @@ int ctcdec_decode_batch_device(const ctcdec_config *cfg, const float *probs, con
   bp.out_tokens = tokens; bp.out_timesteps = timesteps; bp.out_scores = scores; bp.out_lens = lens;
   bp.n_results = nres_dev; bp.out_T = T; bp.flags = flags_dev;
   if ((rc = launch_beam(bp, pl, B, s))) return rc;
-  return launch_finalize(bp, B, s);
+  if (prof) CU(cudaEventRecord(g_prof.ev[2], s));
+  if ((rc = launch_finalize(bp, B, s))) return rc;
+  if (prof) {
+    CU(cudaEventRecord(g_prof.ev[3], s));
+    g_prof.valid = true;
+  }
+  return CTCDEC_OK;
+}
+
+int ctcdec_profile_enable(int on) {
+  g_prof.on = on != 0;
+  g_prof.valid = false;
+  return CTCDEC_OK;
+}
+
+int ctcdec_profile_read(float *ms) {
+  if (!ms) return fail(CTCDEC_E_INVALID, "ms is NULL");
+  if (!g_prof.valid) return fail(CTCDEC_E_INVALID, "no profiled decode on this thread");
+  CU(cudaEventSynchronize(g_prof.ev[3]));
+  for (int i = 0; i < 3; ++i) CU(cudaEventElapsedTime(&ms[i], g_prof.ev[i], g_prof.ev[i + 1]));
+  return CTCDEC_OK;
 }
 
 int ctcdec_decode_batch_host(const ctcdec_config *cfg, const float *probs, const int32_t *seq_lens, int B, int T,

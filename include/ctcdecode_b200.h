@@ -106,6 +106,13 @@ int ctcdec_decode_stream_host(const float *probs, const int32_t *seq_lens, int B
                               const uint8_t *is_eos, int32_t *tokens, int32_t *timesteps, int out_T, float *scores,
                               int32_t *lens, int32_t *n_results, int32_t *flags);
 
+/* ---- measurement hook (bench.py) --------------------------------------------------------------------
+ * With profiling enabled on the calling thread, ctcdec_decode_batch_device records CUDA events on its stream
+ * around each of its three kernels; ctcdec_profile_read waits for the last decode of this thread and returns
+ * the device time in milliseconds of {prune/log scan, beam search, finalize}. */
+int ctcdec_profile_enable(int on);
+int ctcdec_profile_read(float *ms3);
+
 /* ---- diagnostics used by the tests (device self-check of the bit-exact libm restatements) ----------- */
 /* y[i] = f(x[i]) computed ON THE DEVICE; which: 0 expf, 1 logf, 2 float(log(double(x) + FLT_MIN)),
  * 3 log_sum_exp(x[i], x2[i]).  Host pointers. */

@@ -1,0 +1,23 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def cport():
+    from oracle.oracle import CPort
+    return CPort()
+
+
+@pytest.fixture(scope="session")
+def labels29():
+    return ["_"] + [chr(ord("a") + i) for i in range(26)] + [" ", "'"]

@@ -1,0 +1,194 @@
+"""Parity tests proper (B200, -m gpu): the CUDA path, called through the reference-shaped Python interface and
+the C ABI, against (1) committed outputs of the unmodified reference, (2) the CPU oracle on seeded inputs,
+(3) size-independent properties at BASELINE.json's full sizes.  Integers bit-exact, float32 scores bit-exact
+(the spec allows 1e-4)."""
+import numpy as np
+import pytest
+import torch
+
+from ctcdecode_b200.synth import ctc_like_probs, flat_probs
+from tests import golden_util
+from tests.parity import compare
+
+pytestmark = pytest.mark.gpu
+
+VOCAB = ["'", " ", "a", "b", "c", "d", "_"]
+
+
+def _decoder(V, **kw):
+    from ctcdecode_b200 import CTCBeamDecoder
+    return CTCBeamDecoder([str(i) for i in range(V)], beam_width=kw.get("beam", 100),
+                          cutoff_top_n=kw.get("cutoff_top_n", 40), cutoff_prob=kw.get("cutoff_prob", 1.0),
+                          blank_id=kw.get("blank_id", 0), log_probs_input=kw.get("log_input", False),
+                          device_outputs=kw.get("device_outputs", False))
+
+
+def _run(probs, seq_lens=None, on_device=True, **kw):
+    dec = _decoder(probs.shape[2], **kw)
+    p = torch.from_numpy(np.ascontiguousarray(probs))
+    sl = None if seq_lens is None else torch.from_numpy(np.asarray(seq_lens, np.int32))
+    out, scores, ts, lens = dec.decode(p.cuda() if on_device else p, sl)
+    return dict(tokens=out.cpu().numpy(), timesteps=ts.cpu().numpy(), scores=scores.cpu().numpy(),
+                lens=lens.cpu().numpy(), n_results=dec.last_n_results.cpu().numpy(), ties=dec.last_flags.cpu().numpy())
+
+
+@pytest.mark.parametrize("on_device", [True, False])
+@pytest.mark.parametrize("name", golden_util.names())
+def test_cuda_matches_reference_golden(name, on_device):
+    probs, seq_lens, kw, ref = golden_util.load(name)
+    got = _run(probs, seq_lens, on_device=on_device, **kw)
+    checked, skipped = compare(ref, got, None, name)
+    assert not (got["ties"] & 256).any()
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(B=4, T=50, V=6, seed=1, peak=3.0, beam=4),                       # BASELINE config 1
+    dict(B=8, T=1000, V=29, seed=2, beam=100),                             # config 2 shape (8 of 256)
+    dict(B=4, T=300, V=29, seed=3, beam=100, log=True),
+    dict(B=4, T=200, V=29, seed=4, beam=16, cutoff_top_n=10),
+    dict(B=2, T=400, V=256, seed=5, beam=200, cutoff_prob=0.99),           # config 4 shape, short
+    dict(B=4, T=150, V=29, seed=6, beam=16, cutoff_prob=0.5),
+    dict(B=4, T=100, V=29, seed=7, beam=300),
+    dict(B=2, T=100, V=12, seed=8, beam=8, blank_id=11),
+    dict(B=2, T=60, V=29, seed=9, beam=10, cutoff_top_n=1),
+    dict(B=2, T=60, V=29, seed=9, beam=10, cutoff_top_n=0),
+    dict(B=1, T=30, V=1, seed=10, beam=5),
+    dict(B=8, T=200, V=29, seed=11, beam=50, flat=True),
+    dict(B=1, T=70, V=600, seed=12, beam=12, cutoff_top_n=600),
+    dict(B=2, T=90, V=1500, seed=13, beam=20),                             # wide vocabulary, top-40 cut
+])
+def test_cuda_matches_oracle(cport, cfg):
+    cfg = dict(cfg)
+    B, T, V, seed = cfg.pop("B"), cfg.pop("T"), cfg.pop("V"), cfg.pop("seed")
+    peak, log = cfg.pop("peak", 8.0), cfg.pop("log", False)
+    if cfg.pop("flat", False):
+        probs = flat_probs(B, T, V, seed).numpy()
+    elif V == 1:
+        probs = np.ones((B, T, 1), np.float32)
+    else:
+        probs = ctc_like_probs(B, T, V, seed, peak=peak, blank_id=cfg.get("blank_id", 0), log=log).numpy()
+    if log:
+        cfg["log_input"] = True
+    ref = cport.decode(probs, **cfg)
+    got = _run(probs, **cfg)
+    compare(ref, got, ref["ties"], str(cfg))
+    assert np.array_equal(ref["ties"] != 0, (got["ties"] & 7) != 0)
+    assert not (got["ties"] & 256).any()
+
+
+def test_ragged_empty_and_host_path(cport):
+    probs = ctc_like_probs(8, 120, 29, seed=21).numpy()
+    sl = np.array([120, 0, 1, 7, 64, 119, 200, 33], np.int32)
+    ref = cport.decode(probs, sl, beam=32)
+    for on_device in (True, False):
+        got = _run(probs, sl, on_device=on_device, beam=32)
+        compare(ref, got, ref["ties"], "ragged")
+    assert ref["n_results"][1] == 1 and got["lens"][1, 0] == 0      # empty utterance: root only
+    assert np.signbit(got["scores"][1, 0]) and got["scores"][1, 0] == 0  # -0.0 like the reference
+
+
+def test_reference_unit_tests_through_the_mirrored_api():
+    """reference tests/test_decode.py:37-91 re-read against ctcdecode_b200 (same constructor, same calls)."""
+    import ctcdecode_b200 as ctcdecode
+    probs, _, _, _ = golden_util.load("ref_kat_beam20")
+    conv = lambda tokens, n: "".join(VOCAB[x] for x in tokens[0:n])  # noqa: E731
+    decoder = ctcdecode.CTCBeamDecoder(VOCAB, beam_width=20, blank_id=VOCAB.index("_"))
+    beam_result, beam_scores, timesteps, out_seq_len = decoder.decode(torch.FloatTensor(probs[:1]))
+    assert conv(beam_result[0][0], out_seq_len[0][0]) == "acdc"
+    beam_result, beam_scores, timesteps, out_seq_len = decoder.decode(torch.FloatTensor(probs[1:]))
+    assert conv(beam_result[0][0], out_seq_len[0][0]) == "b'a"
+    decoder = ctcdecode.CTCBeamDecoder(VOCAB, beam_width=20, blank_id=VOCAB.index("_"), num_processes=24)
+    beam_result, beam_scores, timesteps, out_seq_len = decoder.decode(torch.FloatTensor(probs))
+    assert conv(beam_result[0][0], out_seq_len[0][0]) == "acdc" and conv(beam_result[1][0], out_seq_len[1][0]) == "b'a"
+    assert beam_result.shape == (2, 20, 6) and timesteps.shape == (2, 20, 6) and beam_scores.shape == (2, 20)
+    assert beam_result.dtype == torch.int32 and beam_scores.dtype == torch.float32 and not beam_result.is_cuda
+    decoder = ctcdecode.CTCBeamDecoder(VOCAB, beam_width=20, blank_id=VOCAB.index("_"), log_probs_input=True)
+    beam_result, beam_scores, timesteps, out_seq_len = decoder.decode(torch.FloatTensor(probs).log())
+    assert conv(beam_result[0][0], out_seq_len[0][0]) == "acdc" and conv(beam_result[1][0], out_seq_len[1][0]) == "b'a"
+
+
+def test_online_decoder_matches_reference_tests_and_offline(cport):
+    """reference tests/test_decode.py:117-139,161-211 (no-LM online tests) + chunked == offline, bit-exact."""
+    import ctcdecode_b200 as ctcdecode
+    probs, _, _, _ = golden_util.load("ref_kat_beam20")
+    conv = lambda tokens, n: "".join(VOCAB[x] for x in tokens[0:n])  # noqa: E731
+    decoder = ctcdecode.OnlineCTCBeamDecoder(VOCAB, beam_width=20, blank_id=VOCAB.index("_"), log_probs_input=True,
+                                             num_processes=24)
+    s1, s2 = ctcdecode.DecoderState(decoder), ctcdecode.DecoderState(decoder)
+    lp = torch.FloatTensor(probs).log()
+    res, scores, ts, lens = decoder.decode(lp, [s1, s2], [True, True])
+    assert conv(res[0][0], lens[0][0]) == "acdc" and conv(res[1][0], lens[1][0]) == "b'a"
+    # two calls
+    s1, s2 = ctcdecode.DecoderState(decoder), ctcdecode.DecoderState(decoder)
+    r0 = decoder.decode(lp[:, :2], [s1, s2], [False, False])
+    assert r0[0].shape == (2, 0, 0)
+    res, scores, ts, lens = decoder.decode(lp[:, 2:], [s1, s2], [True, True])
+    assert conv(res[0][0], lens[0][0]) == "acdc" and conv(res[1][0], lens[1][0]) == "b'a"
+    # a lot of calls, then eos: result shape covers the longest beam (reference :189-211)
+    dec2 = ctcdecode.OnlineCTCBeamDecoder(VOCAB, beam_width=20, blank_id=VOCAB.index("_"), log_probs_input=True)
+    st = ctcdecode.DecoderState(dec2)
+    for _ in range(300):
+        dec2.decode(lp[:1, :2], [st], [False])
+    res, scores, ts, lens = dec2.decode(lp[:1, 2:], [st], [True])
+    assert res.shape[2] >= int(lens.max())
+    # chunked == offline on a seeded utterance batch, all beams
+    p = ctc_like_probs(3, 160, 29, seed=31)
+    ref = cport.decode(p.numpy(), beam=24)
+    dec3 = ctcdecode.OnlineCTCBeamDecoder([str(i) for i in range(29)], beam_width=24)
+    states = [ctcdecode.DecoderState(dec3) for _ in range(3)]
+    for a, b in [(0, 50), (50, 51), (51, 130)]:
+        dec3.decode(p[:, a:b], states, [False] * 3)
+    res, scores, ts, lens = dec3.decode(p[:, 130:], states, [True] * 3)
+    got = dict(tokens=res.numpy(), timesteps=ts.numpy(), scores=scores.numpy(), lens=lens.numpy(),
+               n_results=dec3.last_n_results.numpy(), ties=dec3.last_flags.numpy())
+    compare(ref, got, ref["ties"], "online")
+
+
+def test_full_size_config2_properties(cport):
+    """BASELINE config 2 at full size [256, 1000, 29], beam 100: properties that need no CPU reference at scale,
+    plus an exact check of a slice."""
+    B, T, V, K = 256, 1000, 29, 100
+    probs = ctc_like_probs(B, T, V, seed=0)
+    dec = _decoder(V, beam=K, device_outputs=True)
+    d = probs.cuda()
+    out, scores, ts, lens = dec.decode(d)
+    flags, nres = dec.last_flags.clone(), dec.last_n_results.clone()
+    assert int((flags & 256).sum()) == 0 and bool((nres == K).all())
+    # determinism
+    out2, scores2, ts2, lens2 = dec.decode(d)
+    assert torch.equal(scores, scores2) and torch.equal(lens, lens2)
+    # batch-order invariance: utterances are independent (reference: one thread-pool task each)
+    perm = torch.randperm(B, generator=torch.Generator().manual_seed(1)).cuda()
+    out3, scores3, ts3, lens3 = dec.decode(d[perm])
+    assert torch.equal(scores3, scores[perm]) and torch.equal(lens3, lens[perm])
+    col = torch.arange(T, device="cuda")[None, None, :]
+    valid = col < lens[:, :, None]
+    assert torch.equal(torch.where(valid, out, 0), torch.where(col < lens3[:, :, None], out3, 0)[torch.argsort(perm)])
+    # structure: sorted by score, tokens are non-blank labels, timesteps inside the utterance, lens <= T
+    assert bool((scores[:, 1:] >= scores[:, :-1]).all())
+    assert bool((lens <= T).all()) and bool((lens >= 0).all())
+    tok = torch.where(valid, out, 1)
+    assert bool(((tok >= 1) & (tok < V)).all())
+    tsv = torch.where(valid, ts, 0)
+    assert bool(((tsv >= 0) & (tsv < T)).all())
+    # exact slice against the oracle
+    sl = [0, 77, 255]
+    ref = cport.decode(probs[sl].numpy(), beam=K)
+    got = dict(tokens=out[sl].cpu().numpy(), timesteps=ts[sl].cpu().numpy(), scores=scores[sl].cpu().numpy(),
+               lens=lens[sl].cpu().numpy(), n_results=nres[sl].cpu().numpy(), ties=flags[sl].cpu().numpy())
+    compare(ref, got, ref["ties"], "config2 slice")
+
+
+def test_full_size_config4_slice(cport):
+    """BASELINE config 4 shape [B, 2000, 256], beam 200, cutoff_prob 0.99: a 16-utterance batch on the GPU, 2
+    checked exactly (the oracle needs ~10 s per utterance here)."""
+    probs = ctc_like_probs(16, 2000, 256, seed=4)
+    dec = _decoder(256, beam=200, cutoff_prob=0.99, device_outputs=True)
+    out, scores, ts, lens = dec.decode(probs.cuda())
+    assert int((dec.last_flags & 256).sum()) == 0
+    sl = [3, 12]
+    ref = cport.decode(probs[sl].numpy(), beam=200, cutoff_prob=0.99)
+    got = dict(tokens=out[sl].cpu().numpy(), timesteps=ts[sl].cpu().numpy(), scores=scores[sl].cpu().numpy(),
+               lens=lens[sl].cpu().numpy(), n_results=dec.last_n_results[sl].cpu().numpy(),
+               ties=dec.last_flags[sl].cpu().numpy())
+    compare(ref, got, ref["ties"], "config4 slice")
