@@ -12,12 +12,19 @@
 //   * the beam x pruned-vocab candidates are never materialised -- a candidate's score is one
 //     float add, recomputed on the fly;
 //   * only candidates that survive the cut become nodes of a per-utterance arena in global memory
-//     (parent / first_child / next_sibling / live-child count / lpc / timestep), so "timesteps"
-//     keeps the reference's arg-max-while-parent-in-beam semantics (path_trie.cpp:41-46) including
-//     dead interior nodes that are later revived (path_trie.cpp:50-56);
+//     (16 bytes: parent, char, lpc, timestep).  The arena is WRITE-ONLY inside the frame loop: it is
+//     read again only by the final backtrace (and by the rare "revive" slow path);
+//   * what the reference finds by walking child vectors -- "which children of a beam member already
+//     exist in the trie?" (path_trie.cpp:39-57) -- is kept in shared memory: every member knows the
+//     slot of its parent if the parent is in the beam, and the only other existing children are
+//     DEAD ANCHORS: dead nodes whose parent is in the beam and that still have a beam member below
+//     them.  There are never more of those than beam members, so a K-entry table holds them, with
+//     their lpc / timestep, so "timesteps" keeps the reference's arg-max-while-parent-in-beam
+//     semantics (path_trie.cpp:41-46) including revival of dead interior nodes (path_trie.cpp:50-56);
+//   * removal (path_trie.cpp:144-163) needs no cascade: a dead node is in the reference's trie iff
+//     some member's nearest anchor is that node, which is a per-frame recount in shared memory;
 //   * the top-beam_size cut is an exact radix select over 48-bit keys (ordered float score,
-//     then smaller char first == prefix_compare) with shared-memory histograms;
-//   * removal (path_trie.cpp:144-163) is a tombstone + atomic live-child count cascade.
+//     then smaller char first == prefix_compare) with shared-memory histograms.
 //
 // The source is written as barrier-separated parallel regions (CTC_PAR { ... } CTC_BARRIER();) so
 // the very same text also compiles as a sequential single-threaded emulation for CPU logic tests
@@ -47,33 +54,30 @@ enum : int {
   FLAG_TIE_PRUNE = 1,   // comparator-equivalent prefixes straddled the beam cut (reference: unspecified)
   FLAG_TIE_FINAL = 2,   // comparator-equivalent prefixes adjacent in the final order
   FLAG_TIE_VOCAB = 4,   // equal probabilities straddled the cutoff_top_n / cutoff_prob cut
-  FLAG_ERR_ARENA = 256, // node arena exhausted (cannot happen with the documented sizing)
+  FLAG_ERR_ARENA = 256, // node arena / anchor table exhausted (cannot happen with the documented sizing)
 };
 
 constexpr float kNInf = -FLT_MAX;  // reference NUM_FLT_INF negated (decoder_utils.h:12)
-constexpr int kStDead = -1;        // node in trie, not in beam (reference exists_ == false)
-constexpr int kStDeleted = -2;     // node removed from the trie (tombstone until unlinked)
 constexpr int kNBins = 256;
+constexpr int kNewFlag = 1 << 30;  // in-frame marker: "parent slot refers to this frame's NEW occupant"
 
-// Trie node, one 32-byte sector.  chr_nchild: low 16 bits = character + 1 (root = 0), high 16 bits =
-// number of children currently in the trie (alive or dead).  state: beam slot (>= 0), kStDead or
-// kStDeleted.
-struct alignas(32) Node {
-  int parent;
-  int first_child;
-  int next_sib;
-  unsigned chr_nchild;
-  float lpc;
-  int ts;
-  int state;
-  int depth;
+// Trie node in the global arena: exactly what the final backtrace needs (reference path_trie.cpp:109-126).
+struct alignas(16) Node {
+  int parent;  // node index, -1 for the root
+  int chr;     // character, -1 for the root
+  float lpc;   // reference PathTrie::log_prob_c
+  int ts;      // reference PathTrie::timestep
 };
 
 // Per-utterance persistent state (global memory; survives between chunks of a streaming decode).
-// Layout in ints: [0]=M (beam count) [1]=nnodes [2]=abs_t [3]=flags, then 7 slot arrays of K ints:
-// node, chr, bprev, nbprev, score, fchild, depth (floats stored by bit pattern).
+// Layout in ints: [0]=M (beam count) [1]=nnodes [2]=abs_t [3]=flags, then 10 slot arrays of K ints
+// (node, chr, depth, bprev, nbprev, score, lpc, ts, pslot, anch; floats by bit pattern) and the
+// dead-anchor table, 5 arrays of 2*KP ints (dnode, dchr, dpslot, dlpc, dts), KP = K rounded up to 32.
 constexpr int kStateHeader = 4;
-CTC_HD long long state_ints(int K) { return kStateHeader + 7ll * K; }
+constexpr int kSlotArrays = 10;
+constexpr int kAnchorArrays = 5;
+CTC_HD int kp_of(int K) { return (K + 31) / 32 * 32; }
+CTC_HD long long state_ints(int K) { return kStateHeader + (long long)kSlotArrays * K + (long long)kAnchorArrays * 2 * kp_of(K); }
 
 struct BeamParams {
   const float *lp;        // [B][T][NP] pruned float32 log-probs from the prune kernel
@@ -83,7 +87,7 @@ struct BeamParams {
   int tile_frames;        // frames per staged tile
   Node *arena;            // offline: base of B arenas
   long long arena_stride; // nodes per utterance
-  int *state;             // offline: base of B state blocks
+  int *state;             // offline: base of B state blocks (state_ints(K) ints each, see above)
   long long state_stride; // ints per utterance
   Node *const *arena_ptrs;  // streaming: per-utterance arena (overrides arena/arena_stride)
   int *const *state_ptrs;   // streaming: per-utterance state block
@@ -102,14 +106,18 @@ struct BeamParams {
 // ---- shared memory carve-up (bytes) ---------------------------------------------------------------
 struct SmemLayout {
   int tile_lp, tile_idx, mbar, rank, exptab, logtab;
-  int node, chr, bprev, nbprev, score, fchild, depth;  // persistent slot arrays [KP]
-  int bnew, nbnew, ext, snew;                          // per-frame slot temporaries [KP]
-  int mask, rmask;                                     // [KP][W] bitmasks over pruned ranks
-  int evict;                                           // [KP]
-  int sel, sel2, freel, freel2, newinfo;               // [KP] lists; newinfo [KP][6]
-  int tie, rv;                                         // [2*KP], [KP][2]
-  int hist;                                            // [2][kNBins]
-  int ctl;                                             // control words
+  int node, chr, depth, bprev, nbprev, score, lpc, ts, pslot, anch;  // persistent slot arrays [KP]
+  int bnew, nbnew, snew;                                             // per-frame slot temporaries [KP]
+  int mask, rmask;                                                   // [KP][W] bitmasks over pruned ranks
+  int evict;                                                         // [KP]
+  int sel, sel2, freel, freel2;                                      // [KP] lists
+  int newinfo;                                                       // [KP][10]
+  int tie;                                                           // [2*KP]
+  int dnode, dchr, dpslot, dlpc, dts, drev;                          // dead-anchor table [2*KP]
+  int cnt2;                                                          // [3*KP] anchor reference counts
+  int amap, efree, newp, newa, resq, rvwork;                         // re-anchoring scratch
+  int hist;                                                          // [2][kNBins]
+  int ctl;                                                           // control words
   int total;
   int KP, W;
 };
@@ -125,19 +133,21 @@ CTC_HD SmemLayout make_layout(int K, int V, int NP, int tile_frames, bool sorted
   L.tile_idx = o;  o += sorted ? 2 * tile_frames * NP * 2 : 0;
   o = align_up(o, 16);
   L.mbar = o;      o += 16;
-  L.rank = o;      o += sorted ? align_up(2 * V * 2, 16) : 0;
+  L.rank = o;      o += sorted ? align_up(V * 2, 16) : 0;
   L.exptab = o;    o += 32 * 8;
   L.logtab = o;    o += 32 * 8;
   L.node = o;      o += KP * 4;
   L.chr = o;       o += KP * 4;
+  L.depth = o;     o += KP * 4;
   L.bprev = o;     o += KP * 4;
   L.nbprev = o;    o += KP * 4;
   L.score = o;     o += KP * 4;
-  L.fchild = o;    o += KP * 4;
-  L.depth = o;     o += KP * 4;
+  L.lpc = o;       o += KP * 4;
+  L.ts = o;        o += KP * 4;
+  L.pslot = o;     o += KP * 4;
+  L.anch = o;      o += KP * 4;
   L.bnew = o;      o += KP * 4;
   L.nbnew = o;     o += KP * 4;
-  L.ext = o;       o += KP * 4;
   L.snew = o;      o += KP * 4;
   L.mask = o;      o += KP * W * 4;
   L.rmask = o;     o += KP * W * 4;
@@ -146,20 +156,32 @@ CTC_HD SmemLayout make_layout(int K, int V, int NP, int tile_frames, bool sorted
   L.sel2 = o;      o += KP * 4;
   L.freel = o;     o += KP * 4;
   L.freel2 = o;    o += KP * 4;
-  L.newinfo = o;   o += KP * 6 * 4;
+  L.newinfo = o;   o += KP * 10 * 4;
   L.tie = o;       o += 2 * KP * 4;
-  L.rv = o;        o += KP * 2 * 4;
+  L.dnode = o;     o += 2 * KP * 4;
+  L.dchr = o;      o += 2 * KP * 4;
+  L.dpslot = o;    o += 2 * KP * 4;
+  L.dlpc = o;      o += 2 * KP * 4;
+  L.dts = o;       o += 2 * KP * 4;
+  L.drev = o;      o += 2 * KP * 4;
+  L.cnt2 = o;      o += 3 * KP * 4;
+  L.amap = o;      o += KP * 4;
+  L.efree = o;     o += 2 * KP * 4;
+  L.newp = o;      o += KP * 4;
+  L.newa = o;      o += KP * 4;
+  L.resq = o;      o += KP * 2 * 4;
+  L.rvwork = o;    o += KP * 3 * 4;
   L.hist = o;      o += 2 * kNBins * 4;
   o = align_up(o, 16);
-  L.ctl = o;       o += 32 * 4 + 16 * 8;
+  L.ctl = o;       o += 32 * 4;
   L.total = o;
   return L;
 }
 
-// control words: 32 ints in L.ctl (followed by 16 spare 64-bit words)
+// control words: 32 ints in L.ctl
 enum {
-  C_M = 0, C_NNODES, C_FLAGS, C_NSEL, C_NFREE, C_NTIE, C_NRV, C_NPAIRS, C_ABOVE, C_BIN, C_CNT, C_KMIN, C_KMAX,
-  C_SMAX
+  C_M = 0, C_NNODES, C_FLAGS, C_NSEL, C_NFREE, C_NTIE, C_NREV, C_NPAIRS, C_ABOVE, C_BIN, C_CNT, C_KMIN, C_KMAX,
+  C_SMAX, C_NEFREE, C_NETAKEN, C_NRVWORK
 };
 
 // ---- small helpers --------------------------------------------------------------------------------
@@ -178,12 +200,14 @@ template <class T> static inline T atom_add(T *p, T v) { T o = *p; *p = o + v; r
 static inline int atom_exch(int *p, int v) { int o = *p; *p = v; return o; }
 static inline unsigned atom_sub_u(unsigned *p, unsigned v) { unsigned o = *p; *p = o - v; return o; }
 static inline int atom_or(int *p, int v) { int o = *p; *p = o | v; return o; }
+static inline unsigned atom_or(unsigned *p, unsigned v) { unsigned o = *p; *p = o | v; return o; }
 template <class T> static inline T ld_cg(const T *p) { return *p; }
 #else
 template <class T> CTC_FN T atom_add(T *p, T v) { return atomicAdd(p, v); }
 CTC_FN int atom_exch(int *p, int v) { return atomicExch(p, v); }
 CTC_FN unsigned atom_sub_u(unsigned *p, unsigned v) { return atomicSub(p, v); }
 CTC_FN int atom_or(int *p, int v) { return atomicOr(p, v); }
+CTC_FN unsigned atom_or(unsigned *p, unsigned v) { return atomicOr(p, v); }
 template <class T> CTC_FN T ld_cg(const T *p) { return __ldcg(p); }
 #endif
 
@@ -202,33 +226,35 @@ CTC_FN float lse_smem(float x, float y, const uint64_t *exptab, const double *lo
 // Everything a region needs, by value (pointers into shared memory / this utterance's global state).
 template <bool SORTED>
 struct Cta {
-  // shared
-  int *s_node, *s_chr, *s_fchild, *s_depth, *s_evict, *s_sel, *s_sel2, *s_free, *s_free2, *s_newinfo, *s_tie,
-      *s_rv, *s_hist;
-  float *s_bprev, *s_nbprev, *s_score, *s_bnew, *s_nbnew, *s_ext, *s_snew;
+  // shared: beam slots
+  int *s_node, *s_chr, *s_depth, *s_ts, *s_pslot, *s_anch;
+  float *s_bprev, *s_nbprev, *s_score, *s_lpc, *s_bnew, *s_nbnew, *s_snew;
   uint32_t *s_mask, *s_rmask;
-  int16_t *s_rank;  // [2][V]
-  int *s_ctl;
-  unsigned long long *s_ctl64;
+  // shared: dead-anchor table (2*KP entries; dpslot < 0 = free)
+  int *s_dnode, *s_dchr, *s_dpslot, *s_dts, *s_drev;
+  float *s_dlpc;
+  // shared: scratch
+  int *s_evict, *s_sel, *s_sel2, *s_free, *s_free2, *s_newinfo, *s_tie, *s_cnt2, *s_amap, *s_efree, *s_newp, *s_newa,
+      *s_resq, *s_rvwork, *s_hist, *s_ctl;
+  int16_t *s_rank;  // [V]
   const uint64_t *s_exptab;
   const double *s_logtab;
   // per frame
-  const float *lp;       // [NP]
-  const uint16_t *idx;   // [NP] (sorted mode)
-  const int16_t *rank;   // [V]  (sorted mode): rank of char in this frame's pruned list or -1
+  const float *lp;      // [NP]
+  const uint16_t *idx;  // [NP] (sorted mode)
   // global
   Node *nodes;
-  int K, V, NP, W, blank;
+  int K, KP, V, NP, W, blank;
 
   CTC_MFN int chr_at(int r) const { return SORTED ? (int)idx[r] : r; }
-  CTC_MFN int rank_of(int c) const { return SORTED ? (int)rank[c] : c; }
+  CTC_MFN int rank_of(int c) const { return SORTED ? (int)s_rank[c] : c; }
 
   // Score of candidate (beam slot i) + (pruned entry r); false if it is not a new-prefix candidate.
   // (reference ctc_beam_search_decoder.cpp:108-118 with nb_cur == -inf => lse(-inf, log_p) = log_p)
   CTC_MFN bool cand(int i, int r, float &sc, int &c) const {
     c = chr_at(r);
     if (c == blank) return false;
-    if ((s_mask[i * W + (r >> 5)] >> (r & 31)) & 1u) return false;  // child is itself a beam member
+    if ((s_mask[i * W + (r >> 5)] >> (r & 31)) & 1u) return false;  // that child is itself a beam member
     const float l = lp[r];
     if (c == s_chr[i]) {
       const float b = s_bprev[i];

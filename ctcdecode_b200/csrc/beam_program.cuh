@@ -5,6 +5,15 @@
 
 namespace ctc {
 
+#if defined(CTC_EMULATE) && defined(CTC_STATS)
+struct EmuStats { long long frames, passes, walk_iters, anchors_live, evicted, anchors_new, rv_hops, created, revived,
+                  hist_adds, tie_frames, sel_all_frames, rv_frames; };
+static EmuStats g_stats;
+#define CTC_STAT(x) (x)
+#else
+#define CTC_STAT(x) ((void)0)
+#endif
+
 #if !defined(CTC_EMULATE)
 // ---- TMA (cp.async.bulk) + mbarrier plumbing for the staged [tile_frames x NP] log-prob tiles -------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -112,12 +121,9 @@ CTC_FN Node load_node(const Node *p) {
 #if defined(CTC_EMULATE)
   return *p;
 #else
-  // two 16-byte L2 loads (nodes are written by other threads of this CTA; skip L1)
-  const int4 a = __ldcg(reinterpret_cast<const int4 *>(p));
-  const int4 b = __ldcg(reinterpret_cast<const int4 *>(p) + 1);
+  const int4 a = __ldcg(reinterpret_cast<const int4 *>(p));  // nodes are written by this CTA: read through L2
   Node n;
-  n.parent = a.x; n.first_child = a.y; n.next_sib = a.z; n.chr_nchild = (unsigned)a.w;
-  n.lpc = __int_as_float(b.x); n.ts = b.y; n.state = b.z; n.depth = b.w;
+  n.parent = a.x; n.chr = a.y; n.lpc = __int_as_float(a.z); n.ts = a.w;
   return n;
 #endif
 }
@@ -125,10 +131,14 @@ CTC_FN void store_node(Node *p, const Node &n) {
 #if defined(CTC_EMULATE)
   *p = n;
 #else
-  int4 a = make_int4(n.parent, n.first_child, n.next_sib, (int)n.chr_nchild);
-  int4 b = make_int4(__float_as_int(n.lpc), n.ts, n.state, n.depth);
-  reinterpret_cast<int4 *>(p)[0] = a;
-  reinterpret_cast<int4 *>(p)[1] = b;
+  *reinterpret_cast<int4 *>(p) = make_int4(n.parent, n.chr, __float_as_int(n.lpc), n.ts);
+#endif
+}
+CTC_FN void flush_lpc_ts(Node *p, float lpc, int ts) {
+#if defined(CTC_EMULATE)
+  p->lpc = lpc; p->ts = ts;
+#else
+  *reinterpret_cast<int2 *>(&p->lpc) = make_int2(__float_as_int(lpc), ts);
 #endif
 }
 
@@ -139,27 +149,31 @@ template <int NT, bool SORTED>
 CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) {
   const int K = p.K, V = p.V, NP = p.NP, F = p.tile_frames;
   const SmemLayout L = make_layout(K, V, NP, F, SORTED);
-  const int KP = L.KP, W = L.W;
+  const int KP = L.KP, W = L.W, KP2 = 2 * L.KP;
 
   Cta<SORTED> c;
   c.s_node = (int *)(smem + L.node);      c.s_chr = (int *)(smem + L.chr);
-  c.s_bprev = (float *)(smem + L.bprev);  c.s_nbprev = (float *)(smem + L.nbprev);
-  c.s_score = (float *)(smem + L.score);  c.s_fchild = (int *)(smem + L.fchild);
-  c.s_depth = (int *)(smem + L.depth);    c.s_bnew = (float *)(smem + L.bnew);
-  c.s_nbnew = (float *)(smem + L.nbnew);  c.s_ext = (float *)(smem + L.ext);
+  c.s_depth = (int *)(smem + L.depth);    c.s_bprev = (float *)(smem + L.bprev);
+  c.s_nbprev = (float *)(smem + L.nbprev);  c.s_score = (float *)(smem + L.score);
+  c.s_lpc = (float *)(smem + L.lpc);      c.s_ts = (int *)(smem + L.ts);
+  c.s_pslot = (int *)(smem + L.pslot);    c.s_anch = (int *)(smem + L.anch);
+  c.s_bnew = (float *)(smem + L.bnew);    c.s_nbnew = (float *)(smem + L.nbnew);
   c.s_snew = (float *)(smem + L.snew);    c.s_mask = (uint32_t *)(smem + L.mask);
   c.s_rmask = (uint32_t *)(smem + L.rmask);  c.s_evict = (int *)(smem + L.evict);
   c.s_sel = (int *)(smem + L.sel);        c.s_sel2 = (int *)(smem + L.sel2);
   c.s_free = (int *)(smem + L.freel);     c.s_free2 = (int *)(smem + L.freel2);
   c.s_newinfo = (int *)(smem + L.newinfo);  c.s_tie = (int *)(smem + L.tie);
-  c.s_rv = (int *)(smem + L.rv);          c.s_hist = (int *)(smem + L.hist);
-  c.s_rank = (int16_t *)(smem + L.rank);
-  c.s_ctl = (int *)(smem + L.ctl);
-  c.s_ctl64 = (unsigned long long *)(smem + L.ctl + 32 * 4);
+  c.s_dnode = (int *)(smem + L.dnode);    c.s_dchr = (int *)(smem + L.dchr);
+  c.s_dpslot = (int *)(smem + L.dpslot);  c.s_dlpc = (float *)(smem + L.dlpc);
+  c.s_dts = (int *)(smem + L.dts);        c.s_drev = (int *)(smem + L.drev);
+  c.s_cnt2 = (int *)(smem + L.cnt2);      c.s_amap = (int *)(smem + L.amap);
+  c.s_efree = (int *)(smem + L.efree);    c.s_newp = (int *)(smem + L.newp);
+  c.s_newa = (int *)(smem + L.newa);      c.s_resq = (int *)(smem + L.resq);
+  c.s_rvwork = (int *)(smem + L.rvwork);  c.s_hist = (int *)(smem + L.hist);
+  c.s_rank = (int16_t *)(smem + L.rank);  c.s_ctl = (int *)(smem + L.ctl);
   c.s_exptab = (uint64_t *)(smem + L.exptab);
   c.s_logtab = (double *)(smem + L.logtab);
-  c.K = K; c.V = V; c.NP = NP; c.W = W; c.blank = p.blank;
-  c.rank = c.s_rank;
+  c.K = K; c.KP = KP; c.V = V; c.NP = NP; c.W = W; c.blank = p.blank;
   int *const s_ctl = c.s_ctl;
 
   Node *const nodes = p.arena_ptrs ? p.arena_ptrs[b] : p.arena + (long long)b * p.arena_stride;
@@ -171,6 +185,8 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
   if (Tb < 0) Tb = 0;
   const int fresh = p.fresh;
   const int abs_t0 = fresh ? 0 : st[2];
+  int *const st_slots = st + kStateHeader;
+  int *const st_anchors = st_slots + kSlotArrays * K;
 
   // ---- region: stage tables, load (or create) the beam state --------------------------------------
   CTC_PAR {
@@ -179,19 +195,31 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
       ((double *)c.s_logtab)[i] = kLogfTab[i];
     }
     for (int j = tid; j < KP; j += NT) {
-      int node = 0, chr = -1, fchild = -1, depth = 0;
-      float bprev = kNInf, nbprev = kNInf, score = kNInf;
+      int node = 0, chr = -1, depth = 0, ts = 0, pslot = -1, anch = -1;
+      float bprev = kNInf, nbprev = kNInf, score = kNInf, lpc = kNInf;
       if (fresh) {
         if (j == 0) { bprev = 0.0f; score = 0.0f; }  // reference ctc_beam_search_decoder.cpp:43
       } else if (j < K) {
-        const int *s = st + kStateHeader;
-        node = s[j]; chr = s[K + j]; bprev = bits_f((uint32_t)s[2 * K + j]); nbprev = bits_f((uint32_t)s[3 * K + j]);
-        score = bits_f((uint32_t)s[4 * K + j]); fchild = s[5 * K + j]; depth = s[6 * K + j];
+        const int *s = st_slots;
+        node = s[j]; chr = s[K + j]; depth = s[2 * K + j]; bprev = bits_f((uint32_t)s[3 * K + j]);
+        nbprev = bits_f((uint32_t)s[4 * K + j]); score = bits_f((uint32_t)s[5 * K + j]);
+        lpc = bits_f((uint32_t)s[6 * K + j]); ts = s[7 * K + j]; pslot = s[8 * K + j]; anch = s[9 * K + j];
       }
-      c.s_node[j] = node; c.s_chr[j] = chr; c.s_bprev[j] = bprev; c.s_nbprev[j] = nbprev; c.s_score[j] = score;
-      c.s_fchild[j] = fchild; c.s_depth[j] = depth;
-      c.s_ext[j] = kNInf; c.s_evict[j] = 0;
+      c.s_node[j] = node; c.s_chr[j] = chr; c.s_depth[j] = depth; c.s_bprev[j] = bprev; c.s_nbprev[j] = nbprev;
+      c.s_score[j] = score; c.s_lpc[j] = lpc; c.s_ts[j] = ts; c.s_pslot[j] = pslot; c.s_anch[j] = anch;
+      c.s_evict[j] = 0;
     }
+    for (int a = tid; a < KP2; a += NT) {
+      int dnode = 0, dchr = 0, dpslot = -1, dts = 0;
+      float dlpc = kNInf;
+      if (!fresh) {
+        dnode = st_anchors[a]; dchr = st_anchors[KP2 + a]; dpslot = st_anchors[2 * KP2 + a];
+        dlpc = bits_f((uint32_t)st_anchors[3 * KP2 + a]); dts = st_anchors[4 * KP2 + a];
+      }
+      c.s_dnode[a] = dnode; c.s_dchr[a] = dchr; c.s_dpslot[a] = dpslot; c.s_dlpc[a] = dlpc; c.s_dts[a] = dts;
+      c.s_drev[a] = 0;
+    }
+    for (int x = tid; x < 3 * KP; x += NT) c.s_cnt2[x] = 0;
     for (int x = tid; x < KP * W; x += NT) { c.s_mask[x] = 0u; c.s_rmask[x] = 0u; }
     for (int x = tid; x < 2 * kNBins; x += NT) c.s_hist[x] = 0;
     if (SORTED) for (int v = tid; v < V; v += NT) c.s_rank[v] = (int16_t)-1;
@@ -202,8 +230,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
       s_ctl[C_FLAGS] = fresh ? 0 : st[3];
       s_ctl[C_KMIN] = (int)0xFFFFFFFFu;
       if (fresh) {  // root node (reference path_trie.cpp:11-30)
-        Node root; root.parent = -1; root.first_child = -1; root.next_sib = -1; root.chr_nchild = 0u;
-        root.lpc = kNInf; root.ts = 0; root.state = 0; root.depth = 0;
+        Node root; root.parent = -1; root.chr = -1; root.lpc = kNInf; root.ts = 0;
         store_node(&nodes[0], root);
       }
     }
@@ -234,6 +261,9 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
 #endif
 
   int M = s_ctl[C_M];
+
+  // "is the parent designation q (a beam slot, possibly tagged kNewFlag) alive after this frame?"
+#define CTC_PARENT_ALIVE(q) ((((q) & kNewFlag) != 0) || c.s_evict[(q)] == 0)
 
   // =================================== the frame loop ===============================================
   for (int t = 0; t < Tb; ++t) {
@@ -267,76 +297,57 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
       CTC_BARRIER();
     }
 
-    // ---- region R1: per-member blank / repeat terms, visit existing children -----------------------
-    // (reference ctc_beam_search_decoder.cpp:97-106 and path_trie.cpp:39-57)
-    CTC_PAR {
-      for (int j = tid; j < M; j += NT) {
-        const float sc = c.s_score[j];
-        const int ch = c.s_chr[j];
-        const float bprev = c.s_bprev[j];
-        c.s_bnew[j] = (rblank >= 0) ? f_add(c.lp[rblank], sc) : kNInf;
-        float rep = kNInf;
-        if (ch >= 0) {
-          const int rr = c.rank_of(ch);
-          if (rr >= 0) rep = f_add(c.lp[rr], c.s_nbprev[j]);
-        }
-        c.s_nbnew[j] = rep;
-        int k = c.s_fchild[j], prev = -1, npairs = 0;
-        while (k >= 0) {
-          const Node nd = load_node(&nodes[k]);
-          const int nxt = nd.next_sib;
-          if (nd.state == kStDeleted) {  // lazily unlink tombstones (only this thread edits this list now)
-            if (prev < 0) c.s_fchild[j] = nxt; else nodes[prev].next_sib = nxt;
-            k = nxt;
-            continue;
-          }
-          const int cc = (int)(nd.chr_nchild & 0xFFFFu) - 1;
-          const int rr = c.rank_of(cc);
-          if (rr >= 0) {
-            const float l = c.lp[rr];
-            if (nd.lpc < l) {  // path_trie.cpp:41-46
-              nodes[k].lpc = l;
-              nodes[k].ts = t_abs;
-            }
-            float log_p;
-            if (cc == ch) log_p = (bprev > kNInf) ? f_add(l, bprev) : kNInf;
-            else log_p = f_add(l, sc);
-            if (nd.state >= 0) {  // child is a beam member: its nb gets the extension term
-              c.s_ext[nd.state] = log_p;
-              c.s_mask[j * W + (rr >> 5)] |= 1u << (rr & 31);
-              ++npairs;
-            } else {  // dead interior node: candidate that, if selected, revives this node
-              c.s_rmask[j * W + (rr >> 5)] |= 1u << (rr & 31);
-              const int q = atom_add(&s_ctl[C_NRV], 1);
-              c.s_rv[2 * q] = (j << 16) | rr;
-              c.s_rv[2 * q + 1] = k;
-            }
-          }
-          prev = k;
-          k = nxt;
-        }
-        if (npairs) atom_add(&s_ctl[C_NPAIRS], npairs);
-      }
-    }
-    CTC_BARRIER();
-
-    // ---- region R2: merge (log_sum_exp), new scores, range reductions ---------------------------------
-    // (reference ctc_beam_search_decoder.cpp:138-139 and path_trie.cpp:129-137)
+    // ---- region R1: every member's blank / repeat / extension-from-parent terms, merged with
+    //      log_sum_exp; dead anchors take their lpc / timestep update.  All in shared memory.
+    // (reference ctc_beam_search_decoder.cpp:97-118,138-139; path_trie.cpp:39-57,129-137)
     CTC_PAR {
       for (int x = tid; x < kNBins; x += NT) c.s_hist[x] = 0;  // histogram buffer of radix pass 0
       unsigned kmin = 0xFFFFFFFFu, kmax = 0u, smax = 0u;
+      int npairs = 0;
       for (int j0 = 0; j0 < M; j0 += NT) {
         const int j = j0 + tid;
         if (j < M) {
-          const float nb = lse_smem(c.s_nbnew[j], c.s_ext[j], c.s_exptab, c.s_logtab);
-          const float sn = lse_smem(c.s_bnew[j], nb, c.s_exptab, c.s_logtab);
-          c.s_nbnew[j] = nb;
-          c.s_snew[j] = sn;
+          const float sc = c.s_score[j];
+          const int ch = c.s_chr[j];
+          const float bnew = (rblank >= 0) ? f_add(c.lp[rblank], sc) : kNInf;
+          float rep = kNInf, ext = kNInf;
+          const int rr = (ch >= 0) ? c.rank_of(ch) : -1;
+          if (rr >= 0) {
+            const float l = c.lp[rr];
+            rep = f_add(l, c.s_nbprev[j]);
+            const int i = c.s_pslot[j];
+            if (i >= 0) {  // parent is a beam member: this node is an existing child of it
+              if (c.s_lpc[j] < l) { c.s_lpc[j] = l; c.s_ts[j] = t_abs; }  // path_trie.cpp:41-46
+              if (ch == c.s_chr[i]) {
+                const float pb = c.s_bprev[i];
+                ext = (pb > kNInf) ? f_add(l, pb) : kNInf;
+              } else {
+                ext = f_add(l, c.s_score[i]);
+              }
+              atom_or(&c.s_mask[i * W + (rr >> 5)], 1u << (rr & 31));
+              ++npairs;
+            }
+          }
+          const float nb = lse_smem(rep, ext, c.s_exptab, c.s_logtab);
+          const float sn = lse_smem(bnew, nb, c.s_exptab, c.s_logtab);
+          c.s_bnew[j] = bnew; c.s_nbnew[j] = nb; c.s_snew[j] = sn;
           const unsigned o = ord_f(sn);
           kmin = o < kmin ? o : kmin;
           kmax = o > kmax ? o : kmax;
-          const unsigned os = ord_f(c.s_score[j]);
+          const unsigned os = ord_f(sc);
           smax = os > smax ? os : smax;
+        }
+      }
+      if (npairs) atom_add(&s_ctl[C_NPAIRS], npairs);
+      for (int a = tid; a < KP2; a += NT) {
+        const int i = c.s_dpslot[a];
+        if (i >= 0) {  // dead node whose parent is in the beam: an existing (dead) child of slot i
+          const int rr = c.rank_of(c.s_dchr[a]);
+          if (rr >= 0) {
+            const float l = c.lp[rr];
+            if (c.s_dlpc[a] < l) { c.s_dlpc[a] = l; c.s_dts[a] = t_abs; }
+            atom_or(&c.s_rmask[i * W + (rr >> 5)], 1u << (rr & 31));
+          }
         }
       }
 #if defined(CTC_EMULATE)
@@ -370,16 +381,25 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
       }
       uint64_t width = ((((uint64_t)top) << 16) | 0xFFFFull) - lo + 1ull;
       int shift = 0;
-      while ((width - 1ull) >> shift >= (uint64_t)kNBins) ++shift;
+      {
+        const uint64_t wm = width - 1ull;  // smallest shift with (wm >> shift) < kNBins
+#if defined(CTC_EMULATE)
+        const int bits = wm ? 64 - __builtin_clzll(wm) : 0;
+#else
+        const int bits = 64 - __clzll((long long)wm);
+#endif
+        shift = bits > 8 ? bits - 8 : 0;
+      }
       int pass = 0;
       while (true) {
+        CTC_STAT(g_stats.passes++);
         int *const hist = c.s_hist + (pass & 1) * kNBins;
         CTC_PAR {
           int *const other = c.s_hist + ((pass + 1) & 1) * kNBins;
           for (int x = tid; x < kNBins; x += NT) other[x] = 0;
           for (int j = tid; j < M; j += NT) {
             const uint64_t k = key64(c.s_snew[j], c.s_chr[j]);
-            if (k >= lo && k - lo < width) atom_add(&hist[(int)((k - lo) >> shift)], 1);
+            if (k >= lo && k - lo < width) { atom_add(&hist[(int)((k - lo) >> shift)], 1); CTC_STAT(g_stats.hist_adds++); }
           }
           if (n > 0) {
             int i = tid / n, r = tid - (tid / n) * n;
@@ -388,7 +408,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
               float sc; int ch;
               if (c.cand(i, r, sc, ch)) {
                 const uint64_t k = key64(sc, ch);
-                if (k >= lo && k - lo < width) atom_add(&hist[(int)((k - lo) >> shift)], 1);
+                if (k >= lo && k - lo < width) { atom_add(&hist[(int)((k - lo) >> shift)], 1); CTC_STAT(g_stats.hist_adds++); }
               }
               r += dr; i += di;
               if (r >= n) { r -= n; ++i; }
@@ -488,108 +508,250 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
     }
     CTC_BARRIER();
 
-    // ---- region R4c: selected candidates become trie nodes (or revive a dead one) ----------------------
-    // (reference path_trie.cpp:50-56 revive, :97-105 create)
+    // ---- region R4c: selected candidates become trie nodes (or revive a dead anchor) -------------------
+    // (reference path_trie.cpp:50-56 revive, :97-105 create).  Arena stores are fire-and-forget.
     CTC_PAR {
       for (int q = tid; q < nsel; q += NT) {
         const int v = c.s_sel2[q];
         const int i = v >> 16, r = v & 0xFFFF;
-        const int slot = c.s_free2[q];
         float sc; int ch;
         c.cand(i, r, sc, ch);
-        const float l = c.lp[r];
-        const int pn = c.s_node[i];
-        const int depth = c.s_depth[i] + 1;
-        int nid, fch = -1;
+        float lpc = c.lp[r];
+        int ts = t_abs, nid, rev = -1;
         if ((c.s_rmask[i * W + (r >> 5)] >> (r & 31)) & 1u) {
-          nid = -1;
-          const int nrv = s_ctl[C_NRV];
-          for (int x = 0; x < nrv; ++x)
-            if (c.s_rv[2 * x] == v) nid = c.s_rv[2 * x + 1];
-          nodes[nid].state = slot;
-          fch = ld_cg(&nodes[nid].first_child);
+          for (int a = 0; a < KP2; ++a)
+            if (c.s_dpslot[a] == i && c.s_dchr[a] == ch) rev = a;
+          nid = c.s_dnode[rev]; lpc = c.s_dlpc[rev]; ts = c.s_dts[rev];
+          c.s_drev[rev] = 1;
+          atom_add(&s_ctl[C_NREV], 1);
+          CTC_STAT(g_stats.revived++);
         } else {
           nid = atom_add(&s_ctl[C_NNODES], 1);
+          CTC_STAT(g_stats.created++);
           if (nid >= arena_cap) {  // cannot happen with capacity 1 + K * frames; never write out of bounds
             s_ctl[C_FLAGS] |= FLAG_ERR_ARENA;
             nid = arena_cap - 1;
           }
-          Node nn;
-          nn.parent = pn; nn.first_child = -1; nn.next_sib = atom_exch(&c.s_fchild[i], nid);
-          nn.chr_nchild = (unsigned)(ch + 1); nn.lpc = l; nn.ts = t_abs; nn.state = slot; nn.depth = depth;
+          Node nn; nn.parent = c.s_node[i]; nn.chr = ch; nn.lpc = lpc; nn.ts = ts;
           store_node(&nodes[nid], nn);
-          atom_add(&nodes[pn].chr_nchild, 1u << 16);
         }
-        int *ni = c.s_newinfo + q * 6;
-        ni[0] = nid; ni[1] = ch; ni[2] = (int)f_bits(sc); ni[3] = slot; ni[4] = fch; ni[5] = depth;
+        int *ni = c.s_newinfo + q * 10;
+        ni[0] = nid; ni[1] = ch; ni[2] = (int)f_bits(sc); ni[3] = c.s_free2[q]; ni[4] = i; ni[5] = (int)f_bits(lpc);
+        ni[6] = ts; ni[7] = rev; ni[8] = c.s_depth[i] + 1;
       }
     }
     CTC_BARRIER();
 
-    // ---- region R4d: evicted members leave the beam; survivors roll cur -> prev -------------------------
-    // (reference path_trie.cpp:144-146 `exists_ = false`, :129-137 roll)
-    CTC_PAR {
-      for (int j = tid; j < M; j += NT) {
-        if (c.s_evict[j]) {
-          const int nj = c.s_node[j];
-          nodes[nj].state = kStDead;
-          nodes[nj].first_child = c.s_fchild[j];
-          const unsigned cn = ld_cg(&nodes[nj].chr_nchild);
-          c.s_evict[j] = ((cn >> 16) == 0u) ? 2 : 1;
-          c.s_sel[j] = nj;
-        } else {
-          c.s_bprev[j] = c.s_bnew[j];
-          c.s_nbprev[j] = c.s_nbnew[j];
-          c.s_score[j] = c.s_snew[j];
-        }
-      }
-    }
-    CTC_BARRIER();
-
-    // ---- region R4e: removal cascade; new members take their slots; reset per-frame scratch -------------
-    // (reference path_trie.cpp:147-162)
-    CTC_PAR {
-      for (int j = tid; j < M; j += NT) {
-        if (c.s_evict[j] == 2) {
-          int cur = c.s_sel[j];
-          while (true) {
-            nodes[cur].state = kStDeleted;
-            const int par = ld_cg(&nodes[cur].parent);
-            const unsigned old = atom_sub_u(&nodes[par].chr_nchild, 1u << 16);
-            if ((old >> 16) != 1u) break;            // parent still has other children
-            if (par == 0) break;                      // the root is never removed
-            if (ld_cg(&nodes[par].state) != kStDead) break;  // parent is in the beam
-            cur = par;
+    if (s_ctl[C_NREV] > 0) {
+      // ---- rare slow path: a dead anchor d came back to life.  Members that hung below d need the child
+      //      of d on their own path as their new nearest anchor; only here is the arena read back.
+      CTC_STAT(g_stats.rv_frames++);
+      CTC_PAR {
+        for (int y = tid; y < M; y += NT) {
+          const int a = c.s_anch[y];
+          if (c.s_pslot[y] < 0 && a >= 0 && c.s_drev[a]) {
+            const int d = c.s_dnode[a];
+            int s_new = -1;
+            for (int q = 0; q < nsel; ++q)
+              if (c.s_newinfo[q * 10 + 7] == a) s_new = c.s_newinfo[q * 10 + 3];
+            int cur = c.s_node[y];
+            while (true) {
+              CTC_STAT(g_stats.rv_hops++);
+              const int par = ld_cg(&nodes[cur].parent);
+              if (par == d) break;
+              cur = par;
+            }
+            if (cur == c.s_node[y]) {  // y is a direct child of the revived node
+              c.s_pslot[y] = s_new | kNewFlag;
+              c.s_anch[y] = -1;
+            } else {
+              const int w = atom_add(&s_ctl[C_NRVWORK], 1);
+              c.s_rvwork[3 * w] = y; c.s_rvwork[3 * w + 1] = cur; c.s_rvwork[3 * w + 2] = s_new;
+            }
           }
         }
       }
+      CTC_BARRIER();
+      CTC_PAR {
+        if (tid == 0) {
+          const int nw = s_ctl[C_NRVWORK];
+          for (int w = 0; w < nw; ++w) {
+            const int y = c.s_rvwork[3 * w], cur = c.s_rvwork[3 * w + 1], tag = c.s_rvwork[3 * w + 2] | kNewFlag;
+            int e = -1;
+            for (int a = 0; a < KP2; ++a)
+              if (c.s_dpslot[a] == tag && c.s_dnode[a] == cur) e = a;
+            if (e < 0) {
+              for (int a = 0; a < KP2 && e < 0; ++a)
+                if (c.s_dpslot[a] < 0) e = a;
+              if (e < 0) { s_ctl[C_FLAGS] |= FLAG_ERR_ARENA; e = 0; }
+              const Node nd = load_node(&nodes[cur]);
+              c.s_dnode[e] = cur; c.s_dchr[e] = nd.chr; c.s_dlpc[e] = nd.lpc; c.s_dts[e] = nd.ts;
+              c.s_dpslot[e] = tag; c.s_drev[e] = 0;
+            }
+            c.s_anch[y] = e;
+          }
+          s_ctl[C_NRVWORK] = 0;
+        }
+      }
+      CTC_BARRIER();
+    }
+
+    // ---- region R5a: nearest anchor of every member of the NEW beam (replaces the removal cascade) -----
+    // A member's parent is either in the new beam (pslot), or its nearest anchor is an existing dead
+    // anchor (index a < 2KP), a member evicted right now whose own parent stays (code 2KP + slot), or
+    // nothing (-1).  Walking only crosses members evicted in this very frame.
+    CTC_PAR {
+      for (int y = tid; y < M + nsel; y += NT) {
+        int start, res = -1, newp = -1;
+        bool resolved = false;
+        if (y < M) {
+          if (c.s_evict[y]) continue;
+          const int pq = c.s_pslot[y];
+          if (pq >= 0) {
+            if (CTC_PARENT_ALIVE(pq)) { newp = pq & ~kNewFlag; resolved = true; }
+            start = pq;
+          } else {
+            const int a = c.s_anch[y];
+            if (a < 0) { resolved = true; }
+            else {
+              const int q = c.s_dpslot[a];
+              if (CTC_PARENT_ALIVE(q)) { res = a; resolved = true; }
+              start = q;
+            }
+          }
+        } else {
+          start = c.s_newinfo[(y - M) * 10 + 4];
+          if (c.s_evict[start] == 0) { newp = start; resolved = true; }
+        }
+        if (!resolved) {
+          int cur = start;  // an old slot evicted in this frame
+          while (true) {
+            CTC_STAT(g_stats.walk_iters++);
+            const int pq = c.s_pslot[cur];
+            if (pq >= 0) {
+              if (CTC_PARENT_ALIVE(pq)) { res = KP2 + cur; break; }
+              cur = pq;
+              continue;
+            }
+            const int a = c.s_anch[cur];
+            if (a < 0) { res = -1; break; }
+            const int q = c.s_dpslot[a];
+            if (CTC_PARENT_ALIVE(q)) { res = a; break; }
+            cur = q;
+          }
+        }
+        if (res >= 0) atom_add(&c.s_cnt2[res], 1);
+        if (y < M) { c.s_newp[y] = newp; c.s_newa[y] = res; }
+        else { c.s_resq[2 * (y - M)] = newp; c.s_resq[2 * (y - M) + 1] = res; }
+      }
+    }
+    CTC_BARRIER();
+
+    // ---- region R5b: dead anchors nobody hangs below any more leave the trie (that IS the reference's
+    //      remove(), path_trie.cpp:144-163); anchors whose parent left the beam stop being anchors.
+    //      Evicted members write their lpc / timestep back to the arena.
+    CTC_PAR {
+      for (int a = tid; a < KP2; a += NT) {
+        const int q = c.s_dpslot[a];
+        if (q >= 0) {
+          const bool keep = CTC_PARENT_ALIVE(q) && c.s_cnt2[a] > 0 && !c.s_drev[a];
+          if (!keep) {
+            if (!c.s_drev[a]) flush_lpc_ts(&nodes[c.s_dnode[a]], c.s_dlpc[a], c.s_dts[a]);
+            c.s_dpslot[a] = -1;
+          } else {
+            CTC_STAT(g_stats.anchors_live++);
+          }
+        }
+        if (c.s_dpslot[a] < 0) c.s_efree[atom_add(&s_ctl[C_NEFREE], 1)] = a;
+      }
+      for (int j = tid; j < M; j += NT)
+        if (c.s_evict[j]) {
+          CTC_STAT(g_stats.evicted++);
+          flush_lpc_ts(&nodes[c.s_node[j]], c.s_lpc[j], c.s_ts[j]);
+        }
+    }
+    CTC_BARRIER();
+
+    // ---- region R5c: members evicted now that still have beam members below them and whose parent stays
+    //      become dead anchors (reference: exists_ = false, node stays in the trie)
+    CTC_PAR {
+      const int nefree = s_ctl[C_NEFREE];
+      for (int e = tid; e < M; e += NT) {
+        if (c.s_evict[e] && c.s_cnt2[KP2 + e] > 0) {
+          const int k = atom_add(&s_ctl[C_NETAKEN], 1);
+          int a = 0;
+          if (k < nefree) a = c.s_efree[k];
+          else s_ctl[C_FLAGS] |= FLAG_ERR_ARENA;
+          CTC_STAT(g_stats.anchors_new++);
+          c.s_dnode[a] = c.s_node[e]; c.s_dchr[a] = c.s_chr[e]; c.s_dpslot[a] = c.s_pslot[e];
+          c.s_dlpc[a] = c.s_lpc[e]; c.s_dts[a] = c.s_ts[e];
+          c.s_amap[e] = a;
+        }
+      }
+    }
+    CTC_BARRIER();
+
+    // ---- region R5d: survivors roll cur -> prev, new members take their slots, scratch is reset ----------
+    // (reference path_trie.cpp:129-137 roll)
+    CTC_PAR {
+      for (int j = tid; j < M; j += NT) {
+        if (!c.s_evict[j]) {
+          c.s_bprev[j] = c.s_bnew[j];
+          c.s_nbprev[j] = c.s_nbnew[j];
+          c.s_score[j] = c.s_snew[j];
+          c.s_pslot[j] = c.s_newp[j];
+          const int ra = c.s_newa[j];
+          c.s_anch[j] = ra < 0 ? -1 : (ra < KP2 ? ra : c.s_amap[ra - KP2]);
+        }
+      }
       for (int q = tid; q < nsel; q += NT) {
-        const int *ni = c.s_newinfo + q * 6;
+        const int *ni = c.s_newinfo + q * 10;
         const int slot = ni[3];
         const float sc = bits_f((uint32_t)ni[2]);
-        c.s_node[slot] = ni[0]; c.s_chr[slot] = ni[1];
+        c.s_node[slot] = ni[0]; c.s_chr[slot] = ni[1]; c.s_depth[slot] = ni[8];
         c.s_bprev[slot] = kNInf; c.s_nbprev[slot] = sc; c.s_score[slot] = sc;  // score = lse(-inf, nb)
-        c.s_fchild[slot] = ni[4]; c.s_depth[slot] = ni[5];
+        c.s_lpc[slot] = bits_f((uint32_t)ni[5]); c.s_ts[slot] = ni[6];
+        c.s_pslot[slot] = c.s_resq[2 * q];
+        const int ra = c.s_resq[2 * q + 1];
+        c.s_anch[slot] = ra < 0 ? -1 : (ra < KP2 ? ra : c.s_amap[ra - KP2]);
       }
-      for (int j = tid; j < KP; j += NT) c.s_ext[j] = kNInf;
+      for (int a = tid; a < KP2; a += NT) {
+        const int q = c.s_dpslot[a];
+        if (q >= 0) c.s_dpslot[a] = q & ~kNewFlag;
+        c.s_drev[a] = 0;
+      }
+      for (int x = tid; x < 3 * KP; x += NT) c.s_cnt2[x] = 0;
       for (int x = tid; x < KP * W; x += NT) { c.s_mask[x] = 0u; c.s_rmask[x] = 0u; }
       if (SORTED) for (int r = tid; r < n; r += NT) c.s_rank[c.idx[r]] = (int16_t)-1;
       if (tid == 0) {
-        s_ctl[C_NSEL] = 0; s_ctl[C_NFREE] = 0; s_ctl[C_NTIE] = 0; s_ctl[C_NRV] = 0; s_ctl[C_NPAIRS] = 0;
+        s_ctl[C_NSEL] = 0; s_ctl[C_NFREE] = 0; s_ctl[C_NTIE] = 0; s_ctl[C_NREV] = 0; s_ctl[C_NPAIRS] = 0;
         s_ctl[C_ABOVE] = 0; s_ctl[C_KMIN] = (int)0xFFFFFFFFu; s_ctl[C_KMAX] = 0; s_ctl[C_SMAX] = 0;
+        s_ctl[C_NEFREE] = 0; s_ctl[C_NETAKEN] = 0;
       }
     }
     CTC_BARRIER();
     M = select_all ? (int)total : K;
+    CTC_STAT(g_stats.frames++);
+    CTC_STAT(g_stats.tie_frames += tie_m > 0);
+    CTC_STAT(g_stats.sel_all_frames += select_all);
   }
+#undef CTC_PARENT_ALIVE
 
-  // ---- region: store the beam state (streaming continues from here; finalize kernel reads it) --------
+  // ---- region: store the beam state (streaming continues from here; the finalize kernel reads it) and
+  //      bring the arena's lpc / timestep up to date for everything still held in shared memory
   CTC_PAR {
-    int *s = st + kStateHeader;
+    int *s = st_slots;
     for (int j = tid; j < K; j += NT) {
-      s[j] = c.s_node[j]; s[K + j] = c.s_chr[j]; s[2 * K + j] = (int)f_bits(c.s_bprev[j]);
-      s[3 * K + j] = (int)f_bits(c.s_nbprev[j]); s[4 * K + j] = (int)f_bits(c.s_score[j]);
-      s[5 * K + j] = c.s_fchild[j]; s[6 * K + j] = c.s_depth[j];
+      s[j] = c.s_node[j]; s[K + j] = c.s_chr[j]; s[2 * K + j] = c.s_depth[j];
+      s[3 * K + j] = (int)f_bits(c.s_bprev[j]); s[4 * K + j] = (int)f_bits(c.s_nbprev[j]);
+      s[5 * K + j] = (int)f_bits(c.s_score[j]); s[6 * K + j] = (int)f_bits(c.s_lpc[j]); s[7 * K + j] = c.s_ts[j];
+      s[8 * K + j] = c.s_pslot[j]; s[9 * K + j] = c.s_anch[j];
+      if (j < M) flush_lpc_ts(&nodes[c.s_node[j]], c.s_lpc[j], c.s_ts[j]);
+    }
+    for (int a = tid; a < KP2; a += NT) {
+      st_anchors[a] = c.s_dnode[a]; st_anchors[KP2 + a] = c.s_dchr[a]; st_anchors[2 * KP2 + a] = c.s_dpslot[a];
+      st_anchors[3 * KP2 + a] = (int)f_bits(c.s_dlpc[a]); st_anchors[4 * KP2 + a] = c.s_dts[a];
+      if (c.s_dpslot[a] >= 0) flush_lpc_ts(&nodes[c.s_dnode[a]], c.s_dlpc[a], c.s_dts[a]);
     }
     if (tid == 0) {
       st[0] = M; st[1] = s_ctl[C_NNODES]; st[2] = abs_t0 + Tb; st[3] = s_ctl[C_FLAGS];
@@ -615,7 +777,7 @@ CTC_FN void finalize_cta_run(const BeamParams &p, const int b, unsigned char *sm
   int *s_order = (int *)(smem + (size_t)K * 8);   // [K]
   int *s_flag = s_order + K;
   CTC_PAR {
-    for (int j = tid; j < M; j += NT) s_key[j] = key64(bits_f((uint32_t)s[4 * K + j]), s[K + j]);
+    for (int j = tid; j < M; j += NT) s_key[j] = key64(bits_f((uint32_t)s[5 * K + j]), s[K + j]);
     if (tid == 0) *s_flag = 0;
   }
   CTC_BARRIER();
@@ -637,15 +799,15 @@ CTC_FN void finalize_cta_run(const BeamParams &p, const int b, unsigned char *sm
     for (int q = tid; q < M; q += NT) {
       const int j = s_order[q];
       int nid = s[j];
-      const int depth = s[6 * K + j];
-      const float score = bits_f((uint32_t)s[4 * K + j]);
+      const int depth = s[2 * K + j];
+      const float score = bits_f((uint32_t)s[5 * K + j]);
       const size_t row = ((size_t)b * K + q) * (size_t)p.out_T;
       p.out_scores[(size_t)b * K + q] = (float)(-(double)score);  // decoder_utils.cpp:68, binding.cpp:91
       p.out_lens[(size_t)b * K + q] = depth;
       for (int d = depth - 1; d >= 0; --d) {
         const Node nd = load_node(&nodes[nid]);
         if (d < p.out_T) {
-          p.out_tokens[row + d] = (int)(nd.chr_nchild & 0xFFFFu) - 1;
+          p.out_tokens[row + d] = nd.chr;
           p.out_timesteps[row + d] = nd.ts;
         }
         nid = nd.parent;

@@ -345,7 +345,8 @@ int ctcdec_decode_batch_host(const ctcdec_config *cfg, const float *probs, const
 //  streaming
 // ---------------------------------------------------------------------------------------------------
 static int state_init_device(StreamState *st) {
-  const int K = st->cfg.beam_size;
+  // the root-only beam (reference ctc_beam_search_decoder.cpp:42-44), in the layout of beam_core.cuh
+  const int K = st->cfg.beam_size, KP2 = 2 * kp_of(K);
   const long long n = state_ints(K);
   std::unique_ptr<int[]> h(new int[n]);
   for (long long i = 0; i < n; ++i) h[i] = 0;
@@ -353,16 +354,22 @@ static int state_init_device(StreamState *st) {
   int *s = h.get() + kStateHeader;
   const float ninf = -FLT_MAX, zero = 0.0f;
   for (int j = 0; j < K; ++j) {
-    s[j] = 0; s[K + j] = -1;
-    memcpy(&s[2 * K + j], j == 0 ? &zero : &ninf, 4);
-    memcpy(&s[3 * K + j], &ninf, 4);
-    memcpy(&s[4 * K + j], j == 0 ? &zero : &ninf, 4);
-    s[5 * K + j] = -1; s[6 * K + j] = 0;
+    s[j] = 0; s[K + j] = -1; s[2 * K + j] = 0;
+    memcpy(&s[3 * K + j], j == 0 ? &zero : &ninf, 4);
+    memcpy(&s[4 * K + j], &ninf, 4);
+    memcpy(&s[5 * K + j], j == 0 ? &zero : &ninf, 4);
+    memcpy(&s[6 * K + j], &ninf, 4);
+    s[7 * K + j] = 0; s[8 * K + j] = -1; s[9 * K + j] = -1;
+  }
+  int *a = s + kSlotArrays * K;
+  for (int e = 0; e < KP2; ++e) {
+    a[e] = 0; a[KP2 + e] = 0; a[2 * KP2 + e] = -1;
+    memcpy(&a[3 * KP2 + e], &ninf, 4);
+    a[4 * KP2 + e] = 0;
   }
   CU(cudaMemcpy(st->state, h.get(), n * 4, cudaMemcpyHostToDevice));
   Node root;
-  root.parent = -1; root.first_child = -1; root.next_sib = -1; root.chr_nchild = 0u; root.lpc = -FLT_MAX; root.ts = 0;
-  root.state = 0; root.depth = 0;
+  root.parent = -1; root.chr = -1; root.lpc = -FLT_MAX; root.ts = 0;
   CU(cudaMemcpy(st->arena, &root, sizeof(Node), cudaMemcpyHostToDevice));
   return CTCDEC_OK;
 }

@@ -42,8 +42,8 @@ def test_workspace_and_argument_validation(lib):
     cfg = _native.Config(29, 100, 0, 0, 40, 1.0)
     n = ctypes.c_size_t(0)
     assert lib.ctcdec_workspace_bytes(ctypes.byref(cfg), 256, 1000, ctypes.byref(n)) == 0
-    # lp rows 256*1000*32*4 + arena 256*(1+100*1000)*32 + state
-    assert n.value > 256 * 1000 * 32 * 4 + 256 * 100001 * 32
+    # lp rows 256*1000*32*4 + arena 256*(1+100*1000)*16 + state
+    assert n.value > 256 * 1000 * 32 * 4 + 256 * 100001 * 16
     bad = _native.Config(70000, 100, 0, 0, 40, 1.0)
     assert lib.ctcdec_workspace_bytes(ctypes.byref(bad), 1, 10, ctypes.byref(n)) == -2
     assert b"vocab_size" in lib.ctcdec_last_error()

@@ -45,6 +45,11 @@ def test_emulation_matches_reference_golden(name):
     dict(B=2, T=100, V=29, seed=13, beam=50, flat=True),
     dict(B=2, T=100, V=29, seed=14, beam=7, flat=True, temp=1.0),
     dict(B=1, T=70, V=600, seed=15, beam=12, cutoff_top_n=600),          # wide unsorted vocabulary
+    # tiny vocabularies + flat posteriors: hundreds of dead-anchor revivals per utterance (slow path)
+    dict(B=4, T=400, V=4, seed=5, beam=16, flat=True, temp=1.0),
+    dict(B=4, T=400, V=4, seed=4, beam=16, flat=True, temp=2.0),
+    dict(B=4, T=400, V=3, seed=2, beam=8, flat=True, temp=2.0),
+    dict(B=4, T=400, V=5, seed=1, beam=16, flat=True, temp=2.0),
 ])
 def test_emulation_matches_oracle(cport, cfg):
     cfg = dict(cfg)

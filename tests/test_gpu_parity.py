@@ -55,6 +55,9 @@ def test_cuda_matches_reference_golden(name, on_device):
     dict(B=1, T=30, V=1, seed=10, beam=5),
     dict(B=8, T=200, V=29, seed=11, beam=50, flat=True),
     dict(B=1, T=70, V=600, seed=12, beam=12, cutoff_top_n=600),
+    dict(B=4, T=400, V=4, seed=5, beam=16, flat=True, temp=1.0),            # dead-anchor revivals (slow path)
+    dict(B=4, T=400, V=4, seed=4, beam=16, flat=True, temp=2.0),
+    dict(B=4, T=400, V=3, seed=2, beam=8, flat=True, temp=2.0),
     dict(B=2, T=90, V=1500, seed=13, beam=20),                             # wide vocabulary, top-40 cut
 ])
 def test_cuda_matches_oracle(cport, cfg):
@@ -62,7 +65,7 @@ def test_cuda_matches_oracle(cport, cfg):
     B, T, V, seed = cfg.pop("B"), cfg.pop("T"), cfg.pop("V"), cfg.pop("seed")
     peak, log = cfg.pop("peak", 8.0), cfg.pop("log", False)
     if cfg.pop("flat", False):
-        probs = flat_probs(B, T, V, seed).numpy()
+        probs = flat_probs(B, T, V, seed, temp=cfg.pop("temp", 3.0)).numpy()
     elif V == 1:
         probs = np.ones((B, T, 1), np.float32)
     else:
