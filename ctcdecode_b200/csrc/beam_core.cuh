@@ -101,6 +101,7 @@ struct BeamParams {
   int *n_results;                   // [B]
   int out_T;
   int *flags;  // [B], OR-ed
+  long long *timing;  // optional [B][16]: cycles thread 0 spent between consecutive barriers, per region
 };
 
 // ---- shared memory carve-up (bytes) ---------------------------------------------------------------
@@ -173,7 +174,7 @@ CTC_HD SmemLayout make_layout(int K, int V, int NP, int tile_frames, bool sorted
   L.rvwork = o;    o += KP * 3 * 4;
   L.hist = o;      o += 2 * kNBins * 4;
   o = align_up(o, 16);
-  L.ctl = o;       o += 32 * 4;
+  L.ctl = o;       o += 32 * 4 + 16 * 8;
   L.total = o;
   return L;
 }

@@ -14,6 +14,20 @@ static EmuStats g_stats;
 #define CTC_STAT(x) ((void)0)
 #endif
 
+#if defined(CTC_EMULATE)
+#define CTC_TICK(id) ((void)0)
+#else
+// per-region cycle accounting by thread 0 (only when BeamParams::timing is set; tools/region_timing.py)
+#define CTC_TICK(id)                                                        \
+  do {                                                                      \
+    if (p.timing && threadIdx.x == 0) {                                     \
+      const long long now_ = clock64();                                     \
+      s_tick[id] += now_ - s_tick[15];                                      \
+      s_tick[15] = now_;                                                    \
+    }                                                                       \
+  } while (0)
+#endif
+
 #if !defined(CTC_EMULATE)
 // ---- TMA (cp.async.bulk) + mbarrier plumbing for the staged [tile_frames x NP] log-prob tiles -------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -175,6 +189,13 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
   c.s_logtab = (double *)(smem + L.logtab);
   c.K = K; c.KP = KP; c.V = V; c.NP = NP; c.W = W; c.blank = p.blank;
   int *const s_ctl = c.s_ctl;
+#if !defined(CTC_EMULATE)
+  long long *const s_tick = (long long *)(smem + L.ctl + 32 * 4);
+  if (p.timing && threadIdx.x == 0) {
+    for (int x = 0; x < 15; ++x) s_tick[x] = 0;
+    s_tick[15] = clock64();
+  }
+#endif
 
   Node *const nodes = p.arena_ptrs ? p.arena_ptrs[b] : p.arena + (long long)b * p.arena_stride;
   int *const st = p.state_ptrs ? p.state_ptrs[b] : p.state + (long long)b * p.state_stride;
@@ -285,6 +306,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
 #endif
     // row trailer written by the prune kernel: [NP-2] = n | (rank_of_blank + 1) << 16, [NP-1] = max
     // non-blank log-prob of the frame
+    CTC_TICK(0);  // tile wait
     const uint32_t meta = f_bits(c.lp[NP - 2]);
     const int n = (int)(meta & 0xFFFFu);
     const int rblank = (int)(meta >> 16) - 1;
@@ -295,6 +317,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
         for (int r = tid; r < n; r += NT) c.s_rank[c.idx[r]] = (int16_t)r;
       }
       CTC_BARRIER();
+      CTC_TICK(1);
     }
 
     // ---- region R1: every member's blank / repeat / extension-from-parent terms, merged with
@@ -363,6 +386,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
 #endif
     }
     CTC_BARRIER();
+    CTC_TICK(2);  // R1
 
     const int n_nb = n - (rblank >= 0 ? 1 : 0);
     const long long total = (long long)M * (n_nb + 1) - s_ctl[C_NPAIRS];
@@ -449,6 +473,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
       }
     }
     const int ntie = s_ctl[C_NTIE];
+    CTC_TICK(3);  // R3 (all radix passes + scans)
 
     // ---- region R4a: classify members (keep / evict) and candidates (selected) ----------------------
     CTC_PAR {
@@ -489,6 +514,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
       }
     }
     CTC_BARRIER();
+    CTC_TICK(4);  // R4a
     const int nsel = s_ctl[C_NSEL], nfree = s_ctl[C_NFREE];
 
     // ---- region R4b: order both lists (deterministic slot assignment) ---------------------------------
@@ -507,6 +533,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
       }
     }
     CTC_BARRIER();
+    CTC_TICK(5);  // R4b
 
     // ---- region R4c: selected candidates become trie nodes (or revive a dead anchor) -------------------
     // (reference path_trie.cpp:50-56 revive, :97-105 create).  Arena stores are fire-and-forget.
@@ -541,6 +568,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
       }
     }
     CTC_BARRIER();
+    CTC_TICK(6);  // R4c
 
     if (s_ctl[C_NREV] > 0) {
       // ---- rare slow path: a dead anchor d came back to life.  Members that hung below d need the child
@@ -596,6 +624,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
       CTC_BARRIER();
     }
 
+    CTC_TICK(7);  // revive slow path
     // ---- region R5a: nearest anchor of every member of the NEW beam (replaces the removal cascade) -----
     // A member's parent is either in the new beam (pslot), or its nearest anchor is an existing dead
     // anchor (index a < 2KP), a member evicted right now whose own parent stays (code 2KP + slot), or
@@ -646,6 +675,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
       }
     }
     CTC_BARRIER();
+    CTC_TICK(8);  // R5a
 
     // ---- region R5b: dead anchors nobody hangs below any more leave the trie (that IS the reference's
     //      remove(), path_trie.cpp:144-163); anchors whose parent left the beam stop being anchors.
@@ -671,6 +701,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
         }
     }
     CTC_BARRIER();
+    CTC_TICK(9);  // R5b
 
     // ---- region R5c: members evicted now that still have beam members below them and whose parent stays
     //      become dead anchors (reference: exists_ = false, node stays in the trie)
@@ -690,6 +721,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
       }
     }
     CTC_BARRIER();
+    CTC_TICK(10);  // R5c
 
     // ---- region R5d: survivors roll cur -> prev, new members take their slots, scratch is reset ----------
     // (reference path_trie.cpp:129-137 roll)
@@ -730,6 +762,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
       }
     }
     CTC_BARRIER();
+    CTC_TICK(11);  // R5d
     M = select_all ? (int)total : K;
     CTC_STAT(g_stats.frames++);
     CTC_STAT(g_stats.tie_frames += tie_m > 0);
@@ -757,6 +790,10 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
       st[0] = M; st[1] = s_ctl[C_NNODES]; st[2] = abs_t0 + Tb; st[3] = s_ctl[C_FLAGS];
     }
   }
+#if !defined(CTC_EMULATE)
+  if (p.timing && threadIdx.x == 0)
+    for (int x = 0; x < 16; ++x) p.timing[(size_t)b * 16 + x] = s_tick[x];
+#endif
 }
 
 // ======================================================================================================

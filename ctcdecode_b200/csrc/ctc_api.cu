@@ -170,6 +170,7 @@ static int ensure(DevCache &c, int slot, size_t bytes) {
 struct Profile {
   bool on = false;
   bool valid = false;
+  long long *timing = nullptr;  // device buffer [B][16] for per-region cycle counts (diagnostic)
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 static thread_local Profile g_prof;
@@ -258,6 +259,7 @@ int ctcdec_decode_batch_device(const ctcdec_config *cfg, const float *probs, con
   bp.state = state; bp.state_stride = pl.state_stride; bp.arena_cap = (int)pl.arena_stride; bp.fresh = 1;
   bp.out_tokens = tokens; bp.out_timesteps = timesteps; bp.out_scores = scores; bp.out_lens = lens;
   bp.n_results = nres_dev; bp.out_T = T; bp.flags = flags_dev;
+  bp.timing = g_prof.timing;
   if ((rc = launch_beam(bp, pl, B, s))) return rc;
   if (prof) CU(cudaEventRecord(g_prof.ev[2], s));
   if ((rc = launch_finalize(bp, B, s))) return rc;
@@ -271,6 +273,11 @@ int ctcdec_decode_batch_device(const ctcdec_config *cfg, const float *probs, con
 int ctcdec_profile_enable(int on) {
   g_prof.on = on != 0;
   g_prof.valid = false;
+  return CTCDEC_OK;
+}
+
+int ctcdec_profile_region_cycles(void *device_buffer) {
+  g_prof.timing = static_cast<long long *>(device_buffer);
   return CTCDEC_OK;
 }
 

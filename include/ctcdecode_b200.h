@@ -112,6 +112,10 @@ int ctcdec_decode_stream_host(const float *probs, const int32_t *seq_lens, int B
  * the device time in milliseconds of {prune/log scan, beam search, finalize}. */
 int ctcdec_profile_enable(int on);
 int ctcdec_profile_read(float *ms3);
+/* Diagnostic: if device_buffer (int64 [B][16], device memory) is non-NULL, every following
+ * ctcdec_decode_batch_device call of this thread makes the beam kernel's thread 0 of each CTA record
+ * the clock cycles it spent in each barrier-delimited region of the frame loop (tools/region_timing.py). */
+int ctcdec_profile_region_cycles(void *device_buffer);
 
 /* ---- diagnostics used by the tests (device self-check of the bit-exact libm restatements) ----------- */
 /* y[i] = f(x[i]) computed ON THE DEVICE; which: 0 expf, 1 logf, 2 float(log(double(x) + FLT_MIN)),

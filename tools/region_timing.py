@@ -1,0 +1,36 @@
+#!/usr/bin/env python
+"""Per-region cycle breakdown of the beam kernel's frame loop (thread 0 of each CTA, clock64 between barriers)."""
+import argparse
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from bench import CONFIGS  # noqa: E402
+from ctcdecode_b200 import CTCBeamDecoder, _native  # noqa: E402
+from ctcdecode_b200.synth import ctc_like_probs  # noqa: E402
+
+NAMES = ["tile_wait", "R0_rank", "R1_members", "R3_select", "R4a_classify", "R4b_order", "R4c_nodes", "RV_revive",
+         "R5a_anchor", "R5b_sweep", "R5c_newanchor", "R5d_commit"]
+ap = argparse.ArgumentParser()
+ap.add_argument("--config", default="c2")
+ap.add_argument("--batch", type=int, nargs="*", default=[1, 148, 256])
+a = ap.parse_args()
+cfg = CONFIGS[a.config]
+lib = _native.load()
+for B in a.batch:
+    probs = ctc_like_probs(B, cfg["T"], cfg["V"], seed=0).cuda()
+    dec = CTCBeamDecoder([str(i) for i in range(cfg["V"])], beam_width=cfg["beam"], cutoff_top_n=cfg["cutoff_top_n"],
+                         cutoff_prob=cfg["cutoff_prob"], device_outputs=True)
+    buf = torch.zeros(B, 16, dtype=torch.int64, device="cuda")
+    dec.decode(probs)
+    lib.ctcdec_profile_region_cycles(buf.data_ptr())
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); dec.decode(probs); e1.record(); torch.cuda.synchronize()
+    lib.ctcdec_profile_region_cycles(None)
+    t = buf.double().mean(0).cpu() / cfg["T"]
+    tot = float(t[:12].sum())
+    print(f"B={B}: step {e0.elapsed_time(e1):.2f} ms; cycles/frame (mean over CTAs) total {tot:.0f}")
+    print("   " + "  ".join(f"{n}={float(v):.0f}" for n, v in zip(NAMES, t[:12])))
