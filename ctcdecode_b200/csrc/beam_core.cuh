@@ -35,17 +35,29 @@
 
 #include "glibc_math.cuh"
 
+// CTC_PAR { ... }                 a parallel region over the NT threads of the CTA (variable `tid`)
+// CTC_WARPS { ... CTC_LANES { ... } ... }   a warp-structured region: code directly inside CTC_WARPS is
+//     warp-uniform (variable `warp`); CTC_LANES blocks run per lane (variables `lane`, `LX`); values that
+//     cross a warp collective (ballot) live in CTC_LV arrays indexed by LX (one element per lane in the
+//     emulation, a single register on the device).
 #if defined(CTC_EMULATE)
 #define CTC_PAR for (int tid = 0; tid < NT; ++tid)
+#define CTC_WARPS for (int warp = 0; warp < NT / 32; ++warp)
+#define CTC_LANES for (int lane = 0, LX = 0; lane < 32; ++lane, ++LX)
 #define CTC_BARRIER() ((void)0)
 #define CTC_FN static inline
 #define CTC_MFN inline
+namespace ctc { constexpr int kLW = 32; }
 #else
 #define CTC_PAR for (int tid = (int)threadIdx.x, once_ = 1; once_; once_ = 0)
+#define CTC_WARPS for (int warp = (int)(threadIdx.x >> 5), once_w_ = 1; once_w_; once_w_ = 0)
+#define CTC_LANES for (int lane = (int)(threadIdx.x & 31), LX = 0, once_l_ = 1; once_l_; once_l_ = 0)
 #define CTC_BARRIER() __syncthreads()
 #define CTC_FN __device__ __forceinline__
 #define CTC_MFN __device__ __forceinline__
+namespace ctc { constexpr int kLW = 1; }
 #endif
+#define CTC_LV(type, name) type name[::ctc::kLW]
 
 namespace ctc {
 
@@ -94,6 +106,7 @@ struct BeamParams {
   const int *arena_caps;    // streaming: per-utterance arena capacity (nodes)
   int arena_cap;            // offline capacity per utterance
   int fresh;                // 1: start from the root state instead of loading `state`
+  int force_fallback;       // test knob: run the grid-walking select path every frame
   const unsigned char *finalize;  // [B] or nullptr (= finalize all)
   int *out_tokens, *out_timesteps;  // [B][K][out_T]
   float *out_scores;                // [B][K]
@@ -118,18 +131,26 @@ struct SmemLayout {
   int cnt2;                                                          // [3*KP] anchor reference counts
   int amap, efree, newp, newa, resq, rvwork;                         // re-anchoring scratch
   int hist;                                                          // [2][kNBins]
+  int clk, cli, wcnt, evcnt;                                         // candidate list segments [NW][seg], per-warp counts
   int ctl;                                                           // control words
   int total;
-  int KP, W;
+  int KP, W, NW, seg;
 };
 CTC_HD int align_up(int x, int a) { return (x + a - 1) / a * a; }
-CTC_HD SmemLayout make_layout(int K, int V, int NP, int tile_frames, bool sorted) {
+CTC_HD SmemLayout make_layout(int K, int V, int NP, int tile_frames, bool sorted, int NT) {
   SmemLayout L;
   const int KP = align_up(K, 32);
   const int W = (NP + 31) / 32;
+  const int NW = NT / 32;
+  // candidate-list segment per warp: room for every candidate of the members a warp owns, capped at 64 KB
+  int seg = ((K + NW - 1) / NW) * (NP - 2);
+  if (seg > 8192 / NW) seg = 8192 / NW;
+  if (seg < 32) seg = 32;
   int o = 0;
   L.KP = KP;
   L.W = W;
+  L.NW = NW;
+  L.seg = seg;
   L.tile_lp = o;   o += 2 * tile_frames * NP * 4;
   L.tile_idx = o;  o += sorted ? 2 * tile_frames * NP * 2 : 0;
   o = align_up(o, 16);
@@ -173,6 +194,10 @@ CTC_HD SmemLayout make_layout(int K, int V, int NP, int tile_frames, bool sorted
   L.resq = o;      o += KP * 2 * 4;
   L.rvwork = o;    o += KP * 3 * 4;
   L.hist = o;      o += 2 * kNBins * 4;
+  L.clk = o;       o += NW * seg * 4;
+  L.cli = o;       o += NW * seg * 4;
+  L.wcnt = o;      o += 4 * 32 * 4;
+  L.evcnt = o;     o += (KP / 32) * 4;
   o = align_up(o, 16);
   L.ctl = o;       o += 32 * 4 + 16 * 8;
   L.total = o;
@@ -182,7 +207,7 @@ CTC_HD SmemLayout make_layout(int K, int V, int NP, int tile_frames, bool sorted
 // control words: 32 ints in L.ctl
 enum {
   C_M = 0, C_NNODES, C_FLAGS, C_NSEL, C_NFREE, C_NTIE, C_NREV, C_NPAIRS, C_ABOVE, C_BIN, C_CNT, C_KMIN, C_KMAX,
-  C_SMAX, C_NEFREE, C_NETAKEN, C_NRVWORK
+  C_SMAX, C_NEFREE, C_NETAKEN, C_NRVWORK, C_OVF, C_ANYREF, C_NLIVE
 };
 
 // ---- small helpers --------------------------------------------------------------------------------
@@ -212,6 +237,19 @@ CTC_FN unsigned atom_or(unsigned *p, unsigned v) { return atomicOr(p, v); }
 template <class T> CTC_FN T ld_cg(const T *p) { return __ldcg(p); }
 #endif
 
+#if defined(CTC_EMULATE)
+static inline unsigned ctc_ballot(const int (&pred)[kLW]) {
+  unsigned b = 0;
+  for (int l = 0; l < 32; ++l) b |= (pred[l] ? 1u : 0u) << l;
+  return b;
+}
+static inline int ctc_popc(unsigned x) { return __builtin_popcount(x); }
+#else
+CTC_FN unsigned ctc_ballot(const int (&pred)[kLW]) { return __ballot_sync(0xffffffffu, pred[0]); }
+CTC_FN int ctc_popc(unsigned x) { return __popc(x); }
+#endif
+CTC_FN unsigned ctc_lt_mask(int lane) { return (1u << lane) - 1u; }
+
 // log_sum_exp<float> (reference decoder_utils.h:47-54) with the 32-entry expf / 16-entry logf tables
 // staged in shared memory (a __constant__ table indexed per thread would serialise divergent reads).
 CTC_FN float lse_smem(float x, float y, const uint64_t *exptab, const double *logtab) {
@@ -236,7 +274,8 @@ struct Cta {
   float *s_dlpc;
   // shared: scratch
   int *s_evict, *s_sel, *s_sel2, *s_free, *s_free2, *s_newinfo, *s_tie, *s_cnt2, *s_amap, *s_efree, *s_newp, *s_newa,
-      *s_resq, *s_rvwork, *s_hist, *s_ctl;
+      *s_resq, *s_rvwork, *s_hist, *s_ctl, *s_cli, *s_wcnt, *s_evcnt;
+  uint32_t *s_clk;
   int16_t *s_rank;  // [V]
   const uint64_t *s_exptab;
   const double *s_logtab;

@@ -162,7 +162,7 @@ CTC_FN void flush_lpc_ts(Node *p, float lpc, int ts) {
 template <int NT, bool SORTED>
 CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) {
   const int K = p.K, V = p.V, NP = p.NP, F = p.tile_frames;
-  const SmemLayout L = make_layout(K, V, NP, F, SORTED);
+  const SmemLayout L = make_layout(K, V, NP, F, SORTED, NT);
   const int KP = L.KP, W = L.W, KP2 = 2 * L.KP;
 
   Cta<SORTED> c;
@@ -185,6 +185,8 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
   c.s_newa = (int *)(smem + L.newa);      c.s_resq = (int *)(smem + L.resq);
   c.s_rvwork = (int *)(smem + L.rvwork);  c.s_hist = (int *)(smem + L.hist);
   c.s_rank = (int16_t *)(smem + L.rank);  c.s_ctl = (int *)(smem + L.ctl);
+  c.s_clk = (uint32_t *)(smem + L.clk);   c.s_cli = (int *)(smem + L.cli);
+  c.s_wcnt = (int *)(smem + L.wcnt);      c.s_evcnt = (int *)(smem + L.evcnt);
   c.s_exptab = (uint64_t *)(smem + L.exptab);
   c.s_logtab = (double *)(smem + L.logtab);
   c.K = K; c.KP = KP; c.V = V; c.NP = NP; c.W = W; c.blank = p.blank;
@@ -282,11 +284,23 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
 #endif
 
   int M = s_ctl[C_M];
+  // number of dead anchors currently in the table (0 almost always: lets the frame loop skip their sweeps)
+  CTC_PAR {
+    int cntv = 0;
+    for (int a = tid; a < KP2; a += NT) cntv += (c.s_dpslot[a] >= 0) ? 1 : 0;
+    if (cntv) atom_add(&s_ctl[C_NLIVE], cntv);
+  }
+  CTC_BARRIER();
+  int nlive = s_ctl[C_NLIVE];
+  CTC_BARRIER();
 
   // "is the parent designation q (a beam slot, possibly tagged kNewFlag) alive after this frame?"
 #define CTC_PARENT_ALIVE(q) ((((q) & kNewFlag) != 0) || c.s_evict[(q)] == 0)
 
   // =================================== the frame loop ===============================================
+#if !defined(CTC_EMULATE)
+  int tile = 0, ft = 0;
+#endif
   for (int t = 0; t < Tb; ++t) {
     const int t_abs = abs_t0 + t;
 #if defined(CTC_EMULATE)
@@ -294,7 +308,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
     c.idx = SORTED ? p.idx + ((size_t)b * p.T + t) * NP : nullptr;
 #else
     {
-      const int tile = t / F, ft = t - tile * F;
+      if (ft == F) { ft = 0; ++tile; }
       if (ft == 0) {
         mbar_wait(&mbar[tile & 1], (uint32_t)((tile >> 1) & 1));
         // stage (tile+1)&1 was last read in frame t-1, which every thread has left (closing barrier)
@@ -302,6 +316,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
       }
       c.lp = tile_lp + ((size_t)(tile & 1) * F + ft) * NP;
       c.idx = SORTED ? tile_idx + ((size_t)(tile & 1) * F + ft) * NP : nullptr;
+      ++ft;
     }
 #endif
     // row trailer written by the prune kernel: [NP-2] = n | (rank_of_blank + 1) << 16, [NP-1] = max
@@ -324,7 +339,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
     //      log_sum_exp; dead anchors take their lpc / timestep update.  All in shared memory.
     // (reference ctc_beam_search_decoder.cpp:97-118,138-139; path_trie.cpp:39-57,129-137)
     CTC_PAR {
-      for (int x = tid; x < kNBins; x += NT) c.s_hist[x] = 0;  // histogram buffer of radix pass 0
+      for (int x = tid; x < 2 * kNBins; x += NT) c.s_hist[x] = 0;
       unsigned kmin = 0xFFFFFFFFu, kmax = 0u, smax = 0u;
       int npairs = 0;
       for (int j0 = 0; j0 < M; j0 += NT) {
@@ -362,14 +377,16 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
         }
       }
       if (npairs) atom_add(&s_ctl[C_NPAIRS], npairs);
-      for (int a = tid; a < KP2; a += NT) {
-        const int i = c.s_dpslot[a];
-        if (i >= 0) {  // dead node whose parent is in the beam: an existing (dead) child of slot i
-          const int rr = c.rank_of(c.s_dchr[a]);
-          if (rr >= 0) {
-            const float l = c.lp[rr];
-            if (c.s_dlpc[a] < l) { c.s_dlpc[a] = l; c.s_dts[a] = t_abs; }
-            atom_or(&c.s_rmask[i * W + (rr >> 5)], 1u << (rr & 31));
+      if (nlive > 0) {
+        for (int a = tid; a < KP2; a += NT) {
+          const int i = c.s_dpslot[a];
+          if (i >= 0) {  // dead node whose parent is in the beam: an existing (dead) child of slot i
+            const int rr = c.rank_of(c.s_dchr[a]);
+            if (rr >= 0) {
+              const float l = c.lp[rr];
+              if (c.s_dlpc[a] < l) { c.s_dlpc[a] = l; c.s_dts[a] = t_abs; }
+              atom_or(&c.s_rmask[i * W + (rr >> 5)], 1u << (rr & 31));
+            }
           }
         }
       }
@@ -391,29 +408,170 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
     const int n_nb = n - (rblank >= 0 ? 1 : 0);
     const long long total = (long long)M * (n_nb + 1) - s_ctl[C_NPAIRS];
     const bool select_all = total <= (long long)K;  // reference :149 `prefixes.size() >= beam_size`
+    const int G = (n + 31) >> 5;                     // 32-wide column groups of the candidate grid
+
+    // score-key range of everything that can still be selected: [lo32, top32]
+    const unsigned lo32 = (!select_all && M == K) ? (unsigned)s_ctl[C_KMIN] : 0u;
+    unsigned top32 = (unsigned)s_ctl[C_KMAX];
+    {
+      const unsigned o = ord_f(f_add(unord_f((unsigned)s_ctl[C_SMAX]), lpmax));
+      top32 = o > top32 ? o : top32;
+    }
+    int shift32 = 0;  // smallest shift with ((top32 - lo32) >> shift32) < kNBins
+    {
+      const unsigned wm = top32 - lo32;
+#if defined(CTC_EMULATE)
+      const int bits = wm ? 32 - __builtin_clz(wm) : 0;
+#else
+      const int bits = 32 - __clz((int)wm);
+#endif
+      shift32 = bits > 8 ? bits - 8 : 0;
+    }
+
+    // ---- region G: the ONE walk over the beam x pruned-vocab grid.  A warp owns a beam member per
+    //      iteration (member values are warp-broadcast), lanes own the characters.  Candidates whose score
+    //      key reaches lo32 (the worst member's key once the beam is full) are appended to the warp's
+    //      candidate-list segment -- ballot + popc, no atomics, deterministic -- and counted into the
+    //      first radix histogram.  Everything after this region works on the list.
+    CTC_WARPS {
+      int cnt = 0;
+      uint32_t *const segk = c.s_clk + warp * L.seg;
+      int *const segi = c.s_cli + warp * L.seg;
+      int *const hist0 = c.s_hist;
+      if (!select_all) {
+        CTC_LANES {
+          for (int j = warp * 32 + lane; j < M; j += NT) {
+            const unsigned k = ord_f(c.s_snew[j]);
+            if (k >= lo32) atom_add(&hist0[(int)((k - lo32) >> shift32)], 1);
+          }
+        }
+      }
+      for (int i = warp; i < M; i += L.NW) {
+        const float sc_i = c.s_score[i], b_i = c.s_bprev[i];
+        const int ch_i = c.s_chr[i];
+        for (int g = 0; g < G; ++g) {
+          const uint32_t mw = c.s_mask[i * W + g];
+          CTC_LV(int, pred);
+          CTC_LV(uint32_t, kk);
+          CTC_LANES {
+            const int r = g * 32 + lane;
+            pred[LX] = 0;
+            kk[LX] = 0u;
+            if (r < n) {
+              const int ch = c.chr_at(r);
+              if (ch != c.blank && !((mw >> lane) & 1u)) {
+                const float l = c.lp[r];
+                float sc;
+                if (ch == ch_i) sc = (b_i > kNInf) ? f_add(l, b_i) : kNInf;
+                else sc = f_add(l, sc_i);
+                const unsigned k = ord_f(sc);
+                if (k >= lo32) {
+                  pred[LX] = 1;
+                  kk[LX] = k;
+                  if (!select_all) atom_add(&hist0[(int)((k - lo32) >> shift32)], 1);
+                }
+              }
+            }
+          }
+          const unsigned bal = ctc_ballot(pred);
+          if (bal) {
+            CTC_LANES {
+              if (pred[LX]) {
+                const int pos = cnt + ctc_popc(bal & ctc_lt_mask(lane));
+                if (pos < L.seg) { segk[pos] = kk[LX]; segi[pos] = (i << 16) | (g * 32 + lane); }
+              }
+            }
+            cnt += ctc_popc(bal);
+          }
+        }
+      }
+      CTC_LANES {
+        if (lane == 0) {
+          if (cnt > L.seg) atom_or(&s_ctl[C_OVF], 1);
+          c.s_wcnt[warp] = cnt < L.seg ? cnt : L.seg;
+        }
+      }
+    }
+    CTC_BARRIER();
+    CTC_TICK(3);  // G
+    const bool fallback = s_ctl[C_OVF] != 0 || p.force_fallback;  // a segment overflowed: redo on the grid
 
     uint64_t thr = 0;   // selected <=> key >= thr (no tie) / key > thr or tie-selected (tie)
     int tie_m = 0;      // >0: exactly tie_m of the keys equal to thr are selected
-    if (!select_all) {
-      // ---- region R3: exact radix select of the K-th largest 48-bit key --------------------------------
-      // (replaces std::nth_element + prefix_compare, reference :149-154, decoder_utils.cpp:122-132)
-      uint64_t lo = (M == K) ? ((uint64_t)(unsigned)s_ctl[C_KMIN] << 16) : 0ull;
-      unsigned top = (unsigned)s_ctl[C_KMAX];
-      {
-        const unsigned o = ord_f(f_add(unord_f((unsigned)s_ctl[C_SMAX]), lpmax));
-        top = o > top ? o : top;
+    if (!select_all && !fallback) {
+      // ---- exact radix select of the K-th largest 48-bit key over members + candidate list ---------------
+      // (replaces std::nth_element + prefix_compare, reference :149-154, decoder_utils.cpp:122-132).
+      // Pass 0 (score bits only) was histogrammed during region G.
+      CTC_STAT(g_stats.passes++);
+      CTC_PAR { scan_find_bin<NT>(c.s_hist, K, s_ctl, tid); }
+      CTC_BARRIER();
+      uint64_t lo = ((uint64_t)(lo32 + ((unsigned)s_ctl[C_BIN] << shift32))) << 16;
+      if (s_ctl[C_ABOVE] + s_ctl[C_CNT] == K) {
+        thr = lo;
+      } else {
+        uint64_t width = 1ull << (shift32 + 16);
+        int shift = shift32 + 8;
+        int pass = 1;
+        while (true) {
+          CTC_STAT(g_stats.passes++);
+          int *const hist = c.s_hist + (pass & 1) * kNBins;
+          CTC_PAR {
+            int *const other = c.s_hist + ((pass + 1) & 1) * kNBins;
+            for (int x = tid; x < kNBins; x += NT) other[x] = 0;
+            for (int j = tid; j < M; j += NT) {
+              const uint64_t k = key64(c.s_snew[j], c.s_chr[j]);
+              if (k >= lo && k - lo < width) atom_add(&hist[(int)((k - lo) >> shift)], 1);
+            }
+            const int w = tid >> 5, ln = tid & 31;
+            const int cn = c.s_wcnt[w];
+            for (int e = ln; e < cn; e += 32) {
+              const int r = c.s_cli[w * L.seg + e] & 0xFFFF;
+              const uint64_t k = ((uint64_t)c.s_clk[w * L.seg + e] << 16) | (uint64_t)(0xFFFF - (c.chr_at(r) + 1));
+              if (k >= lo && k - lo < width) atom_add(&hist[(int)((k - lo) >> shift)], 1);
+            }
+          }
+          CTC_BARRIER();
+          const int need = K - s_ctl[C_ABOVE];
+          CTC_PAR { scan_find_bin<NT>(hist, need, s_ctl, tid); }
+          CTC_BARRIER();
+          const int bin = s_ctl[C_BIN], above = s_ctl[C_ABOVE], cnt = s_ctl[C_CNT];
+          lo += (uint64_t)bin << shift;
+          if (above + cnt == K) { thr = lo; tie_m = 0; break; }
+          if (shift == 0) { thr = lo; tie_m = K - above; break; }
+          width = 1ull << shift;
+          shift = shift >= 8 ? shift - 8 : 0;
+          ++pass;
+        }
+        if (tie_m > 0) {
+          // comparator-equivalent prefixes straddle the cut: the reference's choice is unspecified
+          // (libstdc++ introselect); keep the lowest ids (members by slot, then candidates by (i, r)).
+          CTC_PAR {
+            for (int j = tid; j < M; j += NT)
+              if (key64(c.s_snew[j], c.s_chr[j]) == thr) c.s_tie[atom_add(&s_ctl[C_NTIE], 1)] = j;
+            const int w = tid >> 5, ln = tid & 31;
+            const int cn = c.s_wcnt[w];
+            for (int e = ln; e < cn; e += 32) {
+              const int id = c.s_cli[w * L.seg + e];
+              const int r = id & 0xFFFF;
+              const uint64_t k = ((uint64_t)c.s_clk[w * L.seg + e] << 16) | (uint64_t)(0xFFFF - (c.chr_at(r) + 1));
+              if (k == thr) c.s_tie[atom_add(&s_ctl[C_NTIE], 1)] = K + (id >> 16) * NP + r;
+            }
+            if (tid == 0) s_ctl[C_FLAGS] |= FLAG_TIE_PRUNE;
+          }
+          CTC_BARRIER();
+        }
       }
-      uint64_t width = ((((uint64_t)top) << 16) | 0xFFFFull) - lo + 1ull;
-      int shift = 0;
-      {
-        const uint64_t wm = width - 1ull;  // smallest shift with (wm >> shift) < kNBins
-#if defined(CTC_EMULATE)
-        const int bits = wm ? 64 - __builtin_clzll(wm) : 0;
-#else
-        const int bits = 64 - __clzll((long long)wm);
-#endif
-        shift = bits > 8 ? bits - 8 : 0;
+    }
+    if (!select_all && fallback) {
+      // ---- fallback: the same select with every pass walking the grid (48-bit keys from the start) -------
+      CTC_PAR {
+        for (int x = tid; x < 2 * kNBins; x += NT) c.s_hist[x] = 0;
+        if (tid == 0) { s_ctl[C_ABOVE] = 0; }
       }
+      CTC_BARRIER();
+      uint64_t lo = ((uint64_t)lo32) << 16;
+      uint64_t width = ((((uint64_t)top32) << 16) | 0xFFFFull) - lo + 1ull;
+      int shift = shift32 + 16;
       int pass = 0;
       while (true) {
         CTC_STAT(g_stats.passes++);
@@ -423,7 +581,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
           for (int x = tid; x < kNBins; x += NT) other[x] = 0;
           for (int j = tid; j < M; j += NT) {
             const uint64_t k = key64(c.s_snew[j], c.s_chr[j]);
-            if (k >= lo && k - lo < width) { atom_add(&hist[(int)((k - lo) >> shift)], 1); CTC_STAT(g_stats.hist_adds++); }
+            if (k >= lo && k - lo < width) atom_add(&hist[(int)((k - lo) >> shift)], 1);
           }
           if (n > 0) {
             int i = tid / n, r = tid - (tid / n) * n;
@@ -432,7 +590,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
               float sc; int ch;
               if (c.cand(i, r, sc, ch)) {
                 const uint64_t k = key64(sc, ch);
-                if (k >= lo && k - lo < width) { atom_add(&hist[(int)((k - lo) >> shift)], 1); CTC_STAT(g_stats.hist_adds++); }
+                if (k >= lo && k - lo < width) atom_add(&hist[(int)((k - lo) >> shift)], 1);
               }
               r += dr; i += di;
               if (r >= n) { r -= n; ++i; }
@@ -452,8 +610,6 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
         ++pass;
       }
       if (tie_m > 0) {
-        // comparator-equivalent prefixes straddle the cut: the reference's choice is unspecified
-        // (libstdc++ introselect); keep the lowest ids (members by slot, then candidates by (i, r)).
         CTC_PAR {
           for (int j = tid; j < M; j += NT)
             if (key64(c.s_snew[j], c.s_chr[j]) == thr) c.s_tie[atom_add(&s_ctl[C_NTIE], 1)] = j;
@@ -473,79 +629,178 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
       }
     }
     const int ntie = s_ctl[C_NTIE];
-    CTC_TICK(3);  // R3 (all radix passes + scans)
+    CTC_TICK(4);  // select
 
-    // ---- region R4a: classify members (keep / evict) and candidates (selected) ----------------------
-    CTC_PAR {
-      for (int j = tid; j < K; j += NT) {
-        if (j < M) {
-          const uint64_t k = key64(c.s_snew[j], c.s_chr[j]);
-          bool keep = k >= thr;
-          if (tie_m > 0 && k == thr) {
-            int lower = 0;
-            for (int x = 0; x < ntie; ++x) lower += (c.s_tie[x] < j) ? 1 : 0;
-            keep = lower < tie_m;
-          }
-          c.s_evict[j] = keep ? 0 : 1;
-          if (!keep) c.s_free[atom_add(&s_ctl[C_NFREE], 1)] = j;
-        } else {
-          c.s_free[atom_add(&s_ctl[C_NFREE], 1)] = j;  // never-used slots of a not-yet-full beam
-        }
-      }
-      if (n > 0) {
-        int i = tid / n, r = tid - (tid / n) * n;
-        const int di = NT / n, dr = NT - (NT / n) * n;
-        while (i < M) {
-          float sc; int ch;
-          if (c.cand(i, r, sc, ch)) {
-            const uint64_t k = key64(sc, ch);
-            bool sel = k >= thr;
-            if (tie_m > 0 && k == thr) {
-              const int id = K + i * NP + r;
-              int lower = 0;
-              for (int x = 0; x < ntie; ++x) lower += (c.s_tie[x] < id) ? 1 : 0;
-              sel = lower < tie_m;
+    // ---- region R4a: classify members (keep / evict) and candidates (selected); compact both with
+    //      ballots so that slot assignment is deterministic without sorting
+    if (!fallback) {
+      CTC_WARPS {
+        // members, in blocks of 32 slots
+        for (int blk = warp; blk * 32 < M; blk += L.NW) {
+          CTC_LV(int, ev);
+          CTC_LANES {
+            const int j = blk * 32 + lane;
+            ev[LX] = 0;
+            if (j < M) {
+              const uint64_t k = key64(c.s_snew[j], c.s_chr[j]);
+              bool keep = k >= thr;
+              if (tie_m > 0 && k == thr) {
+                int lower = 0;
+                for (int x = 0; x < ntie; ++x) lower += (c.s_tie[x] < j) ? 1 : 0;
+                keep = lower < tie_m;
+              }
+              ev[LX] = keep ? 0 : 1;
+              c.s_evict[j] = ev[LX];
             }
-            if (sel) c.s_sel[atom_add(&s_ctl[C_NSEL], 1)] = (i << 16) | r;
           }
-          r += dr; i += di;
-          if (r >= n) { r -= n; ++i; }
+          const unsigned bal = ctc_ballot(ev);
+          CTC_LANES {
+            if (ev[LX]) c.s_free[blk * 32 + ctc_popc(bal & ctc_lt_mask(lane))] = blk * 32 + lane;
+            if (lane == 0) c.s_evcnt[blk] = ctc_popc(bal);
+          }
+        }
+        // this warp's candidate-list segment, compacted in place
+        const int cn = c.s_wcnt[warp];
+        uint32_t *const segk = c.s_clk + warp * L.seg;
+        int *const segi = c.s_cli + warp * L.seg;
+        const unsigned thr_hi = (unsigned)(thr >> 16);
+        int out = 0;
+        for (int e0 = 0; e0 < cn; e0 += 32) {
+          CTC_LV(int, sel);
+          CTC_LV(int, idv);
+          CTC_LANES {
+            const int e = e0 + lane;
+            sel[LX] = 0;
+            idv[LX] = 0;
+            if (e < cn) {
+              const unsigned k32 = segk[e];
+              const int id = segi[e];
+              idv[LX] = id;
+              bool s = k32 > thr_hi;
+              if (k32 == thr_hi) {
+                const int r = id & 0xFFFF;
+                const uint64_t k = ((uint64_t)k32 << 16) | (uint64_t)(0xFFFF - (c.chr_at(r) + 1));
+                s = k >= thr;
+                if (tie_m > 0 && k == thr) {
+                  const int tid_id = K + (id >> 16) * NP + r;
+                  int lower = 0;
+                  for (int x = 0; x < ntie; ++x) lower += (c.s_tie[x] < tid_id) ? 1 : 0;
+                  s = lower < tie_m;
+                }
+              }
+              sel[LX] = s ? 1 : 0;
+            }
+          }
+          const unsigned bal = ctc_ballot(sel);
+          CTC_LANES {
+            if (sel[LX]) segi[out + ctc_popc(bal & ctc_lt_mask(lane))] = idv[LX];
+          }
+          out += ctc_popc(bal);
+        }
+        CTC_LANES {
+          if (lane == 0) {
+            c.s_wcnt[32 + warp] = out;
+            if (out) atom_add(&s_ctl[C_NSEL], out);
+          }
         }
       }
+      CTC_BARRIER();
+    } else {
+      CTC_PAR {
+        for (int j = tid; j < K; j += NT) {
+          if (j < M) {
+            const uint64_t k = key64(c.s_snew[j], c.s_chr[j]);
+            bool keep = k >= thr;
+            if (tie_m > 0 && k == thr) {
+              int lower = 0;
+              for (int x = 0; x < ntie; ++x) lower += (c.s_tie[x] < j) ? 1 : 0;
+              keep = lower < tie_m;
+            }
+            c.s_evict[j] = keep ? 0 : 1;
+            if (!keep) c.s_sel2[atom_add(&s_ctl[C_NFREE], 1)] = j;
+          }
+        }
+        if (n > 0) {
+          int i = tid / n, r = tid - (tid / n) * n;
+          const int di = NT / n, dr = NT - (NT / n) * n;
+          while (i < M) {
+            float sc; int ch;
+            if (c.cand(i, r, sc, ch)) {
+              const uint64_t k = key64(sc, ch);
+              bool sel = k >= thr;
+              if (tie_m > 0 && k == thr) {
+                const int id = K + i * NP + r;
+                int lower = 0;
+                for (int x = 0; x < ntie; ++x) lower += (c.s_tie[x] < id) ? 1 : 0;
+                sel = lower < tie_m;
+              }
+              if (sel) c.s_sel[atom_add(&s_ctl[C_NSEL], 1)] = (i << 16) | r;
+            }
+            r += dr; i += di;
+            if (r >= n) { r -= n; ++i; }
+          }
+        }
+      }
+      CTC_BARRIER();
+      // order both lists (deterministic slot assignment); evicted slots go to s_free2, selected to s_cli[0..)
+      const int nsel_f = s_ctl[C_NSEL], nfree_f = s_ctl[C_NFREE];
+      CTC_PAR {
+        for (int q = tid; q < nsel_f; q += NT) {
+          const int v = c.s_sel[q];
+          int rk = 0;
+          for (int x = 0; x < nsel_f; ++x) rk += (c.s_sel[x] < v) ? 1 : 0;
+          c.s_free2[rk] = v;  // (s_free2 doubles as the ordered selected list in the fallback)
+        }
+        for (int q = tid; q < nfree_f; q += NT) {
+          const int v = c.s_sel2[q];
+          int rk = 0;
+          for (int x = 0; x < nfree_f; ++x) rk += (c.s_sel2[x] < v) ? 1 : 0;
+          c.s_free[rk] = v;   // ordered evicted slots, dense from 0
+        }
+      }
+      CTC_BARRIER();
     }
-    CTC_BARRIER();
-    CTC_TICK(4);  // R4a
-    const int nsel = s_ctl[C_NSEL], nfree = s_ctl[C_NFREE];
+    CTC_TICK(5);  // classify
+    const int nsel = s_ctl[C_NSEL];
 
-    // ---- region R4b: order both lists (deterministic slot assignment) ---------------------------------
-    CTC_PAR {
-      for (int q = tid; q < nsel; q += NT) {
-        const int v = c.s_sel[q];
-        int rk = 0;
-        for (int x = 0; x < nsel; ++x) rk += (c.s_sel[x] < v) ? 1 : 0;
-        c.s_sel2[rk] = v;
+    // q-th selected candidate / q-th free slot (evicted slots in slot order, then never-used slots)
+    auto sel_entry = [&](int q) -> int {
+      if (fallback) return c.s_free2[q];
+      int acc = 0;
+      for (int w = 0; w < L.NW; ++w) {
+        const int cw = c.s_wcnt[32 + w];
+        if (q < acc + cw) return c.s_cli[w * L.seg + (q - acc)];
+        acc += cw;
       }
-      for (int q = tid; q < nfree; q += NT) {
-        const int v = c.s_free[q];
-        int rk = 0;
-        for (int x = 0; x < nfree; ++x) rk += (c.s_free[x] < v) ? 1 : 0;
-        c.s_free2[rk] = v;
+      return 0;
+    };
+    auto free_slot = [&](int q) -> int {
+      int acc = 0;
+      if (fallback) {
+        acc = s_ctl[C_NFREE];
+        if (q < acc) return c.s_free[q];
+      } else {
+        for (int blk = 0; blk * 32 < M; ++blk) {
+          const int cb = c.s_evcnt[blk];
+          if (q < acc + cb) return c.s_free[blk * 32 + (q - acc)];
+          acc += cb;
+        }
       }
-    }
-    CTC_BARRIER();
-    CTC_TICK(5);  // R4b
+      return M + (q - acc);
+    };
 
     // ---- region R4c: selected candidates become trie nodes (or revive a dead anchor) -------------------
     // (reference path_trie.cpp:50-56 revive, :97-105 create).  Arena stores are fire-and-forget.
     CTC_PAR {
+      if (tid == 0) s_ctl[C_NLIVE] = 0;
       for (int q = tid; q < nsel; q += NT) {
-        const int v = c.s_sel2[q];
+        const int v = sel_entry(q);
         const int i = v >> 16, r = v & 0xFFFF;
         float sc; int ch;
         c.cand(i, r, sc, ch);
         float lpc = c.lp[r];
         int ts = t_abs, nid, rev = -1;
-        if ((c.s_rmask[i * W + (r >> 5)] >> (r & 31)) & 1u) {
+        if (nlive > 0 && ((c.s_rmask[i * W + (r >> 5)] >> (r & 31)) & 1u)) {
           for (int a = 0; a < KP2; ++a)
             if (c.s_dpslot[a] == i && c.s_dchr[a] == ch) rev = a;
           nid = c.s_dnode[rev]; lpc = c.s_dlpc[rev]; ts = c.s_dts[rev];
@@ -563,14 +818,15 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
           store_node(&nodes[nid], nn);
         }
         int *ni = c.s_newinfo + q * 10;
-        ni[0] = nid; ni[1] = ch; ni[2] = (int)f_bits(sc); ni[3] = c.s_free2[q]; ni[4] = i; ni[5] = (int)f_bits(lpc);
+        ni[0] = nid; ni[1] = ch; ni[2] = (int)f_bits(sc); ni[3] = free_slot(q); ni[4] = i; ni[5] = (int)f_bits(lpc);
         ni[6] = ts; ni[7] = rev; ni[8] = c.s_depth[i] + 1;
       }
     }
     CTC_BARRIER();
     CTC_TICK(6);  // R4c
+    const int nrev = s_ctl[C_NREV];
 
-    if (s_ctl[C_NREV] > 0) {
+    if (nrev > 0) {
       // ---- rare slow path: a dead anchor d came back to life.  Members that hung below d need the child
       //      of d on their own path as their new nearest anchor; only here is the arena read back.
       CTC_STAT(g_stats.rv_frames++);
@@ -623,18 +879,23 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
       }
       CTC_BARRIER();
     }
-
     CTC_TICK(7);  // revive slow path
+
     // ---- region R5a: nearest anchor of every member of the NEW beam (replaces the removal cascade) -----
     // A member's parent is either in the new beam (pslot), or its nearest anchor is an existing dead
     // anchor (index a < 2KP), a member evicted right now whose own parent stays (code 2KP + slot), or
-    // nothing (-1).  Walking only crosses members evicted in this very frame.
+    // nothing (-1).  Walking only crosses members evicted in this very frame.  Evicted members write their
+    // lpc / timestep back to the arena.
     CTC_PAR {
       for (int y = tid; y < M + nsel; y += NT) {
-        int start, res = -1, newp = -1;
+        int start = 0, res = -1, newp = -1;
         bool resolved = false;
         if (y < M) {
-          if (c.s_evict[y]) continue;
+          if (c.s_evict[y]) {
+            CTC_STAT(g_stats.evicted++);
+            flush_lpc_ts(&nodes[c.s_node[y]], c.s_lpc[y], c.s_ts[y]);
+            continue;
+          }
           const int pq = c.s_pslot[y];
           if (pq >= 0) {
             if (CTC_PARENT_ALIVE(pq)) { newp = pq & ~kNewFlag; resolved = true; }
@@ -669,59 +930,58 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
             cur = q;
           }
         }
-        if (res >= 0) atom_add(&c.s_cnt2[res], 1);
+        if (res >= 0) { atom_add(&c.s_cnt2[res], 1); s_ctl[C_ANYREF] = 1; }
         if (y < M) { c.s_newp[y] = newp; c.s_newa[y] = res; }
         else { c.s_resq[2 * (y - M)] = newp; c.s_resq[2 * (y - M) + 1] = res; }
       }
     }
     CTC_BARRIER();
     CTC_TICK(8);  // R5a
+    const bool anchors_active = nlive > 0 || nrev > 0 || s_ctl[C_ANYREF] != 0;
 
-    // ---- region R5b: dead anchors nobody hangs below any more leave the trie (that IS the reference's
-    //      remove(), path_trie.cpp:144-163); anchors whose parent left the beam stop being anchors.
-    //      Evicted members write their lpc / timestep back to the arena.
-    CTC_PAR {
-      for (int a = tid; a < KP2; a += NT) {
-        const int q = c.s_dpslot[a];
-        if (q >= 0) {
-          const bool keep = CTC_PARENT_ALIVE(q) && c.s_cnt2[a] > 0 && !c.s_drev[a];
-          if (!keep) {
-            if (!c.s_drev[a]) flush_lpc_ts(&nodes[c.s_dnode[a]], c.s_dlpc[a], c.s_dts[a]);
-            c.s_dpslot[a] = -1;
-          } else {
-            CTC_STAT(g_stats.anchors_live++);
+    if (anchors_active) {
+      // ---- region R5b: dead anchors nobody hangs below any more leave the trie (that IS the reference's
+      //      remove(), path_trie.cpp:144-163); anchors whose parent left the beam stop being anchors.
+      CTC_PAR {
+        for (int a = tid; a < KP2; a += NT) {
+          const int q = c.s_dpslot[a];
+          if (q >= 0) {
+            const bool keep = CTC_PARENT_ALIVE(q) && c.s_cnt2[a] > 0 && !c.s_drev[a];
+            if (!keep) {
+              if (!c.s_drev[a]) flush_lpc_ts(&nodes[c.s_dnode[a]], c.s_dlpc[a], c.s_dts[a]);
+              c.s_dpslot[a] = -1;
+            } else {
+              CTC_STAT(g_stats.anchors_live++);
+              atom_add(&s_ctl[C_NLIVE], 1);
+            }
+          }
+          if (c.s_dpslot[a] < 0) c.s_efree[atom_add(&s_ctl[C_NEFREE], 1)] = a;
+        }
+      }
+      CTC_BARRIER();
+      CTC_TICK(9);  // R5b
+
+      // ---- region R5c: members evicted now that still have beam members below them and whose parent
+      //      stays become dead anchors (reference: exists_ = false, node stays in the trie)
+      CTC_PAR {
+        const int nefree = s_ctl[C_NEFREE];
+        for (int e = tid; e < M; e += NT) {
+          if (c.s_evict[e] && c.s_cnt2[KP2 + e] > 0) {
+            const int k = atom_add(&s_ctl[C_NETAKEN], 1);
+            int a = 0;
+            if (k < nefree) a = c.s_efree[k];
+            else s_ctl[C_FLAGS] |= FLAG_ERR_ARENA;
+            CTC_STAT(g_stats.anchors_new++);
+            atom_add(&s_ctl[C_NLIVE], 1);
+            c.s_dnode[a] = c.s_node[e]; c.s_dchr[a] = c.s_chr[e]; c.s_dpslot[a] = c.s_pslot[e];
+            c.s_dlpc[a] = c.s_lpc[e]; c.s_dts[a] = c.s_ts[e];
+            c.s_amap[e] = a;
           }
         }
-        if (c.s_dpslot[a] < 0) c.s_efree[atom_add(&s_ctl[C_NEFREE], 1)] = a;
       }
-      for (int j = tid; j < M; j += NT)
-        if (c.s_evict[j]) {
-          CTC_STAT(g_stats.evicted++);
-          flush_lpc_ts(&nodes[c.s_node[j]], c.s_lpc[j], c.s_ts[j]);
-        }
+      CTC_BARRIER();
+      CTC_TICK(10);  // R5c
     }
-    CTC_BARRIER();
-    CTC_TICK(9);  // R5b
-
-    // ---- region R5c: members evicted now that still have beam members below them and whose parent stays
-    //      become dead anchors (reference: exists_ = false, node stays in the trie)
-    CTC_PAR {
-      const int nefree = s_ctl[C_NEFREE];
-      for (int e = tid; e < M; e += NT) {
-        if (c.s_evict[e] && c.s_cnt2[KP2 + e] > 0) {
-          const int k = atom_add(&s_ctl[C_NETAKEN], 1);
-          int a = 0;
-          if (k < nefree) a = c.s_efree[k];
-          else s_ctl[C_FLAGS] |= FLAG_ERR_ARENA;
-          CTC_STAT(g_stats.anchors_new++);
-          c.s_dnode[a] = c.s_node[e]; c.s_dchr[a] = c.s_chr[e]; c.s_dpslot[a] = c.s_pslot[e];
-          c.s_dlpc[a] = c.s_lpc[e]; c.s_dts[a] = c.s_ts[e];
-          c.s_amap[e] = a;
-        }
-      }
-    }
-    CTC_BARRIER();
-    CTC_TICK(10);  // R5c
 
     // ---- region R5d: survivors roll cur -> prev, new members take their slots, scratch is reset ----------
     // (reference path_trie.cpp:129-137 roll)
@@ -747,22 +1007,26 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
         const int ra = c.s_resq[2 * q + 1];
         c.s_anch[slot] = ra < 0 ? -1 : (ra < KP2 ? ra : c.s_amap[ra - KP2]);
       }
-      for (int a = tid; a < KP2; a += NT) {
-        const int q = c.s_dpslot[a];
-        if (q >= 0) c.s_dpslot[a] = q & ~kNewFlag;
-        c.s_drev[a] = 0;
+      if (anchors_active) {
+        for (int a = tid; a < KP2; a += NT) {
+          const int q = c.s_dpslot[a];
+          if (q >= 0) c.s_dpslot[a] = q & ~kNewFlag;
+          c.s_drev[a] = 0;
+        }
+        for (int x = tid; x < 3 * KP; x += NT) c.s_cnt2[x] = 0;
       }
-      for (int x = tid; x < 3 * KP; x += NT) c.s_cnt2[x] = 0;
       for (int x = tid; x < KP * W; x += NT) { c.s_mask[x] = 0u; c.s_rmask[x] = 0u; }
       if (SORTED) for (int r = tid; r < n; r += NT) c.s_rank[c.idx[r]] = (int16_t)-1;
-      if (tid == 0) {
+      if (tid == 0) {  // (C_NLIVE is read by everybody below and reset in region R4c of the next frame)
         s_ctl[C_NSEL] = 0; s_ctl[C_NFREE] = 0; s_ctl[C_NTIE] = 0; s_ctl[C_NREV] = 0; s_ctl[C_NPAIRS] = 0;
         s_ctl[C_ABOVE] = 0; s_ctl[C_KMIN] = (int)0xFFFFFFFFu; s_ctl[C_KMAX] = 0; s_ctl[C_SMAX] = 0;
-        s_ctl[C_NEFREE] = 0; s_ctl[C_NETAKEN] = 0;
+        s_ctl[C_NEFREE] = 0; s_ctl[C_NETAKEN] = 0; s_ctl[C_OVF] = 0; s_ctl[C_ANYREF] = 0;
       }
     }
+    const int nlive_next = anchors_active ? s_ctl[C_NLIVE] : 0;
     CTC_BARRIER();
     CTC_TICK(11);  // R5d
+    nlive = nlive_next;
     M = select_all ? (int)total : K;
     CTC_STAT(g_stats.frames++);
     CTC_STAT(g_stats.tie_frames += tie_m > 0);

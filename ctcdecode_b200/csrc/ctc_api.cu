@@ -69,12 +69,10 @@ static int fail(int code, const char *fmt, ...) {
 
 static int make_plan(const ctcdec_config *cfg, int B, int T, Plan *pl) {
   char msg[256];
-  const int rc = make_plan_core(cfg, B, T, pl, msg, sizeof(msg));
+  int nt = 0;
+  if (const char *e = getenv("CTCDEC_NT")) nt = atoi(e);  // tuning knob: threads per CTA of the beam kernel
+  const int rc = make_plan_core(cfg, B, T, pl, msg, sizeof(msg), nt);
   if (rc) return fail(rc, "%s", msg);
-  if (const char *e = getenv("CTCDEC_NT")) {
-    const int v = atoi(e);
-    if (v == 128 || v == 256 || v == 512 || v == 1024) pl->NT = v;
-  }
   return CTCDEC_OK;
 }
 
@@ -260,6 +258,7 @@ int ctcdec_decode_batch_device(const ctcdec_config *cfg, const float *probs, con
   bp.out_tokens = tokens; bp.out_timesteps = timesteps; bp.out_scores = scores; bp.out_lens = lens;
   bp.n_results = nres_dev; bp.out_T = T; bp.flags = flags_dev;
   bp.timing = g_prof.timing;
+  bp.force_fallback = getenv("CTCDEC_FORCE_FALLBACK") ? 1 : 0;  // test knob
   if ((rc = launch_beam(bp, pl, B, s))) return rc;
   if (prof) CU(cudaEventRecord(g_prof.ev[2], s));
   if ((rc = launch_finalize(bp, B, s))) return rc;

@@ -25,7 +25,8 @@ struct Plan {
 
 static inline size_t al256(size_t x) { return (x + 255) / 256 * 256; }
 
-static inline int make_plan_core(const ctcdec_config *cfg, int B, int T, Plan *pl, char *msg, size_t msglen) {
+static inline int make_plan_core(const ctcdec_config *cfg, int B, int T, Plan *pl, char *msg, size_t msglen,
+                                 int nt_override = 0) {
 #define PLAN_FAIL(code, ...) do { snprintf(msg, msglen, __VA_ARGS__); return code; } while (0)
   if (!cfg) PLAN_FAIL(CTCDEC_E_INVALID, "cfg is NULL");
   const int V = cfg->vocab_size, K = cfg->beam_size;
@@ -50,7 +51,9 @@ static inline int make_plan_core(const ctcdec_config *cfg, int B, int T, Plan *p
   pl->F = std::max(1, std::min(32, 4096 / (pl->NP * 4)));
   const long long grid = (long long)K * pl->n_max;
   pl->NT = grid <= 1024 ? 128 : (grid <= 2048 ? 256 : 512);
-  pl->L = make_layout(K, V, pl->NP, pl->F, pl->sorted);
+  if (pl->NT < kp_of(K)) pl->NT = kp_of(K) <= 256 ? 256 : (kp_of(K) <= 512 ? 512 : 1024);
+  if (nt_override == 128 || nt_override == 256 || nt_override == 512 || nt_override == 1024) pl->NT = nt_override;
+  pl->L = make_layout(K, V, pl->NP, pl->F, pl->sorted, pl->NT);
   if (pl->L.total > 227 * 1024)
     PLAN_FAIL(CTCDEC_E_UNSUPPORTED, "beam_size %d x pruned vocab %d needs %d bytes of shared memory (> 227 KB)", K,
               pl->n_max, pl->L.total);

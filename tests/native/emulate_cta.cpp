@@ -108,6 +108,8 @@ int emu_decode_batch(const float *probs, const int *seq_lens, int B, int T, int 
   int rc = make_plan_core(&cfg, B, T, &pl, msg, sizeof(msg));
   if (rc) { fprintf(stderr, "emu: %s\n", msg); return rc; }
   if (NT <= 0) NT = pl.NT;
+  pl.NT = NT;
+  pl.L = make_layout(K, V, pl.NP, pl.F, pl.sorted, NT);
   std::vector<float> lp((size_t)B * T * pl.NP + 8, 0.f);
   std::vector<uint16_t> idx(pl.sorted ? (size_t)B * T * pl.NP + 8 : 8, 0);
   std::vector<Node> arena((size_t)B * pl.arena_stride);
@@ -123,6 +125,7 @@ int emu_decode_batch(const float *probs, const int *seq_lens, int B, int T, int 
   bp.state_stride = pl.state_stride; bp.arena_cap = (int)pl.arena_stride;
   bp.out_tokens = tokens; bp.out_timesteps = timesteps; bp.out_scores = scores; bp.out_lens = lens;
   bp.n_results = n_results; bp.out_T = T; bp.flags = flags;
+  bp.force_fallback = getenv("CTC_EMU_FORCE_FALLBACK") ? 1 : 0;
 
   std::vector<int> chunk_lens(B);
   const int step = chunk > 0 ? chunk : (T > 0 ? T : 1);

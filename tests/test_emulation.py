@@ -97,3 +97,21 @@ def test_emulation_uniform_input_massive_ties(cport):
     assert (got["ties"][0] & 3) != 0 and ref["ties"][0] != 0
     # multiset of scores is still determined
     assert np.array_equal(np.sort(got["scores"][0]), np.sort(ref["scores"][0]))
+
+
+def test_emulation_grid_fallback_path(cport, monkeypatch):
+    """The candidate-list fast path and the grid-walking fallback (taken when a warp's list segment overflows)
+    must agree with the oracle -- force the fallback on every frame."""
+    monkeypatch.setenv("CTC_EMU_FORCE_FALLBACK", "1")
+    _check(cport, ctc_like_probs(2, 150, 29, seed=40).numpy(), beam=60)
+    _check(cport, ctc_like_probs(1, 100, 256, seed=41).numpy(), beam=100, cutoff_prob=0.99)
+    _check(cport, flat_probs(2, 200, 4, seed=5, temp=1.0).numpy(), beam=16)
+    _check(cport, np.full((1, 12, 5), 0.2, np.float32)[:, :0], beam=6)
+
+
+def test_emulation_segment_overflow_takes_fallback(cport):
+    """beam 512 x 40 kept characters: a warp's list segment (capped at 64 KB / warps) cannot hold all candidates of
+    its 32 members while the beam is filling up, so early frames overflow into the fallback and later frames use
+    the list."""
+    probs = ctc_like_probs(1, 12, 64, seed=42).numpy()
+    _check(cport, probs, beam=512)
