@@ -129,7 +129,7 @@ struct SmemLayout {
   int tie;                                                           // [2*KP]
   int dnode, dchr, dpslot, dlpc, dts, drev;                          // dead-anchor table [2*KP]
   int cnt2;                                                          // [3*KP] anchor reference counts
-  int amap, efree, newp, newa, resq, rvwork;                         // re-anchoring scratch
+  int amap, slot2q, stash, efree, newp, newa, resq, rvwork;          // re-anchoring scratch
   int hist;                                                          // [2][kNBins]
   int clk, cli, wcnt, evcnt;                                         // candidate list segments [NW][seg], per-warp counts
   int ctl;                                                           // control words
@@ -166,8 +166,8 @@ CTC_HD SmemLayout make_layout(int K, int V, int NP, int tile_frames, bool sorted
   L.score = o;     o += KP * 4;
   L.lpc = o;       o += KP * 4;
   L.ts = o;        o += KP * 4;
-  L.pslot = o;     o += KP * 4;
-  L.anch = o;      o += KP * 4;
+  L.pslot = o;     o += 2 * KP * 4;  // double buffered: links of the beam of frame t / t+1
+  L.anch = o;      o += 2 * KP * 4;
   L.bnew = o;      o += KP * 4;
   L.nbnew = o;     o += KP * 4;
   L.snew = o;      o += KP * 4;
@@ -188,6 +188,8 @@ CTC_HD SmemLayout make_layout(int K, int V, int NP, int tile_frames, bool sorted
   L.drev = o;      o += 2 * KP * 4;
   L.cnt2 = o;      o += 3 * KP * 4;
   L.amap = o;      o += KP * 4;
+  L.slot2q = o;    o += KP * 4;
+  L.stash = o;     o += 4 * KP * 4;
   L.efree = o;     o += 2 * KP * 4;
   L.newp = o;      o += KP * 4;
   L.newa = o;      o += KP * 4;
@@ -274,7 +276,7 @@ struct Cta {
   float *s_dlpc;
   // shared: scratch
   int *s_evict, *s_sel, *s_sel2, *s_free, *s_free2, *s_newinfo, *s_tie, *s_cnt2, *s_amap, *s_efree, *s_newp, *s_newa,
-      *s_resq, *s_rvwork, *s_hist, *s_ctl, *s_cli, *s_wcnt, *s_evcnt;
+      *s_resq, *s_rvwork, *s_hist, *s_ctl, *s_cli, *s_wcnt, *s_evcnt, *s_slot2q, *s_stash;
   uint32_t *s_clk;
   int16_t *s_rank;  // [V]
   const uint64_t *s_exptab;

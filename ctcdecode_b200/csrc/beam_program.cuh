@@ -113,6 +113,47 @@ CTC_FN void scan_find_bin(const int *hist, int need, int *s_ctl, int tid) {
 #endif
 }
 
+// Same search, executed redundantly by EVERY warp (device) so that no barrier / broadcast is needed afterwards.
+CTC_FN void scan_bin_all(const int *hist, int need, int &bin, int &above, int &cnt) {
+#if defined(CTC_EMULATE)
+  int a = 0;
+  for (int bb = kNBins - 1; bb >= 0; --bb) {
+    if (a + hist[bb] >= need) { bin = bb; above = a; cnt = hist[bb]; return; }
+    a += hist[bb];
+  }
+  bin = 0; above = a - hist[0]; cnt = hist[0];  // unreachable when the invariants hold
+#else
+  constexpr int PER = kNBins / 32;
+  const int lane = (int)(threadIdx.x & 31);
+  const int top = kNBins - 1 - PER * lane;
+  int h[PER];
+  int sum = 0;
+#pragma unroll
+  for (int q = 0; q < PER; ++q) { h[q] = hist[top - q]; sum += h[q]; }
+  int incl = sum;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += v;
+  }
+  const unsigned ball = __ballot_sync(0xffffffffu, incl >= need);
+  const int owner = ball ? (__ffs(ball) - 1) : 31;
+  int a = incl - sum, b = top - PER + 1, cn = h[PER - 1];
+  bool found = false;
+#pragma unroll
+  for (int q = 0; q < PER; ++q) {
+    if (!found) {
+      if (a + h[q] >= need) { b = top - q; cn = h[q]; found = true; }
+      else a += h[q];
+    }
+  }
+  if (!found) a -= h[PER - 1];
+  bin = __shfl_sync(0xffffffffu, b, owner);
+  above = __shfl_sync(0xffffffffu, a, owner);
+  cnt = __shfl_sync(0xffffffffu, cn, owner);
+#endif
+}
+
 // 32-bit block max / min into a shared word (device: hardware warp redux + one atomic per warp).
 CTC_FN void red_max_u32(unsigned *dst, unsigned v) {
 #if defined(CTC_EMULATE)
@@ -187,6 +228,9 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
   c.s_rank = (int16_t *)(smem + L.rank);  c.s_ctl = (int *)(smem + L.ctl);
   c.s_clk = (uint32_t *)(smem + L.clk);   c.s_cli = (int *)(smem + L.cli);
   c.s_wcnt = (int *)(smem + L.wcnt);      c.s_evcnt = (int *)(smem + L.evcnt);
+  c.s_slot2q = (int *)(smem + L.slot2q);  c.s_stash = (int *)(smem + L.stash);
+  int *const pslot_base = (int *)(smem + L.pslot), *const anch_base = (int *)(smem + L.anch);
+  int cur = 0;  // which half of the double-buffered link arrays describes the current beam
   c.s_exptab = (uint64_t *)(smem + L.exptab);
   c.s_logtab = (double *)(smem + L.logtab);
   c.K = K; c.KP = KP; c.V = V; c.NP = NP; c.W = W; c.blank = p.blank;
@@ -446,32 +490,38 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
           }
         }
       }
-      for (int i = warp; i < M; i += L.NW) {
-        const float sc_i = c.s_score[i], b_i = c.s_bprev[i];
-        const int ch_i = c.s_chr[i];
-        for (int g = 0; g < G; ++g) {
+      for (int g = 0; g < G; ++g) {
+        // per-lane column constants: the character this lane owns in this group and its log-prob
+        CTC_LV(int, colc);
+        CTC_LV(float, colv);
+        CTC_LANES {
+          const int r = g * 32 + lane;
+          colc[LX] = -2;  // not a candidate column (beyond n, or the blank)
+          colv[LX] = 0.0f;
+          if (r < n) {
+            const int ch = c.chr_at(r);
+            if (ch != c.blank) { colc[LX] = ch; colv[LX] = c.lp[r]; }
+          }
+        }
+        for (int i = warp; i < M; i += L.NW) {
+          const float sc_i = c.s_score[i];
+          // nothing in this row can reach lo32: every candidate is <= score_i + max non-blank log-prob
+          if (ord_f(f_add(sc_i, lpmax)) < lo32) continue;
+          const float b_i = c.s_bprev[i];
+          const int ch_i = c.s_chr[i];
           const uint32_t mw = c.s_mask[i * W + g];
           CTC_LV(int, pred);
           CTC_LV(uint32_t, kk);
           CTC_LANES {
-            const int r = g * 32 + lane;
-            pred[LX] = 0;
-            kk[LX] = 0u;
-            if (r < n) {
-              const int ch = c.chr_at(r);
-              if (ch != c.blank && !((mw >> lane) & 1u)) {
-                const float l = c.lp[r];
-                float sc;
-                if (ch == ch_i) sc = (b_i > kNInf) ? f_add(l, b_i) : kNInf;
-                else sc = f_add(l, sc_i);
-                const unsigned k = ord_f(sc);
-                if (k >= lo32) {
-                  pred[LX] = 1;
-                  kk[LX] = k;
-                  if (!select_all) atom_add(&hist0[(int)((k - lo32) >> shift32)], 1);
-                }
-              }
-            }
+            const int ch = colc[LX];
+            const bool rep = (ch == ch_i);
+            float sc = f_add(colv[LX], rep ? b_i : sc_i);
+            if (rep && !(b_i > kNInf)) sc = kNInf;
+            const unsigned k = ord_f(sc);
+            const bool ok = (ch >= 0) && !((mw >> lane) & 1u) && (k >= lo32);
+            pred[LX] = ok ? 1 : 0;
+            kk[LX] = k;
+            if (ok && !select_all) atom_add(&hist0[(int)((k - lo32) >> shift32)], 1);
           }
           const unsigned bal = ctc_ballot(pred);
           if (bal) {
@@ -503,10 +553,10 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
       // (replaces std::nth_element + prefix_compare, reference :149-154, decoder_utils.cpp:122-132).
       // Pass 0 (score bits only) was histogrammed during region G.
       CTC_STAT(g_stats.passes++);
-      CTC_PAR { scan_find_bin<NT>(c.s_hist, K, s_ctl, tid); }
-      CTC_BARRIER();
-      uint64_t lo = ((uint64_t)(lo32 + ((unsigned)s_ctl[C_BIN] << shift32))) << 16;
-      if (s_ctl[C_ABOVE] + s_ctl[C_CNT] == K) {
+      int bin, above, cnt;
+      scan_bin_all(c.s_hist, K, bin, above, cnt);  // every warp, redundantly: no barrier, no broadcast
+      uint64_t lo = ((uint64_t)(lo32 + ((unsigned)bin << shift32))) << 16;
+      if (above + cnt == K) {
         thr = lo;
       } else {
         uint64_t width = 1ull << (shift32 + 16);
@@ -515,9 +565,12 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
         while (true) {
           CTC_STAT(g_stats.passes++);
           int *const hist = c.s_hist + (pass & 1) * kNBins;
+          CTC_BARRIER();  // every warp is done scanning the previous histogram
+          if (pass >= 2) {
+            CTC_PAR { for (int x = tid; x < kNBins; x += NT) hist[x] = 0; }
+            CTC_BARRIER();
+          }
           CTC_PAR {
-            int *const other = c.s_hist + ((pass + 1) & 1) * kNBins;
-            for (int x = tid; x < kNBins; x += NT) other[x] = 0;
             for (int j = tid; j < M; j += NT) {
               const uint64_t k = key64(c.s_snew[j], c.s_chr[j]);
               if (k >= lo && k - lo < width) atom_add(&hist[(int)((k - lo) >> shift)], 1);
@@ -531,10 +584,9 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
             }
           }
           CTC_BARRIER();
-          const int need = K - s_ctl[C_ABOVE];
-          CTC_PAR { scan_find_bin<NT>(hist, need, s_ctl, tid); }
-          CTC_BARRIER();
-          const int bin = s_ctl[C_BIN], above = s_ctl[C_ABOVE], cnt = s_ctl[C_CNT];
+          int a2;
+          scan_bin_all(hist, K - above, bin, a2, cnt);
+          above += a2;
           lo += (uint64_t)bin << shift;
           if (above + cnt == K) { thr = lo; tie_m = 0; break; }
           if (shift == 0) { thr = lo; tie_m = K - above; break; }
@@ -635,6 +687,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
     //      ballots so that slot assignment is deterministic without sorting
     if (!fallback) {
       CTC_WARPS {
+        CTC_LANES { for (int j = warp * 32 + lane; j < K; j += NT) c.s_slot2q[j] = -1; }
         // members, in blocks of 32 slots
         for (int blk = warp; blk * 32 < M; blk += L.NW) {
           CTC_LV(int, ev);
@@ -708,6 +761,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
     } else {
       CTC_PAR {
         for (int j = tid; j < K; j += NT) {
+          c.s_slot2q[j] = -1;
           if (j < M) {
             const uint64_t k = key64(c.s_snew[j], c.s_chr[j]);
             bool keep = k >= thr;
@@ -792,7 +846,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
     // ---- region R4c: selected candidates become trie nodes (or revive a dead anchor) -------------------
     // (reference path_trie.cpp:50-56 revive, :97-105 create).  Arena stores are fire-and-forget.
     CTC_PAR {
-      if (tid == 0) s_ctl[C_NLIVE] = 0;
+      if (tid == 0) { s_ctl[C_NLIVE] = 0; s_ctl[C_ANYREF] = 0; }
       for (int q = tid; q < nsel; q += NT) {
         const int v = sel_entry(q);
         const int i = v >> 16, r = v & 0xFFFF;
@@ -820,6 +874,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
         int *ni = c.s_newinfo + q * 10;
         ni[0] = nid; ni[1] = ch; ni[2] = (int)f_bits(sc); ni[3] = free_slot(q); ni[4] = i; ni[5] = (int)f_bits(lpc);
         ni[6] = ts; ni[7] = rev; ni[8] = c.s_depth[i] + 1;
+        c.s_slot2q[ni[3]] = q;
       }
     }
     CTC_BARRIER();
@@ -881,27 +936,30 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
     }
     CTC_TICK(7);  // revive slow path
 
-    // ---- region R5a: nearest anchor of every member of the NEW beam (replaces the removal cascade) -----
-    // A member's parent is either in the new beam (pslot), or its nearest anchor is an existing dead
-    // anchor (index a < 2KP), a member evicted right now whose own parent stays (code 2KP + slot), or
-    // nothing (-1).  Walking only crosses members evicted in this very frame.  Evicted members write their
-    // lpc / timestep back to the arena.
+    // ---- region R5: the new beam takes shape.  Every SLOT OWNER (thread j for slot j) either rolls its
+    //      surviving member cur -> prev (reference path_trie.cpp:129-137), or writes the evicted member's
+    //      lpc / timestep back to the arena and commits the new member that was assigned this slot.  Each
+    //      member of the new beam gets its links: parent slot if the parent is in the new beam, else its
+    //      nearest anchor -- an existing dead anchor (index a < 2KP), a member evicted right now whose own
+    //      parent stays (provisional code 2KP + slot), or nothing (-1).  This replaces the reference's removal
+    //      cascade (path_trie.cpp:144-163); the walk only crosses members evicted in this very frame.  Links
+    //      are double buffered: walks read the old beam's links while the new ones are written.
+    int *const npslot = pslot_base + (cur ^ 1) * KP, *const nanch = anch_base + (cur ^ 1) * KP;
     CTC_PAR {
-      for (int y = tid; y < M + nsel; y += NT) {
+      for (int j = tid; j < K; j += NT) {
         int start = 0, res = -1, newp = -1;
-        bool resolved = false;
-        if (y < M) {
-          if (c.s_evict[y]) {
-            CTC_STAT(g_stats.evicted++);
-            flush_lpc_ts(&nodes[c.s_node[y]], c.s_lpc[y], c.s_ts[y]);
-            continue;
-          }
-          const int pq = c.s_pslot[y];
+        bool have = false, resolved = false;
+        if (j < M && !c.s_evict[j]) {
+          c.s_bprev[j] = c.s_bnew[j];
+          c.s_nbprev[j] = c.s_nbnew[j];
+          c.s_score[j] = c.s_snew[j];
+          have = true;
+          const int pq = c.s_pslot[j];
           if (pq >= 0) {
             if (CTC_PARENT_ALIVE(pq)) { newp = pq & ~kNewFlag; resolved = true; }
             start = pq;
           } else {
-            const int a = c.s_anch[y];
+            const int a = c.s_anch[j];
             if (a < 0) { resolved = true; }
             else {
               const int q = c.s_dpslot[a];
@@ -910,38 +968,64 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
             }
           }
         } else {
-          start = c.s_newinfo[(y - M) * 10 + 4];
-          if (c.s_evict[start] == 0) { newp = start; resolved = true; }
-        }
-        if (!resolved) {
-          int cur = start;  // an old slot evicted in this frame
-          while (true) {
-            CTC_STAT(g_stats.walk_iters++);
-            const int pq = c.s_pslot[cur];
-            if (pq >= 0) {
-              if (CTC_PARENT_ALIVE(pq)) { res = KP2 + cur; break; }
-              cur = pq;
-              continue;
-            }
-            const int a = c.s_anch[cur];
-            if (a < 0) { res = -1; break; }
-            const int q = c.s_dpslot[a];
-            if (CTC_PARENT_ALIVE(q)) { res = a; break; }
-            cur = q;
+          if (j < M) {  // evicted: write back, and remember what a dead anchor made of this node would need
+            CTC_STAT(g_stats.evicted++);
+            flush_lpc_ts(&nodes[c.s_node[j]], c.s_lpc[j], c.s_ts[j]);
+            c.s_stash[j] = c.s_node[j]; c.s_stash[KP + j] = c.s_chr[j];
+            c.s_stash[2 * KP + j] = (int)f_bits(c.s_lpc[j]); c.s_stash[3 * KP + j] = c.s_ts[j];
+          }
+          const int q = c.s_slot2q[j];
+          if (q >= 0) {  // a new member moves into this slot
+            const int *ni = c.s_newinfo + q * 10;
+            const float sc = bits_f((uint32_t)ni[2]);
+            c.s_node[j] = ni[0]; c.s_chr[j] = ni[1]; c.s_depth[j] = ni[8];
+            c.s_bprev[j] = kNInf; c.s_nbprev[j] = sc; c.s_score[j] = sc;  // score = lse(-inf, nb)
+            c.s_lpc[j] = bits_f((uint32_t)ni[5]); c.s_ts[j] = ni[6];
+            have = true;
+            start = ni[4];
+            if (c.s_evict[start] == 0) { newp = start; resolved = true; }
           }
         }
-        if (res >= 0) { atom_add(&c.s_cnt2[res], 1); s_ctl[C_ANYREF] = 1; }
-        if (y < M) { c.s_newp[y] = newp; c.s_newa[y] = res; }
-        else { c.s_resq[2 * (y - M)] = newp; c.s_resq[2 * (y - M) + 1] = res; }
+        if (have) {
+          if (!resolved) {
+            int cs = start & ~kNewFlag;  // an old slot evicted in this frame
+            while (true) {
+              CTC_STAT(g_stats.walk_iters++);
+              const int pq = c.s_pslot[cs];
+              if (pq >= 0) {
+                if (CTC_PARENT_ALIVE(pq)) { res = KP2 + cs; break; }
+                cs = pq;
+                continue;
+              }
+              const int a = c.s_anch[cs];
+              if (a < 0) { res = -1; break; }
+              const int q = c.s_dpslot[a];
+              if (CTC_PARENT_ALIVE(q)) { res = a; break; }
+              cs = q;
+            }
+          }
+          if (res >= 0) { atom_add(&c.s_cnt2[res], 1); s_ctl[C_ANYREF] = 1; }
+          npslot[j] = newp;
+          nanch[j] = res;
+        }
+      }
+      for (int x = tid; x < KP * W; x += NT) { c.s_mask[x] = 0u; c.s_rmask[x] = 0u; }
+      if (SORTED) for (int r = tid; r < n; r += NT) c.s_rank[c.idx[r]] = (int16_t)-1;
+      if (tid == 0) {  // (C_NLIVE / C_ANYREF are read below and reset in region R4c of the next frame)
+        s_ctl[C_NSEL] = 0; s_ctl[C_NFREE] = 0; s_ctl[C_NTIE] = 0; s_ctl[C_NREV] = 0; s_ctl[C_NPAIRS] = 0;
+        s_ctl[C_ABOVE] = 0; s_ctl[C_KMIN] = (int)0xFFFFFFFFu; s_ctl[C_KMAX] = 0; s_ctl[C_SMAX] = 0;
+        s_ctl[C_NEFREE] = 0; s_ctl[C_NETAKEN] = 0; s_ctl[C_OVF] = 0;
       }
     }
     CTC_BARRIER();
-    CTC_TICK(8);  // R5a
+    CTC_TICK(8);  // R5
+    const int M_new = select_all ? (int)total : K;
     const bool anchors_active = nlive > 0 || nrev > 0 || s_ctl[C_ANYREF] != 0;
+    int nlive_next = 0;
 
     if (anchors_active) {
       // ---- region R5b: dead anchors nobody hangs below any more leave the trie (that IS the reference's
-      //      remove(), path_trie.cpp:144-163); anchors whose parent left the beam stop being anchors.
+      //      remove()); anchors whose parent left the beam stop being anchors.
       CTC_PAR {
         for (int a = tid; a < KP2; a += NT) {
           const int q = c.s_dpslot[a];
@@ -973,61 +1057,37 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
             else s_ctl[C_FLAGS] |= FLAG_ERR_ARENA;
             CTC_STAT(g_stats.anchors_new++);
             atom_add(&s_ctl[C_NLIVE], 1);
-            c.s_dnode[a] = c.s_node[e]; c.s_dchr[a] = c.s_chr[e]; c.s_dpslot[a] = c.s_pslot[e];
-            c.s_dlpc[a] = c.s_lpc[e]; c.s_dts[a] = c.s_ts[e];
+            c.s_dnode[a] = c.s_stash[e]; c.s_dchr[a] = c.s_stash[KP + e]; c.s_dpslot[a] = c.s_pslot[e];
+            c.s_dlpc[a] = bits_f((uint32_t)c.s_stash[2 * KP + e]); c.s_dts[a] = c.s_stash[3 * KP + e];
             c.s_amap[e] = a;
           }
         }
       }
       CTC_BARRIER();
       CTC_TICK(10);  // R5c
-    }
-
-    // ---- region R5d: survivors roll cur -> prev, new members take their slots, scratch is reset ----------
-    // (reference path_trie.cpp:129-137 roll)
-    CTC_PAR {
-      for (int j = tid; j < M; j += NT) {
-        if (!c.s_evict[j]) {
-          c.s_bprev[j] = c.s_bnew[j];
-          c.s_nbprev[j] = c.s_nbnew[j];
-          c.s_score[j] = c.s_snew[j];
-          c.s_pslot[j] = c.s_newp[j];
-          const int ra = c.s_newa[j];
-          c.s_anch[j] = ra < 0 ? -1 : (ra < KP2 ? ra : c.s_amap[ra - KP2]);
+      nlive_next = s_ctl[C_NLIVE];
+      // ---- region R5d: provisional anchor codes become table indices; in-frame tags are dropped
+      CTC_PAR {
+        for (int j = tid; j < M_new; j += NT) {
+          const int ra = nanch[j];
+          if (ra >= KP2) nanch[j] = c.s_amap[ra - KP2];
         }
-      }
-      for (int q = tid; q < nsel; q += NT) {
-        const int *ni = c.s_newinfo + q * 10;
-        const int slot = ni[3];
-        const float sc = bits_f((uint32_t)ni[2]);
-        c.s_node[slot] = ni[0]; c.s_chr[slot] = ni[1]; c.s_depth[slot] = ni[8];
-        c.s_bprev[slot] = kNInf; c.s_nbprev[slot] = sc; c.s_score[slot] = sc;  // score = lse(-inf, nb)
-        c.s_lpc[slot] = bits_f((uint32_t)ni[5]); c.s_ts[slot] = ni[6];
-        c.s_pslot[slot] = c.s_resq[2 * q];
-        const int ra = c.s_resq[2 * q + 1];
-        c.s_anch[slot] = ra < 0 ? -1 : (ra < KP2 ? ra : c.s_amap[ra - KP2]);
-      }
-      if (anchors_active) {
         for (int a = tid; a < KP2; a += NT) {
           const int q = c.s_dpslot[a];
           if (q >= 0) c.s_dpslot[a] = q & ~kNewFlag;
           c.s_drev[a] = 0;
         }
         for (int x = tid; x < 3 * KP; x += NT) c.s_cnt2[x] = 0;
+        if (tid == 0) { s_ctl[C_NEFREE] = 0; s_ctl[C_NETAKEN] = 0; }
       }
-      for (int x = tid; x < KP * W; x += NT) { c.s_mask[x] = 0u; c.s_rmask[x] = 0u; }
-      if (SORTED) for (int r = tid; r < n; r += NT) c.s_rank[c.idx[r]] = (int16_t)-1;
-      if (tid == 0) {  // (C_NLIVE is read by everybody below and reset in region R4c of the next frame)
-        s_ctl[C_NSEL] = 0; s_ctl[C_NFREE] = 0; s_ctl[C_NTIE] = 0; s_ctl[C_NREV] = 0; s_ctl[C_NPAIRS] = 0;
-        s_ctl[C_ABOVE] = 0; s_ctl[C_KMIN] = (int)0xFFFFFFFFu; s_ctl[C_KMAX] = 0; s_ctl[C_SMAX] = 0;
-        s_ctl[C_NEFREE] = 0; s_ctl[C_NETAKEN] = 0; s_ctl[C_OVF] = 0; s_ctl[C_ANYREF] = 0;
-      }
+      CTC_BARRIER();
     }
-    const int nlive_next = anchors_active ? s_ctl[C_NLIVE] : 0;
-    CTC_BARRIER();
     CTC_TICK(11);  // R5d
+    cur ^= 1;
+    c.s_pslot = pslot_base + cur * KP;
+    c.s_anch = anch_base + cur * KP;
     nlive = nlive_next;
-    M = select_all ? (int)total : K;
+    M = M_new;
     CTC_STAT(g_stats.frames++);
     CTC_STAT(g_stats.tie_frames += tie_m > 0);
     CTC_STAT(g_stats.sel_all_frames += select_all);

@@ -11,8 +11,8 @@ from bench import CONFIGS  # noqa: E402
 from ctcdecode_b200 import CTCBeamDecoder, _native  # noqa: E402
 from ctcdecode_b200.synth import ctc_like_probs  # noqa: E402
 
-NAMES = ["tile_wait", "R0_rank", "R1_members", "R3_select", "R4a_classify", "R4b_order", "R4c_nodes", "RV_revive",
-         "R5a_anchor", "R5b_sweep", "R5c_newanchor", "R5d_commit"]
+NAMES = ["tile_wait", "R0_rank", "R1_members", "G_gridwalk", "select_scan", "classify", "R4c_nodes", "RV_revive",
+         "R5_commit", "R5b_sweep", "R5c_newanchor", "R5d_fixup"]
 ap = argparse.ArgumentParser()
 ap.add_argument("--config", default="c2")
 ap.add_argument("--batch", type=int, nargs="*", default=[1, 148, 256])
