@@ -21,8 +21,9 @@ namespace ctc {
 // ---------------------------------------------------------------------------------------------------
 //  kernels
 // ---------------------------------------------------------------------------------------------------
+// at least 2048 / NT co-resident CTAs per SM (<= 64 registers per thread) whenever shared memory allows
 template <int NT, bool SORTED>
-__global__ void __launch_bounds__(NT) beam_kernel(const BeamParams p) {
+__global__ void __launch_bounds__(NT, (NT >= 1024 ? 1 : 2048 / NT / 2)) beam_kernel(const BeamParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   beam_cta_run<NT, SORTED>(p, (int)blockIdx.x, smem);
 }
