@@ -246,9 +246,11 @@ static inline unsigned ctc_ballot(const int (&pred)[kLW]) {
   return b;
 }
 static inline int ctc_popc(unsigned x) { return __builtin_popcount(x); }
+static inline int ctc_ffs(unsigned x) { return __builtin_ffs((int)x); }
 #else
 CTC_FN unsigned ctc_ballot(const int (&pred)[kLW]) { return __ballot_sync(0xffffffffu, pred[0]); }
 CTC_FN int ctc_popc(unsigned x) { return __popc(x); }
+CTC_FN int ctc_ffs(unsigned x) { return __ffs((int)x); }
 #endif
 CTC_FN unsigned ctc_lt_mask(int lane) { return (1u << lane) - 1u; }
 

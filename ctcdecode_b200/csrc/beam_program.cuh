@@ -7,7 +7,7 @@ namespace ctc {
 
 #if defined(CTC_EMULATE) && defined(CTC_STATS)
 struct EmuStats { long long frames, passes, walk_iters, anchors_live, evicted, anchors_new, rv_hops, created, revived,
-                  hist_adds, tie_frames, sel_all_frames, rv_frames; };
+                  hist_adds, tie_frames, sel_all_frames, rv_frames, rows, rows_skipped, cl_entries; };
 static EmuStats g_stats;
 #define CTC_STAT(x) (x)
 #else
@@ -490,48 +490,74 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
           }
         }
       }
-      for (int g = 0; g < G; ++g) {
-        // per-lane column constants: the character this lane owns in this group and its log-prob
+      // rows (members) are tested 32 at a time: lane l looks at row base + warp + NW * l.  A row whose best
+      // possible candidate (score + max non-blank log-prob) stays under lo32 contributes nothing; on config 2
+      // that removes 80 % of the rows.
+      for (int base = 0; base < M; base += 32 * L.NW) {
+        CTC_LV(int, rowok);
+        CTC_LANES {
+          const int i = base + warp + L.NW * lane;
+          rowok[LX] = 0;
+          if (i < M) {
+            CTC_STAT(g_stats.rows++);
+            rowok[LX] = (ord_f(f_add(c.s_score[i], lpmax)) >= lo32) ? 1 : 0;
+            CTC_STAT(g_stats.rows_skipped += !rowok[LX]);
+          }
+        }
+        unsigned rows = ctc_ballot(rowok);
+        // per-lane column constants of group 0 (the only group when n <= 32)
         CTC_LV(int, colc);
         CTC_LV(float, colv);
         CTC_LANES {
-          const int r = g * 32 + lane;
           colc[LX] = -2;  // not a candidate column (beyond n, or the blank)
           colv[LX] = 0.0f;
-          if (r < n) {
-            const int ch = c.chr_at(r);
-            if (ch != c.blank) { colc[LX] = ch; colv[LX] = c.lp[r]; }
+          if (rows && lane < n) {
+            const int ch = c.chr_at(lane);
+            if (ch != c.blank) { colc[LX] = ch; colv[LX] = c.lp[lane]; }
           }
         }
-        for (int i = warp; i < M; i += L.NW) {
-          const float sc_i = c.s_score[i];
-          // nothing in this row can reach lo32: every candidate is <= score_i + max non-blank log-prob
-          if (ord_f(f_add(sc_i, lpmax)) < lo32) continue;
-          const float b_i = c.s_bprev[i];
+        while (rows) {
+          const int rl = ctc_ffs(rows) - 1;
+          rows &= rows - 1u;
+          const int i = base + warp + L.NW * rl;
+          const float sc_i = c.s_score[i], b_i = c.s_bprev[i];
           const int ch_i = c.s_chr[i];
-          const uint32_t mw = c.s_mask[i * W + g];
-          CTC_LV(int, pred);
-          CTC_LV(uint32_t, kk);
-          CTC_LANES {
-            const int ch = colc[LX];
-            const bool rep = (ch == ch_i);
-            float sc = f_add(colv[LX], rep ? b_i : sc_i);
-            if (rep && !(b_i > kNInf)) sc = kNInf;
-            const unsigned k = ord_f(sc);
-            const bool ok = (ch >= 0) && !((mw >> lane) & 1u) && (k >= lo32);
-            pred[LX] = ok ? 1 : 0;
-            kk[LX] = k;
-            if (ok && !select_all) atom_add(&hist0[(int)((k - lo32) >> shift32)], 1);
-          }
-          const unsigned bal = ctc_ballot(pred);
-          if (bal) {
+          for (int g = 0; g < G; ++g) {
+            const uint32_t mw = c.s_mask[i * W + g];
+            CTC_LV(int, pred);
+            CTC_LV(uint32_t, kk);
             CTC_LANES {
-              if (pred[LX]) {
-                const int pos = cnt + ctc_popc(bal & ctc_lt_mask(lane));
-                if (pos < L.seg) { segk[pos] = kk[LX]; segi[pos] = (i << 16) | (g * 32 + lane); }
+              int ch = colc[LX];
+              float l = colv[LX];
+              if (g > 0) {  // further groups: load the column on the fly (few rows get here)
+                const int r = g * 32 + lane;
+                ch = -2;
+                l = 0.0f;
+                if (r < n) {
+                  const int c2 = c.chr_at(r);
+                  if (c2 != c.blank) { ch = c2; l = c.lp[r]; }
+                }
               }
+              const bool rep = (ch == ch_i);
+              float sc = f_add(l, rep ? b_i : sc_i);
+              if (rep && !(b_i > kNInf)) sc = kNInf;
+              const unsigned k = ord_f(sc);
+              const bool ok = (ch >= 0) && !((mw >> lane) & 1u) && (k >= lo32);
+              pred[LX] = ok ? 1 : 0;
+              kk[LX] = k;
+              if (ok && !select_all) atom_add(&hist0[(int)((k - lo32) >> shift32)], 1);
             }
-            cnt += ctc_popc(bal);
+            const unsigned bal = ctc_ballot(pred);
+            if (bal) {
+              CTC_LANES {
+                if (pred[LX]) {
+                  const int pos = cnt + ctc_popc(bal & ctc_lt_mask(lane));
+                  if (pos < L.seg) { segk[pos] = kk[LX]; segi[pos] = (i << 16) | (g * 32 + lane); }
+                }
+              }
+              cnt += ctc_popc(bal);
+              CTC_STAT(g_stats.cl_entries += ctc_popc(bal));
+            }
           }
         }
       }

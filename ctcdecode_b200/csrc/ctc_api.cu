@@ -21,9 +21,10 @@ namespace ctc {
 // ---------------------------------------------------------------------------------------------------
 //  kernels
 // ---------------------------------------------------------------------------------------------------
-// at least 2048 / NT co-resident CTAs per SM (<= 64 registers per thread) whenever shared memory allows
+// two co-resident CTAs per SM (one for NT = 1024): 128 registers per thread up to NT = 256, 64 at NT = 512.
+// A config-2 batch of 256 utterances is 1.73 CTAs per SM, and the frame loop wants its registers.
 template <int NT, bool SORTED>
-__global__ void __launch_bounds__(NT, (NT >= 1024 ? 1 : 2048 / NT / 2)) beam_kernel(const BeamParams p) {
+__global__ void __launch_bounds__(NT, (NT >= 1024 ? 1 : 2)) beam_kernel(const BeamParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   beam_cta_run<NT, SORTED>(p, (int)blockIdx.x, smem);
 }
