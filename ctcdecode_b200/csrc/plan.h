@@ -50,8 +50,8 @@ static inline int make_plan_core(const ctcdec_config *cfg, int B, int T, Plan *p
   pl->P = P;
   pl->F = std::max(1, std::min(32, 4096 / (pl->NP * 4)));
   const long long grid = (long long)K * pl->n_max;
-  pl->NT = grid <= 512 ? 128 : (grid <= 4096 ? 256 : 512);  // measured on B200: see profiles/
-  if (pl->NT < kp_of(K)) pl->NT = kp_of(K) <= 256 ? 256 : (kp_of(K) <= 512 ? 512 : 1024);
+  // measured on B200 (profiles/): 8 warps with 128 registers beat 16 warps with 64 on both config 2 and 4
+  pl->NT = grid <= 512 ? 128 : 256;
   if (nt_override == 128 || nt_override == 256 || nt_override == 512 || nt_override == 1024) pl->NT = nt_override;
   pl->L = make_layout(K, V, pl->NP, pl->F, pl->sorted, pl->NT);
   if (pl->L.total > 227 * 1024)
