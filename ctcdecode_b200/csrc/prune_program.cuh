@@ -50,30 +50,64 @@ __global__ void __launch_bounds__(256) prune_kernel(const PruneParams p) {
   const int rblank_unsorted = (p.blank >= 0 && p.blank < V) ? p.blank : -1;
   const unsigned ninf_ord = ord_f(kNInf);
 
+  if (!SORTED) {
+    // Index-order mode (nothing is cut): an element-wise fp64 log with a per-frame max.  Four frames per warp
+    // iteration so that every lane has four independent log chains in flight (the chain is ~45 dependent
+    // DP operations; one chain per lane leaves the fp64 pipe idle).
+    constexpr int U = 4;
+    const long long stride = (long long)gridDim.x * wpc;
+    for (long long f0 = (long long)blockIdx.x * wpc + warp; f0 < nframes; f0 += stride * U) {
+      float v[U];
+      bool live[U];
+      const int r = lane;  // NP - 2 <= 32 is the common case; wider rows loop below
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long f = f0 + stride * u;
+        live[u] = false;
+        v[u] = kNInf;
+        if (f < nframes) {
+          const int b = (int)(f / p.T), t = (int)(f - (long long)b * p.T);
+          const int len = p.seq_lens ? p.seq_lens[b] : p.T;
+          live[u] = t < len;
+          if (live[u] && r < V) v[u] = p.probs[f * V + r];
+        }
+      }
+      if (!p.log_input) {
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (live[u] && r < V) v[u] = logprob_glibc_t(v[u], logtab);  // reference decoder_utils.cpp:40-43
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (!live[u]) continue;  // warp-uniform
+        const long long f = f0 + stride * u;
+        float *out = p.lp + f * NP;
+        unsigned mx = (r < V && r != p.blank) ? ord_f(v[u]) : ninf_ord;
+        if (r < NP - 2) out[r] = v[u];
+        for (int r2 = lane + 32; r2 < NP - 2; r2 += 32) {  // rows wider than a warp
+          float w = kNInf;
+          if (r2 < V) {
+            w = prune_value(p.probs[f * V + r2], p.log_input, logtab);
+            if (r2 != p.blank) { const unsigned o = ord_f(w); mx = o > mx ? o : mx; }
+          }
+          out[r2] = w;
+        }
+        mx = __reduce_max_sync(0xffffffffu, mx);
+        if (lane == 0) {
+          out[NP - 2] = bits_f((uint32_t)V | ((uint32_t)(rblank_unsorted + 1) << 16));
+          out[NP - 1] = unord_f(mx);
+        }
+      }
+    }
+    return;
+  }
+
   for (long long f = (long long)blockIdx.x * wpc + warp; f < nframes; f += (long long)gridDim.x * wpc) {
     const int b = (int)(f / p.T), t = (int)(f - (long long)b * p.T);
     int len = p.seq_lens ? p.seq_lens[b] : p.T;
     if (t >= len) continue;
     const float *row = p.probs + f * V;
     float *out = p.lp + f * NP;
-
-    if (!SORTED) {
-      unsigned mx = ninf_ord;
-      for (int r = lane; r < NP - 2; r += 32) {
-        float v = kNInf;
-        if (r < V) {
-          v = prune_value(row[r], p.log_input, logtab);
-          if (r != p.blank) { const unsigned o = ord_f(v); mx = o > mx ? o : mx; }
-        }
-        out[r] = v;
-      }
-      mx = __reduce_max_sync(0xffffffffu, mx);
-      if (lane == 0) {
-        out[NP - 2] = bits_f((uint32_t)V | ((uint32_t)(rblank_unsorted + 1) << 16));
-        out[NP - 1] = unord_f(mx);
-      }
-      continue;
-    }
 
     // ---- sorted mode: std::sort by probability descending (decoder_utils.cpp:22-24); ties -> lower index
     uint16_t *oidx = p.idx + f * NP;

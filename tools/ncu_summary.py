@@ -28,7 +28,13 @@ with open(out, "w") as f:
     if len(srows) > 2:
         sh = srows[1]
         ix = {h: i for i, h in enumerate(sh)}
-        data = [r for r in srows[2:] if len(r) == len(sh)]
+        data = []
+        for r in srows[2:]:
+            if len(r) != len(sh) or r[ix['# Samples']] == '# Samples':
+                if data:
+                    break  # next kernel's table starts
+                continue
+            data.append(r)
         tot = sum(int(r[ix['# Samples']] or 0) for r in data) or 1
         stalls = [h for h in sh if h.startswith('stall_') and 'Not Issued' not in h]
         agg = sorted(((sum(int(r[ix[s]] or 0) for r in data), s) for s in stalls), reverse=True)
