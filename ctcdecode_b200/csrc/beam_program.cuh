@@ -123,34 +123,39 @@ CTC_FN void scan_bin_all(const int *hist, int need, int &bin, int &above, int &c
   }
   bin = 0; above = a - hist[0]; cnt = hist[0];  // unreachable when the invariants hold
 #else
-  constexpr int PER = kNBins / 32;
+  // lane l reads bins l, l+32, ..., l+224 (bank-conflict free); rows of 32 bins are summed with the hardware
+  // warp reduction, the row holding the need-th key is located by a scalar walk over the 8 row sums, and a
+  // 5-step suffix scan inside that row finds the bin.
+  constexpr int ROWS = kNBins / 32;
   const int lane = (int)(threadIdx.x & 31);
-  const int top = kNBins - 1 - PER * lane;
-  int h[PER];
-  int sum = 0;
+  int h[ROWS], rs[ROWS];
 #pragma unroll
-  for (int q = 0; q < PER; ++q) { h[q] = hist[top - q]; sum += h[q]; }
-  int incl = sum;
+  for (int q = 0; q < ROWS; ++q) h[q] = hist[q * 32 + lane];
 #pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const int v = __shfl_up_sync(0xffffffffu, incl, d);
-    if (lane >= d) incl += v;
-  }
-  const unsigned ball = __ballot_sync(0xffffffffu, incl >= need);
-  const int owner = ball ? (__ffs(ball) - 1) : 31;
-  int a = incl - sum, b = top - PER + 1, cn = h[PER - 1];
+  for (int q = 0; q < ROWS; ++q) rs[q] = __reduce_add_sync(0xffffffffu, h[q]);
+  int a = 0, row = 0;
   bool found = false;
 #pragma unroll
-  for (int q = 0; q < PER; ++q) {
+  for (int q = ROWS - 1; q >= 0; --q) {
     if (!found) {
-      if (a + h[q] >= need) { b = top - q; cn = h[q]; found = true; }
-      else a += h[q];
+      if (a + rs[q] >= need) { row = q; found = true; }
+      else a += rs[q];
     }
   }
-  if (!found) a -= h[PER - 1];
-  bin = __shfl_sync(0xffffffffu, b, owner);
-  above = __shfl_sync(0xffffffffu, a, owner);
-  cnt = __shfl_sync(0xffffffffu, cn, owner);
+  int hv = h[0];
+#pragma unroll
+  for (int q = 1; q < ROWS; ++q) hv = (row == q) ? h[q] : hv;
+  int sfx = hv;  // becomes the sum over lanes >= this lane
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int v = __shfl_down_sync(0xffffffffu, sfx, d);
+    if (lane + d < 32) sfx += v;
+  }
+  const unsigned ball = __ballot_sync(0xffffffffu, sfx >= need - a);  // lanes <= target
+  const int target = ball ? 31 - __clz((int)ball) : 0;
+  bin = row * 32 + target;
+  cnt = __shfl_sync(0xffffffffu, hv, target);
+  above = a + __shfl_sync(0xffffffffu, sfx, target) - cnt;
 #endif
 }
 
@@ -515,6 +520,53 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
             const int ch = c.chr_at(lane);
             if (ch != c.blank) { colc[LX] = ch; colv[LX] = c.lp[lane]; }
           }
+        }
+        // two rows per iteration when the grid is one group wide: two independent load -> add -> key ->
+        // ballot chains in flight instead of one
+        while (G == 1 && (rows & (rows - 1u))) {
+          const int rl1 = ctc_ffs(rows) - 1;
+          rows &= rows - 1u;
+          const int rl2 = ctc_ffs(rows) - 1;
+          rows &= rows - 1u;
+          const int i1 = base + warp + L.NW * rl1, i2 = base + warp + L.NW * rl2;
+          const float sc1 = c.s_score[i1], b1 = c.s_bprev[i1], sc2 = c.s_score[i2], b2 = c.s_bprev[i2];
+          const int ch1 = c.s_chr[i1], ch2 = c.s_chr[i2];
+          const uint32_t mw1 = c.s_mask[i1 * W], mw2 = c.s_mask[i2 * W];
+          CTC_LV(int, pred1);
+          CTC_LV(int, pred2);
+          CTC_LV(uint32_t, kk1);
+          CTC_LV(uint32_t, kk2);
+          CTC_LANES {
+            const int ch = colc[LX];
+            const float l = colv[LX];
+            const bool rep1 = (ch == ch1), rep2 = (ch == ch2);
+            float s1 = f_add(l, rep1 ? b1 : sc1), s2 = f_add(l, rep2 ? b2 : sc2);
+            if (rep1 && !(b1 > kNInf)) s1 = kNInf;
+            if (rep2 && !(b2 > kNInf)) s2 = kNInf;
+            const unsigned k1 = ord_f(s1), k2 = ord_f(s2);
+            const bool ok1 = (ch >= 0) && !((mw1 >> lane) & 1u) && (k1 >= lo32);
+            const bool ok2 = (ch >= 0) && !((mw2 >> lane) & 1u) && (k2 >= lo32);
+            pred1[LX] = ok1 ? 1 : 0; kk1[LX] = k1;
+            pred2[LX] = ok2 ? 1 : 0; kk2[LX] = k2;
+            if (!select_all) {
+              if (ok1) atom_add(&hist0[(int)((k1 - lo32) >> shift32)], 1);
+              if (ok2) atom_add(&hist0[(int)((k2 - lo32) >> shift32)], 1);
+            }
+          }
+          const unsigned bal1 = ctc_ballot(pred1), bal2 = ctc_ballot(pred2);
+          const int n1 = ctc_popc(bal1);
+          CTC_LANES {
+            if (pred1[LX]) {
+              const int pos = cnt + ctc_popc(bal1 & ctc_lt_mask(lane));
+              if (pos < L.seg) { segk[pos] = kk1[LX]; segi[pos] = (i1 << 16) | lane; }
+            }
+            if (pred2[LX]) {
+              const int pos = cnt + n1 + ctc_popc(bal2 & ctc_lt_mask(lane));
+              if (pos < L.seg) { segk[pos] = kk2[LX]; segi[pos] = (i2 << 16) | lane; }
+            }
+          }
+          cnt += n1 + ctc_popc(bal2);
+          CTC_STAT(g_stats.cl_entries += n1 + ctc_popc(bal2));
         }
         while (rows) {
           const int rl = ctc_ffs(rows) - 1;

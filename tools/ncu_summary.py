@@ -25,21 +25,27 @@ with open(out, "w") as f:
                 f.write("%s [%s] = %s\n" % (h, u, v))
     sass = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
     srows = list(csv.reader(sass.splitlines()))
-    if len(srows) > 2:
-        sh = srows[1]
-        ix = {h: i for i, h in enumerate(sh)}
-        data = []
-        for r in srows[2:]:
-            if len(r) != len(sh) or r[ix['# Samples']] == '# Samples':
-                if data:
-                    break  # next kernel's table starts
-                continue
-            data.append(r)
-        tot = sum(int(r[ix['# Samples']] or 0) for r in data) or 1
-        stalls = [h for h in sh if h.startswith('stall_') and 'Not Issued' not in h]
-        agg = sorted(((sum(int(r[ix[s]] or 0) for r in data), s) for s in stalls), reverse=True)
-        f.write("\n## warp stall sampling (first kernel in the report), share of all samples\n")
-        for v, s in agg[:9]:
-            f.write("%s %.1f%%\n" % (s, 100.0 * v / tot))
-        f.write("total warp-level instructions executed: %d\n" % sum(int(r[ix['Instructions Executed']] or 0) for r in data))
+    # the page is a sequence of per-kernel tables: ["Kernel Name", name], header row, data rows
+    i = 0
+    while i < len(srows):
+        if srows[i] and srows[i][0] == "Kernel Name":
+            name = srows[i][1]
+            sh = srows[i + 1]
+            ix = {h: k for k, h in enumerate(sh)}
+            j = i + 2
+            data = []
+            while j < len(srows) and not (srows[j] and srows[j][0] == "Kernel Name"):
+                if len(srows[j]) == len(sh):
+                    data.append(srows[j])
+                j += 1
+            tot = sum(int(r[ix['# Samples']] or 0) for r in data) or 1
+            stalls = [h for h in sh if h.startswith('stall_') and 'Not Issued' not in h]
+            agg = sorted(((sum(int(r[ix[st]] or 0) for r in data), st) for st in stalls), reverse=True)
+            f.write("\n## warp stall sampling, share of all samples: %s\n" % name[:100])
+            for v, st in agg[:9]:
+                f.write("%s %.1f%%\n" % (st, 100.0 * v / tot))
+            f.write("total warp-level instructions executed: %d\n" % sum(int(r[ix['Instructions Executed']] or 0) for r in data))
+            i = j
+        else:
+            i += 1
 print("wrote", out)
