@@ -568,6 +568,61 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
           cnt += n1 + ctc_popc(bal2);
           CTC_STAT(g_stats.cl_entries += n1 + ctc_popc(bal2));
         }
+        if (G == 2) {
+          // two column groups (33..64 kept characters): both groups of a row in one go
+          CTC_LV(int, colc2);
+          CTC_LV(float, colv2);
+          CTC_LANES {
+            colc2[LX] = -2;
+            colv2[LX] = 0.0f;
+            if (rows && 32 + lane < n) {
+              const int ch = c.chr_at(32 + lane);
+              if (ch != c.blank) { colc2[LX] = ch; colv2[LX] = c.lp[32 + lane]; }
+            }
+          }
+          while (rows) {
+            const int rl = ctc_ffs(rows) - 1;
+            rows &= rows - 1u;
+            const int i = base + warp + L.NW * rl;
+            const float sc_i = c.s_score[i], b_i = c.s_bprev[i];
+            const int ch_i = c.s_chr[i];
+            const uint32_t mwa = c.s_mask[i * W], mwb = c.s_mask[i * W + 1];
+            CTC_LV(int, pred1);
+            CTC_LV(int, pred2);
+            CTC_LV(uint32_t, kk1);
+            CTC_LV(uint32_t, kk2);
+            CTC_LANES {
+              const int cha = colc[LX], chb = colc2[LX];
+              const bool repa = (cha == ch_i), repb = (chb == ch_i);
+              float s1 = f_add(colv[LX], repa ? b_i : sc_i), s2 = f_add(colv2[LX], repb ? b_i : sc_i);
+              if (repa && !(b_i > kNInf)) s1 = kNInf;
+              if (repb && !(b_i > kNInf)) s2 = kNInf;
+              const unsigned k1 = ord_f(s1), k2 = ord_f(s2);
+              const bool ok1 = (cha >= 0) && !((mwa >> lane) & 1u) && (k1 >= lo32);
+              const bool ok2 = (chb >= 0) && !((mwb >> lane) & 1u) && (k2 >= lo32);
+              pred1[LX] = ok1 ? 1 : 0; kk1[LX] = k1;
+              pred2[LX] = ok2 ? 1 : 0; kk2[LX] = k2;
+              if (!select_all) {
+                if (ok1) atom_add(&hist0[(int)((k1 - lo32) >> shift32)], 1);
+                if (ok2) atom_add(&hist0[(int)((k2 - lo32) >> shift32)], 1);
+              }
+            }
+            const unsigned bal1 = ctc_ballot(pred1), bal2 = ctc_ballot(pred2);
+            const int n1 = ctc_popc(bal1);
+            CTC_LANES {
+              if (pred1[LX]) {
+                const int pos = cnt + ctc_popc(bal1 & ctc_lt_mask(lane));
+                if (pos < L.seg) { segk[pos] = kk1[LX]; segi[pos] = (i << 16) | lane; }
+              }
+              if (pred2[LX]) {
+                const int pos = cnt + n1 + ctc_popc(bal2 & ctc_lt_mask(lane));
+                if (pos < L.seg) { segk[pos] = kk2[LX]; segi[pos] = (i << 16) | (32 + lane); }
+              }
+            }
+            cnt += n1 + ctc_popc(bal2);
+            CTC_STAT(g_stats.cl_entries += n1 + ctc_popc(bal2));
+          }
+        }
         while (rows) {
           const int rl = ctc_ffs(rows) - 1;
           rows &= rows - 1u;

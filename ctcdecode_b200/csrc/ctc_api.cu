@@ -112,14 +112,23 @@ static int launch_prune(const ctcdec_config *cfg, const Plan &pl, const float *p
   if (!pl.sorted) {
     const int wpc = 8;
     const int grid = (int)std::min<long long>((frames + wpc - 1) / wpc, 148 * 16);
-    prune_kernel<false><<<grid, wpc * 32, 2048, s>>>(pp);
+    prune_kernel<false, 0><<<grid, wpc * 32, 2048, s>>>(pp);
   } else {
     int wpc = (int)std::min<size_t>(8, (200 * 1024 - 2048) / ((size_t)pl.P * 8));
     if (wpc < 1) wpc = 1;
     const size_t smem = 2048 + (size_t)wpc * pl.P * 8;
-    CU(cudaFuncSetAttribute(prune_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = (int)std::min<long long>((frames + wpc - 1) / wpc, 148 * 8);
-    prune_kernel<true><<<grid, wpc * 32, smem, s>>>(pp);
+    const int V = cfg->vocab_size;
+    if (V <= 256) {
+      CU(cudaFuncSetAttribute(prune_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      prune_kernel<true, 8><<<grid, wpc * 32, smem, s>>>(pp);
+    } else if (V <= 1024) {
+      CU(cudaFuncSetAttribute(prune_kernel<true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      prune_kernel<true, 32><<<grid, wpc * 32, smem, s>>>(pp);
+    } else {
+      CU(cudaFuncSetAttribute(prune_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      prune_kernel<true, 0><<<grid, wpc * 32, smem, s>>>(pp);
+    }
   }
   CU(cudaGetLastError());
   return CTCDEC_OK;

@@ -37,7 +37,70 @@ CTC_FN float prune_value(float x, int log_input, const double *logtab) {
   return log_input ? x : logprob_glibc_t(x, logtab);  // reference decoder_utils.cpp:40-43
 }
 
-template <bool SORTED>
+// Top-`lim` of a frame without sorting all of it (lim <= 64, V <= 32 * KPL): every lane keeps KPL ordered
+// float keys in registers; a 32-step bitwise search (compare + hardware warp add per step) finds the lim-th
+// largest key; elements above it, then the needed number of equal ones in index order, are ballot-compacted into
+// shared memory as 64-bit (key, ~index) words and only those <= 64 words are bitonic-sorted.  Same order as the
+// full sort: probability descending, index ascending.  Returns whether an unselected element ties with the last
+// selected probability (the reference's std::sort leaves that order unspecified).
+template <int KPL>
+__device__ __forceinline__ bool top_select(const float *row, int V, int lim, uint64_t *keys, int lane) {
+  uint32_t kr[KPL];
+#pragma unroll
+  for (int q = 0; q < KPL; ++q) {
+    const int e = q * 32 + lane;
+    kr[q] = e < V ? ord_f(row[e]) : 0u;
+  }
+  uint32_t thr = 0u;
+#pragma unroll 1
+  for (int bit = 31; bit >= 0; --bit) {
+    const uint32_t cand = thr | (1u << bit);
+    int cnt = 0;
+#pragma unroll
+    for (int q = 0; q < KPL; ++q) cnt += (kr[q] >= cand) ? 1 : 0;
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if (cnt >= lim) thr = cand;
+  }
+  int base = 0;
+#pragma unroll
+  for (int q = 0; q < KPL; ++q) {
+    const bool pr = kr[q] > thr;
+    const unsigned bal = __ballot_sync(0xffffffffu, pr);
+    if (pr) keys[base + __popc(bal & ((1u << lane) - 1u))] = ((uint64_t)kr[q] << 32) | (uint64_t)(0xFFFFFFFFu - (unsigned)(q * 32 + lane));
+    base += __popc(bal);
+  }
+  const int need = lim - base;
+  int taken = 0;
+#pragma unroll
+  for (int q = 0; q < KPL; ++q) {
+    const bool pr = (kr[q] == thr) && (q * 32 + lane < V);
+    const unsigned bal = __ballot_sync(0xffffffffu, pr);
+    const int rk = taken + __popc(bal & ((1u << lane) - 1u));
+    if (pr && rk < need) keys[base + rk] = ((uint64_t)kr[q] << 32) | (uint64_t)(0xFFFFFFFFu - (unsigned)(q * 32 + lane));
+    taken += __popc(bal);
+  }
+  int pn = 1;
+  while (pn < lim) pn <<= 1;
+  for (int i = lim + lane; i < pn; i += 32) keys[i] = 0ull;
+  __syncwarp();
+  for (int k = 2; k <= pn; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = lane; i < pn; i += 32) {
+        const int l = i ^ j;
+        if (l > i) {
+          const uint64_t a = keys[i], bb = keys[l];
+          const bool desc_block = (i & k) == 0;
+          if (desc_block ? (a < bb) : (a > bb)) { keys[i] = bb; keys[l] = a; }
+        }
+      }
+      __syncwarp();
+    }
+  }
+  return taken > need;
+}
+
+// KPL: keys per lane of the partial top-n selection (0 = always sort the whole vocabulary)
+template <bool SORTED, int KPL>
 __global__ void __launch_bounds__(256) prune_kernel(const PruneParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   double *logtab = reinterpret_cast<double *>(smem);  // 256 doubles
@@ -111,20 +174,29 @@ __global__ void __launch_bounds__(256) prune_kernel(const PruneParams p) {
 
     // ---- sorted mode: std::sort by probability descending (decoder_utils.cpp:22-24); ties -> lower index
     uint16_t *oidx = p.idx + f * NP;
-    for (int c = lane; c < p.P; c += 32)
-      keys[c] = c < V ? (((uint64_t)ord_f(row[c]) << 32) | (uint64_t)(0xFFFFFFFFu - (unsigned)c)) : 0ull;
-    __syncwarp();
-    for (int k = 2; k <= p.P; k <<= 1) {
-      for (int j = k >> 1; j > 0; j >>= 1) {
-        for (int i = lane; i < p.P; i += 32) {
-          const int l = i ^ j;
-          if (l > i) {
-            const uint64_t a = keys[i], bb = keys[l];
-            const bool desc_block = (i & k) == 0;
-            if (desc_block ? (a < bb) : (a > bb)) { keys[i] = bb; keys[l] = a; }
+    // how many sorted entries the rest of this frame can look at: lim (+ the boundary check)
+    const int lim_sel = p.cp_active ? (V < (p.top_n > 1 ? p.top_n : 1) ? V : (p.top_n > 1 ? p.top_n : 1))
+                                    : (p.top_n < V ? p.top_n : V);
+    const bool partial = KPL > 0 && lim_sel > 0 && lim_sel <= 64 && lim_sel < V && V <= 32 * KPL;
+    bool more_equal = false;
+    if (partial) {
+      more_equal = top_select<(KPL > 0 ? KPL : 1)>(row, V, lim_sel, keys, lane);
+    } else {
+      for (int c = lane; c < p.P; c += 32)
+        keys[c] = c < V ? (((uint64_t)ord_f(row[c]) << 32) | (uint64_t)(0xFFFFFFFFu - (unsigned)c)) : 0ull;
+      __syncwarp();
+      for (int k = 2; k <= p.P; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+          for (int i = lane; i < p.P; i += 32) {
+            const int l = i ^ j;
+            if (l > i) {
+              const uint64_t a = keys[i], bb = keys[l];
+              const bool desc_block = (i & k) == 0;
+              if (desc_block ? (a < bb) : (a > bb)) { keys[i] = bb; keys[l] = a; }
+            }
           }
+          __syncwarp();
         }
-        __syncwarp();
       }
     }
     // ---- how many entries survive (decoder_utils.cpp:25-35)
@@ -183,7 +255,11 @@ __global__ void __launch_bounds__(256) prune_kernel(const PruneParams p) {
         n = __shfl_sync(0xffffffffu, nn, 0);
       }
     }
-    if (lane == 0 && n > 0 && n < V && (keys[n - 1] >> 32) == (keys[n] >> 32)) atomicOr(&p.flags[b], FLAG_TIE_VOCAB);
+    if (lane == 0 && n > 0 && n < V) {
+      // is the cut between two equal probabilities?  (with a partial sort only lim_sel entries are ordered)
+      const bool tie = (partial && n == lim_sel) ? more_equal : ((keys[n - 1] >> 32) == (keys[n] >> 32));
+      if (tie) atomicOr(&p.flags[b], FLAG_TIE_VOCAB);
+    }
     // ---- emit
     int rb = 0;
     float first_two = kNInf;  // lp of entry `lane` for lanes 0 and 1
