@@ -270,7 +270,7 @@ def main():
     # vocabulary is cut): its bytes per launch
     is_sorted = cfg["cutoff_prob"] < 1.0 or cfg["cutoff_top_n"] < V
     n_max = min(V, max(1, cfg["cutoff_top_n"])) if is_sorted else V
-    NP = (n_max + 2 + 7) // 8 * 8
+    NP = (n_max + 3 + 7) // 8 * 8
     scan_bytes = alg_bytes + B * T * NP * (6 if is_sorted else 4)
     line = {
         "metric": METRIC, "value": value, "unit": "utterances/s", "n_gpus": world, "steps": K, "warmup": W,

@@ -71,6 +71,7 @@ enum : int {
 
 constexpr float kNInf = -FLT_MAX;  // reference NUM_FLT_INF negated (decoder_utils.h:12)
 constexpr int kNBins = 256;
+constexpr int kRowTrailer = 3;  // trailing floats of a pruned row: blank log-prob (no FLT_MIN), meta, max non-blank
 constexpr int kNewFlag = 1 << 30;  // in-frame marker: "parent slot refers to this frame's NEW occupant"
 
 // Trie node in the global arena: exactly what the final backtrace needs (reference path_trie.cpp:109-126).
@@ -82,12 +83,13 @@ struct alignas(16) Node {
 };
 
 // Per-utterance persistent state (global memory; survives between chunks of a streaming decode).
-// Layout in ints: [0]=M (beam count) [1]=nnodes [2]=abs_t [3]=flags, then 10 slot arrays of K ints
-// (node, chr, depth, bprev, nbprev, score, lpc, ts, pslot, anch; floats by bit pattern) and the
-// dead-anchor table, 5 arrays of 2*KP ints (dnode, dchr, dpslot, dlpc, dts), KP = K rounded up to 32.
+// Layout in ints: [0]=M (beam count) [1]=nnodes [2]=abs_t [3]=flags, then 11 slot arrays of K ints
+// (node, chr, depth, bprev, nbprev, score, lpc, ts, pslot, anch, dstate; floats by bit pattern) and the
+// dead-anchor table, 6 arrays of 2*KP ints (dnode, dchr, dpslot, dlpc, dts, ddstate), KP = K rounded up to 32.
+// dstate / ddstate (dictionary state of the scorer path) are 0 without a scorer.
 constexpr int kStateHeader = 4;
-constexpr int kSlotArrays = 10;
-constexpr int kAnchorArrays = 5;
+constexpr int kSlotArrays = 11;
+constexpr int kAnchorArrays = 6;
 CTC_HD int kp_of(int K) { return (K + 31) / 32 * 32; }
 CTC_HD long long state_ints(int K) { return kStateHeader + (long long)kSlotArrays * K + (long long)kAnchorArrays * 2 * kp_of(K); }
 
@@ -96,6 +98,7 @@ struct BeamParams {
   const uint16_t *idx;    // [B][T][NP] character of each pruned entry, 0xFFFF = unused (sorted mode only)
   const int *seq_lens;    // [B] or nullptr
   int T, V, NP, K, blank;
+  int t0, nframes;        // this launch consumes rows [t0, t0 + nframes) of each utterance (nframes <= 0: all T rows)
   int tile_frames;        // frames per staged tile
   Node *arena;            // offline: base of B arenas
   long long arena_stride; // nodes per utterance
@@ -115,12 +118,26 @@ struct BeamParams {
   int out_T;
   int *flags;  // [B], OR-ed
   long long *timing;  // optional [B][16]: cycles thread 0 spent between consecutive barriers, per region
+  // ---- scorer path (word-based LM + dictionary, reference ctc_beam_search_decoder.cpp:74-82,93-95,120-137 and
+  //      path_trie.cpp:59-96); everything below is unused (0 / nullptr) when no scorer is attached
+  const int *dict_next;             // [n_states][V]: next dictionary state, -1 = no arc
+  const unsigned char *dict_final;  // [n_states]: 1 = final state (the child restarts at dict_start)
+  int dict_start;
+  int space_id;                     // label of " ", -2 if there is none (reference :34-40)
+  double beta;                      // Scorer::beta
+  float *lm_arena;                  // [B][arena_stride]: per node float(cond_log_prob(make_ngram(node)) * alpha)
+  int *dstate_arena;                // [B][arena_stride]: per node dictionary state
+  int *newlist;                     // [B][1 + 4K]: count, then (node, parent, chr, needs_lm) per node created
+  const int *lm_update_count;       // [B]: scores the host computed for nodes created by the previous launch
+  const int *lm_update_nodes;       // [B][K]
+  const float *lm_update_vals;      // [B][K]
 };
 
 // ---- shared memory carve-up (bytes) ---------------------------------------------------------------
 struct SmemLayout {
   int tile_lp, tile_idx, mbar, rank, exptab, logtab;
   int node, chr, depth, bprev, nbprev, score, lpc, ts, pslot, anch;  // persistent slot arrays [KP]
+  int dstate, lmsp, ddstate;                                         // scorer path: [KP], [KP], [2*KP]
   int bnew, nbnew, snew;                                             // per-frame slot temporaries [KP]
   int mask, rmask;                                                   // [KP][W] bitmasks over pruned ranks
   int evict;                                                         // [KP]
@@ -143,7 +160,7 @@ CTC_HD SmemLayout make_layout(int K, int V, int NP, int tile_frames, bool sorted
   const int W = (NP + 31) / 32;
   const int NW = NT / 32;
   // candidate-list segment per warp: room for every candidate of the members a warp owns, capped at 64 KB
-  int seg = ((K + NW - 1) / NW) * (NP - 2);
+  int seg = ((K + NW - 1) / NW) * (NP - kRowTrailer);
   if (seg > 8192 / NW) seg = 8192 / NW;
   if (seg < 32) seg = 32;
   int o = 0;
@@ -168,6 +185,9 @@ CTC_HD SmemLayout make_layout(int K, int V, int NP, int tile_frames, bool sorted
   L.ts = o;        o += KP * 4;
   L.pslot = o;     o += 2 * KP * 4;  // double buffered: links of the beam of frame t / t+1
   L.anch = o;      o += 2 * KP * 4;
+  L.dstate = o;    o += KP * 4;
+  L.lmsp = o;      o += KP * 4;
+  L.ddstate = o;   o += 2 * KP * 4;
   L.bnew = o;      o += KP * 4;
   L.nbnew = o;     o += KP * 4;
   L.snew = o;      o += KP * 4;
@@ -189,7 +209,7 @@ CTC_HD SmemLayout make_layout(int K, int V, int NP, int tile_frames, bool sorted
   L.cnt2 = o;      o += 3 * KP * 4;
   L.amap = o;      o += KP * 4;
   L.slot2q = o;    o += KP * 4;
-  L.stash = o;     o += 4 * KP * 4;
+  L.stash = o;     o += 5 * KP * 4;
   L.efree = o;     o += 2 * KP * 4;
   L.newp = o;      o += KP * 4;
   L.newa = o;      o += KP * 4;
@@ -209,7 +229,7 @@ CTC_HD SmemLayout make_layout(int K, int V, int NP, int tile_frames, bool sorted
 // control words: 32 ints in L.ctl
 enum {
   C_M = 0, C_NNODES, C_FLAGS, C_NSEL, C_NFREE, C_NTIE, C_NREV, C_NPAIRS, C_ABOVE, C_BIN, C_CNT, C_KMIN, C_KMAX,
-  C_SMAX, C_NEFREE, C_NETAKEN, C_NRVWORK, C_OVF, C_ANYREF, C_NLIVE
+  C_SMAX, C_NEFREE, C_NETAKEN, C_NRVWORK, C_OVF, C_ANYREF, C_NLIVE, C_SMIN, C_NCAND
 };
 
 // ---- small helpers --------------------------------------------------------------------------------
@@ -267,14 +287,14 @@ CTC_FN float lse_smem(float x, float y, const uint64_t *exptab, const double *lo
 }
 
 // Everything a region needs, by value (pointers into shared memory / this utterance's global state).
-template <bool SORTED>
+template <bool SORTED, bool LM>
 struct Cta {
   // shared: beam slots
-  int *s_node, *s_chr, *s_depth, *s_ts, *s_pslot, *s_anch;
-  float *s_bprev, *s_nbprev, *s_score, *s_lpc, *s_bnew, *s_nbnew, *s_snew;
+  int *s_node, *s_chr, *s_depth, *s_ts, *s_pslot, *s_anch, *s_dstate;
+  float *s_bprev, *s_nbprev, *s_score, *s_lpc, *s_bnew, *s_nbnew, *s_snew, *s_lmsp;
   uint32_t *s_mask, *s_rmask;
   // shared: dead-anchor table (2*KP entries; dpslot < 0 = free)
-  int *s_dnode, *s_dchr, *s_dpslot, *s_dts, *s_drev;
+  int *s_dnode, *s_dchr, *s_dpslot, *s_dts, *s_drev, *s_ddstate;
   float *s_dlpc;
   // shared: scratch
   int *s_evict, *s_sel, *s_sel2, *s_free, *s_free2, *s_newinfo, *s_tie, *s_cnt2, *s_amap, *s_efree, *s_newp, *s_newa,
@@ -289,9 +309,22 @@ struct Cta {
   // global
   Node *nodes;
   int K, KP, V, NP, W, blank;
+  // scorer path, per frame: prune everything under min_cutoff once the beam is full (reference :74-82,93-95)
+  const int *dict_next;
+  int space_id;
+  double beta;
+  bool lm_full;
+  float lm_cutoff;
 
   CTC_MFN int chr_at(int r) const { return SORTED ? (int)idx[r] : r; }
   CTC_MFN int rank_of(int c) const { return SORTED ? (int)s_rank[c] : c; }
+  // `if (full_beam && log_prob_c + prefix->score < min_cutoff) break;`  (reference :93-95)
+  CTC_MFN bool lm_cut(float l, float score) const { return LM && lm_full && f_add(l, score) < lm_cutoff; }
+  // language model term when the appended character is the space (reference :120-137): log_p += score; log_p += beta
+  CTC_MFN float lm_apply(float log_p, int i) const {
+    const float a = f_add(log_p, s_lmsp[i]);
+    return (float)d_add((double)a, beta);
+  }
 
   // Score of candidate (beam slot i) + (pruned entry r); false if it is not a new-prefix candidate.
   // (reference ctc_beam_search_decoder.cpp:108-118 with nb_cur == -inf => lse(-inf, log_p) = log_p)
@@ -300,12 +333,19 @@ struct Cta {
     if (c == blank) return false;
     if ((s_mask[i * W + (r >> 5)] >> (r & 31)) & 1u) return false;  // that child is itself a beam member
     const float l = lp[r];
+    if (LM) {
+      if (lm_cut(l, s_score[i])) return false;
+      // a child that does not exist yet needs a dictionary arc (reference path_trie.cpp:59-70); an existing dead
+      // child (rmask) is found before the dictionary is consulted (path_trie.cpp:39-57)
+      if (!((s_rmask[i * W + (r >> 5)] >> (r & 31)) & 1u) && dict_next[(long long)s_dstate[i] * V + c] < 0) return false;
+    }
     if (c == s_chr[i]) {
       const float b = s_bprev[i];
       sc = (b > kNInf) ? f_add(l, b) : kNInf;
     } else {
       sc = f_add(l, s_score[i]);
     }
+    if (LM && c == space_id) sc = lm_apply(sc, i);
     return true;
   }
 };

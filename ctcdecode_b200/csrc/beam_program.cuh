@@ -205,18 +205,20 @@ CTC_FN void flush_lpc_ts(Node *p, float lpc, int ts) {
 // ======================================================================================================
 //  beam_cta_run: consume frames [0, Tb) of utterance b, leave the beam state in global memory.
 // ======================================================================================================
-template <int NT, bool SORTED>
+template <int NT, bool SORTED, bool LM>
 CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) {
   const int K = p.K, V = p.V, NP = p.NP, F = p.tile_frames;
   const SmemLayout L = make_layout(K, V, NP, F, SORTED, NT);
   const int KP = L.KP, W = L.W, KP2 = 2 * L.KP;
 
-  Cta<SORTED> c;
+  Cta<SORTED, LM> c;
   c.s_node = (int *)(smem + L.node);      c.s_chr = (int *)(smem + L.chr);
   c.s_depth = (int *)(smem + L.depth);    c.s_bprev = (float *)(smem + L.bprev);
   c.s_nbprev = (float *)(smem + L.nbprev);  c.s_score = (float *)(smem + L.score);
   c.s_lpc = (float *)(smem + L.lpc);      c.s_ts = (int *)(smem + L.ts);
   c.s_pslot = (int *)(smem + L.pslot);    c.s_anch = (int *)(smem + L.anch);
+  c.s_dstate = (int *)(smem + L.dstate);  c.s_lmsp = (float *)(smem + L.lmsp);
+  c.s_ddstate = (int *)(smem + L.ddstate);
   c.s_bnew = (float *)(smem + L.bnew);    c.s_nbnew = (float *)(smem + L.nbnew);
   c.s_snew = (float *)(smem + L.snew);    c.s_mask = (uint32_t *)(smem + L.mask);
   c.s_rmask = (uint32_t *)(smem + L.rmask);  c.s_evict = (int *)(smem + L.evict);
@@ -239,6 +241,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
   c.s_exptab = (uint64_t *)(smem + L.exptab);
   c.s_logtab = (double *)(smem + L.logtab);
   c.K = K; c.KP = KP; c.V = V; c.NP = NP; c.W = W; c.blank = p.blank;
+  c.dict_next = p.dict_next; c.space_id = p.space_id; c.beta = p.beta; c.lm_full = false; c.lm_cutoff = kNInf;
   int *const s_ctl = c.s_ctl;
 #if !defined(CTC_EMULATE)
   long long *const s_tick = (long long *)(smem + L.ctl + 32 * 4);
@@ -252,14 +255,29 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
   int *const st = p.state_ptrs ? p.state_ptrs[b] : p.state + (long long)b * p.state_stride;
   const int arena_cap = p.arena_caps ? p.arena_caps[b] : p.arena_cap;
   c.nodes = nodes;
+  float *const lm_arena = LM ? p.lm_arena + (long long)b * p.arena_stride : nullptr;
+  int *const dstate_arena = LM ? p.dstate_arena + (long long)b * p.arena_stride : nullptr;
+  int *const newlist = LM ? p.newlist + (long long)b * (1 + 4 * K) : nullptr;
   int Tb = p.seq_lens ? p.seq_lens[b] : p.T;  // reference binding.cpp:64-65 clamps to T
   if (Tb > p.T) Tb = p.T;
+  const int t0 = p.nframes > 0 ? p.t0 : 0;
+  Tb -= t0;
+  if (p.nframes > 0 && Tb > p.nframes) Tb = p.nframes;
   if (Tb < 0) Tb = 0;
   const int fresh = p.fresh;
   const int abs_t0 = fresh ? 0 : st[2];
   int *const st_slots = st + kStateHeader;
   int *const st_anchors = st_slots + kSlotArrays * K;
 
+  if (LM) {
+    // scores the host's Scorer hook computed for the nodes created by the previous launch
+    CTC_PAR {
+      const int nu = p.lm_update_count ? p.lm_update_count[b] : 0;
+      for (int q = tid; q < nu; q += NT) lm_arena[p.lm_update_nodes[(long long)b * K + q]] = p.lm_update_vals[(long long)b * K + q];
+      if (tid == 0) newlist[0] = 0;
+    }
+    CTC_BARRIER();
+  }
   // ---- region: stage tables, load (or create) the beam state --------------------------------------
   CTC_PAR {
     for (int i = tid; i < 32; i += NT) {
@@ -267,7 +285,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
       ((double *)c.s_logtab)[i] = kLogfTab[i];
     }
     for (int j = tid; j < KP; j += NT) {
-      int node = 0, chr = -1, depth = 0, ts = 0, pslot = -1, anch = -1;
+      int node = 0, chr = -1, depth = 0, ts = 0, pslot = -1, anch = -1, dstate = LM ? p.dict_start : 0;
       float bprev = kNInf, nbprev = kNInf, score = kNInf, lpc = kNInf;
       if (fresh) {
         if (j == 0) { bprev = 0.0f; score = 0.0f; }  // reference ctc_beam_search_decoder.cpp:43
@@ -276,19 +294,24 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
         node = s[j]; chr = s[K + j]; depth = s[2 * K + j]; bprev = bits_f((uint32_t)s[3 * K + j]);
         nbprev = bits_f((uint32_t)s[4 * K + j]); score = bits_f((uint32_t)s[5 * K + j]);
         lpc = bits_f((uint32_t)s[6 * K + j]); ts = s[7 * K + j]; pslot = s[8 * K + j]; anch = s[9 * K + j];
+        dstate = s[10 * K + j];
       }
       c.s_node[j] = node; c.s_chr[j] = chr; c.s_depth[j] = depth; c.s_bprev[j] = bprev; c.s_nbprev[j] = nbprev;
       c.s_score[j] = score; c.s_lpc[j] = lpc; c.s_ts[j] = ts; c.s_pslot[j] = pslot; c.s_anch[j] = anch;
+      c.s_dstate[j] = dstate;
+      c.s_lmsp[j] = (LM && !fresh && j < st[0]) ? ld_cg(&lm_arena[node]) : 0.0f;
       c.s_evict[j] = 0;
     }
     for (int a = tid; a < KP2; a += NT) {
-      int dnode = 0, dchr = 0, dpslot = -1, dts = 0;
+      int dnode = 0, dchr = 0, dpslot = -1, dts = 0, ddstate = 0;
       float dlpc = kNInf;
       if (!fresh) {
         dnode = st_anchors[a]; dchr = st_anchors[KP2 + a]; dpslot = st_anchors[2 * KP2 + a];
         dlpc = bits_f((uint32_t)st_anchors[3 * KP2 + a]); dts = st_anchors[4 * KP2 + a];
+        ddstate = st_anchors[5 * KP2 + a];
       }
       c.s_dnode[a] = dnode; c.s_dchr[a] = dchr; c.s_dpslot[a] = dpslot; c.s_dlpc[a] = dlpc; c.s_dts[a] = dts;
+      c.s_ddstate[a] = ddstate;
       c.s_drev[a] = 0;
     }
     for (int x = tid; x < 3 * KP; x += NT) c.s_cnt2[x] = 0;
@@ -301,9 +324,11 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
       s_ctl[C_NNODES] = fresh ? 1 : st[1];
       s_ctl[C_FLAGS] = fresh ? 0 : st[3];
       s_ctl[C_KMIN] = (int)0xFFFFFFFFu;
+      s_ctl[C_SMIN] = (int)0xFFFFFFFFu;
       if (fresh) {  // root node (reference path_trie.cpp:11-30)
         Node root; root.parent = -1; root.chr = -1; root.lpc = kNInf; root.ts = 0;
         store_node(&nodes[0], root);
+        if (LM) { dstate_arena[0] = p.dict_start; lm_arena[0] = 0.0f; }
       }
     }
   }
@@ -311,8 +336,8 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
   uint64_t *const mbar = (uint64_t *)(smem + L.mbar);
   float *const tile_lp = (float *)(smem + L.tile_lp);
   uint16_t *const tile_idx = (uint16_t *)(smem + L.tile_idx);
-  const float *const g_lp = p.lp + (size_t)b * p.T * NP;
-  const uint16_t *const g_idx = SORTED ? p.idx + (size_t)b * p.T * NP : nullptr;
+  const float *const g_lp = p.lp + ((size_t)b * p.T + t0) * NP;
+  const uint16_t *const g_idx = SORTED ? p.idx + ((size_t)b * p.T + t0) * NP : nullptr;
   if (threadIdx.x == 0) {
     mbar_init(&mbar[0], 1);
     mbar_init(&mbar[1], 1);
@@ -353,8 +378,8 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
   for (int t = 0; t < Tb; ++t) {
     const int t_abs = abs_t0 + t;
 #if defined(CTC_EMULATE)
-    c.lp = p.lp + ((size_t)b * p.T + t) * NP;
-    c.idx = SORTED ? p.idx + ((size_t)b * p.T + t) * NP : nullptr;
+    c.lp = p.lp + ((size_t)b * p.T + t0 + t) * NP;
+    c.idx = SORTED ? p.idx + ((size_t)b * p.T + t0 + t) * NP : nullptr;
 #else
     {
       if (ft == F) { ft = 0; ++tile; }
@@ -383,6 +408,24 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
       CTC_BARRIER();
       CTC_TICK(1);
     }
+    if (LM) {
+      // min_cutoff = worst beam score + blank_prob - max(0, beta); active once the beam is full
+      // (reference ctc_beam_search_decoder.cpp:74-82: the sorted beam's last element is its minimum)
+      CTC_PAR {
+        unsigned smin = 0xFFFFFFFFu;
+        for (int j = tid; j < M; j += NT) { const unsigned o = ord_f(c.s_score[j]); smin = o < smin ? o : smin; }
+#if defined(CTC_EMULATE)
+        red_min_u32((unsigned *)&s_ctl[C_SMIN], smin);
+#else
+        if (tid < ((M + 31) & ~31)) red_min_u32((unsigned *)&s_ctl[C_SMIN], smin);
+#endif
+      }
+      CTC_BARRIER();
+      const float worst = unord_f((unsigned)s_ctl[C_SMIN]);
+      const double mx0 = p.beta > 0.0 ? p.beta : 0.0;
+      c.lm_full = (M == K);
+      c.lm_cutoff = (float)d_add((double)f_add(worst, c.lp[NP - 3]), -mx0);
+    }
 
     // ---- region R1: every member's blank / repeat / extension-from-parent terms, merged with
     //      log_sum_exp; dead anchors take their lpc / timestep update.  All in shared memory.
@@ -396,14 +439,14 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
         if (j < M) {
           const float sc = c.s_score[j];
           const int ch = c.s_chr[j];
-          const float bnew = (rblank >= 0) ? f_add(c.lp[rblank], sc) : kNInf;
+          const float bnew = (rblank >= 0 && !c.lm_cut(c.lp[rblank], sc)) ? f_add(c.lp[rblank], sc) : kNInf;
           float rep = kNInf, ext = kNInf;
           const int rr = (ch >= 0) ? c.rank_of(ch) : -1;
           if (rr >= 0) {
             const float l = c.lp[rr];
-            rep = f_add(l, c.s_nbprev[j]);
+            if (!c.lm_cut(l, sc)) rep = f_add(l, c.s_nbprev[j]);
             const int i = c.s_pslot[j];
-            if (i >= 0) {  // parent is a beam member: this node is an existing child of it
+            if (i >= 0 && !c.lm_cut(l, c.s_score[i])) {  // parent is a beam member: an existing child of it
               if (c.s_lpc[j] < l) { c.s_lpc[j] = l; c.s_ts[j] = t_abs; }  // path_trie.cpp:41-46
               if (ch == c.s_chr[i]) {
                 const float pb = c.s_bprev[i];
@@ -411,6 +454,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
               } else {
                 ext = f_add(l, c.s_score[i]);
               }
+              if (LM && ch == c.space_id) ext = c.lm_apply(ext, i);
               atom_or(&c.s_mask[i * W + (rr >> 5)], 1u << (rr & 31));
               ++npairs;
             }
@@ -431,7 +475,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
           const int i = c.s_dpslot[a];
           if (i >= 0) {  // dead node whose parent is in the beam: an existing (dead) child of slot i
             const int rr = c.rank_of(c.s_dchr[a]);
-            if (rr >= 0) {
+            if (rr >= 0 && !c.lm_cut(c.lp[rr], c.s_score[i])) {
               const float l = c.lp[rr];
               if (c.s_dlpc[a] < l) { c.s_dlpc[a] = l; c.s_dts[a] = t_abs; }
               atom_or(&c.s_rmask[i * W + (rr >> 5)], 1u << (rr & 31));
@@ -455,8 +499,10 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
     CTC_TICK(2);  // R1
 
     const int n_nb = n - (rblank >= 0 ? 1 : 0);
-    const long long total = (long long)M * (n_nb + 1) - s_ctl[C_NPAIRS];
-    const bool select_all = total <= (long long)K;  // reference :149 `prefixes.size() >= beam_size`
+    // how many prefixes exist after this frame: the members plus every grid cell that is a new candidate.  With a
+    // scorer the dictionary / cutoff decide that per cell, so the count is taken after the grid walk instead.
+    long long total = (long long)M * (n_nb + 1) - s_ctl[C_NPAIRS];
+    bool select_all = !LM && total <= (long long)K;  // reference :149 `prefixes.size() >= beam_size`
     const int G = (n + 31) >> 5;                     // 32-wide column groups of the candidate grid
 
     // score-key range of everything that can still be selected: [lo32, top32]
@@ -505,7 +551,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
           rowok[LX] = 0;
           if (i < M) {
             CTC_STAT(g_stats.rows++);
-            rowok[LX] = (ord_f(f_add(c.s_score[i], lpmax)) >= lo32) ? 1 : 0;
+            rowok[LX] = (LM || ord_f(f_add(c.s_score[i], lpmax)) >= lo32) ? 1 : 0;
             CTC_STAT(g_stats.rows_skipped += !rowok[LX]);
           }
         }
@@ -523,7 +569,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
         }
         // two rows per iteration when the grid is one group wide: two independent load -> add -> key ->
         // ballot chains in flight instead of one
-        while (G == 1 && (rows & (rows - 1u))) {
+        while (!LM && G == 1 && (rows & (rows - 1u))) {
           const int rl1 = ctc_ffs(rows) - 1;
           rows &= rows - 1u;
           const int rl2 = ctc_ffs(rows) - 1;
@@ -568,7 +614,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
           cnt += n1 + ctc_popc(bal2);
           CTC_STAT(g_stats.cl_entries += n1 + ctc_popc(bal2));
         }
-        if (G == 2) {
+        if (!LM && G == 2) {
           // two column groups (33..64 kept characters): both groups of a row in one go
           CTC_LV(int, colc2);
           CTC_LV(float, colv2);
@@ -629,8 +675,10 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
           const int i = base + warp + L.NW * rl;
           const float sc_i = c.s_score[i], b_i = c.s_bprev[i];
           const int ch_i = c.s_chr[i];
+          const long long ds_i = LM ? c.s_dstate[i] : 0;
           for (int g = 0; g < G; ++g) {
             const uint32_t mw = c.s_mask[i * W + g];
+            const uint32_t rmw = LM ? c.s_rmask[i * W + g] : 0u;
             CTC_LV(int, pred);
             CTC_LV(uint32_t, kk);
             CTC_LANES {
@@ -648,8 +696,13 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
               const bool rep = (ch == ch_i);
               float sc = f_add(l, rep ? b_i : sc_i);
               if (rep && !(b_i > kNInf)) sc = kNInf;
+              bool okl = true;
+              if (LM && ch >= 0) {  // cutoff, dictionary arc (unless the child already exists, dead), LM term
+                okl = !c.lm_cut(l, sc_i) && (((rmw >> lane) & 1u) || c.dict_next[ds_i * V + ch] >= 0);
+                if (ch == c.space_id) sc = c.lm_apply(sc, i);
+              }
               const unsigned k = ord_f(sc);
-              const bool ok = (ch >= 0) && !((mw >> lane) & 1u) && (k >= lo32);
+              const bool ok = (ch >= 0) && !((mw >> lane) & 1u) && (k >= lo32) && okl;
               pred[LX] = ok ? 1 : 0;
               kk[LX] = k;
               if (ok && !select_all) atom_add(&hist0[(int)((k - lo32) >> shift32)], 1);
@@ -678,6 +731,32 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
     CTC_BARRIER();
     CTC_TICK(3);  // G
     const bool fallback = s_ctl[C_OVF] != 0 || p.force_fallback;  // a segment overflowed: redo on the grid
+    if (LM && M < K) {
+      // beam not full yet: do fewer than beam_size prefixes exist?  (lo32 == 0, so the lists hold every candidate)
+      long long ncand = 0;
+      if (!fallback) {
+        for (int w = 0; w < L.NW; ++w) ncand += c.s_wcnt[w];
+      } else {
+        CTC_PAR {
+          int mine = 0;
+          if (n > 0) {
+            int i = tid / n, r = tid - (tid / n) * n;
+            const int di = NT / n, dr = NT - (NT / n) * n;
+            while (i < M) {
+              float sc; int ch;
+              if (c.cand(i, r, sc, ch)) ++mine;
+              r += dr; i += di;
+              if (r >= n) { r -= n; ++i; }
+            }
+          }
+          if (mine) atom_add(&s_ctl[C_NCAND], mine);
+        }
+        CTC_BARRIER();
+        ncand = s_ctl[C_NCAND];
+      }
+      total = M + ncand;
+      select_all = total <= (long long)K;
+    }
 
     uint64_t thr = 0;   // selected <=> key >= thr (no tie) / key > thr or tie-selected (tie)
     int tie_m = 0;      // >0: exactly tie_m of the keys equal to thr are selected
@@ -979,21 +1058,26 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
     // ---- region R4c: selected candidates become trie nodes (or revive a dead anchor) -------------------
     // (reference path_trie.cpp:50-56 revive, :97-105 create).  Arena stores are fire-and-forget.
     CTC_PAR {
-      if (tid == 0) { s_ctl[C_NLIVE] = 0; s_ctl[C_ANYREF] = 0; }
+      if (tid == 0) {
+        s_ctl[C_NLIVE] = 0; s_ctl[C_ANYREF] = 0;
+        if (LM) newlist[0] = nsel;
+      }
       for (int q = tid; q < nsel; q += NT) {
         const int v = sel_entry(q);
         const int i = v >> 16, r = v & 0xFFFF;
         float sc; int ch;
         c.cand(i, r, sc, ch);
         float lpc = c.lp[r];
-        int ts = t_abs, nid, rev = -1;
+        int ts = t_abs, nid, rev = -1, dst = 0;
         if (nlive > 0 && ((c.s_rmask[i * W + (r >> 5)] >> (r & 31)) & 1u)) {
           for (int a = 0; a < KP2; ++a)
             if (c.s_dpslot[a] == i && c.s_dchr[a] == ch) rev = a;
           nid = c.s_dnode[rev]; lpc = c.s_dlpc[rev]; ts = c.s_dts[rev];
+          dst = c.s_ddstate[rev];
           c.s_drev[rev] = 1;
           atom_add(&s_ctl[C_NREV], 1);
           CTC_STAT(g_stats.revived++);
+          if (LM) newlist[1 + 4 * q] = -1;  // the host already knows this node
         } else {
           nid = atom_add(&s_ctl[C_NNODES], 1);
           CTC_STAT(g_stats.created++);
@@ -1003,10 +1087,21 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
           }
           Node nn; nn.parent = c.s_node[i]; nn.chr = ch; nn.lpc = lpc; nn.ts = ts;
           store_node(&nodes[nid], nn);
+          if (LM) {
+            // dictionary state of the new node (reference path_trie.cpp:83-92); tell the host about the node: it
+            // mirrors the trie and asks the Scorer hook for the LM term the node will need when a space follows
+            const int nx = c.dict_next[(long long)c.s_dstate[i] * V + ch];
+            dst = p.dict_final[nx] ? p.dict_start : nx;
+            dstate_arena[nid] = dst;
+            lm_arena[nid] = 0.0f;
+            int *nl = newlist + 1 + 4 * q;
+            nl[0] = nid; nl[1] = c.s_node[i]; nl[2] = ch;
+            nl[3] = (c.space_id >= 0 && c.dict_next[(long long)dst * V + c.space_id] >= 0) ? 1 : 0;
+          }
         }
         int *ni = c.s_newinfo + q * 10;
         ni[0] = nid; ni[1] = ch; ni[2] = (int)f_bits(sc); ni[3] = free_slot(q); ni[4] = i; ni[5] = (int)f_bits(lpc);
-        ni[6] = ts; ni[7] = rev; ni[8] = c.s_depth[i] + 1;
+        ni[6] = ts; ni[7] = rev; ni[8] = c.s_depth[i] + 1; ni[9] = dst;
         c.s_slot2q[ni[3]] = q;
       }
     }
@@ -1059,6 +1154,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
               const Node nd = load_node(&nodes[cur]);
               c.s_dnode[e] = cur; c.s_dchr[e] = nd.chr; c.s_dlpc[e] = nd.lpc; c.s_dts[e] = nd.ts;
               c.s_dpslot[e] = tag; c.s_drev[e] = 0;
+              c.s_ddstate[e] = LM ? ld_cg(&dstate_arena[cur]) : 0;
             }
             c.s_anch[y] = e;
           }
@@ -1106,6 +1202,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
             flush_lpc_ts(&nodes[c.s_node[j]], c.s_lpc[j], c.s_ts[j]);
             c.s_stash[j] = c.s_node[j]; c.s_stash[KP + j] = c.s_chr[j];
             c.s_stash[2 * KP + j] = (int)f_bits(c.s_lpc[j]); c.s_stash[3 * KP + j] = c.s_ts[j];
+            c.s_stash[4 * KP + j] = c.s_dstate[j];
           }
           const int q = c.s_slot2q[j];
           if (q >= 0) {  // a new member moves into this slot
@@ -1114,6 +1211,8 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
             c.s_node[j] = ni[0]; c.s_chr[j] = ni[1]; c.s_depth[j] = ni[8];
             c.s_bprev[j] = kNInf; c.s_nbprev[j] = sc; c.s_score[j] = sc;  // score = lse(-inf, nb)
             c.s_lpc[j] = bits_f((uint32_t)ni[5]); c.s_ts[j] = ni[6];
+            c.s_dstate[j] = ni[9];
+            c.s_lmsp[j] = 0.0f;  // supplied by the host's Scorer hook before the next launch
             have = true;
             start = ni[4];
             if (c.s_evict[start] == 0) { newp = start; resolved = true; }
@@ -1147,7 +1246,8 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
       if (tid == 0) {  // (C_NLIVE / C_ANYREF are read below and reset in region R4c of the next frame)
         s_ctl[C_NSEL] = 0; s_ctl[C_NFREE] = 0; s_ctl[C_NTIE] = 0; s_ctl[C_NREV] = 0; s_ctl[C_NPAIRS] = 0;
         s_ctl[C_ABOVE] = 0; s_ctl[C_KMIN] = (int)0xFFFFFFFFu; s_ctl[C_KMAX] = 0; s_ctl[C_SMAX] = 0;
-        s_ctl[C_NEFREE] = 0; s_ctl[C_NETAKEN] = 0; s_ctl[C_OVF] = 0;
+        s_ctl[C_NEFREE] = 0; s_ctl[C_NETAKEN] = 0; s_ctl[C_OVF] = 0; s_ctl[C_SMIN] = (int)0xFFFFFFFFu;
+        s_ctl[C_NCAND] = 0;
       }
     }
     CTC_BARRIER();
@@ -1192,6 +1292,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
             atom_add(&s_ctl[C_NLIVE], 1);
             c.s_dnode[a] = c.s_stash[e]; c.s_dchr[a] = c.s_stash[KP + e]; c.s_dpslot[a] = c.s_pslot[e];
             c.s_dlpc[a] = bits_f((uint32_t)c.s_stash[2 * KP + e]); c.s_dts[a] = c.s_stash[3 * KP + e];
+            c.s_ddstate[a] = c.s_stash[4 * KP + e];
             c.s_amap[e] = a;
           }
         }
@@ -1235,12 +1336,13 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
       s[j] = c.s_node[j]; s[K + j] = c.s_chr[j]; s[2 * K + j] = c.s_depth[j];
       s[3 * K + j] = (int)f_bits(c.s_bprev[j]); s[4 * K + j] = (int)f_bits(c.s_nbprev[j]);
       s[5 * K + j] = (int)f_bits(c.s_score[j]); s[6 * K + j] = (int)f_bits(c.s_lpc[j]); s[7 * K + j] = c.s_ts[j];
-      s[8 * K + j] = c.s_pslot[j]; s[9 * K + j] = c.s_anch[j];
+      s[8 * K + j] = c.s_pslot[j]; s[9 * K + j] = c.s_anch[j]; s[10 * K + j] = c.s_dstate[j];
       if (j < M) flush_lpc_ts(&nodes[c.s_node[j]], c.s_lpc[j], c.s_ts[j]);
     }
     for (int a = tid; a < KP2; a += NT) {
       st_anchors[a] = c.s_dnode[a]; st_anchors[KP2 + a] = c.s_dchr[a]; st_anchors[2 * KP2 + a] = c.s_dpslot[a];
       st_anchors[3 * KP2 + a] = (int)f_bits(c.s_dlpc[a]); st_anchors[4 * KP2 + a] = c.s_dts[a];
+      st_anchors[5 * KP2 + a] = c.s_ddstate[a];
       if (c.s_dpslot[a] >= 0) flush_lpc_ts(&nodes[c.s_dnode[a]], c.s_dlpc[a], c.s_dts[a]);
     }
     if (tid == 0) {

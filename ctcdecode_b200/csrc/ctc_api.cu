@@ -23,10 +23,10 @@ namespace ctc {
 // ---------------------------------------------------------------------------------------------------
 // two co-resident CTAs per SM (one for NT = 1024): 128 registers per thread up to NT = 256, 64 at NT = 512.
 // A config-2 batch of 256 utterances is 1.73 CTAs per SM, and the frame loop wants its registers.
-template <int NT, bool SORTED>
+template <int NT, bool SORTED, bool LM>
 __global__ void __launch_bounds__(NT, (NT >= 1024 ? 1 : 2)) beam_kernel(const BeamParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
-  beam_cta_run<NT, SORTED>(p, (int)blockIdx.x, smem);
+  beam_cta_run<NT, SORTED, LM>(p, (int)blockIdx.x, smem);
 }
 
 template <int NT>
@@ -80,13 +80,15 @@ static int make_plan(const ctcdec_config *cfg, int B, int T, Plan *pl) {
 
 template <int NT>
 static int launch_beam_nt(const BeamParams &bp, const Plan &pl, int B, cudaStream_t s) {
-  if (pl.sorted) {
-    CU(cudaFuncSetAttribute(beam_kernel<NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.L.total));
-    beam_kernel<NT, true><<<B, NT, pl.L.total, s>>>(bp);
-  } else {
-    CU(cudaFuncSetAttribute(beam_kernel<NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.L.total));
-    beam_kernel<NT, false><<<B, NT, pl.L.total, s>>>(bp);
-  }
+  const bool lm = bp.dict_next != nullptr;
+#define CTC_LAUNCH(SORTED_, LM_)                                                                                      \
+  do {                                                                                                                \
+    CU(cudaFuncSetAttribute(beam_kernel<NT, SORTED_, LM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.L.total)); \
+    beam_kernel<NT, SORTED_, LM_><<<B, NT, pl.L.total, s>>>(bp);                                                      \
+  } while (0)
+  if (pl.sorted) { if (lm) CTC_LAUNCH(true, true); else CTC_LAUNCH(true, false); }
+  else { if (lm) CTC_LAUNCH(false, true); else CTC_LAUNCH(false, false); }
+#undef CTC_LAUNCH
   CU(cudaGetLastError());
   return CTCDEC_OK;
 }
@@ -376,13 +378,13 @@ static int state_init_device(StreamState *st) {
     memcpy(&s[4 * K + j], &ninf, 4);
     memcpy(&s[5 * K + j], j == 0 ? &zero : &ninf, 4);
     memcpy(&s[6 * K + j], &ninf, 4);
-    s[7 * K + j] = 0; s[8 * K + j] = -1; s[9 * K + j] = -1;
+    s[7 * K + j] = 0; s[8 * K + j] = -1; s[9 * K + j] = -1; s[10 * K + j] = 0;
   }
   int *a = s + kSlotArrays * K;
   for (int e = 0; e < KP2; ++e) {
     a[e] = 0; a[KP2 + e] = 0; a[2 * KP2 + e] = -1;
     memcpy(&a[3 * KP2 + e], &ninf, 4);
-    a[4 * KP2 + e] = 0;
+    a[4 * KP2 + e] = 0; a[5 * KP2 + e] = 0;
   }
   CU(cudaMemcpy(st->state, h.get(), n * 4, cudaMemcpyHostToDevice));
   Node root;

@@ -1,0 +1,159 @@
+// Host side of the scorer path (word-based language model + dictionary), shared by the CUDA library and the CPU
+// logic-test emulation.
+//
+// The reference keeps KenLM behind its `Scorer` class and calls it from inside the time loop
+// (ctc_beam_search_decoder.cpp:120-137) and once more when results are read out (:173-208).  The language
+// model stays on the host here too, behind a HOOK the integrator supplies (include/ctcdecode_b200.h,
+// ctcdec_scorer_hooks: the reference side wraps its own Scorer / KenLM) -- this library has
+// no KenLM of its own.  What moves to the GPU is everything the hook does not do:
+//   * the dictionary (reference scorer.cpp:196-230, decoder_utils.cpp:147-193, path_trie.cpp:59-96) becomes a
+//     dense [state][label] table the beam kernel consults when a candidate would create a node;
+//   * the per-frame cutoff (:74-82, :93-95) and the application of the LM term (:134-136) run in the kernel;
+//   * the LM term of a prefix depends only on the prefix (the words before the space being appended), so the host
+//     asks the hook ONCE per trie node that can be followed by a space, when the node is created, and the kernel
+//     reads it from a per-node array afterwards.  The host keeps a (parent, char) mirror of the trie for that.
+// The frame loop is therefore: launch one frame -> read back the list of created nodes -> hook calls -> next
+// frame.  One launch per frame is the price of a host-side language model.
+#pragma once
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/ctcdecode_b200.h"
+
+namespace ctc {
+
+// Deterministic dictionary automaton over label ids: words spelled with `labels`, each followed by the space
+// label (reference Scorer::fill_dictionary(true) -> add_word_to_dictionary -> add_word_to_fst, then
+// RmEpsilon / Determinize / Minimize: language-equivalent to this prefix trie).
+struct Dictionary {
+  int V = 0;
+  int start = 0;
+  int n_words = 0;                  // reference Scorer::dict_size_
+  std::vector<int> next;            // [states][V], -1 = no arc
+  std::vector<unsigned char> fin;   // [states]
+
+  int add_state() {
+    next.insert(next.end(), V, -1);
+    fin.push_back(0);
+    return (int)fin.size() - 1;
+  }
+  int states() const { return (int)fin.size(); }
+};
+
+// split into UTF-8 characters like the reference's split_utf8_str (decoder_utils.cpp:83-99)
+static inline std::vector<std::string> utf8_chars(const std::string &s) {
+  std::vector<std::string> out;
+  std::string cur;
+  for (char ch : s) {
+    if ((ch & 0xc0) != 0x80 && !cur.empty()) { out.push_back(cur); cur.clear(); }
+    cur.push_back(ch);
+  }
+  out.push_back(cur);
+  return out;
+}
+
+static inline Dictionary build_dictionary(const std::vector<std::string> &labels, int space_id,
+                                          const std::vector<std::string> &words) {
+  Dictionary d;
+  d.V = (int)labels.size();
+  d.start = d.add_state();
+  std::unordered_map<std::string, int> char_map;
+  for (int i = 0; i < d.V; ++i) char_map[labels[i]] = i;
+  for (const std::string &w : words) {
+    std::vector<int> ids;
+    bool ok = true;
+    for (const std::string &ch : utf8_chars(w)) {
+      if (ch == " ") { ids.push_back(space_id); continue; }
+      auto it = char_map.find(ch);
+      if (it == char_map.end()) { ok = false; break; }  // not spellable: skipped (decoder_utils.cpp:178-183)
+      ids.push_back(it->second);
+    }
+    if (!ok) continue;
+    ids.push_back(space_id);
+    int s = d.start;
+    for (int id : ids) {
+      int &nx = d.next[(size_t)s * d.V + id];
+      if (nx < 0) { const int ns = d.add_state(); d.next[(size_t)s * d.V + id] = ns; s = ns; }
+      else s = nx;
+    }
+    d.fin[s] = 1;
+    d.n_words += 1;
+  }
+  return d;
+}
+
+struct HostScorer {
+  ctcdec_scorer_hooks hooks;
+  double alpha, beta;
+  int max_order, is_character_based, space_id;
+  std::vector<std::string> labels;
+  Dictionary dict;
+  // device copies of the dictionary (CUDA library only)
+  int *d_next = nullptr;
+  unsigned char *d_final = nullptr;
+  int device = -1;
+};
+
+// Per-utterance host mirror of the trie: enough to spell the prefix of any node.
+struct TrieMirror {
+  std::vector<int> parent{-1}, chr{-1};
+  void add(int nid, int par, int ch) {
+    if ((int)parent.size() <= nid) { parent.resize(nid + 1, -1); chr.resize(nid + 1, -1); }
+    parent[nid] = par;
+    chr[nid] = ch;
+  }
+  void labels_of(int nid, std::vector<int> &out) const {
+    out.clear();
+    for (int q = nid; q > 0; q = parent[q]) out.push_back(chr[q]);
+    for (size_t a = 0, b = out.size(); a + 1 < b; ++a, --b) std::swap(out[a], out[b - 1]);
+  }
+};
+
+// After a frame: register the created nodes and compute the LM term of those a space can follow.
+// newlist: [1 + 4K] ints of one utterance (count, then node / parent / chr / needs_lm); outputs the update list.
+static inline void lm_after_frame(const HostScorer &sc, TrieMirror &mirror, const int *newlist, int *upd_count,
+                                  int *upd_nodes, float *upd_vals, std::vector<int> &scratch) {
+  const int cnt = newlist[0];
+  int nu = 0;
+  for (int q = 0; q < cnt; ++q) {
+    const int *e = newlist + 1 + 4 * q;
+    if (e[0] < 0) continue;  // a revived node: already known
+    mirror.add(e[0], e[1], e[2]);
+    if (e[3]) {
+      mirror.labels_of(e[0], scratch);
+      const double cond = sc.hooks.cond_log_prob(sc.hooks.ctx, scratch.data(), (int)scratch.size());
+      upd_nodes[nu] = e[0];
+      upd_vals[nu] = (float)(cond * sc.alpha);  // reference :133 `score = get_log_cond_prob(ngram) * alpha` (float)
+      ++nu;
+    }
+  }
+  *upd_count = nu;
+}
+
+// DecoderState::decode with a word-based scorer (reference ctc_beam_search_decoder.cpp:164-211): the order of the
+// results is by the raw prefix score (decoder_utils.cpp:59), the reported score is the LM-corrected approx_ctc.
+// tokens / lens / scores are one utterance's rows as written by the finalize kernel (scores = -raw score).
+static inline void lm_rescore(const HostScorer &sc, int n_results, int row_stride, const int *tokens, const int *lens,
+                              float *scores) {
+  std::vector<int> lab;
+  for (int p = 0; p < n_results; ++p) {
+    const int len = lens[p];
+    const int *tok = tokens + (size_t)p * row_stride;
+    float ext = -scores[p];  // scores[prefix] = prefix->score
+    if (len > 0 && tok[len - 1] != sc.space_id) {  // :173-185 score the last (unfinished) word
+      float s = (float)(sc.hooks.cond_log_prob(sc.hooks.ctx, tok, len) * sc.alpha);
+      s = (float)((double)s + sc.beta);
+      ext = ext + s;
+    }
+    double approx = (double)ext;  // :194-205
+    approx = approx - (double)len * sc.beta;
+    approx -= sc.hooks.sent_log_prob(sc.hooks.ctx, tok, len) * sc.alpha;
+    const float approx_f = (float)approx;
+    scores[p] = (float)(-(double)approx_f);  // decoder_utils.cpp:68, binding.cpp:91
+  }
+}
+
+}  // namespace ctc

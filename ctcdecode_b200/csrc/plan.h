@@ -14,7 +14,7 @@ struct Plan {
   bool sorted;    // the reference sorts (and possibly cuts) the vocabulary every frame
   int cp_active;  // log(cutoff_prob) < 0
   int n_max;      // most characters a frame can keep
-  int NP;         // row length of the pruned log-prob rows (multiple of 8, >= n_max + 2)
+  int NP;         // row length of the pruned log-prob rows (multiple of 8, >= n_max + kRowTrailer)
   int P;          // next power of two >= V
   int F;          // frames per staged tile
   int NT;         // threads per CTA of the beam kernel
@@ -44,7 +44,7 @@ static inline int make_plan_core(const ctcdec_config *cfg, int B, int T, Plan *p
   if (!pl->sorted) pl->n_max = V;
   else if (pl->cp_active) pl->n_max = std::min(V, std::max(1, cfg->cutoff_top_n));
   else pl->n_max = std::min(V, cfg->cutoff_top_n);
-  pl->NP = align_up(pl->n_max + 2, 8);
+  pl->NP = align_up(pl->n_max + kRowTrailer, 8);
   int P = 1;
   while (P < V) P <<= 1;
   pl->P = P;

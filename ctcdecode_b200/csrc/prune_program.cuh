@@ -7,7 +7,10 @@
 //
 //   lp  row (float32[NP]) : entries 0..n-1 = log-probs of the kept characters, in the reference's
 //                           iteration order (index order if nothing is cut, else probability
-//                           descending); entries n..NP-3 = -FLT_MAX;
+//                           descending); entries n..NP-4 = -FLT_MAX;
+//                           [NP-3] = float(log(double(p_blank))) without FLT_MIN (= p_blank for log input):
+//                                    the reference's `blank_prob` of the scorer path
+//                                    (ctc_beam_search_decoder.cpp:78);
 //                           [NP-2] = bit pattern  n | (rank_of_blank + 1) << 16;
 //                           [NP-1] = largest non-blank kept log-prob (-FLT_MAX if none)
 //   idx row (uint16[NP])  : character of each kept entry, 0xFFFF beyond n   (sorted mode only)
@@ -32,6 +35,17 @@ struct PruneParams {
 };
 
 #if !defined(CTC_EMULATE)
+
+// `blank_prob` of the scorer path: float(log_input ? p : std::log(p)) on the double image of the input
+// (reference ctc_beam_search_decoder.cpp:78) -- no FLT_MIN here, so log(0) = -inf
+CTC_FN float blank_prob_value(const float *row, int blank, int V, int log_input, const double *logtab) {
+  if (blank < 0 || blank >= V) return kNInf;
+  const float x = row[blank];
+  if (log_input) return x;
+  if (x == 0.0f) return -__int_as_float(0x7f800000);
+  if (!(x > 0.0f)) return __int_as_float(0x7fc00000);
+  return (float)log_glibc_t((double)x, logtab);
+}
 
 CTC_FN float prune_value(float x, int log_input, const double *logtab) {
   return log_input ? x : logprob_glibc_t(x, logtab);  // reference decoder_utils.cpp:40-43
@@ -122,7 +136,7 @@ __global__ void __launch_bounds__(256) prune_kernel(const PruneParams p) {
     for (long long f0 = (long long)blockIdx.x * wpc + warp; f0 < nframes; f0 += stride * U) {
       float v[U];
       bool live[U];
-      const int r = lane;  // NP - 2 <= 32 is the common case; wider rows loop below
+      const int r = lane;  // NP - 3 <= 32 is the common case; wider rows loop below
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const long long f = f0 + stride * u;
@@ -146,8 +160,8 @@ __global__ void __launch_bounds__(256) prune_kernel(const PruneParams p) {
         const long long f = f0 + stride * u;
         float *out = p.lp + f * NP;
         unsigned mx = (r < V && r != p.blank) ? ord_f(v[u]) : ninf_ord;
-        if (r < NP - 2) out[r] = v[u];
-        for (int r2 = lane + 32; r2 < NP - 2; r2 += 32) {  // rows wider than a warp
+        if (r < NP - kRowTrailer) out[r] = v[u];
+        for (int r2 = lane + 32; r2 < NP - kRowTrailer; r2 += 32) {  // rows wider than a warp
           float w = kNInf;
           if (r2 < V) {
             w = prune_value(p.probs[f * V + r2], p.log_input, logtab);
@@ -157,6 +171,7 @@ __global__ void __launch_bounds__(256) prune_kernel(const PruneParams p) {
         }
         mx = __reduce_max_sync(0xffffffffu, mx);
         if (lane == 0) {
+          out[NP - 3] = blank_prob_value(p.probs + f * V, p.blank, V, p.log_input, logtab);
           out[NP - 2] = bits_f((uint32_t)V | ((uint32_t)(rblank_unsorted + 1) << 16));
           out[NP - 1] = unord_f(mx);
         }
@@ -272,12 +287,13 @@ __global__ void __launch_bounds__(256) prune_kernel(const PruneParams p) {
         if ((int)c == p.blank) rb = r + 1;
       }
       if (r < 2) first_two = v;
-      if (r < NP - 2) out[r] = v;
+      if (r < NP - kRowTrailer) out[r] = v;
       oidx[r] = (uint16_t)c;
     }
     rb = __reduce_max_sync(0xffffffffu, rb);
     const float l0 = __shfl_sync(0xffffffffu, first_two, 0), l1 = __shfl_sync(0xffffffffu, first_two, 1);
     if (lane == 0) {
+      out[NP - 3] = blank_prob_value(row, p.blank, V, p.log_input, logtab);
       out[NP - 2] = bits_f((uint32_t)n | ((uint32_t)rb << 16));
       out[NP - 1] = (rb == 1) ? (n > 1 ? l1 : kNInf) : (n > 0 ? l0 : kNInf);
     }

@@ -86,6 +86,44 @@ int ctcdec_decode_batch_host(const ctcdec_config *cfg, const float *probs, const
                              int32_t *tokens, int32_t *timesteps, float *scores, int32_t *lens, int32_t *n_results,
                              int32_t *flags, int device);
 
+/* ---- scorer path: word-based language model + dictionary (reference Scorer, scorer.h:41-110) --------------
+ *
+ * The language model itself stays on the HOST behind a hook the integrator supplies -- the reference side wraps its
+ * own Scorer / KenLM; this library contains no KenLM.  Both hooks take a prefix as label ids:
+ *   cond_log_prob(ctx, labels, n)  = Scorer::get_log_cond_prob(Scorer::make_ngram(prefix))   (scorer.cpp:74-93,163-194)
+ *                                    i.e. the natural-log probability of the prefix's last word given the words
+ *                                    before it (up to max_order, "<s>"-padded); OOV -> -1000
+ *   sent_log_prob(ctx, labels, n)  = Scorer::get_sent_log_prob(Scorer::split_labels(prefix))  (scorer.cpp:95-146)
+ * The hooks must be callable from the thread that calls ctcdec_decode_batch_lm_host. */
+typedef struct ctcdec_scorer_hooks {
+  void *ctx;
+  double (*cond_log_prob)(void *ctx, const int32_t *labels, int n);
+  double (*sent_log_prob)(void *ctx, const int32_t *labels, int n);
+} ctcdec_scorer_hooks;
+
+/* Replaces: paddle_get_scorer (binding.cpp:143-150) for word-based language models.  `labels` are the decoder's
+ * labels (UTF-8), `words` the language model's vocabulary (what KenLM's EnumerateVocab reports,
+ * scorer.cpp:55-72): every word spellable with the labels goes into the dictionary, followed by the space label
+ * (scorer.cpp:196-230, decoder_utils.cpp:164-193).  Character-based models (is_character_based != 0) are rejected
+ * with CTCDEC_E_UNSUPPORTED. */
+int ctcdec_scorer_create(const ctcdec_scorer_hooks *hooks, double alpha, double beta, const char *const *labels,
+                         int n_labels, const char *const *words, int n_words, int max_order, int is_character_based,
+                         void **scorer);
+/* Replaces: paddle_release_scorer, is_character_based, get_max_order, get_dict_size, reset_params
+ * (binding.cpp:267-287). */
+int ctcdec_scorer_destroy(void *scorer);
+int ctcdec_scorer_is_character_based(const void *scorer);
+int ctcdec_scorer_max_order(const void *scorer);
+int ctcdec_scorer_dict_size(const void *scorer);
+int ctcdec_scorer_reset_params(void *scorer, double alpha, double beta);
+
+/* Replaces: paddle_beam_decode_lm -> beam_decode -> ctc_beam_search_decoder_batch with a scorer
+ * (binding.cpp:122-140, ctc_beam_search_decoder.cpp:56-211).  HOST buffers, shaped like ctcdec_decode_batch_host.
+ * The beam search runs on `device`, one kernel launch per frame with the hook calls in between. */
+int ctcdec_decode_batch_lm_host(const ctcdec_config *cfg, void *scorer, const float *probs, const int32_t *seq_lens,
+                                int B, int T, int32_t *tokens, int32_t *timesteps, float *scores, int32_t *lens,
+                                int32_t *n_results, int32_t *flags, int device);
+
 /* ---- streaming (OnlineCTCBeamDecoder) ------------------------------------------------------------- */
 
 /* Replaces: paddle_get_decoder_state (binding.cpp:246-261).  The state (beam + trie + absolute frame

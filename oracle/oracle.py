@@ -162,9 +162,32 @@ class Reference:
                                              ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_uint8),
                                              ctypes.c_int, ctypes.c_int, _i32p, _i32p, _f32p, _i32p, ctypes.c_int,
                                              _i32p]
+        L.ref_scorer_cond_from_labels.restype = ctypes.c_double
+        L.ref_scorer_cond_from_labels.argtypes = [ctypes.c_void_p, _i32p, ctypes.c_int]
+        L.ref_scorer_sent_from_labels.restype = ctypes.c_double
+        L.ref_scorer_sent_from_labels.argtypes = [ctypes.c_void_p, _i32p, ctypes.c_int]
+        L.ref_lm_vocabulary.restype = ctypes.c_size_t
+        L.ref_lm_vocabulary.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t]
         self.scorer = None
+        self.model_path = model_path
         if model_path:
             self.scorer = L.ref_scorer_new(alpha, beta, model_path.encode(), self._labels_c, len(self.labels))
+
+    def lm_vocabulary(self):
+        """The LM's vocabulary as KenLM enumerates it (what the reference's Scorer::load_lm collects)."""
+        n = self.lib.ref_lm_vocabulary(self.model_path.encode(), None, 0)
+        buf = ctypes.create_string_buffer(n)
+        self.lib.ref_lm_vocabulary(self.model_path.encode(), buf, n)
+        return buf.value.decode().split("\n")[:-1]
+
+    def max_order(self):
+        return int(self.lib.ref_scorer_max_order(self.scorer))
+
+    def dict_size(self):
+        return int(self.lib.ref_scorer_dict_size(self.scorer))
+
+    def is_character_based(self):
+        return int(self.lib.ref_scorer_is_character_based(self.scorer))
 
     def __del__(self):
         if getattr(self, "scorer", None):

@@ -121,3 +121,45 @@ int ref_decode_with_states(const float *probs, const int *seq_lens, int B, int T
 }
 
 }  // extern "C"
+
+// ---- scorer hooks for the product's host-side LM interface (include/ctcdecode_b200.h: ctcdec_scorer_hooks) -----
+// These are what a maintainer of the reference would write in its own tree: the UNMODIFIED
+// Scorer does the language-model work, the hook only turns a label-id prefix into the arguments it expects.
+#include "lm/config.hh"
+#include "lm/model.hh"
+
+extern "C" {
+
+// Scorer::get_log_cond_prob(Scorer::make_ngram(prefix)) for the prefix spelled by `labels` (scorer.cpp:74-93,163-194)
+double ref_scorer_cond_from_labels(void *scorer, const int *labels, int n) {
+  Scorer *s = static_cast<Scorer *>(scorer);
+  std::vector<PathTrie> chain(static_cast<size_t>(n) + 1);  // chain[0] is the root (character == -1)
+  for (int k = 0; k < n; ++k) {
+    chain[k + 1].character = labels[k];
+    chain[k + 1].parent = &chain[k];
+  }
+  return s->get_log_cond_prob(s->make_ngram(&chain[n]));
+}
+
+// Scorer::get_sent_log_prob(Scorer::split_labels(prefix))  (scorer.cpp:95-146)
+double ref_scorer_sent_from_labels(void *scorer, const int *labels, int n) {
+  Scorer *s = static_cast<Scorer *>(scorer);
+  std::vector<int> v(labels, labels + n);
+  return s->get_sent_log_prob(s->split_labels(v));
+}
+
+// The language model's vocabulary as KenLM enumerates it (what Scorer::load_lm collects, scorer.cpp:55-72),
+// '\n'-separated into buf; returns the number of bytes needed.
+size_t ref_lm_vocabulary(const char *lm_path, char *buf, size_t cap) {
+  RetriveStrEnumerateVocab enumerate;
+  lm::ngram::Config config;
+  config.enumerate_vocab = &enumerate;
+  lm::base::Model *m = lm::ngram::LoadVirtual(lm_path, config);
+  delete m;
+  std::string all;
+  for (const std::string &w : enumerate.vocabulary) { all += w; all += '\n'; }
+  if (buf && cap >= all.size() + 1) memcpy(buf, all.c_str(), all.size() + 1);
+  return all.size() + 1;
+}
+
+}  // extern "C"

@@ -16,8 +16,15 @@
 
 #include "../../ctcdecode_b200/csrc/beam_program.cuh"
 #include "../../ctcdecode_b200/csrc/plan.h"
+#include "../../ctcdecode_b200/csrc/lm_host.h"
 
 using namespace ctc;
+
+static float blank_prob_host(const float *row, const ctcdec_config &cfg) {  // reference ctc_beam_search_decoder.cpp:78
+  if (cfg.blank_id < 0 || cfg.blank_id >= cfg.vocab_size) return kNInf;
+  const float x = row[cfg.blank_id];
+  return cfg.log_input ? x : (float)std::log((double)x);
+}
 
 // Host mirror of prune_program.cuh (same row format); the vocabulary cut follows reference
 // decoder_utils.cpp:10-45 literally.
@@ -32,7 +39,7 @@ static void prune_rows(const ctcdec_config &cfg, const Plan &pl, const float *pr
       float *out = lp + ((size_t)b * T + t) * NP;
       if (!pl.sorted) {
         float mx = kNInf;
-        for (int r = 0; r < NP - 2; ++r) {
+        for (int r = 0; r < NP - kRowTrailer; ++r) {
           float v = kNInf;
           if (r < V) {
             v = cfg.log_input ? row[r] : logprob_glibc(row[r]);
@@ -41,6 +48,7 @@ static void prune_rows(const ctcdec_config &cfg, const Plan &pl, const float *pr
           out[r] = v;
         }
         const int rb = cfg.blank_id < V ? cfg.blank_id : -1;
+        out[NP - 3] = blank_prob_host(row, cfg);
         out[NP - 2] = bits_f((uint32_t)V | ((uint32_t)(rb + 1) << 16));
         out[NP - 1] = mx;
         continue;
@@ -75,9 +83,10 @@ static void prune_rows(const ctcdec_config &cfg, const Plan &pl, const float *pr
           v = cfg.log_input ? row[c] : logprob_glibc(row[c]);
           if ((int)c == cfg.blank_id) rb = r + 1;
         }
-        if (r < NP - 2) out[r] = v;
+        if (r < NP - kRowTrailer) out[r] = v;
         oidx[r] = (uint16_t)c;
       }
+      out[NP - 3] = blank_prob_host(row, cfg);
       out[NP - 2] = bits_f((uint32_t)n | ((uint32_t)rb << 16));
       out[NP - 1] = (rb == 1) ? (n > 1 ? out[1] : kNInf) : (n > 0 ? out[0] : kNInf);
     }
@@ -87,8 +96,9 @@ static void prune_rows(const ctcdec_config &cfg, const Plan &pl, const float *pr
 template <int NT>
 static void run_beam(const BeamParams &bp, bool sorted, int B, unsigned char *smem) {
   for (int b = 0; b < B; ++b) {
-    if (sorted) beam_cta_run<NT, true>(bp, b, smem);
-    else beam_cta_run<NT, false>(bp, b, smem);
+    const bool lm = bp.dict_next != nullptr;
+    if (sorted) { if (lm) beam_cta_run<NT, true, true>(bp, b, smem); else beam_cta_run<NT, true, false>(bp, b, smem); }
+    else { if (lm) beam_cta_run<NT, false, true>(bp, b, smem); else beam_cta_run<NT, false, false>(bp, b, smem); }
   }
 }
 
@@ -157,6 +167,85 @@ int emu_decode_batch(const float *probs, const int *seq_lens, int B, int T, int 
   }
   std::vector<unsigned char> fsmem((size_t)K * 12 + 64);
   for (int b = 0; b < B; ++b) finalize_cta_run<128>(bp, b, fsmem.data());
+  return 0;
+}
+
+
+// Scorer path through the emulated CTA program: one frame per "launch", hook calls in between (lm_host.h).
+int emu_decode_batch_lm(const float *probs, const int *seq_lens, int B, int T, int V, int K, double cutoff_prob,
+                        int cutoff_top_n, int blank, int log_input, int NT, void *hook_ctx,
+                        double (*cond)(void *, const int *, int), double (*sent)(void *, const int *, int),
+                        double alpha, double beta, const char *const *labels, const char *const *words, int n_words,
+                        int max_order, int *tokens, int *timesteps, float *scores, int *lens, int *n_results,
+                        int *flags) {
+  ctcdec_config cfg;
+  cfg.vocab_size = V; cfg.beam_size = K; cfg.blank_id = blank; cfg.log_input = log_input;
+  cfg.cutoff_top_n = cutoff_top_n; cfg.cutoff_prob = cutoff_prob;
+  Plan pl;
+  char msg[256];
+  int rc = make_plan_core(&cfg, B, T, &pl, msg, sizeof(msg));
+  if (rc) { fprintf(stderr, "emu: %s\n", msg); return rc; }
+  if (NT <= 0) NT = pl.NT;
+  pl.NT = NT;
+  pl.L = make_layout(K, V, pl.NP, pl.F, pl.sorted, NT);
+  HostScorer sc;
+  sc.hooks.ctx = hook_ctx; sc.hooks.cond_log_prob = cond; sc.hooks.sent_log_prob = sent;
+  sc.alpha = alpha; sc.beta = beta; sc.max_order = max_order; sc.is_character_based = 0; sc.space_id = -2;
+  for (int i = 0; i < V; ++i) { sc.labels.emplace_back(labels[i]); if (sc.labels.back() == " ") sc.space_id = i; }
+  if (sc.space_id < 0) return CTCDEC_E_UNSUPPORTED;
+  std::vector<std::string> w;
+  for (int i = 0; i < n_words; ++i) w.emplace_back(words[i]);
+  sc.dict = build_dictionary(sc.labels, sc.space_id, w);
+
+  std::vector<float> lp((size_t)B * T * pl.NP + 8, 0.f);
+  std::vector<uint16_t> idx(pl.sorted ? (size_t)B * T * pl.NP + 8 : 8, 0);
+  std::vector<Node> arena((size_t)B * pl.arena_stride);
+  std::vector<float> lm_arena((size_t)B * pl.arena_stride, 0.f);
+  std::vector<int> dstate_arena((size_t)B * pl.arena_stride, 0);
+  std::vector<int> state((size_t)B * pl.state_stride, 0);
+  std::vector<int> newlist((size_t)B * (1 + 4 * K), 0);
+  std::vector<int> upd_count(B, 0), upd_nodes((size_t)B * K, 0);
+  std::vector<float> upd_vals((size_t)B * K, 0.f);
+  std::vector<unsigned char> smem(pl.L.total + 64);
+  for (int b = 0; b < B; ++b) flags[b] = 0;
+  prune_rows(cfg, pl, probs, seq_lens, B, T, lp.data(), idx.data(), flags);
+
+  BeamParams bp;
+  memset(&bp, 0, sizeof(bp));
+  bp.lp = lp.data(); bp.idx = pl.sorted ? idx.data() : nullptr; bp.seq_lens = seq_lens; bp.T = T;
+  bp.V = V; bp.NP = pl.NP; bp.K = K; bp.blank = blank; bp.tile_frames = pl.F;
+  bp.arena = arena.data(); bp.arena_stride = pl.arena_stride; bp.state = state.data();
+  bp.state_stride = pl.state_stride; bp.arena_cap = (int)pl.arena_stride;
+  bp.out_tokens = tokens; bp.out_timesteps = timesteps; bp.out_scores = scores; bp.out_lens = lens;
+  bp.n_results = n_results; bp.out_T = T; bp.flags = flags;
+  bp.force_fallback = getenv("CTC_EMU_FORCE_FALLBACK") ? 1 : 0;
+  bp.dict_next = sc.dict.next.data(); bp.dict_final = sc.dict.fin.data(); bp.dict_start = sc.dict.start;
+  bp.space_id = sc.space_id; bp.beta = beta; bp.lm_arena = lm_arena.data(); bp.dstate_arena = dstate_arena.data();
+  bp.newlist = newlist.data(); bp.lm_update_count = upd_count.data(); bp.lm_update_nodes = upd_nodes.data();
+  bp.lm_update_vals = upd_vals.data();
+
+  std::vector<TrieMirror> mirror(B);
+  std::vector<int> scratch;
+  int tmax = 0;
+  for (int b = 0; b < B; ++b) tmax = std::max(tmax, std::min(seq_lens ? seq_lens[b] : T, T));
+  for (int t = 0; t < std::max(tmax, 1); ++t) {
+    bp.t0 = t; bp.nframes = 1; bp.fresh = (t == 0) ? 1 : 0;
+    switch (NT) {
+      case 32: run_beam<32>(bp, pl.sorted, B, smem.data()); break;
+      case 64: run_beam<64>(bp, pl.sorted, B, smem.data()); break;
+      case 128: run_beam<128>(bp, pl.sorted, B, smem.data()); break;
+      case 512: run_beam<512>(bp, pl.sorted, B, smem.data()); break;
+      default: run_beam<256>(bp, pl.sorted, B, smem.data()); break;
+    }
+    for (int b = 0; b < B; ++b)
+      lm_after_frame(sc, mirror[b], newlist.data() + (size_t)b * (1 + 4 * K), &upd_count[b],
+                     upd_nodes.data() + (size_t)b * K, upd_vals.data() + (size_t)b * K, scratch);
+  }
+  std::vector<unsigned char> fsmem((size_t)K * 12 + 64);
+  for (int b = 0; b < B; ++b) {
+    finalize_cta_run<128>(bp, b, fsmem.data());
+    lm_rescore(sc, n_results[b], T, tokens + (size_t)b * K * T, lens + (size_t)b * K, scores + (size_t)b * K);
+  }
   return 0;
 }
 
