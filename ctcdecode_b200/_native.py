@@ -14,6 +14,11 @@ class Config(ctypes.Structure):
                 ("log_input", ctypes.c_int), ("cutoff_top_n", ctypes.c_int), ("cutoff_prob", ctypes.c_double)]
 
 
+class ScorerHooks(ctypes.Structure):
+    """ctcdec_scorer_hooks: raw C function pointers (addresses) supplied by the integrator."""
+    _fields_ = [("ctx", ctypes.c_void_p), ("cond_log_prob", ctypes.c_void_p), ("sent_log_prob", ctypes.c_void_p)]
+
+
 class NativeError(RuntimeError):
     pass
 
@@ -29,6 +34,16 @@ _SIGNATURES = {
                                                   _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_size_t, _vp]),
     "ctcdec_decode_batch_host": (ctypes.c_int, [ctypes.POINTER(Config), _vp, _vp, ctypes.c_int, ctypes.c_int,
                                                 _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_int]),
+    "ctcdec_scorer_create": (ctypes.c_int, [_vp, ctypes.c_double, ctypes.c_double, ctypes.POINTER(ctypes.c_char_p),
+                                            ctypes.c_int, ctypes.POINTER(ctypes.c_char_p), ctypes.c_int, ctypes.c_int,
+                                            ctypes.c_int, ctypes.POINTER(_vp)]),
+    "ctcdec_scorer_destroy": (ctypes.c_int, [_vp]),
+    "ctcdec_scorer_is_character_based": (ctypes.c_int, [_vp]),
+    "ctcdec_scorer_max_order": (ctypes.c_int, [_vp]),
+    "ctcdec_scorer_dict_size": (ctypes.c_int, [_vp]),
+    "ctcdec_scorer_reset_params": (ctypes.c_int, [_vp, ctypes.c_double, ctypes.c_double]),
+    "ctcdec_decode_batch_lm_host": (ctypes.c_int, [ctypes.POINTER(Config), _vp, _vp, _vp, ctypes.c_int, ctypes.c_int,
+                                                   _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_int]),
     "ctcdec_state_create": (ctypes.c_int, [ctypes.POINTER(Config), ctypes.c_int, ctypes.POINTER(_vp)]),
     "ctcdec_state_destroy": (ctypes.c_int, [_vp]),
     "ctcdec_state_frames": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_int)]),

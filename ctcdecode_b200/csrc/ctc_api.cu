@@ -14,6 +14,7 @@
 #include "../../include/ctcdecode_b200.h"
 #include "beam_program.cuh"
 #include "plan.h"
+#include "lm_host.h"
 #include "prune_program.cuh"
 
 namespace ctc {
@@ -160,8 +161,10 @@ static int check_device() {
 // ---------------------------------------------------------------------------------------------------
 struct DevCache {
   cudaStream_t stream = nullptr;
-  void *buf[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  size_t cap[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  void *buf[12] = {};
+  size_t cap[12] = {};
+  void *pin[4] = {};  // pinned host staging (scorer path: new-node lists, LM updates)
+  size_t pcap[4] = {};
 };
 static DevCache g_cache[64];
 static std::mutex g_mu;
@@ -185,6 +188,16 @@ struct Profile {
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 static thread_local Profile g_prof;
+
+static int ensure_pinned(DevCache &c, int slot, size_t bytes) {
+  if (bytes <= c.pcap[slot]) return CTCDEC_OK;
+  if (c.pin[slot]) CU(cudaFreeHost(c.pin[slot]));
+  c.pin[slot] = nullptr;
+  c.pcap[slot] = 0;
+  CU(cudaMallocHost(&c.pin[slot], bytes + bytes / 8));
+  c.pcap[slot] = bytes + bytes / 8;
+  return CTCDEC_OK;
+}
 
 // streaming state object
 struct StreamState {
@@ -571,6 +584,177 @@ int ctcdec_decode_stream_host(const float *probs, const int32_t *seq_lens, int B
     CU(cudaStreamSynchronize(s));
     if (n_results) memset(n_results, 0, (size_t)B * 4);
   }
+  return CTCDEC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+//  scorer path
+// ---------------------------------------------------------------------------------------------------
+int ctcdec_scorer_create(const ctcdec_scorer_hooks *hooks, double alpha, double beta, const char *const *labels,
+                         int n_labels, const char *const *words, int n_words, int max_order, int is_character_based,
+                         void **scorer) {
+  if (!hooks || !hooks->cond_log_prob || !hooks->sent_log_prob) return fail(CTCDEC_E_INVALID, "scorer hooks are NULL");
+  if (!labels || n_labels < 1 || (!words && n_words > 0) || n_words < 0 || !scorer)
+    return fail(CTCDEC_E_INVALID, "bad labels / words / scorer argument");
+  if (is_character_based)
+    return fail(CTCDEC_E_UNSUPPORTED, "character-based language models are not built (only word-based models with a dictionary)");
+  HostScorer *sc = new HostScorer();
+  sc->hooks = *hooks; sc->alpha = alpha; sc->beta = beta; sc->max_order = max_order; sc->is_character_based = 0;
+  sc->space_id = -2;
+  for (int i = 0; i < n_labels; ++i) {
+    sc->labels.emplace_back(labels[i] ? labels[i] : "");
+    if (sc->labels.back() == " ") sc->space_id = i;  // reference ctc_beam_search_decoder.cpp:34-40
+  }
+  if (sc->space_id < 0) {
+    delete sc;
+    return fail(CTCDEC_E_UNSUPPORTED, "a word-based scorer needs a \" \" label to end words with");
+  }
+  std::vector<std::string> w;
+  for (int i = 0; i < n_words; ++i) w.emplace_back(words[i] ? words[i] : "");
+  sc->dict = build_dictionary(sc->labels, sc->space_id, w);
+  *scorer = sc;
+  return CTCDEC_OK;
+}
+
+int ctcdec_scorer_destroy(void *scorer) {
+  if (!scorer) return CTCDEC_OK;
+  HostScorer *sc = static_cast<HostScorer *>(scorer);
+  if (sc->d_next) { cudaSetDevice(sc->device); cudaFree(sc->d_next); cudaFree(sc->d_final); }
+  delete sc;
+  return CTCDEC_OK;
+}
+int ctcdec_scorer_is_character_based(const void *scorer) { return scorer ? static_cast<const HostScorer *>(scorer)->is_character_based : 0; }
+int ctcdec_scorer_max_order(const void *scorer) { return scorer ? static_cast<const HostScorer *>(scorer)->max_order : 0; }
+int ctcdec_scorer_dict_size(const void *scorer) { return scorer ? static_cast<const HostScorer *>(scorer)->dict.n_words : 0; }
+int ctcdec_scorer_reset_params(void *scorer, double alpha, double beta) {
+  if (!scorer) return fail(CTCDEC_E_INVALID, "scorer is NULL");
+  HostScorer *sc = static_cast<HostScorer *>(scorer);
+  sc->alpha = alpha;  // reference Scorer::reset_params takes floats (scorer.cpp:122-125)
+  sc->beta = beta;
+  return CTCDEC_OK;
+}
+
+int ctcdec_decode_batch_lm_host(const ctcdec_config *cfg, void *scorer, const float *probs, const int32_t *seq_lens,
+                                int B, int T, int32_t *tokens, int32_t *timesteps, float *scores, int32_t *lens,
+                                int32_t *n_results, int32_t *flags, int device) {
+  if (!scorer) return fail(CTCDEC_E_INVALID, "scorer is NULL");
+  HostScorer *sc = static_cast<HostScorer *>(scorer);
+  Plan pl;
+  int rc = make_plan(cfg, B, T, &pl);
+  if (rc) return rc;
+  if ((int)sc->labels.size() != cfg->vocab_size) return fail(CTCDEC_E_INVALID, "scorer was built for %zu labels, decoder has %d", sc->labels.size(), cfg->vocab_size);
+  if (device < 0 || device >= 64) return fail(CTCDEC_E_INVALID, "device %d out of range", device);
+  if (cudaSetDevice(device) != cudaSuccess) return fail(CTCDEC_E_NO_DEVICE, "cudaSetDevice(%d) failed (this library has no CPU fallback)", device);
+  if ((rc = check_device())) return rc;
+  if (B == 0) return CTCDEC_OK;
+  std::lock_guard<std::mutex> lock(g_mu);
+  DevCache &c = g_cache[device];
+  if (!c.stream) CU(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+  cudaStream_t s = c.stream;
+  const int V = cfg->vocab_size, K = cfg->beam_size;
+  // dictionary on the device
+  if (sc->d_next && sc->device != device) { cudaSetDevice(sc->device); cudaFree(sc->d_next); cudaFree(sc->d_final); sc->d_next = nullptr; cudaSetDevice(device); }
+  if (!sc->d_next) {
+    CU(cudaMalloc(&sc->d_next, sc->dict.next.size() * 4));
+    CU(cudaMalloc(&sc->d_final, sc->dict.fin.size()));
+    CU(cudaMemcpy(sc->d_next, sc->dict.next.data(), sc->dict.next.size() * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(sc->d_final, sc->dict.fin.data(), sc->dict.fin.size(), cudaMemcpyHostToDevice));
+    sc->device = device;
+  }
+  const size_t n_probs = (size_t)B * T * V, n_out = (size_t)B * K * T, n_bk = (size_t)B * K;
+  const size_t nl_ints = (size_t)B * (1 + 4 * K);
+  const size_t upd_bytes = al256((size_t)B * 4) + al256(n_bk * 4) + al256(n_bk * 4);
+  const size_t lm_bytes = al256((size_t)B * pl.arena_stride * 4) * 2 + al256(nl_ints * 4) + upd_bytes;
+  if ((rc = ensure(c, 0, n_probs * 4 + 256))) return rc;
+  if ((rc = ensure(c, 1, (size_t)B * 4 + 256))) return rc;
+  if ((rc = ensure(c, 2, n_out * 4 + 256))) return rc;
+  if ((rc = ensure(c, 3, n_out * 4 + 256))) return rc;
+  if ((rc = ensure(c, 4, n_bk * 4 * 2 + (size_t)B * 8 + 1024))) return rc;
+  if ((rc = ensure(c, 5, pl.total + 512))) return rc;
+  if ((rc = ensure(c, 7, lm_bytes + 512))) return rc;
+  if ((rc = ensure_pinned(c, 0, nl_ints * 4))) return rc;
+  if ((rc = ensure_pinned(c, 1, upd_bytes))) return rc;
+  float *d_probs = (float *)c.buf[0];
+  int *d_lens_in = seq_lens ? (int *)c.buf[1] : nullptr;
+  int *d_tok = (int *)c.buf[2], *d_ts = (int *)c.buf[3];
+  float *d_scores = (float *)c.buf[4];
+  int *d_lens = (int *)((char *)c.buf[4] + al256(n_bk * 4));
+  int *d_nres = (int *)((char *)d_lens + al256(n_bk * 4));
+  int *d_flags = d_nres + B;
+  unsigned char *lmb = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(c.buf[7]) + 255) / 256 * 256);
+  float *d_lm_arena = (float *)lmb;
+  int *d_dstate = (int *)(lmb + al256((size_t)B * pl.arena_stride * 4));
+  int *d_newlist = (int *)(lmb + 2 * al256((size_t)B * pl.arena_stride * 4));
+  unsigned char *d_upd = lmb + 2 * al256((size_t)B * pl.arena_stride * 4) + al256(nl_ints * 4);
+  int *d_upd_count = (int *)d_upd;
+  int *d_upd_nodes = (int *)(d_upd + al256((size_t)B * 4));
+  float *d_upd_vals = (float *)(d_upd + al256((size_t)B * 4) + al256(n_bk * 4));
+  int *h_newlist = (int *)c.pin[0];
+  unsigned char *h_upd = (unsigned char *)c.pin[1];
+  int *h_upd_count = (int *)h_upd;
+  int *h_upd_nodes = (int *)(h_upd + al256((size_t)B * 4));
+  float *h_upd_vals = (float *)(h_upd + al256((size_t)B * 4) + al256(n_bk * 4));
+
+  if (n_probs) CU(cudaMemcpyAsync(d_probs, probs, n_probs * 4, cudaMemcpyHostToDevice, s));
+  if (seq_lens) CU(cudaMemcpyAsync(d_lens_in, seq_lens, (size_t)B * 4, cudaMemcpyHostToDevice, s));
+  CU(cudaMemsetAsync(d_flags, 0, (size_t)B * 4, s));
+  unsigned char *ws = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(c.buf[5]) + 255) / 256 * 256);
+  float *lp = reinterpret_cast<float *>(ws + pl.off_lp);
+  uint16_t *idx = pl.sorted ? reinterpret_cast<uint16_t *>(ws + pl.off_idx) : nullptr;
+  if ((rc = launch_prune(cfg, pl, d_probs, d_lens_in, B, T, lp, idx, d_flags, s))) return rc;
+
+  BeamParams bp;
+  memset(&bp, 0, sizeof(bp));
+  bp.lp = lp; bp.idx = idx; bp.seq_lens = d_lens_in; bp.T = T; bp.V = V; bp.NP = pl.NP; bp.K = K;
+  bp.blank = cfg->blank_id; bp.tile_frames = 1;
+  bp.arena = reinterpret_cast<Node *>(ws + pl.off_arena); bp.arena_stride = pl.arena_stride;
+  bp.state = reinterpret_cast<int *>(ws + pl.off_state); bp.state_stride = pl.state_stride;
+  bp.arena_cap = (int)pl.arena_stride;
+  bp.out_tokens = d_tok; bp.out_timesteps = d_ts; bp.out_scores = d_scores; bp.out_lens = d_lens;
+  bp.n_results = d_nres; bp.out_T = T; bp.flags = d_flags;
+  bp.force_fallback = getenv("CTCDEC_FORCE_FALLBACK") ? 1 : 0;
+  bp.dict_next = sc->d_next; bp.dict_final = sc->d_final; bp.dict_start = sc->dict.start;
+  bp.space_id = sc->space_id; bp.beta = sc->beta; bp.lm_arena = d_lm_arena; bp.dstate_arena = d_dstate;
+  bp.newlist = d_newlist; bp.lm_update_count = d_upd_count; bp.lm_update_nodes = d_upd_nodes;
+  bp.lm_update_vals = d_upd_vals;
+  Plan pl1 = pl;  // one frame per launch: the staged tile is one row
+  pl1.F = 1;
+  pl1.L = make_layout(K, V, pl.NP, 1, pl.sorted, pl.NT);
+
+  int tmax = 0;
+  for (int b = 0; b < B; ++b) tmax = std::max(tmax, std::max(0, std::min(seq_lens ? seq_lens[b] : T, T)));
+  std::vector<TrieMirror> mirror(B);
+  std::vector<int> scratch;
+  memset(h_upd_count, 0, (size_t)B * 4);
+  for (int t = 0; t < std::max(tmax, 1); ++t) {
+    CU(cudaMemcpyAsync(d_upd, h_upd, upd_bytes, cudaMemcpyHostToDevice, s));
+    bp.t0 = t; bp.nframes = 1; bp.fresh = (t == 0) ? 1 : 0;
+    if ((rc = launch_beam(bp, pl1, B, s))) return rc;
+    CU(cudaMemcpyAsync(h_newlist, d_newlist, nl_ints * 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    for (int b = 0; b < B; ++b)
+      lm_after_frame(*sc, mirror[b], h_newlist + (size_t)b * (1 + 4 * K), &h_upd_count[b],
+                     h_upd_nodes + (size_t)b * K, h_upd_vals + (size_t)b * K, scratch);
+  }
+  if ((rc = launch_finalize(bp, B, s))) return rc;
+  std::unique_ptr<int[]> h_nres(new int[(size_t)B * 2]);
+  CU(cudaMemcpyAsync(scores, d_scores, n_bk * 4, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(lens, d_lens, n_bk * 4, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(h_nres.get(), d_nres, (size_t)B * 8, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  int max_len = 0;
+  for (int b = 0; b < B; ++b)
+    for (int p = 0; p < h_nres[b] && p < K; ++p) max_len = std::max(max_len, lens[(size_t)b * K + p]);
+  if (max_len > T) max_len = T;
+  if (max_len > 0) {
+    CU(cudaMemcpy2DAsync(tokens, (size_t)T * 4, d_tok, (size_t)T * 4, (size_t)max_len * 4, n_bk, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpy2DAsync(timesteps, (size_t)T * 4, d_ts, (size_t)T * 4, (size_t)max_len * 4, n_bk, cudaMemcpyDeviceToHost, s));
+  }
+  CU(cudaStreamSynchronize(s));
+  for (int b = 0; b < B; ++b)  // reported scores: LM-corrected approx_ctc (reference :194-208)
+    lm_rescore(*sc, h_nres[b], T, tokens + (size_t)b * K * T, lens + (size_t)b * K, scores + (size_t)b * K);
+  if (n_results) memcpy(n_results, h_nres.get(), (size_t)B * 4);
+  if (flags) memcpy(flags, h_nres.get() + B, (size_t)B * 4);
   return CTCDEC_OK;
 }
 

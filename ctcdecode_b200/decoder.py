@@ -12,7 +12,9 @@ Differences from the reference, all additive:
   * ``num_processes`` is accepted and ignored: the batch is a CUDA grid (one CTA per utterance).
   * ``decoder.last_flags`` / ``decoder.last_n_results`` expose the per-utterance tie flags and beam counts
     of the last call (the reference has no equivalent; see include/ctcdecode_b200.h).
-  * the KenLM scorer (``model_path``) is not built yet -- constructing a decoder with one raises.
+  * ``model_path`` (word-based KenLM models): the language model stays on the host behind a hook; the real Scorer
+    comes from a provider library (``scorer_provider=`` / CTCDECODE_B200_SCORER_PROVIDER, see scorer.py and
+    INTEGRATION.md).  Character-based models and the online decoder with a scorer are not built.
 """
 import ctypes
 
@@ -28,7 +30,7 @@ def _cfg(decoder):
 
 class _Base(object):
     def _init_common(self, labels, model_path, alpha, beta, cutoff_top_n, cutoff_prob, beam_width, num_processes,
-                     blank_id, log_probs_input, device):
+                     blank_id, log_probs_input, device, scorer_provider=None, allow_scorer=True):
         self._beam_width = int(beam_width)
         self._scorer = None
         self._num_processes = num_processes
@@ -40,11 +42,12 @@ class _Base(object):
         self._device = device
         self.last_flags = None
         self.last_n_results = None
-        if model_path:
-            raise NotImplementedError(
-                "ctcdecode_b200: the KenLM scorer hook (model_path=...) is not built in this round; "
-                "only the no-LM beam search path is available (there is no CPU fallback)")
         _native.load()
+        if model_path:
+            if not allow_scorer:
+                raise NotImplementedError("ctcdecode_b200: the online decoder with a scorer is not built")
+            from .scorer import ProviderScorer
+            self._scorer = ProviderScorer(self._labels, model_path, alpha, beta, scorer_provider)
 
     def _device_index(self, probs=None):
         if probs is not None and probs.is_cuda:
@@ -54,25 +57,26 @@ class _Base(object):
         return 0
 
     def character_based(self):
-        return None
+        return self._scorer.is_character_based() if self._scorer else None
 
     def max_order(self):
-        return None
+        return self._scorer.max_order() if self._scorer else None
 
     def dict_size(self):
-        return None
+        return self._scorer.dict_size() if self._scorer else None
 
 
 class CTCBeamDecoder(_Base):
     """Drop-in for the reference CTCBeamDecoder (reference ctcdecode/__init__.py:6-140)."""
 
     def __init__(self, labels, model_path=None, alpha=0, beta=0, cutoff_top_n=40, cutoff_prob=1.0, beam_width=100,
-                 num_processes=4, blank_id=0, log_probs_input=False, device=None, device_outputs=False):
+                 num_processes=4, blank_id=0, log_probs_input=False, device=None, device_outputs=False,
+                 scorer_provider=None):
         self.cutoff_top_n = cutoff_top_n  # public attribute name kept from the reference (:39)
         self._device_outputs = device_outputs
         self._ws = None
         self._init_common(labels, model_path, alpha, beta, cutoff_top_n, cutoff_prob, beam_width, num_processes,
-                          blank_id, log_probs_input, device)
+                          blank_id, log_probs_input, device, scorer_provider)
 
     def _cutoff_top_n_value(self):
         return int(self.cutoff_top_n)
@@ -90,9 +94,10 @@ class CTCBeamDecoder(_Base):
             raise ValueError("probs has %d labels, decoder was built with %d" % (V, self._num_labels))
         cfg = _cfg(self)
         K = self._beam_width
-        if probs.is_cuda:
+        if probs.is_cuda and self._scorer is None:
             return self._decode_device(lib, cfg, probs, seq_lens, B, T, K)
-        probs = probs.float().contiguous()
+        dev_index = self._device_index(probs)
+        probs = probs.cpu().float().contiguous()
         if seq_lens is not None:
             seq_lens = seq_lens.cpu().int().contiguous()
         output = torch.empty(B, K, T, dtype=torch.int32)
@@ -101,10 +106,16 @@ class CTCBeamDecoder(_Base):
         out_seq_len = torch.zeros(B, K, dtype=torch.int32)
         n_results = torch.zeros(B, dtype=torch.int32)
         flags = torch.zeros(B, dtype=torch.int32)
-        _native.check(lib.ctcdec_decode_batch_host(
-            ctypes.byref(cfg), probs.data_ptr(), seq_lens.data_ptr() if seq_lens is not None else None, B, T,
-            output.data_ptr(), timesteps.data_ptr(), scores.data_ptr(), out_seq_len.data_ptr(),
-            n_results.data_ptr(), flags.data_ptr(), self._device_index()))
+        if self._scorer is not None:  # reference __init__.py:87-104 paddle_beam_decode_lm
+            _native.check(lib.ctcdec_decode_batch_lm_host(
+                ctypes.byref(cfg), self._scorer.handle, probs.data_ptr(),
+                seq_lens.data_ptr() if seq_lens is not None else None, B, T, output.data_ptr(), timesteps.data_ptr(),
+                scores.data_ptr(), out_seq_len.data_ptr(), n_results.data_ptr(), flags.data_ptr(), dev_index))
+        else:
+            _native.check(lib.ctcdec_decode_batch_host(
+                ctypes.byref(cfg), probs.data_ptr(), seq_lens.data_ptr() if seq_lens is not None else None, B, T,
+                output.data_ptr(), timesteps.data_ptr(), scores.data_ptr(), out_seq_len.data_ptr(),
+                n_results.data_ptr(), flags.data_ptr(), dev_index))
         self.last_flags, self.last_n_results = flags, n_results
         return output, scores, timesteps, out_seq_len
 
@@ -145,7 +156,8 @@ class CTCBeamDecoder(_Base):
         return out_cpu, scores.cpu(), ts_cpu, lens_cpu
 
     def reset_params(self, alpha, beta):
-        pass  # no scorer attached (reference __init__.py:134-136 is a no-op without one)
+        if self._scorer is not None:  # reference __init__.py:134-136
+            self._scorer.reset_params(alpha, beta)
 
 
 class OnlineCTCBeamDecoder(_Base):
@@ -156,7 +168,7 @@ class OnlineCTCBeamDecoder(_Base):
                  num_processes=4, blank_id=0, log_probs_input=False, device=None):
         self._cutoff_top_n = cutoff_top_n  # private name kept from the reference (:175)
         self._init_common(labels, model_path, alpha, beta, cutoff_top_n, cutoff_prob, beam_width, num_processes,
-                          blank_id, log_probs_input, device)
+                          blank_id, log_probs_input, device, allow_scorer=False)
 
     def _cutoff_top_n_value(self):
         return int(self._cutoff_top_n)

@@ -25,3 +25,26 @@ def flat_probs(B, T, V, seed=0, temp=3.0):
     """iid softmax(temp * randn): flat, tie-prone inputs (Appendix D) for stress tests."""
     g = torch.Generator().manual_seed(seed)
     return torch.softmax(temp * torch.randn(B, T, V, generator=g), dim=-1).contiguous()
+
+
+def text_probs(texts, labels, T, seed=0, peak=7.0, blank_id=0, stretch=3):
+    """Posteriors that (noisily) spell `texts` (one string per utterance) over `labels`: every character is held for
+    about `stretch` frames and followed by blanks, with randn noise on all logits.  For the scorer-path tests and
+    the config-5 style benchmark.  Returns float32 [len(texts), T, len(labels)] probabilities on the CPU."""
+    g = torch.Generator().manual_seed(seed)
+    V = len(labels)
+    idx = {c: i for i, c in enumerate(labels)}
+    B = len(texts)
+    tgt = torch.full((B, T), blank_id, dtype=torch.long)
+    for b, text in enumerate(texts):
+        t = int(torch.randint(0, stretch + 1, (1,), generator=g))
+        for ch in text:
+            hold = 1 + int(torch.randint(0, stretch, (1,), generator=g))
+            for _ in range(hold):
+                if t < T:
+                    tgt[b, t] = idx[ch]
+                    t += 1
+            t += 1 + int(torch.randint(0, stretch, (1,), generator=g))  # blanks in between
+    logits = torch.randn(B, T, V, generator=g)
+    logits.scatter_add_(2, tgt.unsqueeze(-1), torch.full((B, T, 1), float(peak)))
+    return torch.softmax(logits, dim=-1).contiguous()

@@ -47,7 +47,34 @@ def emit(name, probs, seq_lens=None, **kw):
     print(name, probs.shape, "n_results", r["n_results"][:4], "top score", r["scores"][:, 0][:4])
 
 
+L29 = ["_"] + [chr(ord("a") + i) for i in range(26)] + [" ", "'"]
+TINY_LM = os.path.join(ROOT, "tests", "data", "tiny_lm.arpa")
+
+
+def emit_lm(name, probs, alpha, beta, seq_lens=None, **kw):
+    """Scorer path of the reference (KenLM + dictionary) on tests/data/tiny_lm.arpa (authored for this repo)."""
+    probs = np.ascontiguousarray(probs, dtype=np.float32)
+    ref = Reference(L29, model_path=TINY_LM, alpha=alpha, beta=beta)
+    r = ref.decode(probs, seq_lens, num_processes=4, **kw)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), probs=probs,
+                        seq_lens=np.zeros(0, np.int32) if seq_lens is None else np.asarray(seq_lens, np.int32),
+                        params=np.array([kw.get("beam", 100), kw.get("cutoff_top_n", 40), kw.get("blank_id", 0),
+                                         int(kw.get("log_input", False))], np.int64),
+                        cutoff_prob=np.array([kw.get("cutoff_prob", 1.0)], np.float64),
+                        lm=np.array([alpha, beta], np.float64), **r)
+    top = ["".join(L29[x] for x in r["tokens"][b, 0, :r["lens"][b, 0]]) for b in range(probs.shape[0])]
+    print(name, probs.shape, "n_results", r["n_results"][:4], "top-1", top[:3])
+
+
 if __name__ == "__main__":
+    from ctcdecode_b200.synth import text_probs
+    texts = ["the cat sat on the mat", "a dog ran fast", "the dog sat on a mat the cat ran"]
+    emit_lm("lm_tiny_a15_b08_beam32", text_probs(texts, L29, 160, seed=1).numpy(), 1.5, 0.8, beam=32)
+    emit_lm("lm_tiny_a0_b0_beam20", text_probs(texts[:2], L29, 120, seed=2).numpy(), 0.0, 0.0, beam=20)
+    emit_lm("lm_tiny_a2_bm1_beam8_ragged", text_probs(texts, L29, 140, seed=3).numpy(), 2.0, -1.0,
+            seq_lens=[140, 60, 0], beam=8)
+    emit_lm("lm_tiny_noise_beam64", ctc_like_probs(2, 150, 29, seed=4).numpy(), 1.0, 0.5, beam=64)
+
     kat = np.array([PROBS_SEQ1, PROBS_SEQ2], np.float32)
     emit("ref_kat_beam20", kat, beam=20, blank_id=6)
     emit("ref_kat_beam20_log", np.log(kat), beam=20, blank_id=6, log_input=True)

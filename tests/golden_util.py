@@ -7,8 +7,16 @@ import numpy as np
 HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-def names():
-    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(HERE, "*.npz")))
+def names(lm=False):
+    """Fixture names; the scorer-path fixtures (lm_*) are listed separately."""
+    allf = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(HERE, "*.npz")))
+    return [n for n in allf if n.startswith("lm_") == lm]
+
+
+def load_lm(name):
+    z = np.load(os.path.join(HERE, name + ".npz"))
+    probs, seq_lens, kw, ref = load(name)
+    return probs, seq_lens, kw, ref, float(z["lm"][0]), float(z["lm"][1])
 
 
 def load(name):

@@ -75,7 +75,29 @@ def test_product_never_imports_the_oracle():
                 assert "emulate_cta" not in text or f.endswith((".cuh",)), f
 
 
-def test_lm_path_says_not_built():
+def test_lm_path_needs_a_provider(monkeypatch):
     import ctcdecode_b200
+    monkeypatch.delenv("CTCDECODE_B200_SCORER_PROVIDER", raising=False)
+    with pytest.raises(RuntimeError, match="scorer provider"):
+        ctcdecode_b200.CTCBeamDecoder(list("_abc "), model_path="/nonexistent.arpa")
     with pytest.raises(NotImplementedError):
-        ctcdecode_b200.CTCBeamDecoder(list("_abc"), model_path="/nonexistent.arpa")
+        ctcdecode_b200.OnlineCTCBeamDecoder(list("_abc "), model_path="/nonexistent.arpa")
+
+
+def test_scorer_abi_builds_the_dictionary(lib):
+    """ctcdec_scorer_create without any GPU: dictionary size follows reference Scorer::fill_dictionary (words that
+    cannot be spelled with the labels are skipped)."""
+    cond = ctypes.CFUNCTYPE(ctypes.c_double, ctypes.c_void_p, ctypes.POINTER(ctypes.c_int32), ctypes.c_int)(lambda c, l, n: -1.0)
+    hooks = _native.ScorerHooks(None, ctypes.cast(cond, ctypes.c_void_p).value, ctypes.cast(cond, ctypes.c_void_p).value)
+    labels = ["_", "a", "b", " "]
+    words = ["<unk>", "<s>", "</s>", "ab", "ba", "abc", "a"]
+    lab = (ctypes.c_char_p * 4)(*[x.encode() for x in labels])
+    wrd = (ctypes.c_char_p * len(words))(*[x.encode() for x in words])
+    h = ctypes.c_void_p()
+    assert lib.ctcdec_scorer_create(ctypes.byref(hooks), 1.0, 0.5, lab, 4, wrd, len(words), 3, 0, ctypes.byref(h)) == 0
+    assert lib.ctcdec_scorer_dict_size(h) == 3 and lib.ctcdec_scorer_max_order(h) == 3
+    assert lib.ctcdec_scorer_is_character_based(h) == 0
+    assert lib.ctcdec_scorer_destroy(h) == 0
+    assert lib.ctcdec_scorer_create(ctypes.byref(hooks), 1.0, 0.5, lab, 4, wrd, len(words), 3, 1, ctypes.byref(h)) == -2
+    nospace = (ctypes.c_char_p * 3)(b"_", b"a", b"b")
+    assert lib.ctcdec_scorer_create(ctypes.byref(hooks), 1.0, 0.5, nospace, 3, wrd, len(words), 3, 0, ctypes.byref(h)) == -2

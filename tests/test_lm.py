@@ -1,0 +1,153 @@
+"""Scorer path (word-based KenLM model + dictionary; BASELINE config 5, reference tests/test_decode.py:55-64).
+
+The language model stays behind the host hook: in these tests the hook is the UNMODIFIED reference Scorer
+(oracle/_ref/libctcref.so, test infrastructure) so the LM arithmetic is the reference's own, and everything the
+product adds -- dictionary automaton, cutoff, LM-term application, per-node memoisation, final rescoring -- is
+compared with the reference's results: tokens, timesteps, lens bit-exact, float32 scores bit-exact."""
+import os
+
+import numpy as np
+import pytest
+
+from ctcdecode_b200.synth import ctc_like_probs, flat_probs, text_probs
+from oracle import oracle as orc
+from tests import emul, golden_util
+from tests.parity import compare
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TINY = os.path.join(ROOT, "tests", "data", "tiny_lm.arpa")
+REF_ARPA = "/root/reference/tests/test.arpa"
+L29 = ["_"] + [chr(ord("a") + i) for i in range(26)] + [" ", "'"]
+TEXTS = ["the cat sat on the mat", "a dog ran fast", "the dog sat on a mat the cat ran"]
+PROVIDER = os.path.join(ROOT, "oracle", "_ref", "libctcref.so")
+
+needs_ref = pytest.mark.skipif(not orc.reference_available(), reason="oracle/_ref not built (needs /root/reference)")
+
+
+def _emul_lm(ref, probs, labels, alpha, beta, seq_lens=None, **kw):
+    return emul.decode_lm(probs, ref.lib, ref.scorer, labels, ref.lm_vocabulary(), ref.max_order(), alpha, beta,
+                          seq_lens=seq_lens, **kw)
+
+
+@needs_ref
+@pytest.mark.parametrize("name", golden_util.names(lm=True))
+def test_emulation_lm_matches_reference_golden(name):
+    probs, seq_lens, kw, gold, alpha, beta = golden_util.load_lm(name)
+    ref = orc.Reference(L29, model_path=TINY, alpha=alpha, beta=beta)
+    got = _emul_lm(ref, probs, L29, alpha, beta, seq_lens=seq_lens, **kw)
+    compare(gold, got, None, name)
+    live = ref.decode(probs, seq_lens, num_processes=2, **kw)   # and the fixture still is what the reference says
+    compare(gold, live, None, name + " (live reference)")
+
+
+@needs_ref
+@pytest.mark.parametrize("cfg", [
+    dict(alpha=1.5, beta=0.8, beam=32, T=160, seed=11),
+    dict(alpha=0.0, beta=0.0, beam=20, T=100, seed=12),
+    dict(alpha=0.5, beta=-0.5, beam=48, T=200, seed=13),
+    dict(alpha=2.0, beta=1.0, beam=16, T=120, seed=14, cutoff_prob=0.99),
+    dict(alpha=2.0, beta=1.0, beam=16, T=120, seed=15, log_input=True),
+    dict(alpha=1.0, beta=2.0, beam=4, T=150, seed=16),
+    dict(alpha=1.0, beta=0.5, beam=64, T=100, seed=17, noise=True),
+    dict(alpha=1.0, beta=0.5, beam=30, T=80, seed=18, flat=True),
+])
+def test_emulation_lm_matches_reference(cfg):
+    cfg = dict(cfg)
+    alpha, beta, T, seed = cfg.pop("alpha"), cfg.pop("beta"), cfg.pop("T"), cfg.pop("seed")
+    if cfg.pop("noise", False):
+        probs = ctc_like_probs(3, T, 29, seed=seed)
+    elif cfg.pop("flat", False):
+        probs = flat_probs(3, T, 29, seed=seed)
+    else:
+        probs = text_probs(TEXTS, L29, T, seed=seed)
+    if cfg.get("log_input"):
+        probs = probs.log()
+    ref = orc.Reference(L29, model_path=TINY, alpha=alpha, beta=beta)
+    want = ref.decode(probs.numpy(), num_processes=2, **cfg)
+    got = _emul_lm(ref, probs.numpy(), L29, alpha, beta, **cfg)
+    compare(want, got, None, str(cfg))
+
+
+@needs_ref
+@pytest.mark.skipif(not os.path.exists(REF_ARPA), reason="reference test LM not present")
+def test_emulation_lm_reference_unit_test_and_config5_shape():
+    """reference tests/test_decode.py:55-64 ("a a", 7 results) and a BASELINE config-5 shaped batch (test.arpa,
+    alpha 2.0, beta 1.0, beam 100) -- with the reference's own LM file, which exists only in the build container."""
+    vocab = ["'", " ", "a", "b", "c", "d", "_"]
+    kat, _, _, _ = golden_util.load("ref_kat_beam20")
+    ref = orc.Reference(vocab, model_path=REF_ARPA, alpha=0.0, beta=0.0)
+    want = ref.decode(kat, beam=20, blank_id=6, num_processes=2)
+    got = _emul_lm(ref, kat, vocab, 0.0, 0.0, beam=20, blank_id=6)
+    compare(want, got, None, "test_beam_search_decoder_3")
+    assert got["n_results"][1] == 7
+    assert "".join(vocab[x] for x in got["tokens"][1, 0, :got["lens"][1, 0]]) == "a a"
+    ref = orc.Reference(L29, model_path=REF_ARPA, alpha=2.0, beta=1.0)
+    probs = ctc_like_probs(2, 300, 29, seed=5).numpy()
+    want = ref.decode(probs, beam=100, num_processes=2)
+    got = _emul_lm(ref, probs, L29, 2.0, 1.0, beam=100)
+    compare(want, got, None, "config 5 shape")
+
+
+@needs_ref
+def test_scorer_accessors_match_reference():
+    ref = orc.Reference(L29, model_path=TINY, alpha=1.0, beta=1.0)
+    assert ref.dict_size() == 9 and ref.max_order() == 3 and ref.is_character_based() == 0
+    import ctypes
+    from ctcdecode_b200 import _native
+    lib = _native.load()
+    words = ref.lm_vocabulary()
+    cond = ctypes.cast(ref.lib.ref_scorer_cond_from_labels, ctypes.c_void_p).value
+    sent = ctypes.cast(ref.lib.ref_scorer_sent_from_labels, ctypes.c_void_p).value
+    hooks = _native.ScorerHooks(ref.scorer, cond, sent)
+    lab = (ctypes.c_char_p * 29)(*[x.encode() for x in L29])
+    wrd = (ctypes.c_char_p * len(words))(*[x.encode() for x in words])
+    h = ctypes.c_void_p()
+    assert lib.ctcdec_scorer_create(ctypes.byref(hooks), 1.0, 1.0, lab, 29, wrd, len(words), ref.max_order(), 0,
+                                    ctypes.byref(h)) == 0
+    assert lib.ctcdec_scorer_dict_size(h) == ref.dict_size()   # 9 of the 12 LM words are spellable
+    lib.ctcdec_scorer_destroy(h)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(PROVIDER), reason="scorer provider (oracle/_ref/libctcref.so) not shipped")
+@pytest.mark.parametrize("name", golden_util.names(lm=True))
+def test_cuda_lm_matches_reference_golden(name):
+    import torch
+    import ctcdecode_b200
+    probs, seq_lens, kw, gold, alpha, beta = golden_util.load_lm(name)
+    dec = ctcdecode_b200.CTCBeamDecoder(L29, model_path=TINY, alpha=alpha, beta=beta, beam_width=kw["beam"],
+                                        cutoff_top_n=kw["cutoff_top_n"], cutoff_prob=kw["cutoff_prob"],
+                                        log_probs_input=kw["log_input"], scorer_provider=PROVIDER)
+    assert dec.dict_size() == 9 and dec.max_order() == 3 and dec.character_based() == 0
+    sl = None if seq_lens is None else torch.from_numpy(seq_lens)
+    out, scores, ts, lens = dec.decode(torch.from_numpy(probs), sl)
+    got = dict(tokens=out.numpy(), timesteps=ts.numpy(), scores=scores.numpy(), lens=lens.numpy(),
+               n_results=dec.last_n_results.numpy(), ties=dec.last_flags.numpy())
+    compare(gold, got, None, name)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(PROVIDER), reason="scorer provider (oracle/_ref/libctcref.so) not shipped")
+def test_cuda_lm_matches_live_reference_and_reset_params():
+    """BASELINE config-5 shape on the tiny LM: 8 utterances x T=400, beam 100, alpha 2.0, beta 1.0, against the
+    reference Scorer path run on the same box; then reset_params (reference __init__.py:134-136)."""
+    import torch
+    import ctcdecode_b200
+    probs = text_probs(TEXTS * 2 + TEXTS[:2], L29, 400, seed=21)
+    ref = orc.Reference(L29, model_path=TINY, alpha=2.0, beta=1.0)
+    want = ref.decode(probs.numpy(), beam=100)
+    dec = ctcdecode_b200.CTCBeamDecoder(L29, model_path=TINY, alpha=2.0, beta=1.0, beam_width=100,
+                                        scorer_provider=PROVIDER)
+    out, scores, ts, lens = dec.decode(probs)
+    got = dict(tokens=out.numpy(), timesteps=ts.numpy(), scores=scores.numpy(), lens=lens.numpy(),
+               n_results=dec.last_n_results.numpy(), ties=dec.last_flags.numpy())
+    compare(want, got, None, "config-5 shape")
+    assert "".join(L29[x] for x in out[0, 0, :lens[0, 0]]) == TEXTS[0]
+    dec.reset_params(0.5, -0.25)
+    ref.lib.ref_scorer_reset_params(ref.scorer, 0.5, -0.25)
+    want = ref.decode(probs.numpy(), beam=100)
+    out, scores, ts, lens = dec.decode(probs.cuda())
+    got = dict(tokens=out.numpy(), timesteps=ts.numpy(), scores=scores.numpy(), lens=lens.numpy(),
+               n_results=dec.last_n_results.numpy(), ties=dec.last_flags.numpy())
+    compare(want, got, None, "after reset_params")
