@@ -40,7 +40,31 @@ CONFIGS = {
                name="config2: [256 x T=1000 x V=29] per GPU, beam 100, cutoff_top_n 40, cutoff_prob 1.0, no LM"),
     "c4": dict(B=256, T=2000, V=256, beam=200, cutoff_top_n=40, cutoff_prob=0.99,
                name="config4: [256 x T=2000 x V=256] per GPU, beam 200, cutoff_top_n 40, cutoff_prob 0.99, no LM"),
+    # BASELINE config 5: KenLM scorer path.  The reference's tests/test.arpa is not on the GPU box, so the model is
+    # tests/data/tiny_lm.arpa (authored for this repo) and the posteriors spell sentences over its vocabulary.
+    "c5": dict(B=64, T=1000, V=29, beam=100, cutoff_top_n=40, cutoff_prob=1.0, lm=True, alpha=2.0, beta=1.0,
+               name="config5: [64 x T=1000 x V=29], beam 100, KenLM scorer hook (tests/data/tiny_lm.arpa, alpha 2.0, beta 1.0)"),
 }
+L29 = ["_"] + [chr(ord("a") + i) for i in range(26)] + [" ", "'"]
+TINY_LM = os.path.join(ROOT, "tests", "data", "tiny_lm.arpa")
+PROVIDER = os.path.join(ROOT, "oracle", "_ref", "libctcref.so")
+
+
+def c5_inputs(B, T, seed):
+    """Random sentences over the tiny LM's vocabulary, ~T/5 characters each."""
+    import random
+    from ctcdecode_b200.synth import text_probs
+    rng = random.Random(seed)
+    words = ["the", "a", "cat", "dog", "sat", "ran", "on", "mat", "fast"]
+    texts = []
+    for _ in range(B):
+        s = ""
+        while len(s) < T // 5:
+            s += (" " if s else "") + rng.choice(words)
+        texts.append(s[: T // 4])
+    return text_probs(texts, L29, T, seed=seed)
+
+
 METRIC = "utterances/sec at beam_width=100, T=1000, V=29; HBM GB/s vs roofline"
 
 
@@ -92,10 +116,21 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+_REF_CACHE = {}
+
+
 def reference_cpu(probs_np, cfg, n_utts, threads):
     """Times the reference's CPU path on the first n_utts utterances.  Returns (seconds, kind)."""
     from oracle import oracle as orc
     sample = probs_np[:n_utts]
+    if cfg.get("lm"):
+        if "lm" not in _REF_CACHE:
+            _REF_CACHE["lm"] = orc.Reference(L29, model_path=TINY_LM, alpha=cfg["alpha"], beta=cfg["beta"])
+        ref = _REF_CACHE["lm"]
+        t0 = time.perf_counter()
+        ref.decode(sample, beam=cfg["beam"], cutoff_prob=cfg["cutoff_prob"], cutoff_top_n=cfg["cutoff_top_n"],
+                   num_processes=threads)
+        return time.perf_counter() - t0, "reference"
     if orc.reference_available():
         ref = orc.Reference([str(i) for i in range(cfg["V"])])
         t0 = time.perf_counter()
@@ -106,6 +141,47 @@ def reference_cpu(probs_np, cfg, n_utts, threads):
     t0 = time.perf_counter()
     cp.decode(sample, beam=cfg["beam"], cutoff_prob=cfg["cutoff_prob"], cutoff_top_n=cfg["cutoff_top_n"])
     return time.perf_counter() - t0, "port"
+
+
+def bench_lm(args, cfg, config, rank, world, local_rank, dev, K, W, cores):
+    """Config 5: the scorer path is a host-buffer API (the LM hook lives on the host), so value == e2e."""
+    import torch
+    import torch.distributed as dist
+    from ctcdecode_b200 import CTCBeamDecoder
+    B, T = cfg["B"], cfg["T"]
+    probs = c5_inputs(B, T, rank)
+    dec = CTCBeamDecoder(L29, model_path=TINY_LM, alpha=cfg["alpha"], beta=cfg["beta"], beam_width=cfg["beam"],
+                         cutoff_top_n=cfg["cutoff_top_n"], cutoff_prob=cfg["cutoff_prob"], scorer_provider=PROVIDER,
+                         device="cuda:%d" % local_rank)
+    for _ in range(W):
+        out = dec.decode(probs)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        out = dec.decode(probs)
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    val = B * world * K / float(t[0])
+    top1 = "".join(L29[x] for x in out[0][0, 0, :out[3][0, 0]])
+    line = {"metric": METRIC, "value": val, "unit": "utterances/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": 1e3 * float(t[0]) / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": config,
+            "e2e": {"value": val, "unit": "utterances/s", "h2d_bytes_per_step": B * T * 29 * 4,
+                    "d2h_bytes_per_step": None, "note": "host-buffer API: the LM hook runs on the host between one-frame launches"},
+            "gpu_launches": K * (T + 2), "roofline": None, "sample_top1": top1}
+    if world == 1 and not args.no_cpu_baseline:
+        n = max(1, min(B, cores))
+        dtr, kind = reference_cpu(probs.numpy(), cfg, n, cores)
+        line["cpu_baseline"] = {"value": n / dtr, "unit": "utterances/s", "cores": cores, "kind": kind,
+                                "sample": "the first %d utterances of the same batch, reference Scorer path" % n}
+    print(json.dumps(line))
 
 
 def main():
@@ -135,7 +211,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        probs = ctc_like_probs(B, T, V, seed=0).numpy()
+        probs = (c5_inputs(B, T, 0) if cfg.get("lm") else ctc_like_probs(B, T, V, seed=0)).numpy()
         n = max(1, min(B, cores))  # one utterance per host thread per step
         times, kind = [], "reference"
         for i in range(W + K):
@@ -163,6 +239,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _native.load()
+    if cfg.get("lm"):
+        return bench_lm(args, cfg, config, rank, world, local_rank, dev, K, W, cores)
     probs_cpu = ctc_like_probs(B, T, V, seed=rank)  # every rank its own shard of the global batch
     probs_dev = probs_cpu.to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
