@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
+#include <chrono>
 #include <memory>
 #include <mutex>
 
@@ -726,16 +727,30 @@ int ctcdec_decode_batch_lm_host(const ctcdec_config *cfg, void *scorer, const fl
   std::vector<TrieMirror> mirror(B);
   std::vector<int> scratch;
   memset(h_upd_count, 0, (size_t)B * 4);
+  const bool lm_timing = getenv("CTCDEC_LM_TIMING") != nullptr;
+  double t_gpu = 0.0, t_hook = 0.0;
+  long long n_hook = 0, n_new = 0;
   for (int t = 0; t < std::max(tmax, 1); ++t) {
+    const auto c0 = std::chrono::steady_clock::now();
     CU(cudaMemcpyAsync(d_upd, h_upd, upd_bytes, cudaMemcpyHostToDevice, s));
     bp.t0 = t; bp.nframes = 1; bp.fresh = (t == 0) ? 1 : 0;
     if ((rc = launch_beam(bp, pl1, B, s))) return rc;
     CU(cudaMemcpyAsync(h_newlist, d_newlist, nl_ints * 4, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
-    for (int b = 0; b < B; ++b)
+    const auto c1 = std::chrono::steady_clock::now();
+    for (int b = 0; b < B; ++b) {
       lm_after_frame(*sc, mirror[b], h_newlist + (size_t)b * (1 + 4 * K), &h_upd_count[b],
                      h_upd_nodes + (size_t)b * K, h_upd_vals + (size_t)b * K, scratch);
+      n_hook += h_upd_count[b];
+      n_new += h_newlist[(size_t)b * (1 + 4 * K)];
+    }
+    const auto c2 = std::chrono::steady_clock::now();
+    t_gpu += std::chrono::duration<double>(c1 - c0).count();
+    t_hook += std::chrono::duration<double>(c2 - c1).count();
   }
+  if (lm_timing)
+    fprintf(stderr, "[ctcdec lm] frames %d: launch+copy+sync %.1f ms, host mirror+hooks %.1f ms (%lld hook calls, %lld new nodes)\n",
+            tmax, t_gpu * 1e3, t_hook * 1e3, n_hook, n_new);
   if ((rc = launch_finalize(bp, B, s))) return rc;
   std::unique_ptr<int[]> h_nres(new int[(size_t)B * 2]);
   CU(cudaMemcpyAsync(scores, d_scores, n_bk * 4, cudaMemcpyDeviceToHost, s));
@@ -751,8 +766,7 @@ int ctcdec_decode_batch_lm_host(const ctcdec_config *cfg, void *scorer, const fl
     CU(cudaMemcpy2DAsync(timesteps, (size_t)T * 4, d_ts, (size_t)T * 4, (size_t)max_len * 4, n_bk, cudaMemcpyDeviceToHost, s));
   }
   CU(cudaStreamSynchronize(s));
-  for (int b = 0; b < B; ++b)  // reported scores: LM-corrected approx_ctc (reference :194-208)
-    lm_rescore(*sc, h_nres[b], T, tokens + (size_t)b * K * T, lens + (size_t)b * K, scores + (size_t)b * K);
+  lm_rescore_batch(*sc, B, K, T, h_nres.get(), tokens, lens, scores);  // reported scores: approx_ctc (reference :194-208)
   if (n_results) memcpy(n_results, h_nres.get(), (size_t)B * 4);
   if (flags) memcpy(flags, h_nres.get() + B, (size_t)B * 4);
   return CTCDEC_OK;

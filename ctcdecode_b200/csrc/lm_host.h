@@ -18,6 +18,7 @@
 #include <cstdint>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -86,6 +87,9 @@ static inline Dictionary build_dictionary(const std::vector<std::string> &labels
 }
 
 struct HostScorer {
+  // cond_log_prob depends only on the last max_order words of the prefix, and beams share word histories: cache it
+  // keyed by that tail of the label sequence (the hook is pure, so the values are the hook's own)
+  std::unordered_map<std::string, double> cond_cache;
   ctcdec_scorer_hooks hooks;
   double alpha, beta;
   int max_order, is_character_based, space_id;
@@ -105,16 +109,41 @@ struct TrieMirror {
     parent[nid] = par;
     chr[nid] = ch;
   }
-  void labels_of(int nid, std::vector<int> &out) const {
+  // The labels of node nid's prefix from just after the max_words-th space from the end (walking up, every space
+  // ends a word): exactly the part Scorer::make_ngram looks at (scorer.cpp:163-194); the whole prefix if it has
+  // fewer words.
+  void tail_labels_of(int nid, int space_id, int max_words, std::vector<int> &out) const {
     out.clear();
-    for (int q = nid; q > 0; q = parent[q]) out.push_back(chr[q]);
+    int words = 0;
+    for (int q = nid; q > 0; q = parent[q]) {
+      if (chr[q] == space_id && ++words == max_words) break;
+      out.push_back(chr[q]);
+    }
     for (size_t a = 0, b = out.size(); a + 1 < b; ++a, --b) std::swap(out[a], out[b - 1]);
   }
 };
 
+// the same tail of a label array
+static inline int tail_start(const int *labels, int n, int space_id, int max_words) {
+  int words = 0;
+  for (int i = n - 1; i >= 0; --i)
+    if (labels[i] == space_id && ++words == max_words) return i + 1;
+  return 0;
+}
+
+static inline double cached_cond(HostScorer &sc, const int *labels, int n) {
+  std::string key(reinterpret_cast<const char *>(labels), (size_t)n * sizeof(int));
+  auto it = sc.cond_cache.find(key);
+  if (it != sc.cond_cache.end()) return it->second;
+  const double v = sc.hooks.cond_log_prob(sc.hooks.ctx, labels, n);
+  if (sc.cond_cache.size() > (1u << 22)) sc.cond_cache.clear();
+  sc.cond_cache.emplace(std::move(key), v);
+  return v;
+}
+
 // After a frame: register the created nodes and compute the LM term of those a space can follow.
 // newlist: [1 + 4K] ints of one utterance (count, then node / parent / chr / needs_lm); outputs the update list.
-static inline void lm_after_frame(const HostScorer &sc, TrieMirror &mirror, const int *newlist, int *upd_count,
+static inline void lm_after_frame(HostScorer &sc, TrieMirror &mirror, const int *newlist, int *upd_count,
                                   int *upd_nodes, float *upd_vals, std::vector<int> &scratch) {
   const int cnt = newlist[0];
   int nu = 0;
@@ -123,8 +152,8 @@ static inline void lm_after_frame(const HostScorer &sc, TrieMirror &mirror, cons
     if (e[0] < 0) continue;  // a revived node: already known
     mirror.add(e[0], e[1], e[2]);
     if (e[3]) {
-      mirror.labels_of(e[0], scratch);
-      const double cond = sc.hooks.cond_log_prob(sc.hooks.ctx, scratch.data(), (int)scratch.size());
+      mirror.tail_labels_of(e[0], sc.space_id, sc.max_order, scratch);
+      const double cond = cached_cond(sc, scratch.data(), (int)scratch.size());
       upd_nodes[nu] = e[0];
       upd_vals[nu] = (float)(cond * sc.alpha);  // reference :133 `score = get_log_cond_prob(ngram) * alpha` (float)
       ++nu;
@@ -136,15 +165,17 @@ static inline void lm_after_frame(const HostScorer &sc, TrieMirror &mirror, cons
 // DecoderState::decode with a word-based scorer (reference ctc_beam_search_decoder.cpp:164-211): the order of the
 // results is by the raw prefix score (decoder_utils.cpp:59), the reported score is the LM-corrected approx_ctc.
 // tokens / lens / scores are one utterance's rows as written by the finalize kernel (scores = -raw score).
+// cond_rows[p] must hold cond_log_prob of row p's prefix when the row does not end in a space (computed by the
+// caller through the cache, single-threaded); the sentence hook is called here, so this function may run on
+// several threads over disjoint utterances.
 static inline void lm_rescore(const HostScorer &sc, int n_results, int row_stride, const int *tokens, const int *lens,
-                              float *scores) {
-  std::vector<int> lab;
+                              const double *cond_rows, float *scores) {
   for (int p = 0; p < n_results; ++p) {
     const int len = lens[p];
     const int *tok = tokens + (size_t)p * row_stride;
     float ext = -scores[p];  // scores[prefix] = prefix->score
     if (len > 0 && tok[len - 1] != sc.space_id) {  // :173-185 score the last (unfinished) word
-      float s = (float)(sc.hooks.cond_log_prob(sc.hooks.ctx, tok, len) * sc.alpha);
+      float s = (float)(cond_rows[p] * sc.alpha);
       s = (float)((double)s + sc.beta);
       ext = ext + s;
     }
@@ -154,6 +185,36 @@ static inline void lm_rescore(const HostScorer &sc, int n_results, int row_strid
     const float approx_f = (float)approx;
     scores[p] = (float)(-(double)approx_f);  // decoder_utils.cpp:68, binding.cpp:91
   }
+}
+
+}  // namespace ctc
+
+namespace ctc {
+
+// Result read-out for a whole batch: last-word terms through the cache, sentence terms on a few host threads.
+static inline void lm_rescore_batch(HostScorer &sc, int B, int K, int T, const int *n_results, const int *tokens,
+                                    const int *lens, float *scores) {
+  std::vector<double> cond((size_t)B * K, 0.0);
+  for (int b = 0; b < B; ++b)
+    for (int p = 0; p < n_results[b] && p < K; ++p) {
+      const int len = lens[(size_t)b * K + p];
+      const int *tok = tokens + ((size_t)b * K + p) * T;
+      if (len > 0 && tok[len - 1] != sc.space_id) {
+        const int st = tail_start(tok, len, sc.space_id, sc.max_order);
+        cond[(size_t)b * K + p] = cached_cond(sc, tok + st, len - st);
+      }
+    }
+  unsigned nt = std::thread::hardware_concurrency();
+  nt = nt == 0 ? 1 : (nt > 16 ? 16 : nt);
+  if ((unsigned)B < nt) nt = (unsigned)B;
+  std::vector<std::thread> pool;
+  for (unsigned w = 0; w < nt; ++w)
+    pool.emplace_back([&, w]() {
+      for (int b = (int)w; b < B; b += (int)nt)
+        lm_rescore(sc, n_results[b] < K ? n_results[b] : K, T, tokens + (size_t)b * K * T, lens + (size_t)b * K,
+                   cond.data() + (size_t)b * K, scores + (size_t)b * K);
+    });
+  for (auto &th : pool) th.join();
 }
 
 }  // namespace ctc

@@ -20,7 +20,7 @@ def build():
     if os.path.exists(_OUT) and all(os.path.getmtime(_OUT) >= os.path.getmtime(d) for d in deps):
         return _OUT
     subprocess.run(["g++", "-O2", "-std=c++17", "-mfma", "-ffp-contract=off", "-fPIC", "-shared", "-nostdlib++",
-                    "-Wno-unused-function", _SRC, "-o", _OUT, "-l:libstdc++.so.6", "-lm"], check=True)
+                    "-Wno-unused-function", "-pthread", _SRC, "-o", _OUT, "-l:libstdc++.so.6", "-lm"], check=True)
     return _OUT
 
 

@@ -242,10 +242,8 @@ int emu_decode_batch_lm(const float *probs, const int *seq_lens, int B, int T, i
                      upd_nodes.data() + (size_t)b * K, upd_vals.data() + (size_t)b * K, scratch);
   }
   std::vector<unsigned char> fsmem((size_t)K * 12 + 64);
-  for (int b = 0; b < B; ++b) {
-    finalize_cta_run<128>(bp, b, fsmem.data());
-    lm_rescore(sc, n_results[b], T, tokens + (size_t)b * K * T, lens + (size_t)b * K, scores + (size_t)b * K);
-  }
+  for (int b = 0; b < B; ++b) finalize_cta_run<128>(bp, b, fsmem.data());
+  lm_rescore_batch(sc, B, K, T, n_results, tokens, lens, scores);
   return 0;
 }
 
