@@ -716,8 +716,12 @@ int ctcdec_decode_batch_lm_host(const ctcdec_config *cfg, void *scorer, const fl
   bp.force_fallback = getenv("CTCDEC_FORCE_FALLBACK") ? 1 : 0;
   bp.dict_next = sc->d_next; bp.dict_final = sc->d_final; bp.dict_start = sc->dict.start;
   bp.space_id = sc->space_id; bp.beta = sc->beta; bp.lm_arena = d_lm_arena; bp.dstate_arena = d_dstate;
-  bp.newlist = d_newlist; bp.lm_update_count = d_upd_count; bp.lm_update_nodes = d_upd_nodes;
-  bp.lm_update_vals = d_upd_vals;
+  // The per-frame exchange with the host goes through pinned, device-mapped host memory (unified addressing):
+  // the kernel reads the few LM updates and writes the new-node list straight over PCIe, so a frame costs one
+  // launch and one stream synchronisation, no memcpy calls.
+  bp.newlist = h_newlist; bp.lm_update_count = h_upd_count; bp.lm_update_nodes = h_upd_nodes;
+  bp.lm_update_vals = h_upd_vals;
+  (void)d_newlist; (void)d_upd_count; (void)d_upd_nodes; (void)d_upd_vals;
   Plan pl1 = pl;  // one frame per launch: the staged tile is one row
   pl1.F = 1;
   pl1.L = make_layout(K, V, pl.NP, 1, pl.sorted, pl.NT);
@@ -725,6 +729,7 @@ int ctcdec_decode_batch_lm_host(const ctcdec_config *cfg, void *scorer, const fl
   int tmax = 0;
   for (int b = 0; b < B; ++b) tmax = std::max(tmax, std::max(0, std::min(seq_lens ? seq_lens[b] : T, T)));
   std::vector<TrieMirror> mirror(B);
+  for (int b = 0; b < B; ++b) mirror[b].reserve((size_t)1 + (size_t)K * std::max(0, std::min(seq_lens ? seq_lens[b] : T, T)));
   std::vector<int> scratch;
   memset(h_upd_count, 0, (size_t)B * 4);
   const bool lm_timing = getenv("CTCDEC_LM_TIMING") != nullptr;
@@ -732,10 +737,8 @@ int ctcdec_decode_batch_lm_host(const ctcdec_config *cfg, void *scorer, const fl
   long long n_hook = 0, n_new = 0;
   for (int t = 0; t < std::max(tmax, 1); ++t) {
     const auto c0 = std::chrono::steady_clock::now();
-    CU(cudaMemcpyAsync(d_upd, h_upd, upd_bytes, cudaMemcpyHostToDevice, s));
     bp.t0 = t; bp.nframes = 1; bp.fresh = (t == 0) ? 1 : 0;
     if ((rc = launch_beam(bp, pl1, B, s))) return rc;
-    CU(cudaMemcpyAsync(h_newlist, d_newlist, nl_ints * 4, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
     const auto c1 = std::chrono::steady_clock::now();
     for (int b = 0; b < B; ++b) {

@@ -103,9 +103,13 @@ struct HostScorer {
 
 // Per-utterance host mirror of the trie: enough to spell the prefix of any node.
 struct TrieMirror {
-  std::vector<int> parent{-1}, chr{-1};
+  std::vector<int> parent, chr;  // sized for the arena up front: adding a node is two stores
+  void reserve(size_t nodes) {
+    parent.assign(nodes > 0 ? nodes : 1, -1);
+    chr.assign(nodes > 0 ? nodes : 1, -1);
+  }
   void add(int nid, int par, int ch) {
-    if ((int)parent.size() <= nid) { parent.resize(nid + 1, -1); chr.resize(nid + 1, -1); }
+    if ((size_t)nid >= parent.size()) { parent.resize((size_t)nid * 2 + 1, -1); chr.resize((size_t)nid * 2 + 1, -1); }
     parent[nid] = par;
     chr[nid] = ch;
   }

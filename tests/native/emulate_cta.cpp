@@ -225,6 +225,7 @@ int emu_decode_batch_lm(const float *probs, const int *seq_lens, int B, int T, i
   bp.lm_update_vals = upd_vals.data();
 
   std::vector<TrieMirror> mirror(B);
+  for (int b = 0; b < B; ++b) mirror[b].reserve(64);  // small on purpose: exercises the growth path
   std::vector<int> scratch;
   int tmax = 0;
   for (int b = 0; b < B; ++b) tmax = std::max(tmax, std::min(seq_lens ? seq_lens[b] : T, T));
