@@ -146,7 +146,7 @@ struct SmemLayout {
   int tie;                                                           // [2*KP]
   int dnode, dchr, dpslot, dlpc, dts, drev;                          // dead-anchor table [2*KP]
   int cnt2;                                                          // [3*KP] anchor reference counts
-  int amap, slot2q, stash, efree, newp, newa, resq, rvwork;          // re-anchoring scratch
+  int amap, slot2q, stash, efree, rvwork;                            // re-anchoring scratch
   int hist;                                                          // [2][kNBins]
   int clk, cli, wcnt, evcnt;                                         // candidate list segments [NW][seg], per-warp counts
   int ctl;                                                           // control words
@@ -159,15 +159,10 @@ CTC_HD SmemLayout make_layout(int K, int V, int NP, int tile_frames, bool sorted
   const int KP = align_up(K, 32);
   const int W = (NP + 31) / 32;
   const int NW = NT / 32;
-  // candidate-list segment per warp: room for every candidate of the members a warp owns, capped at 64 KB
-  int seg = ((K + NW - 1) / NW) * (NP - kRowTrailer);
-  if (seg > 8192 / NW) seg = 8192 / NW;
-  if (seg < 32) seg = 32;
   int o = 0;
   L.KP = KP;
   L.W = W;
   L.NW = NW;
-  L.seg = seg;
   L.tile_lp = o;   o += 2 * tile_frames * NP * 4;
   L.tile_idx = o;  o += sorted ? 2 * tile_frames * NP * 2 : 0;
   o = align_up(o, 16);
@@ -211,11 +206,21 @@ CTC_HD SmemLayout make_layout(int K, int V, int NP, int tile_frames, bool sorted
   L.slot2q = o;    o += KP * 4;
   L.stash = o;     o += 5 * KP * 4;
   L.efree = o;     o += 2 * KP * 4;
-  L.newp = o;      o += KP * 4;
-  L.newa = o;      o += KP * 4;
-  L.resq = o;      o += KP * 2 * 4;
   L.rvwork = o;    o += KP * 3 * 4;
   L.hist = o;      o += 2 * kNBins * 4;
+  // candidate-list segment per warp: room for every candidate of the members a warp owns, capped at 64 KB in
+  // total -- and at what still lets two CTAs share an SM (2 x (111 KB + 1 KB reserved) <= 227 KB) if that is at least 16 KB: a batch of 256
+  // utterances is 1.73 CTAs per SM, and a segment that overflows only costs that frame the grid-walking fallback
+  int seg = ((K + NW - 1) / NW) * (NP - kRowTrailer);
+  {
+    const int rest = o + 4 * 32 * 4 + (KP / 32) * 4 + 32 * 4 + 16 * 8 + 64;
+    int cap_bytes = 111 * 1024 - rest;
+    if (cap_bytes > 64 * 1024) cap_bytes = 64 * 1024;
+    if (cap_bytes < 16 * 1024) cap_bytes = 64 * 1024;
+    if (seg > cap_bytes / 8 / NW) seg = cap_bytes / 8 / NW;
+  }
+  if (seg < 32) seg = 32;
+  L.seg = seg;
   L.clk = o;       o += NW * seg * 4;
   L.cli = o;       o += NW * seg * 4;
   L.wcnt = o;      o += 4 * 32 * 4;
@@ -297,8 +302,8 @@ struct Cta {
   int *s_dnode, *s_dchr, *s_dpslot, *s_dts, *s_drev, *s_ddstate;
   float *s_dlpc;
   // shared: scratch
-  int *s_evict, *s_sel, *s_sel2, *s_free, *s_free2, *s_newinfo, *s_tie, *s_cnt2, *s_amap, *s_efree, *s_newp, *s_newa,
-      *s_resq, *s_rvwork, *s_hist, *s_ctl, *s_cli, *s_wcnt, *s_evcnt, *s_slot2q, *s_stash;
+  int *s_evict, *s_sel, *s_sel2, *s_free, *s_free2, *s_newinfo, *s_tie, *s_cnt2, *s_amap, *s_efree,
+      *s_rvwork, *s_hist, *s_ctl, *s_cli, *s_wcnt, *s_evcnt, *s_slot2q, *s_stash;
   uint32_t *s_clk;
   int16_t *s_rank;  // [V]
   const uint64_t *s_exptab;

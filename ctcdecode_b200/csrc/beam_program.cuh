@@ -229,8 +229,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
   c.s_dpslot = (int *)(smem + L.dpslot);  c.s_dlpc = (float *)(smem + L.dlpc);
   c.s_dts = (int *)(smem + L.dts);        c.s_drev = (int *)(smem + L.drev);
   c.s_cnt2 = (int *)(smem + L.cnt2);      c.s_amap = (int *)(smem + L.amap);
-  c.s_efree = (int *)(smem + L.efree);    c.s_newp = (int *)(smem + L.newp);
-  c.s_newa = (int *)(smem + L.newa);      c.s_resq = (int *)(smem + L.resq);
+  c.s_efree = (int *)(smem + L.efree);
   c.s_rvwork = (int *)(smem + L.rvwork);  c.s_hist = (int *)(smem + L.hist);
   c.s_rank = (int16_t *)(smem + L.rank);  c.s_ctl = (int *)(smem + L.ctl);
   c.s_clk = (uint32_t *)(smem + L.clk);   c.s_cli = (int *)(smem + L.cli);
