@@ -128,9 +128,17 @@ struct BeamParams {
   float *lm_arena;                  // [B][arena_stride]: per node float(cond_log_prob(make_ngram(node)) * alpha)
   int *dstate_arena;                // [B][arena_stride]: per node dictionary state
   int *newlist;                     // [B][1 + 4K]: count, then (node, parent, chr, needs_lm) per node created
-  const int *lm_update_count;       // [B]: scores the host computed for nodes created by the previous launch
+  const int *lm_update_count;       // [B]: scores the host computed for nodes created by the previous frame
   const int *lm_update_nodes;       // [B][K]
   const float *lm_update_vals;      // [B][K]
+  // persistent scorer mode: ONE launch for the whole utterance; after every frame the CTA publishes its new-node
+  // list in device-mapped host memory, raises hs_done[b] and spins on hs_go[b] until the host has answered.
+  int lm_persistent;
+  int *hs_done;                     // [B] mapped host memory, written by the device: frames finished
+  int *hs_go;                       // [B] mapped host memory, written by the host: frames answered
+  int *hs_abort;                    // [1] mapped host memory: host asks the kernel to stop waiting
+  void (*emu_handshake)(void *ctx, int b);  // CPU emulation only: the host side of the handshake, called in place
+  void *emu_ctx;
 };
 
 // ---- shared memory carve-up (bytes) ---------------------------------------------------------------

@@ -256,7 +256,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
   c.nodes = nodes;
   float *const lm_arena = LM ? p.lm_arena + (long long)b * p.arena_stride : nullptr;
   int *const dstate_arena = LM ? p.dstate_arena + (long long)b * p.arena_stride : nullptr;
-  int *const newlist = LM ? p.newlist + (long long)b * (1 + 4 * K) : nullptr;
+  int *const newlist = LM ? p.newlist + (long long)b * (4 + 4 * K) : nullptr;
   int Tb = p.seq_lens ? p.seq_lens[b] : p.T;  // reference binding.cpp:64-65 clamps to T
   if (Tb > p.T) Tb = p.T;
   const int t0 = p.nframes > 0 ? p.t0 : 0;
@@ -1076,7 +1076,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
           c.s_drev[rev] = 1;
           atom_add(&s_ctl[C_NREV], 1);
           CTC_STAT(g_stats.revived++);
-          if (LM) newlist[1 + 4 * q] = -1;  // the host already knows this node
+          if (LM) newlist[4 + 4 * q] = -1;  // the host already knows this node
         } else {
           nid = atom_add(&s_ctl[C_NNODES], 1);
           CTC_STAT(g_stats.created++);
@@ -1093,9 +1093,11 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
             dst = p.dict_final[nx] ? p.dict_start : nx;
             dstate_arena[nid] = dst;
             lm_arena[nid] = 0.0f;
-            int *nl = newlist + 1 + 4 * q;
-            nl[0] = nid; nl[1] = c.s_node[i]; nl[2] = ch;
-            nl[3] = (c.space_id >= 0 && c.dict_next[(long long)dst * V + c.space_id] >= 0) ? 1 : 0;
+            // one 16-byte store per entry: the list lives in device-mapped host memory
+            Node e;  // (same 16-byte shape as an arena node)
+            e.parent = nid; e.chr = c.s_node[i]; e.lpc = bits_f((uint32_t)ch);
+            e.ts = (c.space_id >= 0 && c.dict_next[(long long)dst * V + c.space_id] >= 0) ? 1 : 0;
+            store_node(reinterpret_cast<Node *>(newlist + 4 + 4 * q), e);
           }
         }
         int *ni = c.s_newinfo + q * 10;
@@ -1321,6 +1323,34 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
     c.s_anch = anch_base + cur * KP;
     nlive = nlive_next;
     M = M_new;
+    if (LM && p.lm_persistent && t + 1 < Tb) {
+      // ---- scorer path, persistent mode: hand the new nodes to the host, wait for their LM terms -----------
+#if defined(CTC_EMULATE)
+      p.emu_handshake(p.emu_ctx, b);
+#else
+      if (threadIdx.x == 0) {
+        __threadfence_system();  // the new-node list (written before the barriers above) before the flag
+        *(volatile int *)&p.hs_done[b] = t0 + t + 1;
+        const long long deadline = clock64() + 20000000000ll;  // ~10 s: never hang the GPU on a dead host
+        while (*(volatile int *)&p.hs_go[b] < t0 + t + 1) {
+          if (*(volatile int *)p.hs_abort || clock64() > deadline) { s_ctl[C_FLAGS] |= FLAG_ERR_ARENA; break; }
+        }
+        __threadfence_system();
+      }
+#endif
+      CTC_BARRIER();
+      CTC_PAR {
+        const int nu = ((volatile const int *)p.lm_update_count)[b];
+        for (int q = tid; q < nu; q += NT)
+          lm_arena[((volatile const int *)p.lm_update_nodes)[(long long)b * K + q]] =
+              ((volatile const float *)p.lm_update_vals)[(long long)b * K + q];
+      }
+      CTC_BARRIER();
+      CTC_PAR {
+        for (int j = tid; j < M; j += NT) c.s_lmsp[j] = ld_cg(&lm_arena[c.s_node[j]]);
+      }
+      CTC_BARRIER();
+    }
     CTC_STAT(g_stats.frames++);
     CTC_STAT(g_stats.tie_frames += tie_m > 0);
     CTC_STAT(g_stats.sel_all_frames += select_all);

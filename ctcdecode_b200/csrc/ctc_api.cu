@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <memory>
 #include <mutex>
@@ -663,7 +664,7 @@ int ctcdec_decode_batch_lm_host(const ctcdec_config *cfg, void *scorer, const fl
     sc->device = device;
   }
   const size_t n_probs = (size_t)B * T * V, n_out = (size_t)B * K * T, n_bk = (size_t)B * K;
-  const size_t nl_ints = (size_t)B * (1 + 4 * K);
+  const size_t nl_ints = (size_t)B * (4 + 4 * K);
   const size_t upd_bytes = al256((size_t)B * 4) + al256(n_bk * 4) + al256(n_bk * 4);
   const size_t lm_bytes = al256((size_t)B * pl.arena_stride * 4) * 2 + al256(nl_ints * 4) + upd_bytes;
   if ((rc = ensure(c, 0, n_probs * 4 + 256))) return rc;
@@ -722,38 +723,109 @@ int ctcdec_decode_batch_lm_host(const ctcdec_config *cfg, void *scorer, const fl
   bp.newlist = h_newlist; bp.lm_update_count = h_upd_count; bp.lm_update_nodes = h_upd_nodes;
   bp.lm_update_vals = h_upd_vals;
   (void)d_newlist; (void)d_upd_count; (void)d_upd_nodes; (void)d_upd_vals;
-  Plan pl1 = pl;  // one frame per launch: the staged tile is one row
-  pl1.F = 1;
-  pl1.L = make_layout(K, V, pl.NP, 1, pl.sorted, pl.NT);
-
+  std::vector<int> need(B);
   int tmax = 0;
-  for (int b = 0; b < B; ++b) tmax = std::max(tmax, std::max(0, std::min(seq_lens ? seq_lens[b] : T, T)));
+  for (int b = 0; b < B; ++b) {
+    need[b] = std::max(0, std::min(seq_lens ? seq_lens[b] : T, T));
+    tmax = std::max(tmax, need[b]);
+  }
   std::vector<TrieMirror> mirror(B);
-  for (int b = 0; b < B; ++b) mirror[b].reserve((size_t)1 + (size_t)K * std::max(0, std::min(seq_lens ? seq_lens[b] : T, T)));
-  std::vector<int> scratch;
+  for (int b = 0; b < B; ++b) mirror[b].reserve((size_t)1 + (size_t)K * need[b]);
   memset(h_upd_count, 0, (size_t)B * 4);
   const bool lm_timing = getenv("CTCDEC_LM_TIMING") != nullptr;
-  double t_gpu = 0.0, t_hook = 0.0;
-  long long n_hook = 0, n_new = 0;
-  for (int t = 0; t < std::max(tmax, 1); ++t) {
+  if (getenv("CTCDEC_LM_PER_FRAME") == nullptr) {
+    // ---- persistent mode (default): ONE launch decodes every utterance start to end.  After each frame a CTA
+    // publishes its new nodes in mapped host memory, raises hs_done[b] and spins on hs_go[b]; host workers (each
+    // owning every nt-th utterance, with its own hook cache) answer with the LM terms.  CTAs never wait on each
+    // other, so the scheme needs no co-residency; a kernel-side deadline and the abort flag bound every wait.
+    if ((rc = ensure_pinned(c, 2, al256((size_t)B * 4) * 2 + 256))) return rc;
+    int *hs_done = (int *)c.pin[2];
+    int *hs_go = (int *)((unsigned char *)c.pin[2] + al256((size_t)B * 4));
+    int *hs_abort = (int *)((unsigned char *)c.pin[2] + 2 * al256((size_t)B * 4));
+    memset(c.pin[2], 0, al256((size_t)B * 4) * 2 + 256);
+    bp.lm_persistent = 1; bp.hs_done = hs_done; bp.hs_go = hs_go; bp.hs_abort = hs_abort;
+    bp.t0 = 0; bp.nframes = 0; bp.fresh = 1;
     const auto c0 = std::chrono::steady_clock::now();
-    bp.t0 = t; bp.nframes = 1; bp.fresh = (t == 0) ? 1 : 0;
-    if ((rc = launch_beam(bp, pl1, B, s))) return rc;
-    CU(cudaStreamSynchronize(s));
-    const auto c1 = std::chrono::steady_clock::now();
-    for (int b = 0; b < B; ++b) {
-      lm_after_frame(*sc, mirror[b], h_newlist + (size_t)b * (1 + 4 * K), &h_upd_count[b],
-                     h_upd_nodes + (size_t)b * K, h_upd_vals + (size_t)b * K, scratch);
-      n_hook += h_upd_count[b];
-      n_new += h_newlist[(size_t)b * (1 + 4 * K)];
+    if ((rc = launch_beam(bp, pl, B, s))) return rc;
+    unsigned nt = std::thread::hardware_concurrency();
+    if (const char *e = getenv("CTCDEC_LM_THREADS")) nt = (unsigned)atoi(e);
+    nt = nt == 0 ? 1 : (nt > 8 ? 8 : nt);
+    if ((unsigned)B < nt) nt = (unsigned)B;
+    if (sc->cond_caches.size() < nt) sc->cond_caches.resize(nt);
+    std::atomic<int> failed{0};
+    std::atomic<long long> n_hook{0}, n_new{0};
+    auto worker = [&](unsigned w) {
+      std::vector<int> scratch;
+      HostScorer::CondCache &cache = sc->cond_caches[w];
+      int remaining = 0;
+      for (int b = (int)w; b < B; b += (int)nt) remaining += need[b] > 1 ? 1 : 0;
+      std::vector<int> served(B, 0);
+      auto last_progress = std::chrono::steady_clock::now();
+      long long hooks = 0, created = 0;
+      unsigned idle = 0;
+      while (remaining > 0 && !failed.load(std::memory_order_relaxed)) {
+        bool progress = false;
+        for (int b = (int)w; b < B; b += (int)nt) {
+          if (served[b] >= need[b] - 1) continue;
+          const int d = reinterpret_cast<std::atomic<int> *>(&hs_done[b])->load(std::memory_order_acquire);
+          if (d <= served[b]) continue;
+          const int *nl = h_newlist + (size_t)b * (4 + 4 * K);
+          lm_after_frame(*sc, cache, mirror[b], nl, &h_upd_count[b], h_upd_nodes + (size_t)b * K,
+                         h_upd_vals + (size_t)b * K, scratch);
+          hooks += h_upd_count[b];
+          created += nl[0];
+          reinterpret_cast<std::atomic<int> *>(&hs_go[b])->store(d, std::memory_order_release);
+          served[b] = d;
+          if (d >= need[b] - 1) --remaining;
+          progress = true;
+        }
+        if (progress) { idle = 0; last_progress = std::chrono::steady_clock::now(); }
+        else if ((++idle & 0xFFFF) == 0 &&
+                 std::chrono::duration<double>(std::chrono::steady_clock::now() - last_progress).count() > 8.0)
+          failed.store(1);  // the kernel stopped making progress (fault or lost launch): stop waiting
+      }
+      n_hook += hooks; n_new += created;
+    };
+    std::vector<std::thread> pool;
+    for (unsigned w = 1; w < nt; ++w) pool.emplace_back(worker, w);
+    worker(0);
+    for (auto &th : pool) th.join();
+    if (failed.load()) reinterpret_cast<std::atomic<int> *>(hs_abort)->store(1, std::memory_order_release);
+    const cudaError_t e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) return fail(CTCDEC_E_CUDA, "beam kernel (scorer path): %s", cudaGetErrorString(e));
+    if (failed.load()) return fail(CTCDEC_E_CUDA, "beam kernel (scorer path) stopped answering the per-frame handshake");
+    if (lm_timing)
+      fprintf(stderr, "[ctcdec lm] persistent: frames %d, %u host workers, kernel+handshakes %.1f ms (%lld hook calls, %lld new nodes)\n",
+              tmax, nt, std::chrono::duration<double>(std::chrono::steady_clock::now() - c0).count() * 1e3,
+              (long long)n_hook, (long long)n_new);
+  } else {
+    Plan pl1 = pl;  // one frame per launch: the staged tile is one row
+    pl1.F = 1;
+    pl1.L = make_layout(K, V, pl.NP, 1, pl.sorted, pl.NT);
+
+    std::vector<int> scratch;
+    double t_gpu = 0.0, t_hook = 0.0;
+    long long n_hook = 0, n_new = 0;
+    for (int t = 0; t < std::max(tmax, 1); ++t) {
+      const auto c0 = std::chrono::steady_clock::now();
+      bp.t0 = t; bp.nframes = 1; bp.fresh = (t == 0) ? 1 : 0;
+      if ((rc = launch_beam(bp, pl1, B, s))) return rc;
+      CU(cudaStreamSynchronize(s));
+      const auto c1 = std::chrono::steady_clock::now();
+      for (int b = 0; b < B; ++b) {
+        lm_after_frame(*sc, sc->cond_caches[0], mirror[b], h_newlist + (size_t)b * (4 + 4 * K), &h_upd_count[b],
+                       h_upd_nodes + (size_t)b * K, h_upd_vals + (size_t)b * K, scratch);
+        n_hook += h_upd_count[b];
+        n_new += h_newlist[(size_t)b * (4 + 4 * K)];
+      }
+      const auto c2 = std::chrono::steady_clock::now();
+      t_gpu += std::chrono::duration<double>(c1 - c0).count();
+      t_hook += std::chrono::duration<double>(c2 - c1).count();
     }
-    const auto c2 = std::chrono::steady_clock::now();
-    t_gpu += std::chrono::duration<double>(c1 - c0).count();
-    t_hook += std::chrono::duration<double>(c2 - c1).count();
+    if (lm_timing)
+      fprintf(stderr, "[ctcdec lm] frames %d: launch+copy+sync %.1f ms, host mirror+hooks %.1f ms (%lld hook calls, %lld new nodes)\n",
+              tmax, t_gpu * 1e3, t_hook * 1e3, n_hook, n_new);
   }
-  if (lm_timing)
-    fprintf(stderr, "[ctcdec lm] frames %d: launch+copy+sync %.1f ms, host mirror+hooks %.1f ms (%lld hook calls, %lld new nodes)\n",
-            tmax, t_gpu * 1e3, t_hook * 1e3, n_hook, n_new);
   if ((rc = launch_finalize(bp, B, s))) return rc;
   std::unique_ptr<int[]> h_nres(new int[(size_t)B * 2]);
   CU(cudaMemcpyAsync(scores, d_scores, n_bk * 4, cudaMemcpyDeviceToHost, s));

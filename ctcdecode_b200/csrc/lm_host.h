@@ -12,8 +12,9 @@
 //   * the LM term of a prefix depends only on the prefix (the words before the space being appended), so the host
 //     asks the hook ONCE per trie node that can be followed by a space, when the node is created, and the kernel
 //     reads it from a per-node array afterwards.  The host keeps a (parent, char) mirror of the trie for that.
-// The frame loop is therefore: launch one frame -> read back the list of created nodes -> hook calls -> next
-// frame.  One launch per frame is the price of a host-side language model.
+// The frame loop is therefore: frame -> list of created nodes to the host -> hook calls -> LM terms back -> next
+// frame; by default inside ONE persistent launch (per-frame handshake through device-mapped pinned memory, see
+// ctc_api.cu), optionally as one launch per frame.
 #pragma once
 #include <cstdint>
 #include <cstring>
@@ -89,7 +90,9 @@ static inline Dictionary build_dictionary(const std::vector<std::string> &labels
 struct HostScorer {
   // cond_log_prob depends only on the last max_order words of the prefix, and beams share word histories: cache it
   // keyed by that tail of the label sequence (the hook is pure, so the values are the hook's own)
-  std::unordered_map<std::string, double> cond_cache;
+  // (one cache per host worker thread: each utterance is served by one worker, so no locking)
+  typedef std::unordered_map<std::string, double> CondCache;
+  std::vector<CondCache> cond_caches = std::vector<CondCache>(1);
   ctcdec_scorer_hooks hooks;
   double alpha, beta;
   int max_order, is_character_based, space_id;
@@ -135,29 +138,31 @@ static inline int tail_start(const int *labels, int n, int space_id, int max_wor
   return 0;
 }
 
-static inline double cached_cond(HostScorer &sc, const int *labels, int n) {
+static inline double cached_cond(const HostScorer &sc, HostScorer::CondCache &cache, const int *labels, int n) {
   std::string key(reinterpret_cast<const char *>(labels), (size_t)n * sizeof(int));
-  auto it = sc.cond_cache.find(key);
-  if (it != sc.cond_cache.end()) return it->second;
+  auto it = cache.find(key);
+  if (it != cache.end()) return it->second;
   const double v = sc.hooks.cond_log_prob(sc.hooks.ctx, labels, n);
-  if (sc.cond_cache.size() > (1u << 22)) sc.cond_cache.clear();
-  sc.cond_cache.emplace(std::move(key), v);
+  if (cache.size() > (1u << 20)) cache.clear();
+  cache.emplace(std::move(key), v);
   return v;
 }
 
 // After a frame: register the created nodes and compute the LM term of those a space can follow.
-// newlist: [1 + 4K] ints of one utterance (count, then node / parent / chr / needs_lm); outputs the update list.
-static inline void lm_after_frame(HostScorer &sc, TrieMirror &mirror, const int *newlist, int *upd_count,
-                                  int *upd_nodes, float *upd_vals, std::vector<int> &scratch) {
+// newlist: [4 + 4K] ints of one utterance (count and 3 pad ints, then 16-byte entries node / parent / chr /
+// needs_lm); outputs the update list.
+static inline void lm_after_frame(const HostScorer &sc, HostScorer::CondCache &cache, TrieMirror &mirror,
+                                  const int *newlist, int *upd_count, int *upd_nodes, float *upd_vals,
+                                  std::vector<int> &scratch) {
   const int cnt = newlist[0];
   int nu = 0;
   for (int q = 0; q < cnt; ++q) {
-    const int *e = newlist + 1 + 4 * q;
+    const int *e = newlist + 4 + 4 * q;
     if (e[0] < 0) continue;  // a revived node: already known
     mirror.add(e[0], e[1], e[2]);
     if (e[3]) {
       mirror.tail_labels_of(e[0], sc.space_id, sc.max_order, scratch);
-      const double cond = cached_cond(sc, scratch.data(), (int)scratch.size());
+      const double cond = cached_cond(sc, cache, scratch.data(), (int)scratch.size());
       upd_nodes[nu] = e[0];
       upd_vals[nu] = (float)(cond * sc.alpha);  // reference :133 `score = get_log_cond_prob(ngram) * alpha` (float)
       ++nu;
@@ -205,7 +210,7 @@ static inline void lm_rescore_batch(HostScorer &sc, int B, int K, int T, const i
       const int *tok = tokens + ((size_t)b * K + p) * T;
       if (len > 0 && tok[len - 1] != sc.space_id) {
         const int st = tail_start(tok, len, sc.space_id, sc.max_order);
-        cond[(size_t)b * K + p] = cached_cond(sc, tok + st, len - st);
+        cond[(size_t)b * K + p] = cached_cond(sc, sc.cond_caches[0], tok + st, len - st);
       }
     }
   unsigned nt = std::thread::hardware_concurrency();

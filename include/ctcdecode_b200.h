@@ -94,7 +94,9 @@ int ctcdec_decode_batch_host(const ctcdec_config *cfg, const float *probs, const
  *                                    i.e. the natural-log probability of the prefix's last word given the words
  *                                    before it (up to max_order, "<s>"-padded); OOV -> -1000
  *   sent_log_prob(ctx, labels, n)  = Scorer::get_sent_log_prob(Scorer::split_labels(prefix))  (scorer.cpp:95-146)
- * The hooks must be callable from the thread that calls ctcdec_decode_batch_lm_host. */
+ * The hooks must be pure and thread-safe: the library calls them concurrently from a few worker threads of its own
+ * (each utterance is served by one worker), like the reference calls its Scorer from the thread pool of
+ * ctc_beam_search_decoder_batch (ctc_beam_search_decoder.cpp:228-247). */
 typedef struct ctcdec_scorer_hooks {
   void *ctx;
   double (*cond_log_prob)(void *ctx, const int32_t *labels, int n);
@@ -119,7 +121,10 @@ int ctcdec_scorer_reset_params(void *scorer, double alpha, double beta);
 
 /* Replaces: paddle_beam_decode_lm -> beam_decode -> ctc_beam_search_decoder_batch with a scorer
  * (binding.cpp:122-140, ctc_beam_search_decoder.cpp:56-211).  HOST buffers, shaped like ctcdec_decode_batch_host.
- * The beam search runs on `device`, one kernel launch per frame with the hook calls in between. */
+ * The beam search runs on `device` in ONE kernel launch; after every frame each utterance's CTA hands the trie
+ * nodes it created to the host through device-mapped pinned memory and waits for their LM terms (hook calls).
+ * Environment: CTCDEC_LM_PER_FRAME=1 selects the older protocol (one launch per frame), CTCDEC_LM_THREADS=n the
+ * number of host workers (default min(8, cores)). */
 int ctcdec_decode_batch_lm_host(const ctcdec_config *cfg, void *scorer, const float *probs, const int32_t *seq_lens,
                                 int B, int T, int32_t *tokens, int32_t *timesteps, float *scores, int32_t *lens,
                                 int32_t *n_results, int32_t *flags, int device);

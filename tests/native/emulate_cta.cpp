@@ -203,7 +203,7 @@ int emu_decode_batch_lm(const float *probs, const int *seq_lens, int B, int T, i
   std::vector<float> lm_arena((size_t)B * pl.arena_stride, 0.f);
   std::vector<int> dstate_arena((size_t)B * pl.arena_stride, 0);
   std::vector<int> state((size_t)B * pl.state_stride, 0);
-  std::vector<int> newlist((size_t)B * (1 + 4 * K), 0);
+  std::vector<int> newlist((size_t)B * (4 + 4 * K), 0);
   std::vector<int> upd_count(B, 0), upd_nodes((size_t)B * K, 0);
   std::vector<float> upd_vals((size_t)B * K, 0.f);
   std::vector<unsigned char> smem(pl.L.total + 64);
@@ -227,6 +227,30 @@ int emu_decode_batch_lm(const float *probs, const int *seq_lens, int B, int T, i
   std::vector<TrieMirror> mirror(B);
   for (int b = 0; b < B; ++b) mirror[b].reserve(64);  // small on purpose: exercises the growth path
   std::vector<int> scratch;
+  if (getenv("CTC_EMU_LM_PER_FRAME") == nullptr) {
+    // persistent mode: one "launch" per utterance, the host side of the per-frame handshake is called in place
+    struct Ctx { HostScorer *sc; std::vector<TrieMirror> *mirror; int *newlist, *uc, *un; float *uv; int K; std::vector<int> *scratch; };
+    Ctx ctx{&sc, &mirror, newlist.data(), upd_count.data(), upd_nodes.data(), upd_vals.data(), K, &scratch};
+    bp.lm_persistent = 1;
+    bp.emu_ctx = &ctx;
+    bp.emu_handshake = [](void *c, int b) {
+      Ctx *x = static_cast<Ctx *>(c);
+      lm_after_frame(*x->sc, x->sc->cond_caches[0], (*x->mirror)[b], x->newlist + (size_t)b * (4 + 4 * x->K), &x->uc[b],
+                     x->un + (size_t)b * x->K, x->uv + (size_t)b * x->K, *x->scratch);
+    };
+    bp.t0 = 0; bp.nframes = 0; bp.fresh = 1;
+    switch (NT) {
+      case 32: run_beam<32>(bp, pl.sorted, B, smem.data()); break;
+      case 64: run_beam<64>(bp, pl.sorted, B, smem.data()); break;
+      case 128: run_beam<128>(bp, pl.sorted, B, smem.data()); break;
+      case 512: run_beam<512>(bp, pl.sorted, B, smem.data()); break;
+      default: run_beam<256>(bp, pl.sorted, B, smem.data()); break;
+    }
+    std::vector<unsigned char> fsmem2((size_t)K * 12 + 64);
+    for (int b = 0; b < B; ++b) finalize_cta_run<128>(bp, b, fsmem2.data());
+    lm_rescore_batch(sc, B, K, T, n_results, tokens, lens, scores);
+    return 0;
+  }
   int tmax = 0;
   for (int b = 0; b < B; ++b) tmax = std::max(tmax, std::min(seq_lens ? seq_lens[b] : T, T));
   for (int t = 0; t < std::max(tmax, 1); ++t) {
@@ -239,7 +263,7 @@ int emu_decode_batch_lm(const float *probs, const int *seq_lens, int B, int T, i
       default: run_beam<256>(bp, pl.sorted, B, smem.data()); break;
     }
     for (int b = 0; b < B; ++b)
-      lm_after_frame(sc, mirror[b], newlist.data() + (size_t)b * (1 + 4 * K), &upd_count[b],
+      lm_after_frame(sc, sc.cond_caches[0], mirror[b], newlist.data() + (size_t)b * (4 + 4 * K), &upd_count[b],
                      upd_nodes.data() + (size_t)b * K, upd_vals.data() + (size_t)b * K, scratch);
   }
   std::vector<unsigned char> fsmem((size_t)K * 12 + 64);

@@ -30,8 +30,12 @@ def _emul_lm(ref, probs, labels, alpha, beta, seq_lens=None, **kw):
 
 
 @needs_ref
+@pytest.mark.parametrize("per_frame", [False, True], ids=["persistent", "per_frame_launch"])
 @pytest.mark.parametrize("name", golden_util.names(lm=True))
-def test_emulation_lm_matches_reference_golden(name):
+def test_emulation_lm_matches_reference_golden(name, per_frame, monkeypatch):
+    """both host/kernel protocols: one persistent launch with a per-frame handshake (default), one launch per frame"""
+    if per_frame:
+        monkeypatch.setenv("CTC_EMU_LM_PER_FRAME", "1")
     probs, seq_lens, kw, gold, alpha, beta = golden_util.load_lm(name)
     ref = orc.Reference(L29, model_path=TINY, alpha=alpha, beta=beta)
     got = _emul_lm(ref, probs, L29, alpha, beta, seq_lens=seq_lens, **kw)
@@ -111,10 +115,13 @@ def test_scorer_accessors_match_reference():
 # ---------------------------------------------------------------------------------------------------------------
 @pytest.mark.gpu
 @pytest.mark.skipif(not os.path.exists(PROVIDER), reason="scorer provider (oracle/_ref/libctcref.so) not shipped")
+@pytest.mark.parametrize("per_frame", [False, True], ids=["persistent", "per_frame_launch"])
 @pytest.mark.parametrize("name", golden_util.names(lm=True))
-def test_cuda_lm_matches_reference_golden(name):
+def test_cuda_lm_matches_reference_golden(name, per_frame, monkeypatch):
     import torch
     import ctcdecode_b200
+    if per_frame:
+        monkeypatch.setenv("CTCDEC_LM_PER_FRAME", "1")
     probs, seq_lens, kw, gold, alpha, beta = golden_util.load_lm(name)
     dec = ctcdecode_b200.CTCBeamDecoder(L29, model_path=TINY, alpha=alpha, beta=beta, beam_width=kw["beam"],
                                         cutoff_top_n=kw["cutoff_top_n"], cutoff_prob=kw["cutoff_prob"],

@@ -1,0 +1,23 @@
+#!/usr/bin/env python
+"""Small decodes for compute-sanitizer (racecheck / memcheck / synccheck) under gpurun:
+   compute-sanitizer --tool racecheck python tools/sanitize_run.py"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from ctcdecode_b200 import CTCBeamDecoder, DecoderState, OnlineCTCBeamDecoder  # noqa: E402
+from ctcdecode_b200.synth import ctc_like_probs, flat_probs  # noqa: E402
+
+L29 = [str(i) for i in range(29)]
+p = ctc_like_probs(3, 80, 29, seed=1)
+CTCBeamDecoder(L29, beam_width=32).decode(p.cuda())                                   # index-order vocabulary
+CTCBeamDecoder(L29, beam_width=16, cutoff_top_n=8).decode(p.cuda())                   # sorted / cut vocabulary
+CTCBeamDecoder([str(i) for i in range(4)], beam_width=16).decode(flat_probs(2, 120, 4, seed=5, temp=1.0).cuda())  # revivals
+dec = OnlineCTCBeamDecoder(L29, beam_width=16)
+st = [DecoderState(dec) for _ in range(3)]
+dec.decode(p[:, :30], st, [False] * 3)
+dec.decode(p[:, 30:], st, [True] * 3)
+torch.cuda.synchronize()
+print("sanitize_run done")
