@@ -2,7 +2,7 @@
 """bench.py -- utterances/sec of the CTC beam-search hot path on BASELINE.json's config 2
 ([256, T=1000, V=29] per GPU, beam 100, cutoff_top_n 40, cutoff_prob 1.0, no LM; synthetic CTC-like input).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c2|c4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c2|c3|c4|c5]
 
 One process per GPU (torchrun sets RANK / LOCAL_RANK / WORLD_SIZE); utterances are independent, so each
 rank decodes its own [256, T, V] shard and there is no data-path collective ("weak" scaling, N=8 is
@@ -38,6 +38,10 @@ sys.path.insert(0, ROOT)
 CONFIGS = {
     "c2": dict(B=256, T=1000, V=29, beam=100, cutoff_top_n=40, cutoff_prob=1.0,
                name="config2: [256 x T=1000 x V=29] per GPU, beam 100, cutoff_top_n 40, cutoff_prob 1.0, no LM"),
+    # BASELINE config 3: a FIXED total of 2048 utterances, split over the ranks ("strong" scaling: 1 GPU runs ~7 waves
+    # of CTAs, 8 GPUs one wave each -- SURVEY.md 8e)
+    "c3": dict(B=2048, T=1000, V=29, beam=100, cutoff_top_n=40, cutoff_prob=1.0, strong=True,
+               name="config3: [2048 x T=1000 x V=29] in total, split over the GPUs, beam 100, cutoff_top_n 40, cutoff_prob 1.0, no LM"),
     "c4": dict(B=256, T=2000, V=256, beam=200, cutoff_top_n=40, cutoff_prob=0.99,
                name="config4: [256 x T=2000 x V=256] per GPU, beam 200, cutoff_top_n 40, cutoff_prob 0.99, no LM"),
     # BASELINE config 5: KenLM scorer path.  The reference's tests/test.arpa is not on the GPU box, so the model is
@@ -199,6 +203,10 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     K, W = args.steps, max(args.warmup, 3 if args.impl == "ours" else 0)
     B, T, V = cfg["B"], cfg["T"], cfg["V"]
+    scaling = "weak"
+    if cfg.get("strong"):  # fixed global batch: every rank takes its contiguous share
+        scaling = "strong"
+        B = B // world
     cores = len(os.sched_getaffinity(0))
     config = {"workload": cfg["name"], "batch_per_gpu": B, "global_batch": B * world, "T": T, "V": V,
               "beam_width": cfg["beam"], "cutoff_top_n": cfg["cutoff_top_n"], "cutoff_prob": cfg["cutoff_prob"],
@@ -223,7 +231,7 @@ def main():
         sample = "%d of the %d utterances of the same seeded batch per step (one per host thread)" % (n, B)
         print(json.dumps({
             "impl": "reference", "metric": METRIC, "value": val, "unit": "utterances/s", "n_gpus": args.gpus,
-            "steps": K, "warmup": W, "ms_per_step": 1e3 * total / K, "higher_is_better": True, "scaling": "weak",
+            "steps": K, "warmup": W, "ms_per_step": 1e3 * total / K, "higher_is_better": True, "scaling": scaling,
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
             "cpu_baseline": {"value": val, "unit": "utterances/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": "utterances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
@@ -352,7 +360,7 @@ def main():
     scan_bytes = alg_bytes + B * T * NP * (6 if is_sorted else 4)
     line = {
         "metric": METRIC, "value": value, "unit": "utterances/s", "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": config,
         "e2e": {"value": e2e_val, "unit": "utterances/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms_max / K, "host_equals_device": same},

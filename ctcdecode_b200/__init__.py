@@ -6,6 +6,6 @@
 Only the beam-search hot path is here; the CUDA library must be built
 (`python -m ctcdecode_b200.build`) and a B200 present -- there is no CPU fallback.
 """
-from .decoder import CTCBeamDecoder, DecoderState, OnlineCTCBeamDecoder  # noqa: F401
+from .decoder import CTCBeamDecoder, DecoderState, OnlineCTCBeamDecoder, convert_to_string  # noqa: F401
 
-__all__ = ["CTCBeamDecoder", "OnlineCTCBeamDecoder", "DecoderState"]
+__all__ = ["CTCBeamDecoder", "OnlineCTCBeamDecoder", "DecoderState", "convert_to_string"]

@@ -32,6 +32,11 @@ _SIGNATURES = {
                                               ctypes.POINTER(ctypes.c_size_t)]),
     "ctcdec_decode_batch_device": (ctypes.c_int, [ctypes.POINTER(Config), _vp, _vp, ctypes.c_int, ctypes.c_int,
                                                   _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_size_t, _vp]),
+    "ctcdec_decode_batch_device_logits": (ctypes.c_int, [ctypes.POINTER(Config), _vp, ctypes.c_int, _vp, ctypes.c_int,
+                                                         ctypes.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                                         ctypes.c_size_t, _vp]),
+    "ctcdec_pack_results_device": (ctypes.c_int, [_vp, _vp, _vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp,
+                                                  _vp, _vp, ctypes.c_size_t, _vp]),
     "ctcdec_decode_batch_host": (ctypes.c_int, [ctypes.POINTER(Config), _vp, _vp, ctypes.c_int, ctypes.c_int,
                                                 _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_int]),
     "ctcdec_scorer_create": (ctypes.c_int, [_vp, ctypes.c_double, ctypes.c_double, ctypes.POINTER(ctypes.c_char_p),
@@ -45,6 +50,7 @@ _SIGNATURES = {
     "ctcdec_decode_batch_lm_host": (ctypes.c_int, [ctypes.POINTER(Config), _vp, _vp, _vp, ctypes.c_int, ctypes.c_int,
                                                    _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_int]),
     "ctcdec_state_create": (ctypes.c_int, [ctypes.POINTER(Config), ctypes.c_int, ctypes.POINTER(_vp)]),
+    "ctcdec_state_create_lm": (ctypes.c_int, [ctypes.POINTER(Config), _vp, ctypes.c_int, ctypes.POINTER(_vp)]),
     "ctcdec_state_destroy": (ctypes.c_int, [_vp]),
     "ctcdec_state_frames": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_int)]),
     "ctcdec_decode_stream_host": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(_vp), _vp,

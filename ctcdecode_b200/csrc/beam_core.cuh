@@ -134,6 +134,9 @@ struct BeamParams {
   // persistent scorer mode: ONE launch for the whole utterance; after every frame the CTA publishes its new-node
   // list in device-mapped host memory, raises hs_done[b] and spins on hs_go[b] until the host has answered.
   int lm_persistent;
+  int lm_hs_last;                   // also hand shake after the LAST frame of the launch (streaming: a next chunk follows)
+  float *const *lm_arena_ptrs;      // streaming: per-stream LM / dictionary-state arrays (else lm_arena + b * stride)
+  int *const *dstate_ptrs;
   int *hs_done;                     // [B] mapped host memory, written by the device: frames finished
   int *hs_go;                       // [B] mapped host memory, written by the host: frames answered
   int *hs_abort;                    // [1] mapped host memory: host asks the kernel to stop waiting

@@ -254,8 +254,8 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
   int *const st = p.state_ptrs ? p.state_ptrs[b] : p.state + (long long)b * p.state_stride;
   const int arena_cap = p.arena_caps ? p.arena_caps[b] : p.arena_cap;
   c.nodes = nodes;
-  float *const lm_arena = LM ? p.lm_arena + (long long)b * p.arena_stride : nullptr;
-  int *const dstate_arena = LM ? p.dstate_arena + (long long)b * p.arena_stride : nullptr;
+  float *const lm_arena = !LM ? nullptr : p.lm_arena_ptrs ? p.lm_arena_ptrs[b] : p.lm_arena + (long long)b * p.arena_stride;
+  int *const dstate_arena = !LM ? nullptr : p.dstate_ptrs ? p.dstate_ptrs[b] : p.dstate_arena + (long long)b * p.arena_stride;
   int *const newlist = LM ? p.newlist + (long long)b * (4 + 4 * K) : nullptr;
   int Tb = p.seq_lens ? p.seq_lens[b] : p.T;  // reference binding.cpp:64-65 clamps to T
   if (Tb > p.T) Tb = p.T;
@@ -1323,7 +1323,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
     c.s_anch = anch_base + cur * KP;
     nlive = nlive_next;
     M = M_new;
-    if (LM && p.lm_persistent && t + 1 < Tb) {
+    if (LM && p.lm_persistent && (t + 1 < Tb || p.lm_hs_last)) {
       // ---- scorer path, persistent mode: hand the new nodes to the host, wait for their LM terms -----------
 #if defined(CTC_EMULATE)
       p.emu_handshake(p.emu_ctx, b);

@@ -18,6 +18,7 @@
 #include "plan.h"
 #include "lm_host.h"
 #include "prune_program.cuh"
+#include "pack_program.cuh"
 
 namespace ctc {
 
@@ -105,36 +106,58 @@ static int launch_beam(const BeamParams &bp, const Plan &pl, int B, cudaStream_t
   }
 }
 
-static int launch_prune(const ctcdec_config *cfg, const Plan &pl, const float *probs, const int *seq_lens, int B,
+struct PruneInput {
+  const void *data;   // probabilities / log-probabilities (kind IN_F32) or logits
+  int kind;           // IN_F32, IN_LOGITS_F32, IN_LOGITS_F16, IN_LOGITS_BF16
+  float *lsm_out;     // optional: the float32 log-softmax rows (logits kinds)
+};
+
+template <bool SORTED, int KPL, bool LOGITS>
+static int launch_prune_k(const PruneParams &pp, int grid, int threads, size_t smem, cudaStream_t s) {
+  if (smem > 48 * 1024)
+    CU(cudaFuncSetAttribute(prune_kernel<SORTED, KPL, LOGITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  prune_kernel<SORTED, KPL, LOGITS><<<grid, threads, smem, s>>>(pp);
+  return CTCDEC_OK;
+}
+
+static int launch_prune(const ctcdec_config *cfg, const Plan &pl, const PruneInput &in, const int *seq_lens, int B,
                         int T, float *lp, uint16_t *idx, int *flags, cudaStream_t s) {
   PruneParams pp;
-  pp.probs = probs; pp.seq_lens = seq_lens; pp.B = B; pp.T = T; pp.V = cfg->vocab_size; pp.NP = pl.NP;
-  pp.blank = cfg->blank_id; pp.log_input = cfg->log_input; pp.top_n = cfg->cutoff_top_n;
+  memset(&pp, 0, sizeof(pp));
+  const bool logits = in.kind != IN_F32;
+  pp.probs = logits ? nullptr : static_cast<const float *>(in.data);
+  pp.logits = logits ? in.data : nullptr;
+  pp.in_kind = in.kind; pp.lsm_out = logits ? in.lsm_out : nullptr;
+  pp.seq_lens = seq_lens; pp.B = B; pp.T = T; pp.V = cfg->vocab_size; pp.NP = pl.NP;
+  pp.blank = cfg->blank_id; pp.log_input = logits ? 1 : cfg->log_input; pp.top_n = cfg->cutoff_top_n;
   pp.cp_active = pl.cp_active; pp.cutoff_prob = cfg->cutoff_prob; pp.P = pl.P; pp.lp = lp; pp.idx = idx;
   pp.flags = flags;
+  const int V = cfg->vocab_size;
+  pp.Vpad = (V + 3) / 4 * 4;
+  const size_t row_bytes = logits ? (size_t)pp.Vpad * 4 : 0;  // per-warp staging row of the log-softmax
   const long long frames = (long long)B * T;
   if (frames == 0) return CTCDEC_OK;
+  int rc = CTCDEC_OK;
   if (!pl.sorted) {
-    const int wpc = 8;
+    int wpc = 8;
+    if (logits) wpc = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024 - 2048) / row_bytes));
+    const size_t smem = 2048 + (size_t)wpc * row_bytes;
     const int grid = (int)std::min<long long>((frames + wpc - 1) / wpc, 148 * 16);
-    prune_kernel<false, 0><<<grid, wpc * 32, 2048, s>>>(pp);
+    rc = logits ? launch_prune_k<false, 0, true>(pp, grid, wpc * 32, smem, s)
+                : launch_prune_k<false, 0, false>(pp, grid, wpc * 32, smem, s);
   } else {
-    int wpc = (int)std::min<size_t>(8, (200 * 1024 - 2048) / ((size_t)pl.P * 8));
+    int wpc = (int)std::min<size_t>(8, (200 * 1024 - 2048) / ((size_t)pl.P * 8 + row_bytes));
     if (wpc < 1) wpc = 1;
-    const size_t smem = 2048 + (size_t)wpc * pl.P * 8;
+    const size_t smem = 2048 + (size_t)wpc * ((size_t)pl.P * 8 + row_bytes);
     const int grid = (int)std::min<long long>((frames + wpc - 1) / wpc, 148 * 8);
-    const int V = cfg->vocab_size;
-    if (V <= 256) {
-      CU(cudaFuncSetAttribute(prune_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      prune_kernel<true, 8><<<grid, wpc * 32, smem, s>>>(pp);
-    } else if (V <= 1024) {
-      CU(cudaFuncSetAttribute(prune_kernel<true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      prune_kernel<true, 32><<<grid, wpc * 32, smem, s>>>(pp);
-    } else {
-      CU(cudaFuncSetAttribute(prune_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      prune_kernel<true, 0><<<grid, wpc * 32, smem, s>>>(pp);
-    }
+    if (V <= 256)
+      rc = logits ? launch_prune_k<true, 8, true>(pp, grid, wpc * 32, smem, s) : launch_prune_k<true, 8, false>(pp, grid, wpc * 32, smem, s);
+    else if (V <= 1024)
+      rc = logits ? launch_prune_k<true, 32, true>(pp, grid, wpc * 32, smem, s) : launch_prune_k<true, 32, false>(pp, grid, wpc * 32, smem, s);
+    else
+      rc = logits ? launch_prune_k<true, 0, true>(pp, grid, wpc * 32, smem, s) : launch_prune_k<true, 0, false>(pp, grid, wpc * 32, smem, s);
   }
+  if (rc) return rc;
   CU(cudaGetLastError());
   return CTCDEC_OK;
 }
@@ -209,7 +232,81 @@ struct StreamState {
   int arena_cap;
   int *state;
   int frames;
+  // scorer path (ctcdec_state_create_lm): the borrowed scorer (reference DecoderState::ext_scorer,
+  // ctc_beam_search_decoder.cpp:31), per-node LM terms / dictionary states, the host mirror of the trie
+  HostScorer *sc = nullptr;
+  float *lm_arena = nullptr;
+  int *dstate = nullptr;
+  TrieMirror mirror;
 };
+
+static int ensure_dict_on_device(HostScorer *sc, int device) {
+  if (sc->d_next && sc->device != device) {
+    cudaSetDevice(sc->device); cudaFree(sc->d_next); cudaFree(sc->d_final); sc->d_next = nullptr; cudaSetDevice(device);
+  }
+  if (!sc->d_next) {
+    CU(cudaMalloc(&sc->d_next, sc->dict.next.size() * 4));
+    CU(cudaMalloc(&sc->d_final, sc->dict.fin.size()));
+    CU(cudaMemcpy(sc->d_next, sc->dict.next.data(), sc->dict.next.size() * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(sc->d_final, sc->dict.fin.data(), sc->dict.fin.size(), cudaMemcpyHostToDevice));
+    sc->device = device;
+  }
+  return CTCDEC_OK;
+}
+
+// Host side of the per-frame handshake of a persistent scorer-path launch (beam_program.cuh, "persistent mode"):
+// workers own every nt-th utterance (and one hook cache each, so nothing is locked); utterance b is answered
+// need[b] times.  Returns non-zero when the kernel stopped making progress (the caller raises the abort flag).
+struct HandshakeStats { long long hooks = 0, created = 0; unsigned workers = 0; };
+static int serve_handshakes(HostScorer *sc, int B, int K, const int *need, TrieMirror *const *mirrors,
+                            const int *h_newlist, int *h_upd_count, int *h_upd_nodes, float *h_upd_vals, int *hs_done,
+                            int *hs_go, HandshakeStats *stats) {
+  unsigned nt = std::thread::hardware_concurrency();
+  if (const char *e = getenv("CTCDEC_LM_THREADS")) nt = (unsigned)atoi(e);
+  nt = nt == 0 ? 1 : (nt > 8 ? 8 : nt);
+  if ((unsigned)B < nt) nt = (unsigned)B;
+  if (sc->cond_caches.size() < nt) sc->cond_caches.resize(nt);
+  std::atomic<int> failed{0};
+  std::atomic<long long> n_hook{0}, n_new{0};
+  auto worker = [&](unsigned w) {
+    std::vector<int> scratch;
+    HostScorer::CondCache &cache = sc->cond_caches[w];
+    int remaining = 0;
+    for (int b = (int)w; b < B; b += (int)nt) remaining += need[b] > 0 ? 1 : 0;
+    std::vector<int> served(B, 0);
+    auto last_progress = std::chrono::steady_clock::now();
+    long long hooks = 0, created = 0;
+    unsigned idle = 0;
+    while (remaining > 0 && !failed.load(std::memory_order_relaxed)) {
+      bool progress = false;
+      for (int b = (int)w; b < B; b += (int)nt) {
+        if (served[b] >= need[b]) continue;
+        const int d = reinterpret_cast<std::atomic<int> *>(&hs_done[b])->load(std::memory_order_acquire);
+        if (d <= served[b]) continue;
+        const int *nl = h_newlist + (size_t)b * (4 + 4 * K);
+        lm_after_frame(*sc, cache, *mirrors[b], nl, &h_upd_count[b], h_upd_nodes + (size_t)b * K,
+                       h_upd_vals + (size_t)b * K, scratch);
+        hooks += h_upd_count[b];
+        created += nl[0];
+        reinterpret_cast<std::atomic<int> *>(&hs_go[b])->store(d, std::memory_order_release);
+        served[b] = d;
+        if (d >= need[b]) --remaining;
+        progress = true;
+      }
+      if (progress) { idle = 0; last_progress = std::chrono::steady_clock::now(); }
+      else if ((++idle & 0xFFFF) == 0 &&
+               std::chrono::duration<double>(std::chrono::steady_clock::now() - last_progress).count() > 8.0)
+        failed.store(1);  // the kernel stopped making progress (fault or lost launch): stop waiting
+    }
+    n_hook += hooks; n_new += created;
+  };
+  std::vector<std::thread> pool;
+  for (unsigned w = 1; w < nt; ++w) pool.emplace_back(worker, w);
+  worker(0);
+  for (auto &th : pool) th.join();
+  if (stats) { stats->hooks = n_hook; stats->created = n_new; stats->workers = nt; }
+  return failed.load();
+}
 
 }  // namespace ctc
 
@@ -240,16 +337,16 @@ int ctcdec_workspace_bytes(const ctcdec_config *cfg, int B, int T, size_t *bytes
   return CTCDEC_OK;
 }
 
-int ctcdec_decode_batch_device(const ctcdec_config *cfg, const float *probs, const int32_t *seq_lens, int B, int T,
-                               int32_t *tokens, int32_t *timesteps, float *scores, int32_t *lens,
-                               int32_t *n_results, int32_t *flags, void *workspace, size_t workspace_bytes,
-                               void *stream) {
+static int decode_device_impl(const ctcdec_config *cfg, const PruneInput &in, const int32_t *seq_lens, int B, int T,
+                              int32_t *tokens, int32_t *timesteps, float *scores, int32_t *lens,
+                              int32_t *n_results, int32_t *flags, void *workspace, size_t workspace_bytes,
+                              void *stream) {
   Plan pl;
   int rc = make_plan(cfg, B, T, &pl);
   if (rc) return rc;
   if ((rc = check_device())) return rc;
   if (B == 0) return CTCDEC_OK;
-  if (!probs && T > 0) return fail(CTCDEC_E_INVALID, "probs is NULL");
+  if (!in.data && T > 0) return fail(CTCDEC_E_INVALID, "probs is NULL");
   if (!tokens || !timesteps || !scores || !lens) return fail(CTCDEC_E_INVALID, "an output pointer is NULL");
   unsigned char *ws = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(workspace) + 255) / 256 * 256);
   if (!workspace || ws + pl.total > reinterpret_cast<unsigned char *>(workspace) + workspace_bytes)
@@ -274,7 +371,7 @@ int ctcdec_decode_batch_device(const ctcdec_config *cfg, const float *probs, con
     g_prof.valid = false;
     CU(cudaEventRecord(g_prof.ev[0], s));
   }
-  if ((rc = launch_prune(cfg, pl, probs, seq_lens, B, T, lp, idx, flags_dev, s))) return rc;
+  if ((rc = launch_prune(cfg, pl, in, seq_lens, B, T, lp, idx, flags_dev, s))) return rc;
   if (prof) CU(cudaEventRecord(g_prof.ev[1], s));
 
   BeamParams bp;
@@ -293,6 +390,48 @@ int ctcdec_decode_batch_device(const ctcdec_config *cfg, const float *probs, con
   if (prof) {
     CU(cudaEventRecord(g_prof.ev[3], s));
     g_prof.valid = true;
+  }
+  return CTCDEC_OK;
+}
+
+int ctcdec_decode_batch_device(const ctcdec_config *cfg, const float *probs, const int32_t *seq_lens, int B, int T,
+                               int32_t *tokens, int32_t *timesteps, float *scores, int32_t *lens,
+                               int32_t *n_results, int32_t *flags, void *workspace, size_t workspace_bytes,
+                               void *stream) {
+  return decode_device_impl(cfg, PruneInput{probs, IN_F32, nullptr}, seq_lens, B, T, tokens, timesteps, scores, lens,
+                            n_results, flags, workspace, workspace_bytes, stream);
+}
+
+int ctcdec_decode_batch_device_logits(const ctcdec_config *cfg, const void *logits, int dtype, const int32_t *seq_lens,
+                                      int B, int T, int32_t *tokens, int32_t *timesteps, float *scores, int32_t *lens,
+                                      int32_t *n_results, int32_t *flags, float *log_probs_out, void *workspace,
+                                      size_t workspace_bytes, void *stream) {
+  if (dtype != CTCDEC_DTYPE_F32 && dtype != CTCDEC_DTYPE_F16 && dtype != CTCDEC_DTYPE_BF16)
+    return fail(CTCDEC_E_INVALID, "dtype %d is not one of CTCDEC_DTYPE_F32 / F16 / BF16", dtype);
+  const int kind = dtype == CTCDEC_DTYPE_F32 ? IN_LOGITS_F32 : dtype == CTCDEC_DTYPE_F16 ? IN_LOGITS_F16 : IN_LOGITS_BF16;
+  return decode_device_impl(cfg, PruneInput{logits, kind, log_probs_out}, seq_lens, B, T, tokens, timesteps, scores,
+                            lens, n_results, flags, workspace, workspace_bytes, stream);
+}
+
+int ctcdec_pack_results_device(const int32_t *tokens, const int32_t *timesteps, const int32_t *lens,
+                               const int32_t *n_results, int B, int K, int T, int64_t *offsets,
+                               int32_t *packed_tokens, int32_t *packed_timesteps, size_t capacity, void *stream) {
+  if (B < 0 || K < 1 || T < 0) return fail(CTCDEC_E_INVALID, "bad shape B=%d beam=%d T=%d", B, K, T);
+  if (!tokens || !timesteps || !lens || !n_results || !offsets || (capacity > 0 && (!packed_tokens || !packed_timesteps)))
+    return fail(CTCDEC_E_INVALID, "NULL argument");
+  int rc = check_device();
+  if (rc) return rc;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  static_assert(sizeof(long long) == sizeof(int64_t), "offsets are 64-bit");
+  pack_offsets_kernel<<<1, 1024, 0, s>>>(lens, n_results, B, K, reinterpret_cast<long long *>(offsets));
+  CU(cudaGetLastError());
+  const long long rows = (long long)B * K;
+  if (rows > 0 && capacity > 0) {
+    const int grid = (int)std::min<long long>((rows + 7) / 8, 148 * 8);
+    pack_rows_kernel<<<grid, 256, 0, s>>>(tokens, timesteps, lens, n_results, B, K, T,
+                                          reinterpret_cast<const long long *>(offsets), packed_tokens,
+                                          packed_timesteps, (long long)capacity);
+    CU(cudaGetLastError());
   }
   return CTCDEC_OK;
 }
@@ -429,12 +568,35 @@ int ctcdec_state_create(const ctcdec_config *cfg, int device, void **state) {
   return CTCDEC_OK;
 }
 
+int ctcdec_state_create_lm(const ctcdec_config *cfg, void *scorer, int device, void **state) {
+  if (!scorer) return ctcdec_state_create(cfg, device, state);
+  HostScorer *sc = static_cast<HostScorer *>(scorer);
+  if (cfg && (int)sc->labels.size() != cfg->vocab_size)
+    return fail(CTCDEC_E_INVALID, "scorer was built for %zu labels, decoder has %d", sc->labels.size(), cfg->vocab_size);
+  int rc = ctcdec_state_create(cfg, device, state);
+  if (rc) return rc;
+  StreamState *st = static_cast<StreamState *>(*state);
+  // node 0 (the root): dictionary start state (0) and LM term 0, reference path_trie.cpp:11-30 / :165-174
+  if (cudaMalloc(&st->lm_arena, (size_t)st->arena_cap * 4) != cudaSuccess ||
+      cudaMalloc(&st->dstate, (size_t)st->arena_cap * 4) != cudaSuccess ||
+      cudaMemset(st->lm_arena, 0, 4) != cudaSuccess || cudaMemset(st->dstate, 0, 4) != cudaSuccess) {
+    ctcdec_state_destroy(st);
+    *state = nullptr;
+    return fail(CTCDEC_E_CUDA, "cudaMalloc failed for the streaming state (scorer arrays)");
+  }
+  st->sc = sc;
+  st->mirror.reserve((size_t)st->arena_cap);
+  return CTCDEC_OK;
+}
+
 int ctcdec_state_destroy(void *state) {
   if (!state) return CTCDEC_OK;
   StreamState *st = static_cast<StreamState *>(state);
   cudaSetDevice(st->device);
   cudaFree(st->arena);
   cudaFree(st->state);
+  if (st->lm_arena) cudaFree(st->lm_arena);
+  if (st->dstate) cudaFree(st->dstate);
   delete st;
   return CTCDEC_OK;
 }
@@ -456,8 +618,8 @@ int ctcdec_decode_stream_host(const float *probs, const int32_t *seq_lens, int B
   const ctcdec_config cfg = s0->cfg;
   for (int b = 1; b < B; ++b) {
     StreamState *sb = static_cast<StreamState *>(states[b]);
-    if (memcmp(&sb->cfg, &cfg, sizeof(cfg)) != 0 || sb->device != s0->device)
-      return fail(CTCDEC_E_UNSUPPORTED, "all states of one call must come from the same decoder configuration and device");
+    if (memcmp(&sb->cfg, &cfg, sizeof(cfg)) != 0 || sb->device != s0->device || sb->sc != s0->sc)
+      return fail(CTCDEC_E_UNSUPPORTED, "all states of one call must come from the same decoder configuration, scorer and device");
     for (int a = 0; a < b; ++a)
       if (states[a] == states[b]) return fail(CTCDEC_E_INVALID, "states[%d] and states[%d] are the same object", a, b);
   }
@@ -491,6 +653,19 @@ int ctcdec_decode_stream_host(const float *probs, const int32_t *seq_lens, int B
       CU(cudaStreamSynchronize(s));
       CU(cudaFree(sb->arena));
       sb->arena = na;
+      if (sb->sc) {
+        float *nl = nullptr;
+        int *nd = nullptr;
+        CU(cudaMalloc(&nl, (size_t)cap * 4));
+        CU(cudaMalloc(&nd, (size_t)cap * 4));
+        CU(cudaMemcpyAsync(nl, sb->lm_arena, (size_t)used * 4, cudaMemcpyDeviceToDevice, s));
+        CU(cudaMemcpyAsync(nd, sb->dstate, (size_t)used * 4, cudaMemcpyDeviceToDevice, s));
+        CU(cudaStreamSynchronize(s));
+        CU(cudaFree(sb->lm_arena));
+        CU(cudaFree(sb->dstate));
+        sb->lm_arena = nl;
+        sb->dstate = nd;
+      }
       sb->arena_cap = (int)cap;
     }
     h_len_max = std::max(h_len_max, sb->frames + len);
@@ -498,7 +673,9 @@ int ctcdec_decode_stream_host(const float *probs, const int32_t *seq_lens, int B
   if (any_eos && (!tokens || !timesteps || !scores || !lens)) return fail(CTCDEC_E_INVALID, "an output pointer is NULL");
   if (any_eos && out_T < 0) return fail(CTCDEC_E_INVALID, "out_T < 0");
   const size_t n_probs = (size_t)B * T * V, n_bk = (size_t)B * K, n_out = any_eos ? n_bk * (size_t)out_T : 0;
-  const size_t ptr_bytes = al256((size_t)B * 8) * 2 + al256((size_t)B * 4) + al256((size_t)B);
+  const size_t ptr_bytes = al256((size_t)B * 8) * 4 + al256((size_t)B * 4) + al256((size_t)B);
+  HostScorer *const sc = s0->sc;
+  if (sc && (rc = ensure_dict_on_device(sc, device))) return rc;
   if ((rc = ensure(c, 0, n_probs * 4 + 256))) return rc;
   if ((rc = ensure(c, 1, (size_t)B * 4 + 256))) return rc;
   if ((rc = ensure(c, 2, n_out * 4 + 256))) return rc;
@@ -519,9 +696,13 @@ int ctcdec_decode_stream_host(const float *probs, const int32_t *seq_lens, int B
   int **h_states = (int **)(h_tab.get() + al256((size_t)B * 8));
   int *h_caps = (int *)(h_tab.get() + 2 * al256((size_t)B * 8));
   unsigned char *h_fin = h_tab.get() + 2 * al256((size_t)B * 8) + al256((size_t)B * 4);
+  const size_t off_lmar = 2 * al256((size_t)B * 8) + al256((size_t)B * 4) + al256((size_t)B);
+  float **h_lmar = (float **)(h_tab.get() + off_lmar);
+  int **h_dst = (int **)(h_tab.get() + off_lmar + al256((size_t)B * 8));
   for (int b = 0; b < B; ++b) {
     StreamState *sb = static_cast<StreamState *>(states[b]);
     h_arenas[b] = sb->arena; h_states[b] = sb->state; h_caps[b] = sb->arena_cap; h_fin[b] = is_eos[b] ? 1 : 0;
+    h_lmar[b] = sb->lm_arena; h_dst[b] = sb->dstate;
   }
   unsigned char *d_tab = (unsigned char *)c.buf[6];
   CU(cudaMemcpyAsync(d_tab, h_tab.get(), ptr_bytes, cudaMemcpyHostToDevice, s));
@@ -533,7 +714,7 @@ int ctcdec_decode_stream_host(const float *probs, const int32_t *seq_lens, int B
   ws = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(ws) + 255) / 256 * 256);
   float *lp = reinterpret_cast<float *>(ws + pl.off_lp);
   uint16_t *idx = pl.sorted ? reinterpret_cast<uint16_t *>(ws + pl.off_idx) : nullptr;
-  if (T > 0 && (rc = launch_prune(&cfg, pl, d_probs, d_lens_in, B, T, lp, idx, d_flags, s))) return rc;
+  if (T > 0 && (rc = launch_prune(&cfg, pl, PruneInput{d_probs, IN_F32, nullptr}, d_lens_in, B, T, lp, idx, d_flags, s))) return rc;
   BeamParams bp;
   memset(&bp, 0, sizeof(bp));
   bp.lp = lp; bp.idx = idx; bp.seq_lens = d_lens_in; bp.T = T; bp.V = V; bp.NP = pl.NP; bp.K = K;
@@ -544,7 +725,47 @@ int ctcdec_decode_stream_host(const float *probs, const int32_t *seq_lens, int B
   bp.fresh = 0;
   bp.out_tokens = d_tok; bp.out_timesteps = d_ts; bp.out_scores = d_scores; bp.out_lens = d_lens;
   bp.n_results = d_nres; bp.out_T = out_T; bp.flags = d_flags;
-  if (T > 0 && (rc = launch_beam(bp, pl, B, s))) return rc;
+  if (sc && T > 0) {
+    // scorer path: one persistent launch per chunk, hand shake after EVERY frame (the frame after the chunk's last
+    // one, in the next call, needs the LM terms of the nodes created now)
+    const size_t nl_ints = (size_t)B * (4 + 4 * K);
+    const size_t upd_bytes = al256((size_t)B * 4) + al256(n_bk * 4) + al256(n_bk * 4);
+    if ((rc = ensure_pinned(c, 0, nl_ints * 4))) return rc;
+    if ((rc = ensure_pinned(c, 1, upd_bytes))) return rc;
+    if ((rc = ensure_pinned(c, 2, al256((size_t)B * 4) * 2 + 256))) return rc;
+    int *h_newlist = (int *)c.pin[0];
+    unsigned char *h_upd = (unsigned char *)c.pin[1];
+    int *h_upd_count = (int *)h_upd;
+    int *h_upd_nodes = (int *)(h_upd + al256((size_t)B * 4));
+    float *h_upd_vals = (float *)(h_upd + al256((size_t)B * 4) + al256(n_bk * 4));
+    int *hs_done = (int *)c.pin[2];
+    int *hs_go = (int *)((unsigned char *)c.pin[2] + al256((size_t)B * 4));
+    int *hs_abort = (int *)((unsigned char *)c.pin[2] + 2 * al256((size_t)B * 4));
+    memset(c.pin[2], 0, al256((size_t)B * 4) * 2 + 256);
+    memset(h_upd_count, 0, (size_t)B * 4);
+    bp.dict_next = sc->d_next; bp.dict_final = sc->d_final; bp.dict_start = sc->dict.start;
+    bp.space_id = sc->space_id; bp.beta = sc->beta;
+    bp.lm_arena_ptrs = (float *const *)(d_tab + off_lmar);
+    bp.dstate_ptrs = (int *const *)(d_tab + off_lmar + al256((size_t)B * 8));
+    bp.newlist = h_newlist; bp.lm_update_count = h_upd_count; bp.lm_update_nodes = h_upd_nodes;
+    bp.lm_update_vals = h_upd_vals;
+    bp.lm_persistent = 1; bp.lm_hs_last = 1; bp.hs_done = hs_done; bp.hs_go = hs_go; bp.hs_abort = hs_abort;
+    if ((rc = launch_beam(bp, pl, B, s))) return rc;
+    std::vector<TrieMirror *> mirrors(B);
+    std::vector<int> answers(B);
+    for (int b = 0; b < B; ++b) {
+      mirrors[b] = &static_cast<StreamState *>(states[b])->mirror;
+      answers[b] = std::max(0, std::min(seq_lens ? seq_lens[b] : T, T));
+    }
+    const int failed = serve_handshakes(sc, B, K, answers.data(), mirrors.data(), h_newlist, h_upd_count, h_upd_nodes,
+                                        h_upd_vals, hs_done, hs_go, nullptr);
+    if (failed) reinterpret_cast<std::atomic<int> *>(hs_abort)->store(1, std::memory_order_release);
+    const cudaError_t e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) return fail(CTCDEC_E_CUDA, "beam kernel (scorer path, streaming): %s", cudaGetErrorString(e));
+    if (failed) return fail(CTCDEC_E_CUDA, "beam kernel (scorer path, streaming) stopped answering the per-frame handshake");
+  } else if (T > 0 && (rc = launch_beam(bp, pl, B, s))) {
+    return rc;
+  }
   for (int b = 0; b < B; ++b) {
     int len = seq_lens ? seq_lens[b] : T;
     static_cast<StreamState *>(states[b])->frames += std::max(0, std::min(len, T));
@@ -580,6 +801,11 @@ int ctcdec_decode_stream_host(const float *probs, const int32_t *seq_lens, int B
       }
     }
     CU(cudaStreamSynchronize(s));
+    if (sc) {  // reported scores of the finished streams: approx_ctc (reference ctc_beam_search_decoder.cpp:173-208)
+      std::vector<int> nres_eos(B);
+      for (int b = 0; b < B; ++b) nres_eos[b] = is_eos[b] ? h_nres[b] : 0;
+      lm_rescore_batch(*sc, B, K, out_T, nres_eos.data(), tokens, lens, scores);
+    }
     if (n_results) memcpy(n_results, h_nres.get(), (size_t)B * 4);
     if (flags) memcpy(flags, h_nres.get() + B, (size_t)B * 4);
   } else {
@@ -654,15 +880,7 @@ int ctcdec_decode_batch_lm_host(const ctcdec_config *cfg, void *scorer, const fl
   if (!c.stream) CU(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
   cudaStream_t s = c.stream;
   const int V = cfg->vocab_size, K = cfg->beam_size;
-  // dictionary on the device
-  if (sc->d_next && sc->device != device) { cudaSetDevice(sc->device); cudaFree(sc->d_next); cudaFree(sc->d_final); sc->d_next = nullptr; cudaSetDevice(device); }
-  if (!sc->d_next) {
-    CU(cudaMalloc(&sc->d_next, sc->dict.next.size() * 4));
-    CU(cudaMalloc(&sc->d_final, sc->dict.fin.size()));
-    CU(cudaMemcpy(sc->d_next, sc->dict.next.data(), sc->dict.next.size() * 4, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(sc->d_final, sc->dict.fin.data(), sc->dict.fin.size(), cudaMemcpyHostToDevice));
-    sc->device = device;
-  }
+  if ((rc = ensure_dict_on_device(sc, device))) return rc;
   const size_t n_probs = (size_t)B * T * V, n_out = (size_t)B * K * T, n_bk = (size_t)B * K;
   const size_t nl_ints = (size_t)B * (4 + 4 * K);
   const size_t upd_bytes = al256((size_t)B * 4) + al256(n_bk * 4) + al256(n_bk * 4);
@@ -703,7 +921,7 @@ int ctcdec_decode_batch_lm_host(const ctcdec_config *cfg, void *scorer, const fl
   unsigned char *ws = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(c.buf[5]) + 255) / 256 * 256);
   float *lp = reinterpret_cast<float *>(ws + pl.off_lp);
   uint16_t *idx = pl.sorted ? reinterpret_cast<uint16_t *>(ws + pl.off_idx) : nullptr;
-  if ((rc = launch_prune(cfg, pl, d_probs, d_lens_in, B, T, lp, idx, d_flags, s))) return rc;
+  if ((rc = launch_prune(cfg, pl, PruneInput{d_probs, IN_F32, nullptr}, d_lens_in, B, T, lp, idx, d_flags, s))) return rc;
 
   BeamParams bp;
   memset(&bp, 0, sizeof(bp));
@@ -747,57 +965,20 @@ int ctcdec_decode_batch_lm_host(const ctcdec_config *cfg, void *scorer, const fl
     bp.t0 = 0; bp.nframes = 0; bp.fresh = 1;
     const auto c0 = std::chrono::steady_clock::now();
     if ((rc = launch_beam(bp, pl, B, s))) return rc;
-    unsigned nt = std::thread::hardware_concurrency();
-    if (const char *e = getenv("CTCDEC_LM_THREADS")) nt = (unsigned)atoi(e);
-    nt = nt == 0 ? 1 : (nt > 8 ? 8 : nt);
-    if ((unsigned)B < nt) nt = (unsigned)B;
-    if (sc->cond_caches.size() < nt) sc->cond_caches.resize(nt);
-    std::atomic<int> failed{0};
-    std::atomic<long long> n_hook{0}, n_new{0};
-    auto worker = [&](unsigned w) {
-      std::vector<int> scratch;
-      HostScorer::CondCache &cache = sc->cond_caches[w];
-      int remaining = 0;
-      for (int b = (int)w; b < B; b += (int)nt) remaining += need[b] > 1 ? 1 : 0;
-      std::vector<int> served(B, 0);
-      auto last_progress = std::chrono::steady_clock::now();
-      long long hooks = 0, created = 0;
-      unsigned idle = 0;
-      while (remaining > 0 && !failed.load(std::memory_order_relaxed)) {
-        bool progress = false;
-        for (int b = (int)w; b < B; b += (int)nt) {
-          if (served[b] >= need[b] - 1) continue;
-          const int d = reinterpret_cast<std::atomic<int> *>(&hs_done[b])->load(std::memory_order_acquire);
-          if (d <= served[b]) continue;
-          const int *nl = h_newlist + (size_t)b * (4 + 4 * K);
-          lm_after_frame(*sc, cache, mirror[b], nl, &h_upd_count[b], h_upd_nodes + (size_t)b * K,
-                         h_upd_vals + (size_t)b * K, scratch);
-          hooks += h_upd_count[b];
-          created += nl[0];
-          reinterpret_cast<std::atomic<int> *>(&hs_go[b])->store(d, std::memory_order_release);
-          served[b] = d;
-          if (d >= need[b] - 1) --remaining;
-          progress = true;
-        }
-        if (progress) { idle = 0; last_progress = std::chrono::steady_clock::now(); }
-        else if ((++idle & 0xFFFF) == 0 &&
-                 std::chrono::duration<double>(std::chrono::steady_clock::now() - last_progress).count() > 8.0)
-          failed.store(1);  // the kernel stopped making progress (fault or lost launch): stop waiting
-      }
-      n_hook += hooks; n_new += created;
-    };
-    std::vector<std::thread> pool;
-    for (unsigned w = 1; w < nt; ++w) pool.emplace_back(worker, w);
-    worker(0);
-    for (auto &th : pool) th.join();
-    if (failed.load()) reinterpret_cast<std::atomic<int> *>(hs_abort)->store(1, std::memory_order_release);
+    std::vector<TrieMirror *> mirrors(B);
+    std::vector<int> answers(B);
+    for (int b = 0; b < B; ++b) { mirrors[b] = &mirror[b]; answers[b] = std::max(0, need[b] - 1); }
+    HandshakeStats hst;
+    const int failed = serve_handshakes(sc, B, K, answers.data(), mirrors.data(), h_newlist, h_upd_count, h_upd_nodes,
+                                        h_upd_vals, hs_done, hs_go, &hst);
+    if (failed) reinterpret_cast<std::atomic<int> *>(hs_abort)->store(1, std::memory_order_release);
     const cudaError_t e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) return fail(CTCDEC_E_CUDA, "beam kernel (scorer path): %s", cudaGetErrorString(e));
-    if (failed.load()) return fail(CTCDEC_E_CUDA, "beam kernel (scorer path) stopped answering the per-frame handshake");
+    if (failed) return fail(CTCDEC_E_CUDA, "beam kernel (scorer path) stopped answering the per-frame handshake");
     if (lm_timing)
       fprintf(stderr, "[ctcdec lm] persistent: frames %d, %u host workers, kernel+handshakes %.1f ms (%lld hook calls, %lld new nodes)\n",
-              tmax, nt, std::chrono::duration<double>(std::chrono::steady_clock::now() - c0).count() * 1e3,
-              (long long)n_hook, (long long)n_new);
+              tmax, hst.workers, std::chrono::duration<double>(std::chrono::steady_clock::now() - c0).count() * 1e3,
+              hst.hooks, hst.created);
   } else {
     Plan pl1 = pl;  // one frame per launch: the staged tile is one row
     pl1.F = 1;

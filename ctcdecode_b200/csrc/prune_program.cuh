@@ -15,14 +15,28 @@
 //                           [NP-1] = largest non-blank kept log-prob (-FLT_MAX if none)
 //   idx row (uint16[NP])  : character of each kept entry, 0xFFFF beyond n   (sorted mode only)
 //
+// LOGITS variants (the "step before" of the path): the input is the acoustic model's raw
+// logits in fp32 / fp16 / bf16; the warp computes the frame's log-softmax in float32 into a shared-memory row first
+// (one HBM read of the logits, no probability tensor in between) and continues exactly like log-probability input
+// (reference log_input != 0).  The float32 log-softmax is DEFINED by lsm_row() below (fixed reduction order), and
+// can be written out (lsm_out) so that the reference can be fed bit-identical log-probabilities.
+//
 // Device-only (the CPU logic tests use the mirror in tests/native/emulate_cta.cpp).
 #pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include "beam_core.cuh"
 
 namespace ctc {
 
+enum : int { IN_F32 = 0, IN_LOGITS_F32 = 1, IN_LOGITS_F16 = 2, IN_LOGITS_BF16 = 3 };
+
 struct PruneParams {
-  const float *probs;   // [B][T][V]
+  const float *probs;   // [B][T][V]  probabilities / log-probabilities (in_kind == IN_F32)
+  const void *logits;   // [B][T][V]  raw logits (in_kind != IN_F32)
+  int in_kind;
+  int Vpad;             // floats per staged log-softmax row (LOGITS kernels)
+  float *lsm_out;       // optional [B][T][V] float32: the log-softmax rows the decode used
   const int *seq_lens;  // [B] or nullptr
   int B, T, V, NP, blank, log_input;
   int top_n;            // cutoff_top_n
@@ -49,6 +63,37 @@ CTC_FN float blank_prob_value(const float *row, int blank, int V, int log_input,
 
 CTC_FN float prune_value(float x, int log_input, const double *logtab) {
   return log_input ? x : logprob_glibc_t(x, logtab);  // reference decoder_utils.cpp:40-43
+}
+
+CTC_FN float load_logit(const void *base, int kind, long long i) {
+  if (kind == IN_LOGITS_F16) return __half2float(static_cast<const __half *>(base)[i]);
+  if (kind == IN_LOGITS_BF16) return __bfloat162float(static_cast<const __nv_bfloat16 *>(base)[i]);
+  return static_cast<const float *>(base)[i];
+}
+
+// float32 log-softmax of one frame into rowb[0..V): lane-strided loads, maximum and sum of expf(x - max) reduced
+// over lanes by xor butterflies (fixed order => reproducible), lse = max + logf(sum), value = x - lse.
+__device__ __forceinline__ void lsm_row(const void *logits, int kind, long long f, int V, float *rowb, float *dump,
+                                        int lane) {
+  float m = -__int_as_float(0x7f800000);
+  for (int e = lane; e < V; e += 32) {
+    const float x = load_logit(logits, kind, f * V + e);
+    rowb[e] = x;
+    m = fmaxf(m, x);
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
+  float s = 0.0f;
+  for (int e = lane; e < V; e += 32) s += expf(rowb[e] - m);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+  const float lse = m + logf(s);
+  for (int e = lane; e < V; e += 32) {
+    const float v = rowb[e] - lse;
+    rowb[e] = v;
+    if (dump) dump[f * V + e] = v;
+  }
+  __syncwarp();
 }
 
 // Top-`lim` of a frame without sorting all of it (lim <= 64, V <= 32 * KPL): every lane keeps KPL ordered
@@ -114,7 +159,7 @@ __device__ __forceinline__ bool top_select(const float *row, int V, int lim, uin
 }
 
 // KPL: keys per lane of the partial top-n selection (0 = always sort the whole vocabulary)
-template <bool SORTED, int KPL>
+template <bool SORTED, int KPL, bool LOGITS>
 __global__ void __launch_bounds__(256) prune_kernel(const PruneParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   double *logtab = reinterpret_cast<double *>(smem);  // 256 doubles
@@ -122,11 +167,41 @@ __global__ void __launch_bounds__(256) prune_kernel(const PruneParams p) {
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
   uint64_t *keys = reinterpret_cast<uint64_t *>(smem + 2048) + (size_t)warp * p.P;
+  // LOGITS: per-warp staging row behind the sort keys
+  float *rowb = reinterpret_cast<float *>(smem + 2048 + (SORTED ? (size_t)wpc * p.P * 8 : 0)) + (size_t)warp * p.Vpad;
+  const int log_input = LOGITS ? 1 : p.log_input;
   const long long nframes = (long long)p.B * p.T;
   const int V = p.V, NP = p.NP;
   const int rblank_unsorted = (p.blank >= 0 && p.blank < V) ? p.blank : -1;
   const unsigned ninf_ord = ord_f(kNInf);
 
+  if (!SORTED && LOGITS) {
+    // Index-order mode on logits: log-softmax into the staging row, emit (HBM-bound: no fp64 log on this path)
+    for (long long f = (long long)blockIdx.x * wpc + warp; f < nframes; f += (long long)gridDim.x * wpc) {
+      const int b = (int)(f / p.T), t = (int)(f - (long long)b * p.T);
+      const int len = p.seq_lens ? p.seq_lens[b] : p.T;
+      if (t >= len) continue;
+      lsm_row(p.logits, p.in_kind, f, V, rowb, p.lsm_out, lane);
+      float *out = p.lp + f * NP;
+      unsigned mx = ninf_ord;
+      for (int r = lane; r < NP - kRowTrailer; r += 32) {
+        float w = kNInf;
+        if (r < V) {
+          w = rowb[r];
+          if (r != p.blank) { const unsigned o = ord_f(w); mx = o > mx ? o : mx; }
+        }
+        out[r] = w;
+      }
+      mx = __reduce_max_sync(0xffffffffu, mx);
+      if (lane == 0) {
+        out[NP - 3] = rblank_unsorted >= 0 ? rowb[rblank_unsorted] : kNInf;
+        out[NP - 2] = bits_f((uint32_t)V | ((uint32_t)(rblank_unsorted + 1) << 16));
+        out[NP - 1] = unord_f(mx);
+      }
+      __syncwarp();
+    }
+    return;
+  }
   if (!SORTED) {
     // Index-order mode (nothing is cut): an element-wise fp64 log with a per-frame max.  Four frames per warp
     // iteration so that every lane has four independent log chains in flight (the chain is ~45 dependent
@@ -185,6 +260,10 @@ __global__ void __launch_bounds__(256) prune_kernel(const PruneParams p) {
     int len = p.seq_lens ? p.seq_lens[b] : p.T;
     if (t >= len) continue;
     const float *row = p.probs + f * V;
+    if (LOGITS) {
+      lsm_row(p.logits, p.in_kind, f, V, rowb, p.lsm_out, lane);
+      row = rowb;
+    }
     float *out = p.lp + f * NP;
 
     // ---- sorted mode: std::sort by probability descending (decoder_utils.cpp:22-24); ties -> lower index
@@ -230,7 +309,7 @@ __global__ void __launch_bounds__(256) prune_kernel(const PruneParams p) {
         double pv = 0.0;
         if (i < lim) {
           const double v = (double)unord_f((uint32_t)(keys[i] >> 32));
-          pv = p.log_input ? exp(v) : v;
+          pv = log_input ? exp(v) : v;
         }
         double s = pv;
         for (int d = 1; d < 32; d <<= 1) {
@@ -260,7 +339,7 @@ __global__ void __launch_bounds__(256) prune_kernel(const PruneParams p) {
           double cum = 0.0;  // reference starts the log-domain accumulator at 0.0 (decoder_utils.cpp:26)
           for (int i = 0; i < V; ++i) {
             const double v = (double)unord_f((uint32_t)(keys[i] >> 32));
-            const double term = p.log_input ? v : log(v);
+            const double term = log_input ? v : log(v);
             const double m = cum > term ? cum : term;
             cum = (term <= -DBL_MAX) ? cum : log(exp(cum - m) + exp(term - m)) + m;
             nn += 1;
@@ -283,7 +362,7 @@ __global__ void __launch_bounds__(256) prune_kernel(const PruneParams p) {
       unsigned c = 0xFFFFu;
       if (r < n) {
         c = 0xFFFFFFFFu - (unsigned)(keys[r] & 0xFFFFFFFFull);
-        v = prune_value(unord_f((uint32_t)(keys[r] >> 32)), p.log_input, logtab);
+        v = prune_value(unord_f((uint32_t)(keys[r] >> 32)), log_input, logtab);
         if ((int)c == p.blank) rb = r + 1;
       }
       if (r < 2) first_two = v;
@@ -293,7 +372,7 @@ __global__ void __launch_bounds__(256) prune_kernel(const PruneParams p) {
     rb = __reduce_max_sync(0xffffffffu, rb);
     const float l0 = __shfl_sync(0xffffffffu, first_two, 0), l1 = __shfl_sync(0xffffffffu, first_two, 1);
     if (lane == 0) {
-      out[NP - 3] = blank_prob_value(row, p.blank, V, p.log_input, logtab);
+      out[NP - 3] = blank_prob_value(row, p.blank, V, log_input, logtab);
       out[NP - 2] = bits_f((uint32_t)n | ((uint32_t)rb << 16));
       out[NP - 1] = (rb == 1) ? (n > 1 ? l1 : kNInf) : (n > 0 ? l0 : kNInf);
     }

@@ -23,6 +23,13 @@ import torch
 from . import _native
 
 
+def convert_to_string(tokens, vocabulary, seq_len):
+    """Label ids -> text for one beam: the helper the reference's README suggests callers write themselves
+    (README.md:99-109), e.g. convert_to_string(beam_results[0][0], labels, out_lens[0][0])."""
+    n = int(seq_len)
+    return "".join(vocabulary[int(x)] for x in tokens[:n])
+
+
 def _cfg(decoder):
     return _native.Config(decoder._num_labels, decoder._beam_width, decoder._blank_id, decoder._log_probs,
                           decoder._cutoff_top_n_value(), float(decoder._cutoff_prob))
@@ -30,7 +37,7 @@ def _cfg(decoder):
 
 class _Base(object):
     def _init_common(self, labels, model_path, alpha, beta, cutoff_top_n, cutoff_prob, beam_width, num_processes,
-                     blank_id, log_probs_input, device, scorer_provider=None, allow_scorer=True):
+                     blank_id, log_probs_input, device, scorer_provider=None):
         self._beam_width = int(beam_width)
         self._scorer = None
         self._num_processes = num_processes
@@ -44,8 +51,6 @@ class _Base(object):
         self.last_n_results = None
         _native.load()
         if model_path:
-            if not allow_scorer:
-                raise NotImplementedError("ctcdecode_b200: the online decoder with a scorer is not built")
             from .scorer import ProviderScorer
             self._scorer = ProviderScorer(self._labels, model_path, alpha, beta, scorer_provider)
 
@@ -119,9 +124,60 @@ class CTCBeamDecoder(_Base):
         self.last_flags, self.last_n_results = flags, n_results
         return output, scores, timesteps, out_seq_len
 
-    def _decode_device(self, lib, cfg, probs, seq_lens, B, T, K):
+    def decode_logits(self, logits, seq_lens=None, return_log_probs=False):
+        """Extension ("the step before"): decode the acoustic model's raw LOGITS, a CUDA
+        tensor [B, T, V] in float32 / float16 / bfloat16, without the caller-side softmax the reference asks for
+        (README.md:54-57): the scan kernel computes each frame's float32 log-softmax on the fly and decodes as with
+        log_probs_input=True.  Returns the usual four tensors, plus -- with return_log_probs -- the float32
+        log-softmax the decode used (feeding that to the reference with log_probs_input=True reproduces the result
+        bit for bit)."""
+        lib = _native.load()
+        if self._scorer is not None:
+            raise NotImplementedError("ctcdecode_b200: decode_logits with a scorer is not built")
+        if logits.dim() != 3 or not logits.is_cuda:
+            raise ValueError("logits must be a CUDA tensor [batch, time, labels]")
+        dtypes = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
+        if logits.dtype not in dtypes:
+            raise ValueError("logits must be float32, float16 or bfloat16, got %s" % logits.dtype)
+        B, T, V = logits.shape
+        if V != self._num_labels:
+            raise ValueError("logits has %d labels, decoder was built with %d" % (V, self._num_labels))
+        lsm = torch.empty(B, T, V, dtype=torch.float32, device=logits.device) if return_log_probs else None
+        res = self._decode_device(lib, _cfg(self), logits.contiguous(), seq_lens, B, T, self._beam_width,
+                                  logits_dtype=dtypes[logits.dtype], lsm_out=lsm)
+        return res + (lsm,) if return_log_probs else res
+
+    def pack_results(self, beam_results, timesteps, out_lens, n_results=None):
+        """Extension ("the step after"): compact dense CUDA results [B, beam, T] (from a
+        decoder built with device_outputs=True) into a ragged layout on the device.  Returns (offsets int64
+        [B * beam + 1], tokens int32 [total], timesteps int32 [total]); row r = b * beam + p is
+        tokens[offsets[r]:offsets[r + 1]].  n_results defaults to the last decode's."""
+        lib = _native.load()
+        if not (beam_results.is_cuda and timesteps.is_cuda and out_lens.is_cuda):
+            raise ValueError("pack_results takes the CUDA tensors of a device_outputs=True decode")
+        n_results = self.last_n_results if n_results is None else n_results
+        dev = beam_results.device
+        n_results = n_results.to(device=dev, dtype=torch.int32).contiguous()
+        B, K, T = beam_results.shape
+        beam_results, timesteps, out_lens = beam_results.contiguous(), timesteps.contiguous(), out_lens.contiguous()
+        offsets = torch.empty(B * K + 1, dtype=torch.int64, device=dev)
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _native.check(lib.ctcdec_pack_results_device(
+                beam_results.data_ptr(), timesteps.data_ptr(), out_lens.data_ptr(), n_results.data_ptr(), B, K, T,
+                offsets.data_ptr(), None, None, 0, stream))
+            total = int(offsets[-1])
+            tok = torch.empty(total, dtype=torch.int32, device=dev)
+            ts = torch.empty(total, dtype=torch.int32, device=dev)
+            _native.check(lib.ctcdec_pack_results_device(
+                beam_results.data_ptr(), timesteps.data_ptr(), out_lens.data_ptr(), n_results.data_ptr(), B, K, T,
+                offsets.data_ptr(), tok.data_ptr(), ts.data_ptr(), total, stream))
+        return offsets, tok, ts
+
+    def _decode_device(self, lib, cfg, probs, seq_lens, B, T, K, logits_dtype=None, lsm_out=None):
         dev = probs.device
-        probs = probs.float().contiguous()
+        if logits_dtype is None:
+            probs = probs.float().contiguous()
         if seq_lens is not None:
             seq_lens = seq_lens.to(device=dev, dtype=torch.int32).contiguous()
         nbytes = ctypes.c_size_t(0)
@@ -137,10 +193,18 @@ class CTCBeamDecoder(_Base):
         flags = torch.zeros(B, dtype=torch.int32, device=dev)
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
-            _native.check(lib.ctcdec_decode_batch_device(
-                ctypes.byref(cfg), probs.data_ptr(), seq_lens.data_ptr() if seq_lens is not None else None, B, T,
-                output.data_ptr(), timesteps.data_ptr(), scores.data_ptr(), out_seq_len.data_ptr(),
-                n_results.data_ptr(), flags.data_ptr(), self._ws.data_ptr(), self._ws.numel(), stream))
+            if logits_dtype is None:
+                _native.check(lib.ctcdec_decode_batch_device(
+                    ctypes.byref(cfg), probs.data_ptr(), seq_lens.data_ptr() if seq_lens is not None else None, B, T,
+                    output.data_ptr(), timesteps.data_ptr(), scores.data_ptr(), out_seq_len.data_ptr(),
+                    n_results.data_ptr(), flags.data_ptr(), self._ws.data_ptr(), self._ws.numel(), stream))
+            else:
+                _native.check(lib.ctcdec_decode_batch_device_logits(
+                    ctypes.byref(cfg), probs.data_ptr(), logits_dtype,
+                    seq_lens.data_ptr() if seq_lens is not None else None, B, T, output.data_ptr(),
+                    timesteps.data_ptr(), scores.data_ptr(), out_seq_len.data_ptr(), n_results.data_ptr(),
+                    flags.data_ptr(), lsm_out.data_ptr() if lsm_out is not None else None, self._ws.data_ptr(),
+                    self._ws.numel(), stream))
         self.last_flags, self.last_n_results = flags, n_results
         if self._device_outputs:
             return output, scores, timesteps, out_seq_len
@@ -165,10 +229,10 @@ class OnlineCTCBeamDecoder(_Base):
     DecoderState (beam, trie, absolute frame counter) lives in GPU memory between chunks."""
 
     def __init__(self, labels, model_path=None, alpha=0, beta=0, cutoff_top_n=40, cutoff_prob=1.0, beam_width=100,
-                 num_processes=4, blank_id=0, log_probs_input=False, device=None):
+                 num_processes=4, blank_id=0, log_probs_input=False, device=None, scorer_provider=None):
         self._cutoff_top_n = cutoff_top_n  # private name kept from the reference (:175)
         self._init_common(labels, model_path, alpha, beta, cutoff_top_n, cutoff_prob, beam_width, num_processes,
-                          blank_id, log_probs_input, device, allow_scorer=False)
+                          blank_id, log_probs_input, device, scorer_provider=scorer_provider)
 
     def _cutoff_top_n_value(self):
         return int(self._cutoff_top_n)
@@ -229,7 +293,11 @@ class DecoderState(object):
         lib = _native.load()
         cfg = _cfg(decoder)
         handle = ctypes.c_void_p()
-        _native.check(lib.ctcdec_state_create(ctypes.byref(cfg), decoder._device_index(), ctypes.byref(handle)))
+        # the scorer is borrowed by the state (reference ctc_beam_search_decoder.cpp:31): keep the decoder alive
+        self._decoder = decoder
+        scorer = decoder._scorer.handle if decoder._scorer else None
+        _native.check(lib.ctcdec_state_create_lm(ctypes.byref(cfg), scorer, decoder._device_index(),
+                                                 ctypes.byref(handle)))
         self.state = handle.value
 
     def release(self):

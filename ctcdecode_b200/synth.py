@@ -6,8 +6,8 @@ on the CPU so that the reference/oracle and the CUDA path see identical float32 
 import torch
 
 
-def ctc_like_probs(B, T, V, seed=0, peak=8.0, p_blank=0.8, blank_id=0, log=False):
-    """Returns float32 [B, T, V] probabilities (or log-probabilities) on the CPU."""
+def ctc_like_probs(B, T, V, seed=0, peak=8.0, p_blank=0.8, blank_id=0, log=False, raw_logits=False):
+    """Returns float32 [B, T, V] probabilities (or log-probabilities, or the raw logits) on the CPU."""
     g = torch.Generator().manual_seed(seed)
     nonblank = torch.randint(1, V, (B, T), generator=g)
     if blank_id != 0:
@@ -16,6 +16,8 @@ def ctc_like_probs(B, T, V, seed=0, peak=8.0, p_blank=0.8, blank_id=0, log=False
     tgt = torch.where(torch.rand(B, T, generator=g) < p_blank, torch.full((B, T), blank_id), nonblank)
     logits = torch.randn(B, T, V, generator=g)
     logits.scatter_add_(2, tgt.unsqueeze(-1), torch.full((B, T, 1), float(peak)))
+    if raw_logits:
+        return logits.contiguous()
     if log:
         return torch.log_softmax(logits, dim=-1).contiguous()
     return torch.softmax(logits, dim=-1).contiguous()

@@ -80,6 +80,31 @@ int ctcdec_decode_batch_device(const ctcdec_config *cfg, const float *probs, con
                                int32_t *n_results, int32_t *flags, void *workspace, size_t workspace_bytes,
                                void *stream);
 
+/* The step BEFORE the path, fused: the acoustic model's raw LOGITS [B, T, V] on the
+ * device, in float32 / float16 / bfloat16.  The reference makes callers soft-max on their side and then re-takes the
+ * logarithm per frame (README.md:54-57, decoder_utils.cpp:40-43); here the scan kernel computes the float32
+ * log-softmax of each frame on the fly and decodes as with log_probs_input (cfg->log_input is ignored): one HBM
+ * read of the logits, no probability tensor.  If log_probs_out is not NULL the [B, T, V] float32 log-softmax rows
+ * the decode used are written there; the reference, fed those values with log_probs_input=True, gives bit-identical
+ * results (that is how the parity test for this entry point works).  Everything else as above. */
+#define CTCDEC_DTYPE_F32 0
+#define CTCDEC_DTYPE_F16 1
+#define CTCDEC_DTYPE_BF16 2
+int ctcdec_decode_batch_device_logits(const ctcdec_config *cfg, const void *logits, int dtype, const int32_t *seq_lens,
+                                      int B, int T, int32_t *tokens, int32_t *timesteps, float *scores, int32_t *lens,
+                                      int32_t *n_results, int32_t *flags, float *log_probs_out, void *workspace,
+                                      size_t workspace_bytes, void *stream);
+
+/* The step AFTER the path: compact the dense [B, beam, T] results of
+ * ctcdec_decode_batch_device (of which only [b, p, :lens[b, p]] is meaningful, reference binding.cpp:79-99) into a
+ * ragged layout on the device.  offsets [B * beam + 1] (int64): exclusive prefix sum of the row lengths, rows
+ * p >= n_results[b] counting 0, offsets[B * beam] = total; packed_tokens / packed_timesteps [capacity]: rows whose
+ * end exceeds `capacity` are not written (compare offsets[B * beam] with capacity).  All DEVICE pointers; enqueued
+ * on `stream`. */
+int ctcdec_pack_results_device(const int32_t *tokens, const int32_t *timesteps, const int32_t *lens,
+                               const int32_t *n_results, int B, int K, int T, int64_t *offsets,
+                               int32_t *packed_tokens, int32_t *packed_timesteps, size_t capacity, void *stream);
+
 /* Same operation with HOST buffers shaped exactly like the reference's CPU tensors
  * (reference __init__.py:77-86); copies in and out through pinned staging on `device`. */
 int ctcdec_decode_batch_host(const ctcdec_config *cfg, const float *probs, const int32_t *seq_lens, int B, int T,
@@ -134,6 +159,12 @@ int ctcdec_decode_batch_lm_host(const ctcdec_config *cfg, void *scorer, const fl
 /* Replaces: paddle_get_decoder_state (binding.cpp:246-261).  The state (beam + trie + absolute frame
  * counter, reference ctc_beam_search_decoder.h:73-124) lives in device memory of `device`. */
 int ctcdec_state_create(const ctcdec_config *cfg, int device, void **state);
+/* The same with a word-based scorer (the `void *scorer` argument of paddle_get_decoder_state, binding.cpp:246-261).
+ * The scorer is BORROWED and must outlive the state (reference ctc_beam_search_decoder.cpp:31); scorer == NULL is
+ * ctcdec_state_create.  Chunks of such states are decoded by ctcdec_decode_stream_host: one persistent launch per
+ * chunk with the per-frame hook handshake of ctcdec_decode_batch_lm_host, scores re-computed at eos like
+ * DecoderState::decode (ctc_beam_search_decoder.cpp:164-211). */
+int ctcdec_state_create_lm(const ctcdec_config *cfg, void *scorer, int device, void **state);
 /* Replaces: paddle_release_state (binding.cpp:263-265). */
 int ctcdec_state_destroy(void *state);
 /* Frames consumed so far (reference DecoderState::abs_time_step). */

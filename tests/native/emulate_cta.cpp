@@ -238,13 +238,21 @@ int emu_decode_batch_lm(const float *probs, const int *seq_lens, int B, int T, i
       lm_after_frame(*x->sc, x->sc->cond_caches[0], (*x->mirror)[b], x->newlist + (size_t)b * (4 + 4 * x->K), &x->uc[b],
                      x->un + (size_t)b * x->K, x->uv + (size_t)b * x->K, *x->scratch);
     };
-    bp.t0 = 0; bp.nframes = 0; bp.fresh = 1;
-    switch (NT) {
-      case 32: run_beam<32>(bp, pl.sorted, B, smem.data()); break;
-      case 64: run_beam<64>(bp, pl.sorted, B, smem.data()); break;
-      case 128: run_beam<128>(bp, pl.sorted, B, smem.data()); break;
-      case 512: run_beam<512>(bp, pl.sorted, B, smem.data()); break;
-      default: run_beam<256>(bp, pl.sorted, B, smem.data()); break;
+    // CTC_EMU_LM_CHUNK=n: the streaming shape -- launches of n frames over saved state, handshake after the last
+    // frame of every launch too (a next chunk follows)
+    const int chunk = getenv("CTC_EMU_LM_CHUNK") ? atoi(getenv("CTC_EMU_LM_CHUNK")) : 0;
+    int tm = 0;
+    for (int b = 0; b < B; ++b) tm = std::max(tm, std::min(seq_lens ? seq_lens[b] : T, T));
+    for (int t0 = 0; t0 < std::max(tm, 1); t0 += (chunk > 0 ? chunk : std::max(tm, 1))) {
+      bp.t0 = t0; bp.nframes = chunk > 0 ? chunk : 0; bp.fresh = t0 == 0 ? 1 : 0;
+      bp.lm_hs_last = chunk > 0 ? 1 : 0;
+      switch (NT) {
+        case 32: run_beam<32>(bp, pl.sorted, B, smem.data()); break;
+        case 64: run_beam<64>(bp, pl.sorted, B, smem.data()); break;
+        case 128: run_beam<128>(bp, pl.sorted, B, smem.data()); break;
+        case 512: run_beam<512>(bp, pl.sorted, B, smem.data()); break;
+        default: run_beam<256>(bp, pl.sorted, B, smem.data()); break;
+      }
     }
     std::vector<unsigned char> fsmem2((size_t)K * 12 + 64);
     for (int b = 0; b < B; ++b) finalize_cta_run<128>(bp, b, fsmem2.data());

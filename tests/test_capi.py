@@ -80,7 +80,7 @@ def test_lm_path_needs_a_provider(monkeypatch):
     monkeypatch.delenv("CTCDECODE_B200_SCORER_PROVIDER", raising=False)
     with pytest.raises(RuntimeError, match="scorer provider"):
         ctcdecode_b200.CTCBeamDecoder(list("_abc "), model_path="/nonexistent.arpa")
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError, match="scorer provider"):
         ctcdecode_b200.OnlineCTCBeamDecoder(list("_abc "), model_path="/nonexistent.arpa")
 
 

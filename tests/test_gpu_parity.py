@@ -195,3 +195,83 @@ def test_full_size_config4_slice(cport):
                lens=lens[sl].cpu().numpy(), n_results=dec.last_n_results[sl].cpu().numpy(),
                ties=dec.last_flags[sl].cpu().numpy())
     compare(ref, got, ref["ties"], "config4 slice")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16], ids=["f32", "f16", "bf16"])
+@pytest.mark.parametrize("cfg", [
+    dict(V=29, beam=24),                                   # index-order scan
+    dict(V=29, beam=16, cutoff_top_n=8),                   # partial top-n selection
+    dict(V=64, beam=16, cutoff_prob=0.99),                 # cumulative cutoff (quirk Q1: still top-n)
+    dict(V=300, beam=12, cutoff_top_n=300),                # index-order rows wider than a warp
+    dict(V=1500, beam=8, cutoff_top_n=20),                 # full bitonic sort
+], ids=["plain", "top8", "cp99", "wide", "sort1500"])
+def test_decode_logits_fused_log_softmax(cport, dtype, cfg):
+    """raw logits (fp32 / fp16 / bf16) in, log-softmax fused into the scan kernel.  The float32
+    log-softmax the kernel used (a) is the log-softmax of the input to float32 rounding and (b) fed to the oracle
+    as log-probability input gives the identical decode -- integers and float32 scores bit for bit."""
+    from ctcdecode_b200 import CTCBeamDecoder
+    cfg = dict(cfg)
+    V, beam = cfg.pop("V"), cfg.pop("beam")
+    x = ctc_like_probs(3, 120, V, seed=61, raw_logits=True).to(dtype).cuda()
+    seq_lens = torch.tensor([120, 77, 0], dtype=torch.int32)
+    dec = CTCBeamDecoder([str(i) for i in range(V)], beam_width=beam, **cfg)
+    out, scores, ts, lens, lsm = dec.decode_logits(x, seq_lens, return_log_probs=True)
+    want_lsm = torch.log_softmax(x.float(), dim=-1)
+    for b, n in enumerate(seq_lens.tolist()):
+        assert torch.allclose(lsm[b, :n], want_lsm[b, :n], rtol=0, atol=4e-6)
+    lsm_cpu = lsm.cpu()
+    for b, n in enumerate(seq_lens.tolist()):
+        lsm_cpu[b, n:] = 0.0   # frames beyond seq_len are never read (nor written)
+    want = cport.decode(lsm_cpu.numpy(), seq_lens.numpy(), beam=beam, log_input=True, **cfg)
+    got = dict(tokens=out.numpy(), timesteps=ts.numpy(), scores=scores.numpy(), lens=lens.numpy(),
+               n_results=dec.last_n_results.numpy(), ties=dec.last_flags.numpy())
+    compare(want, got, want["ties"], "logits %s %s" % (dtype, cfg))
+    # and the public contract: the same as decoding the log-softmax with log_probs_input=True
+    dec2 = CTCBeamDecoder([str(i) for i in range(V)], beam_width=beam, log_probs_input=True, **cfg)
+    out2, scores2, ts2, lens2 = dec2.decode(lsm_cpu.cuda(), seq_lens)
+    assert torch.equal(lens, lens2)
+    for b in range(3):
+        for p in range(int(dec.last_n_results[b])):
+            n = int(lens[b, p])
+            assert torch.equal(out[b, p, :n], out2[b, p, :n]) and torch.equal(ts[b, p, :n], ts2[b, p, :n])
+            assert scores[b, p] == scores2[b, p]
+
+
+def test_pack_results_ragged_layout_and_string_helper():
+    """SURVEY.md 8f row 4: dense [B, beam, T] device results -> ragged (offsets, tokens, timesteps) on the device;
+    every row equals the dense row's meaningful prefix; rows beyond n_results are empty."""
+    import ctcdecode_b200
+    V, K = 29, 24
+    labels = ["_"] + [chr(ord("a") + i) for i in range(26)] + [" ", "'"]
+    p = ctc_like_probs(5, 150, V, seed=71)
+    sl = torch.tensor([150, 3, 0, 80, 149], dtype=torch.int32)
+    dec = ctcdecode_b200.CTCBeamDecoder(labels, beam_width=K, device_outputs=True)
+    out, scores, ts, lens = dec.decode(p.cuda(), sl)
+    offsets, ptok, pts = dec.pack_results(out, ts, lens)
+    offsets, ptok, pts = offsets.cpu(), ptok.cpu(), pts.cpu()
+    out, ts, lens, nres = out.cpu(), ts.cpu(), lens.cpu(), dec.last_n_results.cpu()
+    assert offsets[0] == 0 and offsets[-1] == ptok.numel() == pts.numel()
+    total = 0
+    for b in range(5):
+        for q in range(K):
+            r = b * K + q
+            n = int(lens[b, q]) if q < int(nres[b]) else 0
+            assert int(offsets[r + 1] - offsets[r]) == n
+            assert torch.equal(ptok[offsets[r]:offsets[r + 1]], out[b, q, :n])
+            assert torch.equal(pts[offsets[r]:offsets[r + 1]], ts[b, q, :n])
+            total += n
+    assert total == int(offsets[-1]) and total < out.numel() // 3
+    text = ctcdecode_b200.convert_to_string(out[0, 0], labels, lens[0, 0])
+    assert len(text) == int(lens[0, 0]) and set(text) <= set(labels)
+    # a batch larger than one scan tile (B * beam > 1024)
+    dec2 = ctcdecode_b200.CTCBeamDecoder(labels, beam_width=100, device_outputs=True)
+    p2 = ctc_like_probs(24, 60, V, seed=72)
+    out, scores, ts, lens = dec2.decode(p2.cuda())
+    offsets, ptok, pts = dec2.pack_results(out, ts, lens)
+    nres = dec2.last_n_results
+    mask = torch.arange(100, device=lens.device)[None, :] < nres[:, None]
+    want = torch.cumsum((lens * mask).flatten().long(), 0)
+    assert torch.equal(offsets[1:], want)
+    r = 24 * 100 - 1 - 37
+    b, q = divmod(r, 100)
+    assert torch.equal(ptok[offsets[r]:offsets[r + 1]], out[b, q, :int(offsets[r + 1] - offsets[r])])

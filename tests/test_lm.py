@@ -30,12 +30,15 @@ def _emul_lm(ref, probs, labels, alpha, beta, seq_lens=None, **kw):
 
 
 @needs_ref
-@pytest.mark.parametrize("per_frame", [False, True], ids=["persistent", "per_frame_launch"])
+@pytest.mark.parametrize("per_frame", [False, True, 7], ids=["persistent", "per_frame_launch", "chunks_of_7"])
 @pytest.mark.parametrize("name", golden_util.names(lm=True))
 def test_emulation_lm_matches_reference_golden(name, per_frame, monkeypatch):
-    """both host/kernel protocols: one persistent launch with a per-frame handshake (default), one launch per frame"""
-    if per_frame:
+    """the host/kernel protocols: one persistent launch with a per-frame handshake (default), one launch per frame,
+    and the streaming shape (launches of 7 frames over saved state)"""
+    if per_frame is True:
         monkeypatch.setenv("CTC_EMU_LM_PER_FRAME", "1")
+    elif per_frame:
+        monkeypatch.setenv("CTC_EMU_LM_CHUNK", str(per_frame))
     probs, seq_lens, kw, gold, alpha, beta = golden_util.load_lm(name)
     ref = orc.Reference(L29, model_path=TINY, alpha=alpha, beta=beta)
     got = _emul_lm(ref, probs, L29, alpha, beta, seq_lens=seq_lens, **kw)
@@ -158,3 +161,50 @@ def test_cuda_lm_matches_live_reference_and_reset_params():
     got = dict(tokens=out.numpy(), timesteps=ts.numpy(), scores=scores.numpy(), lens=lens.numpy(),
                n_results=dec.last_n_results.numpy(), ties=dec.last_flags.numpy())
     compare(want, got, None, "after reset_params")
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(PROVIDER), reason="scorer provider (oracle/_ref/libctcref.so) not shipped")
+def test_cuda_online_decoder_with_scorer_matches_reference_online_path():
+    """reference tests/test_decode.py:93-115,141-159 shape (OnlineCTCBeamDecoder with a language model, one call and
+    several calls), on the tiny LM: chunked decoding through device-resident DecoderStates against the reference's
+    own decode-with-states path AND against its offline path -- all beams, scores bit-exact; streams of one call
+    end at different times."""
+    import torch
+    import ctcdecode_b200
+    probs = text_probs(TEXTS, L29, 240, seed=41)
+    ref = orc.Reference(L29, model_path=TINY, alpha=1.5, beta=0.7)
+    want_off = ref.decode(probs.numpy(), beam=32)
+    dec = ctcdecode_b200.OnlineCTCBeamDecoder(L29, model_path=TINY, alpha=1.5, beta=0.7, beam_width=32,
+                                              scorer_provider=PROVIDER)
+    assert dec.dict_size() == 9
+
+    def as_dict(res, scores, ts, lens, d):
+        return dict(tokens=res.numpy(), timesteps=ts.numpy(), scores=scores.numpy(), lens=lens.numpy(),
+                    n_results=d.last_n_results.numpy(), ties=d.last_flags.numpy())
+    # one call
+    st = [ctcdecode_b200.DecoderState(dec) for _ in range(3)]
+    got = as_dict(*dec.decode(probs, st, [True] * 3), dec)
+    compare(want_off, got, None, "online+scorer, one call")
+    assert "".join(L29[x] for x in got["tokens"][0, 0, :got["lens"][0, 0]]) == TEXTS[0]
+    # several calls, against the reference's own streaming path fed the same chunks
+    st = [ctcdecode_b200.DecoderState(dec) for _ in range(3)]
+    rst = [ref.state_new(32) for _ in range(3)]
+    cuts = [(0, 1), (1, 60), (60, 61), (61, 200)]
+    for a, b in cuts:
+        r = dec.decode(probs[:, a:b], st, [False] * 3)
+        assert r[0].shape == (3, 0, 0)
+        ref.decode_with_states(probs[:, a:b].numpy(), rst, [False] * 3, 32)
+    got = as_dict(*dec.decode(probs[:, 200:], st, [True] * 3), dec)
+    want = ref.decode_with_states(probs[:, 200:].numpy(), rst, [True] * 3, 32, max_len=240)
+    n = got["tokens"].shape[2]
+    want_c = dict(tokens=want["tokens"][:, :, :n], timesteps=want["timesteps"][:, :, :n], scores=want["scores"],
+                  lens=want["lens"], n_results=want_off["n_results"])
+    compare(want_c, got, None, "online+scorer, five calls vs reference streaming")
+    compare(want_off, got, None, "online+scorer, five calls vs reference offline")
+    for s in rst:
+        ref.state_free(s)
+    # a state created without a scorer cannot be mixed with scorer states
+    plain = ctcdecode_b200.OnlineCTCBeamDecoder(L29, beam_width=32)
+    with pytest.raises(Exception):
+        dec.decode(probs[:2, :4], [ctcdecode_b200.DecoderState(dec), ctcdecode_b200.DecoderState(plain)], [False] * 2)

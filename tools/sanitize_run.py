@@ -21,3 +21,16 @@ dec.decode(p[:, :30], st, [False] * 3)
 dec.decode(p[:, 30:], st, [True] * 3)
 torch.cuda.synchronize()
 print("sanitize_run done")
+# scorer path (both host/kernel protocols), when the provider library travelled with the snapshot
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PROVIDER = os.path.join(ROOT, "oracle", "_ref", "libctcref.so")
+if os.path.exists(PROVIDER):
+    from ctcdecode_b200.synth import text_probs  # noqa: E402
+    LBL = ["_"] + [chr(ord("a") + i) for i in range(26)] + [" ", "'"]
+    q = text_probs(["the cat sat on the mat", "a dog ran fast"], LBL, 60, seed=3)
+    d = CTCBeamDecoder(LBL, model_path=os.path.join(ROOT, "tests", "data", "tiny_lm.arpa"), alpha=1.0, beta=0.5,
+                       beam_width=16, scorer_provider=PROVIDER)
+    d.decode(q)
+    os.environ["CTCDEC_LM_PER_FRAME"] = "1"
+    d.decode(q)
+    print("scorer path done")
