@@ -45,6 +45,7 @@
 #define CTC_WARPS for (int warp = 0; warp < NT / 32; ++warp)
 #define CTC_LANES for (int lane = 0, LX = 0; lane < 32; ++lane, ++LX)
 #define CTC_BARRIER() ((void)0)
+#define CTC_SYNCWARP() ((void)0)
 #define CTC_FN static inline
 #define CTC_MFN inline
 namespace ctc { constexpr int kLW = 32; }
@@ -53,6 +54,7 @@ namespace ctc { constexpr int kLW = 32; }
 #define CTC_WARPS for (int warp = (int)(threadIdx.x >> 5), once_w_ = 1; once_w_; once_w_ = 0)
 #define CTC_LANES for (int lane = (int)(threadIdx.x & 31), LX = 0, once_l_ = 1; once_l_; once_l_ = 0)
 #define CTC_BARRIER() __syncthreads()
+#define CTC_SYNCWARP() __syncwarp()
 #define CTC_FN __device__ __forceinline__
 #define CTC_MFN __device__ __forceinline__
 namespace ctc { constexpr int kLW = 1; }

@@ -431,6 +431,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
     // (reference ctc_beam_search_decoder.cpp:97-118,138-139; path_trie.cpp:39-57,129-137)
     CTC_PAR {
       for (int x = tid; x < 2 * kNBins; x += NT) c.s_hist[x] = 0;
+      if (tid == 0) s_ctl[C_NREV] = 0;  // (not with the other counters in R5: slow threads may still be reading it there)
       unsigned kmin = 0xFFFFFFFFu, kmax = 0u, smax = 0u;
       int npairs = 0;
       for (int j0 = 0; j0 < M; j0 += NT) {
@@ -956,6 +957,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
             }
           }
           const unsigned bal = ctc_ballot(sel);
+          CTC_SYNCWARP();  // in-place compaction: every lane has read its entry before any lane overwrites one
           CTC_LANES {
             if (sel[LX]) segi[out + ctc_popc(bal & ctc_lt_mask(lane))] = idv[LX];
           }
@@ -1245,7 +1247,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
       for (int x = tid; x < KP * W; x += NT) { c.s_mask[x] = 0u; c.s_rmask[x] = 0u; }
       if (SORTED) for (int r = tid; r < n; r += NT) c.s_rank[c.idx[r]] = (int16_t)-1;
       if (tid == 0) {  // (C_NLIVE / C_ANYREF are read below and reset in region R4c of the next frame)
-        s_ctl[C_NSEL] = 0; s_ctl[C_NFREE] = 0; s_ctl[C_NTIE] = 0; s_ctl[C_NREV] = 0; s_ctl[C_NPAIRS] = 0;
+        s_ctl[C_NSEL] = 0; s_ctl[C_NFREE] = 0; s_ctl[C_NTIE] = 0; s_ctl[C_NPAIRS] = 0;
         s_ctl[C_ABOVE] = 0; s_ctl[C_KMIN] = (int)0xFFFFFFFFu; s_ctl[C_KMAX] = 0; s_ctl[C_SMAX] = 0;
         s_ctl[C_NEFREE] = 0; s_ctl[C_NETAKEN] = 0; s_ctl[C_OVF] = 0; s_ctl[C_SMIN] = (int)0xFFFFFFFFu;
         s_ctl[C_NCAND] = 0;
@@ -1339,6 +1341,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
       }
 #endif
       CTC_BARRIER();
+      CTC_TICK(12);  // handshake: fence, flag, wait for the host
       CTC_PAR {
         const int nu = ((volatile const int *)p.lm_update_count)[b];
         for (int q = tid; q < nu; q += NT)
@@ -1350,6 +1353,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
         for (int j = tid; j < M; j += NT) c.s_lmsp[j] = ld_cg(&lm_arena[c.s_node[j]]);
       }
       CTC_BARRIER();
+      CTC_TICK(13);  // LM terms in
     }
     CTC_STAT(g_stats.frames++);
     CTC_STAT(g_stats.tie_frames += tie_m > 0);

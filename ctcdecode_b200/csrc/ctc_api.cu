@@ -935,6 +935,7 @@ int ctcdec_decode_batch_lm_host(const ctcdec_config *cfg, void *scorer, const fl
   bp.force_fallback = getenv("CTCDEC_FORCE_FALLBACK") ? 1 : 0;
   bp.dict_next = sc->d_next; bp.dict_final = sc->d_final; bp.dict_start = sc->dict.start;
   bp.space_id = sc->space_id; bp.beta = sc->beta; bp.lm_arena = d_lm_arena; bp.dstate_arena = d_dstate;
+  bp.timing = g_prof.timing;
   // The per-frame exchange with the host goes through pinned, device-mapped host memory (unified addressing):
   // the kernel reads the few LM updates and writes the new-node list straight over PCIe, so a frame costs one
   // launch and one stream synchronisation, no memcpy calls.
