@@ -74,7 +74,11 @@ enum : int {
 constexpr float kNInf = -FLT_MAX;  // reference NUM_FLT_INF negated (decoder_utils.h:12)
 constexpr int kNBins = 256;
 constexpr int kRowTrailer = 3;  // trailing floats of a pruned row: blank log-prob (no FLT_MIN), meta, max non-blank
-constexpr int kNewFlag = 1 << 30;  // in-frame marker: "parent slot refers to this frame's NEW occupant"
+constexpr int kNewFlag = 1 << 30;
+// packed dictionary arc (lm_host.h pack_dictionary): the target state in the low bits, plus
+constexpr int kDictFinal = 1 << 30;        // the target is a final state: the child restarts at the start state
+constexpr int kDictSpace = 1 << 29;        // the state the child ends up in has an arc for the space label
+constexpr int kDictStateMask = (1 << 29) - 1;  // in-frame marker: "parent slot refers to this frame's NEW occupant"
 
 // Trie node in the global arena: exactly what the final backtrace needs (reference path_trie.cpp:109-126).
 struct alignas(16) Node {
@@ -122,25 +126,29 @@ struct BeamParams {
   long long *timing;  // optional [B][16]: cycles thread 0 spent between consecutive barriers, per region
   // ---- scorer path (word-based LM + dictionary, reference ctc_beam_search_decoder.cpp:74-82,93-95,120-137 and
   //      path_trie.cpp:59-96); everything below is unused (0 / nullptr) when no scorer is attached
-  const int *dict_next;             // [n_states][V]: next dictionary state, -1 = no arc
-  const unsigned char *dict_final;  // [n_states]: 1 = final state (the child restarts at dict_start)
+  const int *dict_next;             // [n_states][V]: -1 = no arc, else next state | kDictFinal | kDictSpace
+  const uint32_t *dict_mask;        // [n_states][dict_wc]: bit c = the state has an arc for character c
+  int dict_wc;                      // words per mask row, ceil(V / 32)
   int dict_start;
   int space_id;                     // label of " ", -2 if there is none (reference :34-40)
   double beta;                      // Scorer::beta
   float *lm_arena;                  // [B][arena_stride]: per node float(cond_log_prob(make_ngram(node)) * alpha)
   int *dstate_arena;                // [B][arena_stride]: per node dictionary state
-  int *newlist;                     // [B][1 + 4K]: count, then (node, parent, chr, needs_lm) per node created
-  const int *lm_update_count;       // [B]: scores the host computed for nodes created by the previous frame
-  const int *lm_update_nodes;       // [B][K]
-  const float *lm_update_vals;      // [B][K]
+  // The exchange with the host's Scorer hook: two blocks per utterance in device-mapped pinned host memory, each
+  // starting on its own 128-byte line (lm_nl_stride / lm_up_stride ints apart, lm_host.h exchange_strides):
+  //   newlist  (device -> host)  [0] = number of entries, [1] = frames finished ("done" flag, persistent mode),
+  //                              from [4]: 16-byte entries (node, parent, chr, needs_lm) per node created this frame
+  //   lm_upd   (host -> device)  [0] = frames answered ("go" flag, persistent mode), [1] = number of pairs,
+  //                              from [2]: (node, float bits of its LM term) pairs for the nodes of the last list
+  int *newlist;
+  const int *lm_upd;
+  int lm_nl_stride, lm_up_stride;
   // persistent scorer mode: ONE launch for the whole utterance; after every frame the CTA publishes its new-node
-  // list in device-mapped host memory, raises hs_done[b] and spins on hs_go[b] until the host has answered.
+  // list, raises the done flag and warp 0 polls the go flag's line until the host has answered.
   int lm_persistent;
   int lm_hs_last;                   // also hand shake after the LAST frame of the launch (streaming: a next chunk follows)
   float *const *lm_arena_ptrs;      // streaming: per-stream LM / dictionary-state arrays (else lm_arena + b * stride)
   int *const *dstate_ptrs;
-  int *hs_done;                     // [B] mapped host memory, written by the device: frames finished
-  int *hs_go;                       // [B] mapped host memory, written by the host: frames answered
   int *hs_abort;                    // [1] mapped host memory: host asks the kernel to stop waiting
   void (*emu_handshake)(void *ctx, int b);  // CPU emulation only: the host side of the handshake, called in place
   void *emu_ctx;
@@ -151,6 +159,7 @@ struct SmemLayout {
   int tile_lp, tile_idx, mbar, rank, exptab, logtab;
   int node, chr, depth, bprev, nbprev, score, lpc, ts, pslot, anch;  // persistent slot arrays [KP]
   int dstate, lmsp, ddstate;                                         // scorer path: [KP], [KP], [2*KP]
+  int dmask, WC;                                                     // scorer path: [KP][WC] dictionary arc bits
   int bnew, nbnew, snew;                                             // per-frame slot temporaries [KP]
   int mask, rmask;                                                   // [KP][W] bitmasks over pruned ranks
   int evict;                                                         // [KP]
@@ -167,7 +176,7 @@ struct SmemLayout {
   int KP, W, NW, seg;
 };
 CTC_HD int align_up(int x, int a) { return (x + a - 1) / a * a; }
-CTC_HD SmemLayout make_layout(int K, int V, int NP, int tile_frames, bool sorted, int NT) {
+CTC_HD SmemLayout make_layout(int K, int V, int NP, int tile_frames, bool sorted, int NT, bool lm = false) {
   SmemLayout L;
   const int KP = align_up(K, 32);
   const int W = (NP + 31) / 32;
@@ -196,6 +205,8 @@ CTC_HD SmemLayout make_layout(int K, int V, int NP, int tile_frames, bool sorted
   L.dstate = o;    o += KP * 4;
   L.lmsp = o;      o += KP * 4;
   L.ddstate = o;   o += 2 * KP * 4;
+  L.WC = (V + 31) / 32;
+  L.dmask = o;     o += lm ? KP * L.WC * 4 : 0;
   L.bnew = o;      o += KP * 4;
   L.nbnew = o;     o += KP * 4;
   L.snew = o;      o += KP * 4;
@@ -329,6 +340,8 @@ struct Cta {
   int K, KP, V, NP, W, blank;
   // scorer path, per frame: prune everything under min_cutoff once the beam is full (reference :74-82,93-95)
   const int *dict_next;
+  uint32_t *s_dmask;    // [KP][WC]: which characters the dictionary lets follow each member
+  int WC;
   int space_id;
   double beta;
   bool lm_full;
@@ -337,6 +350,7 @@ struct Cta {
   CTC_MFN int chr_at(int r) const { return SORTED ? (int)idx[r] : r; }
   CTC_MFN int rank_of(int c) const { return SORTED ? (int)s_rank[c] : c; }
   // `if (full_beam && log_prob_c + prefix->score < min_cutoff) break;`  (reference :93-95)
+  CTC_MFN bool dict_ok(int i, int c) const { return (s_dmask[i * WC + (c >> 5)] >> (c & 31)) & 1u; }
   CTC_MFN bool lm_cut(float l, float score) const { return LM && lm_full && f_add(l, score) < lm_cutoff; }
   // language model term when the appended character is the space (reference :120-137): log_p += score; log_p += beta
   CTC_MFN float lm_apply(float log_p, int i) const {
@@ -355,7 +369,7 @@ struct Cta {
       if (lm_cut(l, s_score[i])) return false;
       // a child that does not exist yet needs a dictionary arc (reference path_trie.cpp:59-70); an existing dead
       // child (rmask) is found before the dictionary is consulted (path_trie.cpp:39-57)
-      if (!((s_rmask[i * W + (r >> 5)] >> (r & 31)) & 1u) && dict_next[(long long)s_dstate[i] * V + c] < 0) return false;
+      if (!((s_rmask[i * W + (r >> 5)] >> (r & 31)) & 1u) && !dict_ok(i, c)) return false;
     }
     if (c == s_chr[i]) {
       const float b = s_bprev[i];

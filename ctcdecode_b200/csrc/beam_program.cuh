@@ -208,7 +208,7 @@ CTC_FN void flush_lpc_ts(Node *p, float lpc, int ts) {
 template <int NT, bool SORTED, bool LM>
 CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) {
   const int K = p.K, V = p.V, NP = p.NP, F = p.tile_frames;
-  const SmemLayout L = make_layout(K, V, NP, F, SORTED, NT);
+  const SmemLayout L = make_layout(K, V, NP, F, SORTED, NT, LM);
   const int KP = L.KP, W = L.W, KP2 = 2 * L.KP;
 
   Cta<SORTED, LM> c;
@@ -240,6 +240,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
   c.s_exptab = (uint64_t *)(smem + L.exptab);
   c.s_logtab = (double *)(smem + L.logtab);
   c.K = K; c.KP = KP; c.V = V; c.NP = NP; c.W = W; c.blank = p.blank;
+  c.s_dmask = (uint32_t *)(smem + L.dmask); c.WC = L.WC;
   c.dict_next = p.dict_next; c.space_id = p.space_id; c.beta = p.beta; c.lm_full = false; c.lm_cutoff = kNInf;
   int *const s_ctl = c.s_ctl;
 #if !defined(CTC_EMULATE)
@@ -256,7 +257,45 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
   c.nodes = nodes;
   float *const lm_arena = !LM ? nullptr : p.lm_arena_ptrs ? p.lm_arena_ptrs[b] : p.lm_arena + (long long)b * p.arena_stride;
   int *const dstate_arena = !LM ? nullptr : p.dstate_ptrs ? p.dstate_ptrs[b] : p.dstate_arena + (long long)b * p.arena_stride;
-  int *const newlist = LM ? p.newlist + (long long)b * (4 + 4 * K) : nullptr;
+  int *const newlist = LM ? p.newlist + (long long)b * p.lm_nl_stride : nullptr;
+  const int *const lm_upd = LM ? p.lm_upd + (long long)b * p.lm_up_stride : nullptr;
+  int *const s_upd = (int *)(smem + L.newinfo);  // staging for the host's answer (free outside R4c..R5: 10 * KP ints)
+  // Fetch the host's (node, LM term) pairs into s_upd; wait_for > 0: first poll the block's go flag until it
+  // reaches wait_for.  One warp, whole 128-byte lines per request: the block lives in host memory and every
+  // request is a PCIe round trip (tools/micro/sysmem_pingpong.cu: ~8 us per handshake for 64..148 CTAs).
+  auto lm_fetch_updates = [&](int wait_for) {
+#if defined(CTC_EMULATE)
+    (void)wait_for;
+    const int words = 2 + 2 * lm_upd[1];
+    for (int w = 0; w < words; ++w) s_upd[w] = lm_upd[w];
+#else
+    if (threadIdx.x < 32) {
+      const int lane = (int)threadIdx.x;
+      const volatile int *blk = lm_upd;
+      if (wait_for > 0) {
+        const long long deadline = clock64() + 20000000000ll;  // ~10 s: never hang the GPU on a dead host
+        unsigned it = 0;
+        for (;;) {
+          const int v = blk[lane];
+          if (__shfl_sync(0xffffffffu, v, 0) >= wait_for) break;
+          if ((++it & 255u) == 0u) {
+            int bad = 0;
+            if (lane == 0) bad = (*(volatile int *)p.hs_abort != 0 || clock64() > deadline) ? 1 : 0;
+            if (__shfl_sync(0xffffffffu, bad, 0)) {
+              if (lane == 0) s_ctl[C_FLAGS] |= FLAG_ERR_ARENA;
+              break;
+            }
+          }
+        }
+      }
+      const int v = blk[lane];  // read (again) after the flag: the host writes the pairs first, the flag last
+      int cnt = __shfl_sync(0xffffffffu, v, 1);
+      if (cnt > K) cnt = K;
+      s_upd[lane] = lane == 1 ? cnt : v;
+      for (int w = 32 + lane; w < 2 + 2 * cnt; w += 32) s_upd[w] = blk[w];
+    }
+#endif
+  };
   int Tb = p.seq_lens ? p.seq_lens[b] : p.T;  // reference binding.cpp:64-65 clamps to T
   if (Tb > p.T) Tb = p.T;
   const int t0 = p.nframes > 0 ? p.t0 : 0;
@@ -271,9 +310,13 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
   if (LM) {
     // scores the host's Scorer hook computed for the nodes created by the previous launch
     CTC_PAR {
-      const int nu = p.lm_update_count ? p.lm_update_count[b] : 0;
-      for (int q = tid; q < nu; q += NT) lm_arena[p.lm_update_nodes[(long long)b * K + q]] = p.lm_update_vals[(long long)b * K + q];
       if (tid == 0) newlist[0] = 0;
+    }
+    lm_fetch_updates(0);
+    CTC_BARRIER();
+    CTC_PAR {
+      const int nu = s_upd[1];
+      for (int q = tid; q < nu; q += NT) lm_arena[s_upd[2 + 2 * q]] = bits_f((uint32_t)s_upd[3 + 2 * q]);
     }
     CTC_BARRIER();
   }
@@ -298,6 +341,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
       c.s_node[j] = node; c.s_chr[j] = chr; c.s_depth[j] = depth; c.s_bprev[j] = bprev; c.s_nbprev[j] = nbprev;
       c.s_score[j] = score; c.s_lpc[j] = lpc; c.s_ts[j] = ts; c.s_pslot[j] = pslot; c.s_anch[j] = anch;
       c.s_dstate[j] = dstate;
+      if (LM) for (int w = 0; w < L.WC; ++w) c.s_dmask[j * L.WC + w] = p.dict_mask[(long long)dstate * L.WC + w];
       c.s_lmsp[j] = (LM && !fresh && j < st[0]) ? ld_cg(&lm_arena[node]) : 0.0f;
       c.s_evict[j] = 0;
     }
@@ -675,7 +719,6 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
           const int i = base + warp + L.NW * rl;
           const float sc_i = c.s_score[i], b_i = c.s_bprev[i];
           const int ch_i = c.s_chr[i];
-          const long long ds_i = LM ? c.s_dstate[i] : 0;
           for (int g = 0; g < G; ++g) {
             const uint32_t mw = c.s_mask[i * W + g];
             const uint32_t rmw = LM ? c.s_rmask[i * W + g] : 0u;
@@ -698,7 +741,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
               if (rep && !(b_i > kNInf)) sc = kNInf;
               bool okl = true;
               if (LM && ch >= 0) {  // cutoff, dictionary arc (unless the child already exists, dead), LM term
-                okl = !c.lm_cut(l, sc_i) && (((rmw >> lane) & 1u) || c.dict_next[ds_i * V + ch] >= 0);
+                okl = !c.lm_cut(l, sc_i) && (((rmw >> lane) & 1u) || c.dict_ok(i, ch));
                 if (ch == c.space_id) sc = c.lm_apply(sc, i);
               }
               const unsigned k = ord_f(sc);
@@ -1091,14 +1134,14 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
           if (LM) {
             // dictionary state of the new node (reference path_trie.cpp:83-92); tell the host about the node: it
             // mirrors the trie and asks the Scorer hook for the LM term the node will need when a space follows
-            const int nx = c.dict_next[(long long)c.s_dstate[i] * V + ch];
-            dst = p.dict_final[nx] ? p.dict_start : nx;
+            const int arc = c.dict_next[(long long)c.s_dstate[i] * V + ch];
+            dst = (arc & kDictFinal) ? p.dict_start : (arc & kDictStateMask);
             dstate_arena[nid] = dst;
             lm_arena[nid] = 0.0f;
             // one 16-byte store per entry: the list lives in device-mapped host memory
             Node e;  // (same 16-byte shape as an arena node)
             e.parent = nid; e.chr = c.s_node[i]; e.lpc = bits_f((uint32_t)ch);
-            e.ts = (c.space_id >= 0 && c.dict_next[(long long)dst * V + c.space_id] >= 0) ? 1 : 0;
+            e.ts = (arc & kDictSpace) ? 1 : 0;
             store_node(reinterpret_cast<Node *>(newlist + 4 + 4 * q), e);
           }
         }
@@ -1215,6 +1258,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
             c.s_bprev[j] = kNInf; c.s_nbprev[j] = sc; c.s_score[j] = sc;  // score = lse(-inf, nb)
             c.s_lpc[j] = bits_f((uint32_t)ni[5]); c.s_ts[j] = ni[6];
             c.s_dstate[j] = ni[9];
+            if (LM) for (int w = 0; w < L.WC; ++w) c.s_dmask[j * L.WC + w] = p.dict_mask[(long long)ni[9] * L.WC + w];
             c.s_lmsp[j] = 0.0f;  // supplied by the host's Scorer hook before the next launch
             have = true;
             start = ni[4];
@@ -1332,21 +1376,15 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
 #else
       if (threadIdx.x == 0) {
         __threadfence_system();  // the new-node list (written before the barriers above) before the flag
-        *(volatile int *)&p.hs_done[b] = t0 + t + 1;
-        const long long deadline = clock64() + 20000000000ll;  // ~10 s: never hang the GPU on a dead host
-        while (*(volatile int *)&p.hs_go[b] < t0 + t + 1) {
-          if (*(volatile int *)p.hs_abort || clock64() > deadline) { s_ctl[C_FLAGS] |= FLAG_ERR_ARENA; break; }
-        }
-        __threadfence_system();
+        *(volatile int *)&newlist[1] = t0 + t + 1;
       }
 #endif
+      lm_fetch_updates(t0 + t + 1);
       CTC_BARRIER();
-      CTC_TICK(12);  // handshake: fence, flag, wait for the host
+      CTC_TICK(12);  // handshake: fence, flag, wait for the host, fetch its answer
       CTC_PAR {
-        const int nu = ((volatile const int *)p.lm_update_count)[b];
-        for (int q = tid; q < nu; q += NT)
-          lm_arena[((volatile const int *)p.lm_update_nodes)[(long long)b * K + q]] =
-              ((volatile const float *)p.lm_update_vals)[(long long)b * K + q];
+        const int nu = s_upd[1];
+        for (int q = tid; q < nu; q += NT) lm_arena[s_upd[2 + 2 * q]] = bits_f((uint32_t)s_upd[3 + 2 * q]);
       }
       CTC_BARRIER();
       CTC_PAR {

@@ -242,13 +242,13 @@ struct StreamState {
 
 static int ensure_dict_on_device(HostScorer *sc, int device) {
   if (sc->d_next && sc->device != device) {
-    cudaSetDevice(sc->device); cudaFree(sc->d_next); cudaFree(sc->d_final); sc->d_next = nullptr; cudaSetDevice(device);
+    cudaSetDevice(sc->device); cudaFree(sc->d_next); cudaFree(sc->d_mask); sc->d_next = nullptr; cudaSetDevice(device);
   }
   if (!sc->d_next) {
-    CU(cudaMalloc(&sc->d_next, sc->dict.next.size() * 4));
-    CU(cudaMalloc(&sc->d_final, sc->dict.fin.size()));
-    CU(cudaMemcpy(sc->d_next, sc->dict.next.data(), sc->dict.next.size() * 4, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(sc->d_final, sc->dict.fin.data(), sc->dict.fin.size(), cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&sc->d_next, sc->dict.packed.size() * 4));
+    CU(cudaMalloc(&sc->d_mask, sc->dict.mask.size() * 4));
+    CU(cudaMemcpy(sc->d_next, sc->dict.packed.data(), sc->dict.packed.size() * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(sc->d_mask, sc->dict.mask.data(), sc->dict.mask.size() * 4, cudaMemcpyHostToDevice));
     sc->device = device;
   }
   return CTCDEC_OK;
@@ -259,8 +259,9 @@ static int ensure_dict_on_device(HostScorer *sc, int device) {
 // need[b] times.  Returns non-zero when the kernel stopped making progress (the caller raises the abort flag).
 struct HandshakeStats { long long hooks = 0, created = 0; unsigned workers = 0; };
 static int serve_handshakes(HostScorer *sc, int B, int K, const int *need, TrieMirror *const *mirrors,
-                            const int *h_newlist, int *h_upd_count, int *h_upd_nodes, float *h_upd_vals, int *hs_done,
-                            int *hs_go, HandshakeStats *stats) {
+                            int *h_newlist, int *h_upd, HandshakeStats *stats) {
+  int nls = 0, ups = 0;
+  exchange_strides(K, &nls, &ups);
   unsigned nt = std::thread::hardware_concurrency();
   if (const char *e = getenv("CTCDEC_LM_THREADS")) nt = (unsigned)atoi(e);
   nt = nt == 0 ? 1 : (nt > 8 ? 8 : nt);
@@ -281,14 +282,12 @@ static int serve_handshakes(HostScorer *sc, int B, int K, const int *need, TrieM
       bool progress = false;
       for (int b = (int)w; b < B; b += (int)nt) {
         if (served[b] >= need[b]) continue;
-        const int d = reinterpret_cast<std::atomic<int> *>(&hs_done[b])->load(std::memory_order_acquire);
+        int *nl = h_newlist + (size_t)b * nls, *up = h_upd + (size_t)b * ups;
+        const int d = reinterpret_cast<std::atomic<int> *>(&nl[1])->load(std::memory_order_acquire);  // "done"
         if (d <= served[b]) continue;
-        const int *nl = h_newlist + (size_t)b * (4 + 4 * K);
-        lm_after_frame(*sc, cache, *mirrors[b], nl, &h_upd_count[b], h_upd_nodes + (size_t)b * K,
-                       h_upd_vals + (size_t)b * K, scratch);
-        hooks += h_upd_count[b];
+        hooks += lm_after_frame(*sc, cache, *mirrors[b], nl, up, scratch);
         created += nl[0];
-        reinterpret_cast<std::atomic<int> *>(&hs_go[b])->store(d, std::memory_order_release);
+        reinterpret_cast<std::atomic<int> *>(&up[0])->store(d, std::memory_order_release);            // "go"
         served[b] = d;
         if (d >= need[b]) --remaining;
         progress = true;
@@ -676,6 +675,7 @@ int ctcdec_decode_stream_host(const float *probs, const int32_t *seq_lens, int B
   const size_t ptr_bytes = al256((size_t)B * 8) * 4 + al256((size_t)B * 4) + al256((size_t)B);
   HostScorer *const sc = s0->sc;
   if (sc && (rc = ensure_dict_on_device(sc, device))) return rc;
+  if (sc) pl.L = make_layout(cfg.beam_size, cfg.vocab_size, pl.NP, pl.F, pl.sorted, pl.NT, true);  // + dictionary masks
   if ((rc = ensure(c, 0, n_probs * 4 + 256))) return rc;
   if ((rc = ensure(c, 1, (size_t)B * 4 + 256))) return rc;
   if ((rc = ensure(c, 2, n_out * 4 + 256))) return rc;
@@ -728,28 +728,20 @@ int ctcdec_decode_stream_host(const float *probs, const int32_t *seq_lens, int B
   if (sc && T > 0) {
     // scorer path: one persistent launch per chunk, hand shake after EVERY frame (the frame after the chunk's last
     // one, in the next call, needs the LM terms of the nodes created now)
-    const size_t nl_ints = (size_t)B * (4 + 4 * K);
-    const size_t upd_bytes = al256((size_t)B * 4) + al256(n_bk * 4) + al256(n_bk * 4);
-    if ((rc = ensure_pinned(c, 0, nl_ints * 4))) return rc;
-    if ((rc = ensure_pinned(c, 1, upd_bytes))) return rc;
-    if ((rc = ensure_pinned(c, 2, al256((size_t)B * 4) * 2 + 256))) return rc;
-    int *h_newlist = (int *)c.pin[0];
-    unsigned char *h_upd = (unsigned char *)c.pin[1];
-    int *h_upd_count = (int *)h_upd;
-    int *h_upd_nodes = (int *)(h_upd + al256((size_t)B * 4));
-    float *h_upd_vals = (float *)(h_upd + al256((size_t)B * 4) + al256(n_bk * 4));
-    int *hs_done = (int *)c.pin[2];
-    int *hs_go = (int *)((unsigned char *)c.pin[2] + al256((size_t)B * 4));
-    int *hs_abort = (int *)((unsigned char *)c.pin[2] + 2 * al256((size_t)B * 4));
-    memset(c.pin[2], 0, al256((size_t)B * 4) * 2 + 256);
-    memset(h_upd_count, 0, (size_t)B * 4);
-    bp.dict_next = sc->d_next; bp.dict_final = sc->d_final; bp.dict_start = sc->dict.start;
+    int nls = 0, ups = 0;
+    exchange_strides(K, &nls, &ups);
+    if ((rc = ensure_pinned(c, 0, (size_t)B * nls * 4))) return rc;
+    if ((rc = ensure_pinned(c, 1, (size_t)B * ups * 4))) return rc;
+    if ((rc = ensure_pinned(c, 2, 256))) return rc;
+    int *h_newlist = (int *)c.pin[0], *h_upd = (int *)c.pin[1], *hs_abort = (int *)c.pin[2];
+    for (int b = 0; b < B; ++b) { memset(h_newlist + (size_t)b * nls, 0, 16); memset(h_upd + (size_t)b * ups, 0, 8); }
+    *hs_abort = 0;
+    bp.dict_next = sc->d_next; bp.dict_mask = sc->d_mask; bp.dict_wc = sc->dict.wc; bp.dict_start = sc->dict.start;
     bp.space_id = sc->space_id; bp.beta = sc->beta;
     bp.lm_arena_ptrs = (float *const *)(d_tab + off_lmar);
     bp.dstate_ptrs = (int *const *)(d_tab + off_lmar + al256((size_t)B * 8));
-    bp.newlist = h_newlist; bp.lm_update_count = h_upd_count; bp.lm_update_nodes = h_upd_nodes;
-    bp.lm_update_vals = h_upd_vals;
-    bp.lm_persistent = 1; bp.lm_hs_last = 1; bp.hs_done = hs_done; bp.hs_go = hs_go; bp.hs_abort = hs_abort;
+    bp.newlist = h_newlist; bp.lm_upd = h_upd; bp.lm_nl_stride = nls; bp.lm_up_stride = ups;
+    bp.lm_persistent = 1; bp.lm_hs_last = 1; bp.hs_abort = hs_abort;
     if ((rc = launch_beam(bp, pl, B, s))) return rc;
     std::vector<TrieMirror *> mirrors(B);
     std::vector<int> answers(B);
@@ -757,8 +749,7 @@ int ctcdec_decode_stream_host(const float *probs, const int32_t *seq_lens, int B
       mirrors[b] = &static_cast<StreamState *>(states[b])->mirror;
       answers[b] = std::max(0, std::min(seq_lens ? seq_lens[b] : T, T));
     }
-    const int failed = serve_handshakes(sc, B, K, answers.data(), mirrors.data(), h_newlist, h_upd_count, h_upd_nodes,
-                                        h_upd_vals, hs_done, hs_go, nullptr);
+    const int failed = serve_handshakes(sc, B, K, answers.data(), mirrors.data(), h_newlist, h_upd, nullptr);
     if (failed) reinterpret_cast<std::atomic<int> *>(hs_abort)->store(1, std::memory_order_release);
     const cudaError_t e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) return fail(CTCDEC_E_CUDA, "beam kernel (scorer path, streaming): %s", cudaGetErrorString(e));
@@ -840,6 +831,7 @@ int ctcdec_scorer_create(const ctcdec_scorer_hooks *hooks, double alpha, double 
   std::vector<std::string> w;
   for (int i = 0; i < n_words; ++i) w.emplace_back(words[i] ? words[i] : "");
   sc->dict = build_dictionary(sc->labels, sc->space_id, w);
+  pack_dictionary(sc->dict, sc->space_id);
   *scorer = sc;
   return CTCDEC_OK;
 }
@@ -847,7 +839,7 @@ int ctcdec_scorer_create(const ctcdec_scorer_hooks *hooks, double alpha, double 
 int ctcdec_scorer_destroy(void *scorer) {
   if (!scorer) return CTCDEC_OK;
   HostScorer *sc = static_cast<HostScorer *>(scorer);
-  if (sc->d_next) { cudaSetDevice(sc->device); cudaFree(sc->d_next); cudaFree(sc->d_final); }
+  if (sc->d_next) { cudaSetDevice(sc->device); cudaFree(sc->d_next); cudaFree(sc->d_mask); }
   delete sc;
   return CTCDEC_OK;
 }
@@ -881,10 +873,11 @@ int ctcdec_decode_batch_lm_host(const ctcdec_config *cfg, void *scorer, const fl
   cudaStream_t s = c.stream;
   const int V = cfg->vocab_size, K = cfg->beam_size;
   if ((rc = ensure_dict_on_device(sc, device))) return rc;
+  pl.L = make_layout(cfg->beam_size, cfg->vocab_size, pl.NP, pl.F, pl.sorted, pl.NT, true);  // + dictionary masks
   const size_t n_probs = (size_t)B * T * V, n_out = (size_t)B * K * T, n_bk = (size_t)B * K;
-  const size_t nl_ints = (size_t)B * (4 + 4 * K);
-  const size_t upd_bytes = al256((size_t)B * 4) + al256(n_bk * 4) + al256(n_bk * 4);
-  const size_t lm_bytes = al256((size_t)B * pl.arena_stride * 4) * 2 + al256(nl_ints * 4) + upd_bytes;
+  int nls = 0, ups = 0;
+  exchange_strides(K, &nls, &ups);
+  const size_t lm_bytes = al256((size_t)B * pl.arena_stride * 4) * 2;
   if ((rc = ensure(c, 0, n_probs * 4 + 256))) return rc;
   if ((rc = ensure(c, 1, (size_t)B * 4 + 256))) return rc;
   if ((rc = ensure(c, 2, n_out * 4 + 256))) return rc;
@@ -892,8 +885,9 @@ int ctcdec_decode_batch_lm_host(const ctcdec_config *cfg, void *scorer, const fl
   if ((rc = ensure(c, 4, n_bk * 4 * 2 + (size_t)B * 8 + 1024))) return rc;
   if ((rc = ensure(c, 5, pl.total + 512))) return rc;
   if ((rc = ensure(c, 7, lm_bytes + 512))) return rc;
-  if ((rc = ensure_pinned(c, 0, nl_ints * 4))) return rc;
-  if ((rc = ensure_pinned(c, 1, upd_bytes))) return rc;
+  if ((rc = ensure_pinned(c, 0, (size_t)B * nls * 4))) return rc;
+  if ((rc = ensure_pinned(c, 1, (size_t)B * ups * 4))) return rc;
+  if ((rc = ensure_pinned(c, 2, 256))) return rc;
   float *d_probs = (float *)c.buf[0];
   int *d_lens_in = seq_lens ? (int *)c.buf[1] : nullptr;
   int *d_tok = (int *)c.buf[2], *d_ts = (int *)c.buf[3];
@@ -904,16 +898,9 @@ int ctcdec_decode_batch_lm_host(const ctcdec_config *cfg, void *scorer, const fl
   unsigned char *lmb = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(c.buf[7]) + 255) / 256 * 256);
   float *d_lm_arena = (float *)lmb;
   int *d_dstate = (int *)(lmb + al256((size_t)B * pl.arena_stride * 4));
-  int *d_newlist = (int *)(lmb + 2 * al256((size_t)B * pl.arena_stride * 4));
-  unsigned char *d_upd = lmb + 2 * al256((size_t)B * pl.arena_stride * 4) + al256(nl_ints * 4);
-  int *d_upd_count = (int *)d_upd;
-  int *d_upd_nodes = (int *)(d_upd + al256((size_t)B * 4));
-  float *d_upd_vals = (float *)(d_upd + al256((size_t)B * 4) + al256(n_bk * 4));
-  int *h_newlist = (int *)c.pin[0];
-  unsigned char *h_upd = (unsigned char *)c.pin[1];
-  int *h_upd_count = (int *)h_upd;
-  int *h_upd_nodes = (int *)(h_upd + al256((size_t)B * 4));
-  float *h_upd_vals = (float *)(h_upd + al256((size_t)B * 4) + al256(n_bk * 4));
+  int *h_newlist = (int *)c.pin[0], *h_upd = (int *)c.pin[1], *hs_abort = (int *)c.pin[2];
+  for (int b = 0; b < B; ++b) { memset(h_newlist + (size_t)b * nls, 0, 16); memset(h_upd + (size_t)b * ups, 0, 8); }
+  *hs_abort = 0;
 
   if (n_probs) CU(cudaMemcpyAsync(d_probs, probs, n_probs * 4, cudaMemcpyHostToDevice, s));
   if (seq_lens) CU(cudaMemcpyAsync(d_lens_in, seq_lens, (size_t)B * 4, cudaMemcpyHostToDevice, s));
@@ -933,15 +920,13 @@ int ctcdec_decode_batch_lm_host(const ctcdec_config *cfg, void *scorer, const fl
   bp.out_tokens = d_tok; bp.out_timesteps = d_ts; bp.out_scores = d_scores; bp.out_lens = d_lens;
   bp.n_results = d_nres; bp.out_T = T; bp.flags = d_flags;
   bp.force_fallback = getenv("CTCDEC_FORCE_FALLBACK") ? 1 : 0;
-  bp.dict_next = sc->d_next; bp.dict_final = sc->d_final; bp.dict_start = sc->dict.start;
+  bp.dict_next = sc->d_next; bp.dict_mask = sc->d_mask; bp.dict_wc = sc->dict.wc; bp.dict_start = sc->dict.start;
   bp.space_id = sc->space_id; bp.beta = sc->beta; bp.lm_arena = d_lm_arena; bp.dstate_arena = d_dstate;
   bp.timing = g_prof.timing;
   // The per-frame exchange with the host goes through pinned, device-mapped host memory (unified addressing):
   // the kernel reads the few LM updates and writes the new-node list straight over PCIe, so a frame costs one
   // launch and one stream synchronisation, no memcpy calls.
-  bp.newlist = h_newlist; bp.lm_update_count = h_upd_count; bp.lm_update_nodes = h_upd_nodes;
-  bp.lm_update_vals = h_upd_vals;
-  (void)d_newlist; (void)d_upd_count; (void)d_upd_nodes; (void)d_upd_vals;
+  bp.newlist = h_newlist; bp.lm_upd = h_upd; bp.lm_nl_stride = nls; bp.lm_up_stride = ups;
   std::vector<int> need(B);
   int tmax = 0;
   for (int b = 0; b < B; ++b) {
@@ -950,19 +935,13 @@ int ctcdec_decode_batch_lm_host(const ctcdec_config *cfg, void *scorer, const fl
   }
   std::vector<TrieMirror> mirror(B);
   for (int b = 0; b < B; ++b) mirror[b].reserve((size_t)1 + (size_t)K * need[b]);
-  memset(h_upd_count, 0, (size_t)B * 4);
   const bool lm_timing = getenv("CTCDEC_LM_TIMING") != nullptr;
   if (getenv("CTCDEC_LM_PER_FRAME") == nullptr) {
     // ---- persistent mode (default): ONE launch decodes every utterance start to end.  After each frame a CTA
-    // publishes its new nodes in mapped host memory, raises hs_done[b] and spins on hs_go[b]; host workers (each
+    // publishes its new nodes in mapped host memory, raises its done flag and polls its go flag; host workers (each
     // owning every nt-th utterance, with its own hook cache) answer with the LM terms.  CTAs never wait on each
     // other, so the scheme needs no co-residency; a kernel-side deadline and the abort flag bound every wait.
-    if ((rc = ensure_pinned(c, 2, al256((size_t)B * 4) * 2 + 256))) return rc;
-    int *hs_done = (int *)c.pin[2];
-    int *hs_go = (int *)((unsigned char *)c.pin[2] + al256((size_t)B * 4));
-    int *hs_abort = (int *)((unsigned char *)c.pin[2] + 2 * al256((size_t)B * 4));
-    memset(c.pin[2], 0, al256((size_t)B * 4) * 2 + 256);
-    bp.lm_persistent = 1; bp.hs_done = hs_done; bp.hs_go = hs_go; bp.hs_abort = hs_abort;
+    bp.lm_persistent = 1; bp.hs_abort = hs_abort;
     bp.t0 = 0; bp.nframes = 0; bp.fresh = 1;
     const auto c0 = std::chrono::steady_clock::now();
     if ((rc = launch_beam(bp, pl, B, s))) return rc;
@@ -970,8 +949,7 @@ int ctcdec_decode_batch_lm_host(const ctcdec_config *cfg, void *scorer, const fl
     std::vector<int> answers(B);
     for (int b = 0; b < B; ++b) { mirrors[b] = &mirror[b]; answers[b] = std::max(0, need[b] - 1); }
     HandshakeStats hst;
-    const int failed = serve_handshakes(sc, B, K, answers.data(), mirrors.data(), h_newlist, h_upd_count, h_upd_nodes,
-                                        h_upd_vals, hs_done, hs_go, &hst);
+    const int failed = serve_handshakes(sc, B, K, answers.data(), mirrors.data(), h_newlist, h_upd, &hst);
     if (failed) reinterpret_cast<std::atomic<int> *>(hs_abort)->store(1, std::memory_order_release);
     const cudaError_t e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) return fail(CTCDEC_E_CUDA, "beam kernel (scorer path): %s", cudaGetErrorString(e));
@@ -983,7 +961,7 @@ int ctcdec_decode_batch_lm_host(const ctcdec_config *cfg, void *scorer, const fl
   } else {
     Plan pl1 = pl;  // one frame per launch: the staged tile is one row
     pl1.F = 1;
-    pl1.L = make_layout(K, V, pl.NP, 1, pl.sorted, pl.NT);
+    pl1.L = make_layout(K, V, pl.NP, 1, pl.sorted, pl.NT, true);
 
     std::vector<int> scratch;
     double t_gpu = 0.0, t_hook = 0.0;
@@ -995,10 +973,9 @@ int ctcdec_decode_batch_lm_host(const ctcdec_config *cfg, void *scorer, const fl
       CU(cudaStreamSynchronize(s));
       const auto c1 = std::chrono::steady_clock::now();
       for (int b = 0; b < B; ++b) {
-        lm_after_frame(*sc, sc->cond_caches[0], mirror[b], h_newlist + (size_t)b * (4 + 4 * K), &h_upd_count[b],
-                       h_upd_nodes + (size_t)b * K, h_upd_vals + (size_t)b * K, scratch);
-        n_hook += h_upd_count[b];
-        n_new += h_newlist[(size_t)b * (4 + 4 * K)];
+        n_hook += lm_after_frame(*sc, sc->cond_caches[0], mirror[b], h_newlist + (size_t)b * nls,
+                                 h_upd + (size_t)b * ups, scratch);
+        n_new += h_newlist[(size_t)b * nls];
       }
       const auto c2 = std::chrono::steady_clock::now();
       t_gpu += std::chrono::duration<double>(c1 - c0).count();

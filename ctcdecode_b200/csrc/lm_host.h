@@ -36,6 +36,11 @@ struct Dictionary {
   int n_words = 0;                  // reference Scorer::dict_size_
   std::vector<int> next;            // [states][V], -1 = no arc
   std::vector<unsigned char> fin;   // [states]
+  // what the kernel reads (pack_dictionary): arcs with the flags of beam_core.cuh (kDictFinal, kDictSpace) and one
+  // bit per (state, character) "has an arc"
+  std::vector<int> packed;          // [states][V]
+  std::vector<uint32_t> mask;       // [states][wc]
+  int wc = 0;
 
   int add_state() {
     next.insert(next.end(), V, -1);
@@ -87,6 +92,26 @@ static inline Dictionary build_dictionary(const std::vector<std::string> &labels
   return d;
 }
 
+// reference path_trie.cpp:83-92: a child whose arc ends in a final state restarts at the start state; the kernel
+// also wants to know, when it creates the child, whether a space can follow it (= the host must score it)
+static inline void pack_dictionary(Dictionary &d, int space_id) {
+  const int S = d.states(), V = d.V;
+  d.wc = (V + 31) / 32;
+  d.packed.assign((size_t)S * V, -1);
+  d.mask.assign((size_t)S * d.wc, 0u);
+  for (int s = 0; s < S; ++s)
+    for (int c = 0; c < V; ++c) {
+      const int nx = d.next[(size_t)s * V + c];
+      if (nx < 0) continue;
+      const int dst = d.fin[nx] ? d.start : nx;
+      int e = nx;
+      if (d.fin[nx]) e |= 1 << 30;
+      if (space_id >= 0 && d.next[(size_t)dst * V + space_id] >= 0) e |= 1 << 29;
+      d.packed[(size_t)s * V + c] = e;
+      d.mask[(size_t)s * d.wc + (c >> 5)] |= 1u << (c & 31);
+    }
+}
+
 struct HostScorer {
   // cond_log_prob depends only on the last max_order words of the prefix, and beams share word histories: cache it
   // keyed by that tail of the label sequence (the hook is pure, so the values are the hook's own)
@@ -100,7 +125,7 @@ struct HostScorer {
   Dictionary dict;
   // device copies of the dictionary (CUDA library only)
   int *d_next = nullptr;
-  unsigned char *d_final = nullptr;
+  uint32_t *d_mask = nullptr;
   int device = -1;
 };
 
@@ -148,12 +173,19 @@ static inline double cached_cond(const HostScorer &sc, HostScorer::CondCache &ca
   return v;
 }
 
+// The two per-utterance exchange blocks (beam_core.cuh BeamParams::newlist / lm_upd): strides in ints, each a
+// multiple of 128 bytes so that no two utterances (host workers, CTAs) share a line.
+static inline void exchange_strides(int K, int *nl_stride, int *up_stride) {
+  *nl_stride = (4 + 4 * K + 31) / 32 * 32;
+  *up_stride = (2 + 2 * K + 31) / 32 * 32;
+}
+
 // After a frame: register the created nodes and compute the LM term of those a space can follow.
-// newlist: [4 + 4K] ints of one utterance (count and 3 pad ints, then 16-byte entries node / parent / chr /
-// needs_lm); outputs the update list.
-static inline void lm_after_frame(const HostScorer &sc, HostScorer::CondCache &cache, TrieMirror &mirror,
-                                  const int *newlist, int *upd_count, int *upd_nodes, float *upd_vals,
-                                  std::vector<int> &scratch) {
+// newlist: one utterance's block ([0] = count, from [4]: 16-byte entries node / parent / chr / needs_lm); writes
+// the answer into the utterance's lm_upd block: [1] = number of pairs, from [2]: (node, float bits) pairs.  The
+// caller publishes it ([0], the go flag) afterwards.  Returns the number of pairs.
+static inline int lm_after_frame(const HostScorer &sc, HostScorer::CondCache &cache, TrieMirror &mirror,
+                                 const int *newlist, int *upd, std::vector<int> &scratch) {
   const int cnt = newlist[0];
   int nu = 0;
   for (int q = 0; q < cnt; ++q) {
@@ -163,12 +195,14 @@ static inline void lm_after_frame(const HostScorer &sc, HostScorer::CondCache &c
     if (e[3]) {
       mirror.tail_labels_of(e[0], sc.space_id, sc.max_order, scratch);
       const double cond = cached_cond(sc, cache, scratch.data(), (int)scratch.size());
-      upd_nodes[nu] = e[0];
-      upd_vals[nu] = (float)(cond * sc.alpha);  // reference :133 `score = get_log_cond_prob(ngram) * alpha` (float)
+      const float val = (float)(cond * sc.alpha);  // reference :133 `score = get_log_cond_prob(ngram) * alpha` (float)
+      upd[2 + 2 * nu] = e[0];
+      memcpy(&upd[3 + 2 * nu], &val, 4);
       ++nu;
     }
   }
-  *upd_count = nu;
+  upd[1] = nu;
+  return nu;
 }
 
 // DecoderState::decode with a word-based scorer (reference ctc_beam_search_decoder.cpp:164-211): the order of the

@@ -187,7 +187,7 @@ int emu_decode_batch_lm(const float *probs, const int *seq_lens, int B, int T, i
   if (rc) { fprintf(stderr, "emu: %s\n", msg); return rc; }
   if (NT <= 0) NT = pl.NT;
   pl.NT = NT;
-  pl.L = make_layout(K, V, pl.NP, pl.F, pl.sorted, NT);
+  pl.L = make_layout(K, V, pl.NP, pl.F, pl.sorted, NT, true);
   HostScorer sc;
   sc.hooks.ctx = hook_ctx; sc.hooks.cond_log_prob = cond; sc.hooks.sent_log_prob = sent;
   sc.alpha = alpha; sc.beta = beta; sc.max_order = max_order; sc.is_character_based = 0; sc.space_id = -2;
@@ -203,9 +203,9 @@ int emu_decode_batch_lm(const float *probs, const int *seq_lens, int B, int T, i
   std::vector<float> lm_arena((size_t)B * pl.arena_stride, 0.f);
   std::vector<int> dstate_arena((size_t)B * pl.arena_stride, 0);
   std::vector<int> state((size_t)B * pl.state_stride, 0);
-  std::vector<int> newlist((size_t)B * (4 + 4 * K), 0);
-  std::vector<int> upd_count(B, 0), upd_nodes((size_t)B * K, 0);
-  std::vector<float> upd_vals((size_t)B * K, 0.f);
+  int nls = 0, ups = 0;
+  exchange_strides(K, &nls, &ups);
+  std::vector<int> newlist((size_t)B * nls, 0), upd((size_t)B * ups, 0);
   std::vector<unsigned char> smem(pl.L.total + 64);
   for (int b = 0; b < B; ++b) flags[b] = 0;
   prune_rows(cfg, pl, probs, seq_lens, B, T, lp.data(), idx.data(), flags);
@@ -219,24 +219,25 @@ int emu_decode_batch_lm(const float *probs, const int *seq_lens, int B, int T, i
   bp.out_tokens = tokens; bp.out_timesteps = timesteps; bp.out_scores = scores; bp.out_lens = lens;
   bp.n_results = n_results; bp.out_T = T; bp.flags = flags;
   bp.force_fallback = getenv("CTC_EMU_FORCE_FALLBACK") ? 1 : 0;
-  bp.dict_next = sc.dict.next.data(); bp.dict_final = sc.dict.fin.data(); bp.dict_start = sc.dict.start;
+  pack_dictionary(sc.dict, sc.space_id);
+  bp.dict_next = sc.dict.packed.data(); bp.dict_mask = sc.dict.mask.data(); bp.dict_wc = sc.dict.wc;
+  bp.dict_start = sc.dict.start;
   bp.space_id = sc.space_id; bp.beta = beta; bp.lm_arena = lm_arena.data(); bp.dstate_arena = dstate_arena.data();
-  bp.newlist = newlist.data(); bp.lm_update_count = upd_count.data(); bp.lm_update_nodes = upd_nodes.data();
-  bp.lm_update_vals = upd_vals.data();
+  bp.newlist = newlist.data(); bp.lm_upd = upd.data(); bp.lm_nl_stride = nls; bp.lm_up_stride = ups;
 
   std::vector<TrieMirror> mirror(B);
   for (int b = 0; b < B; ++b) mirror[b].reserve(64);  // small on purpose: exercises the growth path
   std::vector<int> scratch;
   if (getenv("CTC_EMU_LM_PER_FRAME") == nullptr) {
     // persistent mode: one "launch" per utterance, the host side of the per-frame handshake is called in place
-    struct Ctx { HostScorer *sc; std::vector<TrieMirror> *mirror; int *newlist, *uc, *un; float *uv; int K; std::vector<int> *scratch; };
-    Ctx ctx{&sc, &mirror, newlist.data(), upd_count.data(), upd_nodes.data(), upd_vals.data(), K, &scratch};
+    struct Ctx { HostScorer *sc; std::vector<TrieMirror> *mirror; int *newlist, *upd; int nls, ups; std::vector<int> *scratch; };
+    Ctx ctx{&sc, &mirror, newlist.data(), upd.data(), nls, ups, &scratch};
     bp.lm_persistent = 1;
     bp.emu_ctx = &ctx;
     bp.emu_handshake = [](void *c, int b) {
       Ctx *x = static_cast<Ctx *>(c);
-      lm_after_frame(*x->sc, x->sc->cond_caches[0], (*x->mirror)[b], x->newlist + (size_t)b * (4 + 4 * x->K), &x->uc[b],
-                     x->un + (size_t)b * x->K, x->uv + (size_t)b * x->K, *x->scratch);
+      lm_after_frame(*x->sc, x->sc->cond_caches[0], (*x->mirror)[b], x->newlist + (size_t)b * x->nls,
+                     x->upd + (size_t)b * x->ups, *x->scratch);
     };
     // CTC_EMU_LM_CHUNK=n: the streaming shape -- launches of n frames over saved state, handshake after the last
     // frame of every launch too (a next chunk follows)
@@ -271,8 +272,8 @@ int emu_decode_batch_lm(const float *probs, const int *seq_lens, int B, int T, i
       default: run_beam<256>(bp, pl.sorted, B, smem.data()); break;
     }
     for (int b = 0; b < B; ++b)
-      lm_after_frame(sc, sc.cond_caches[0], mirror[b], newlist.data() + (size_t)b * (4 + 4 * K), &upd_count[b],
-                     upd_nodes.data() + (size_t)b * K, upd_vals.data() + (size_t)b * K, scratch);
+      lm_after_frame(sc, sc.cond_caches[0], mirror[b], newlist.data() + (size_t)b * nls, upd.data() + (size_t)b * ups,
+                     scratch);
   }
   std::vector<unsigned char> fsmem((size_t)K * 12 + 64);
   for (int b = 0; b < B; ++b) finalize_cta_run<128>(bp, b, fsmem.data());
