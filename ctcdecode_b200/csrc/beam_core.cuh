@@ -99,6 +99,82 @@ constexpr int kAnchorArrays = 6;
 CTC_HD int kp_of(int K) { return (K + 31) / 32 * 32; }
 CTC_HD long long state_ints(int K) { return kStateHeader + (long long)kSlotArrays * K + (long long)kAnchorArrays * 2 * kp_of(K); }
 
+// ---- shared memory carve-up (bytes) ---------------------------------------------------------------
+// Three parts: a fixed-size head (offsets are compile-time constants), the SLOT BLOCK -- every array whose length
+// is a multiple of KP = beam size rounded up to 32, at offset kSmemHead + unit * KP * 4, so that with KP a
+// template constant (beam_cta_run<..., KPT>) every slot-array address folds into the immediate field of the
+// shared-memory instruction -- and a tail whose sizes depend on the pruned vocabulary / tile / thread count.
+enum : int {  // head, bytes
+  H_MBAR = 0, H_EXPTAB = 16, H_LOGTAB = H_EXPTAB + 32 * 8, H_HIST = H_LOGTAB + 32 * 8,
+  H_WCNT = H_HIST + 2 * 256 * 4, H_CTL = H_WCNT + 4 * 32 * 4, kSmemHead = H_CTL + 32 * 4 + 16 * 8
+};
+static_assert(kSmemHead % 16 == 0, "slot block alignment");
+enum : int {  // slot block, in units of KP ints
+  U_NODE = 0, U_CHR, U_DEPTH, U_BPREV, U_NBPREV, U_SCORE, U_LPC, U_TS,
+  U_PSLOT,                // 2 units: double buffered links of the beam of frame t / t+1
+  U_ANCH = U_PSLOT + 2,   // 2 units
+  U_DSTATE = U_ANCH + 2, U_LMSP,
+  U_DDSTATE,              // 2 units
+  U_BNEW = U_DDSTATE + 2, U_NBNEW, U_SNEW, U_EVICT, U_SEL, U_SEL2, U_FREEL, U_FREEL2,
+  U_NEWINFO,              // 10 units
+  U_TIE = U_NEWINFO + 10, // 2 units
+  U_DNODE = U_TIE + 2, U_DCHR = U_DNODE + 2, U_DPSLOT = U_DCHR + 2, U_DLPC = U_DPSLOT + 2, U_DTS = U_DLPC + 2,
+  U_DREV = U_DTS + 2,     // dead-anchor table: 2 units each
+  U_CNT2 = U_DREV + 2,    // 3 units
+  U_AMAP = U_CNT2 + 3, U_SLOT2Q,
+  U_STASH,                // 5 units
+  U_EFREE = U_STASH + 5,  // 2 units
+  U_RVWORK = U_EFREE + 2, // 3 units
+  U_SLOT_UNITS = U_RVWORK + 3
+};
+CTC_HD int slot_off(int unit, int KP) { return kSmemHead + unit * KP * 4; }
+
+struct SmemLayout {
+  int evcnt, mask, rmask, dmask, rank, tile_lp, tile_idx, clk, cli;  // tail offsets
+  int total;
+  int KP, W, WC, NW, seg;
+};
+CTC_HD int align_up(int x, int a) { return (x + a - 1) / a * a; }
+// budget_kb: shared memory one CTA may take so that the intended number of CTAs fits an SM (227 KB, 1 KB reserved
+// per CTA): 111 = two per SM (default), 74 = three, 55 = four (plan.h picks it from the batch size).  Only the
+// candidate-list segments give way; a segment that overflows costs that frame the grid-walking fallback.
+CTC_HD SmemLayout make_layout(int K, int V, int NP, int tile_frames, bool sorted, int NT, bool lm = false,
+                              int budget_kb = 111) {
+  SmemLayout L;
+  const int KP = align_up(K, 32);
+  const int W = (NP + 31) / 32;
+  const int NW = NT / 32;
+  L.KP = KP;
+  L.W = W;
+  L.NW = NW;
+  L.WC = (V + 31) / 32;
+  int o = slot_off(U_SLOT_UNITS, KP);
+  L.evcnt = o;     o += (KP / 32) * 4;
+  L.mask = o;      o += KP * W * 4;    // [KP][W] bitmasks over pruned ranks
+  L.rmask = o;     o += KP * W * 4;
+  L.dmask = o;     o += lm ? KP * L.WC * 4 : 0;   // scorer path: [KP][WC] dictionary arc bits
+  L.rank = o;      o += sorted ? align_up(V * 2, 16) : 0;
+  o = align_up(o, 128);
+  L.tile_lp = o;   o += 2 * tile_frames * NP * 4;
+  L.tile_idx = o;  o += sorted ? 2 * tile_frames * NP * 2 : 0;
+  o = align_up(o, 16);
+  // candidate-list segment per warp: room for every candidate of the members a warp owns, capped at 64 KB in
+  // total -- and at what the budget leaves, if that is at least 8 KB
+  int seg = ((K + NW - 1) / NW) * (NP - kRowTrailer);
+  {
+    int cap_bytes = budget_kb * 1024 - o - 64;
+    if (cap_bytes > 64 * 1024) cap_bytes = 64 * 1024;
+    if (cap_bytes < 8 * 1024) cap_bytes = 64 * 1024;
+    if (seg > cap_bytes / 8 / NW) seg = cap_bytes / 8 / NW;
+  }
+  if (seg < 32) seg = 32;
+  L.seg = seg;
+  L.clk = o;       o += NW * seg * 4;
+  L.cli = o;       o += NW * seg * 4;
+  L.total = align_up(o, 16);
+  return L;
+}
+
 struct BeamParams {
   const float *lp;        // [B][T][NP] pruned float32 log-probs from the prune kernel
   const uint16_t *idx;    // [B][T][NP] character of each pruned entry, 0xFFFF = unused (sorted mode only)
@@ -106,6 +182,7 @@ struct BeamParams {
   int T, V, NP, K, blank;
   int t0, nframes;        // this launch consumes rows [t0, t0 + nframes) of each utterance (nframes <= 0: all T rows)
   int tile_frames;        // frames per staged tile
+  SmemLayout L;           // shared-memory carve-up (make_layout), filled in by the launcher
   Node *arena;            // offline: base of B arenas
   long long arena_stride; // nodes per utterance
   int *state;             // offline: base of B state blocks (state_ints(K) ints each, see above)
@@ -153,107 +230,6 @@ struct BeamParams {
   void (*emu_handshake)(void *ctx, int b);  // CPU emulation only: the host side of the handshake, called in place
   void *emu_ctx;
 };
-
-// ---- shared memory carve-up (bytes) ---------------------------------------------------------------
-struct SmemLayout {
-  int tile_lp, tile_idx, mbar, rank, exptab, logtab;
-  int node, chr, depth, bprev, nbprev, score, lpc, ts, pslot, anch;  // persistent slot arrays [KP]
-  int dstate, lmsp, ddstate;                                         // scorer path: [KP], [KP], [2*KP]
-  int dmask, WC;                                                     // scorer path: [KP][WC] dictionary arc bits
-  int bnew, nbnew, snew;                                             // per-frame slot temporaries [KP]
-  int mask, rmask;                                                   // [KP][W] bitmasks over pruned ranks
-  int evict;                                                         // [KP]
-  int sel, sel2, freel, freel2;                                      // [KP] lists
-  int newinfo;                                                       // [KP][10]
-  int tie;                                                           // [2*KP]
-  int dnode, dchr, dpslot, dlpc, dts, drev;                          // dead-anchor table [2*KP]
-  int cnt2;                                                          // [3*KP] anchor reference counts
-  int amap, slot2q, stash, efree, rvwork;                            // re-anchoring scratch
-  int hist;                                                          // [2][kNBins]
-  int clk, cli, wcnt, evcnt;                                         // candidate list segments [NW][seg], per-warp counts
-  int ctl;                                                           // control words
-  int total;
-  int KP, W, NW, seg;
-};
-CTC_HD int align_up(int x, int a) { return (x + a - 1) / a * a; }
-CTC_HD SmemLayout make_layout(int K, int V, int NP, int tile_frames, bool sorted, int NT, bool lm = false) {
-  SmemLayout L;
-  const int KP = align_up(K, 32);
-  const int W = (NP + 31) / 32;
-  const int NW = NT / 32;
-  int o = 0;
-  L.KP = KP;
-  L.W = W;
-  L.NW = NW;
-  L.tile_lp = o;   o += 2 * tile_frames * NP * 4;
-  L.tile_idx = o;  o += sorted ? 2 * tile_frames * NP * 2 : 0;
-  o = align_up(o, 16);
-  L.mbar = o;      o += 16;
-  L.rank = o;      o += sorted ? align_up(V * 2, 16) : 0;
-  L.exptab = o;    o += 32 * 8;
-  L.logtab = o;    o += 32 * 8;
-  L.node = o;      o += KP * 4;
-  L.chr = o;       o += KP * 4;
-  L.depth = o;     o += KP * 4;
-  L.bprev = o;     o += KP * 4;
-  L.nbprev = o;    o += KP * 4;
-  L.score = o;     o += KP * 4;
-  L.lpc = o;       o += KP * 4;
-  L.ts = o;        o += KP * 4;
-  L.pslot = o;     o += 2 * KP * 4;  // double buffered: links of the beam of frame t / t+1
-  L.anch = o;      o += 2 * KP * 4;
-  L.dstate = o;    o += KP * 4;
-  L.lmsp = o;      o += KP * 4;
-  L.ddstate = o;   o += 2 * KP * 4;
-  L.WC = (V + 31) / 32;
-  L.dmask = o;     o += lm ? KP * L.WC * 4 : 0;
-  L.bnew = o;      o += KP * 4;
-  L.nbnew = o;     o += KP * 4;
-  L.snew = o;      o += KP * 4;
-  L.mask = o;      o += KP * W * 4;
-  L.rmask = o;     o += KP * W * 4;
-  L.evict = o;     o += KP * 4;
-  L.sel = o;       o += KP * 4;
-  L.sel2 = o;      o += KP * 4;
-  L.freel = o;     o += KP * 4;
-  L.freel2 = o;    o += KP * 4;
-  L.newinfo = o;   o += KP * 10 * 4;
-  L.tie = o;       o += 2 * KP * 4;
-  L.dnode = o;     o += 2 * KP * 4;
-  L.dchr = o;      o += 2 * KP * 4;
-  L.dpslot = o;    o += 2 * KP * 4;
-  L.dlpc = o;      o += 2 * KP * 4;
-  L.dts = o;       o += 2 * KP * 4;
-  L.drev = o;      o += 2 * KP * 4;
-  L.cnt2 = o;      o += 3 * KP * 4;
-  L.amap = o;      o += KP * 4;
-  L.slot2q = o;    o += KP * 4;
-  L.stash = o;     o += 5 * KP * 4;
-  L.efree = o;     o += 2 * KP * 4;
-  L.rvwork = o;    o += KP * 3 * 4;
-  L.hist = o;      o += 2 * kNBins * 4;
-  // candidate-list segment per warp: room for every candidate of the members a warp owns, capped at 64 KB in
-  // total -- and at what still lets two CTAs share an SM (2 x (111 KB + 1 KB reserved) <= 227 KB) if that is at least 16 KB: a batch of 256
-  // utterances is 1.73 CTAs per SM, and a segment that overflows only costs that frame the grid-walking fallback
-  int seg = ((K + NW - 1) / NW) * (NP - kRowTrailer);
-  {
-    const int rest = o + 4 * 32 * 4 + (KP / 32) * 4 + 32 * 4 + 16 * 8 + 64;
-    int cap_bytes = 111 * 1024 - rest;
-    if (cap_bytes > 64 * 1024) cap_bytes = 64 * 1024;
-    if (cap_bytes < 16 * 1024) cap_bytes = 64 * 1024;
-    if (seg > cap_bytes / 8 / NW) seg = cap_bytes / 8 / NW;
-  }
-  if (seg < 32) seg = 32;
-  L.seg = seg;
-  L.clk = o;       o += NW * seg * 4;
-  L.cli = o;       o += NW * seg * 4;
-  L.wcnt = o;      o += 4 * 32 * 4;
-  L.evcnt = o;     o += (KP / 32) * 4;
-  o = align_up(o, 16);
-  L.ctl = o;       o += 32 * 4 + 16 * 8;
-  L.total = o;
-  return L;
-}
 
 // control words: 32 ints in L.ctl
 enum {

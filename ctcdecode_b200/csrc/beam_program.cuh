@@ -17,10 +17,10 @@ static EmuStats g_stats;
 #if defined(CTC_EMULATE)
 #define CTC_TICK(id) ((void)0)
 #else
-// per-region cycle accounting by thread 0 (only when BeamParams::timing is set; tools/region_timing.py)
+// per-region cycle accounting by thread 0 (TIMING instantiations only; tools/region_timing.py)
 #define CTC_TICK(id)                                                        \
   do {                                                                      \
-    if (p.timing && threadIdx.x == 0) {                                     \
+    if (TIMING && threadIdx.x == 0) {                                       \
       const long long now_ = clock64();                                     \
       s_tick[id] += now_ - s_tick[15];                                      \
       s_tick[15] = now_;                                                    \
@@ -205,47 +205,52 @@ CTC_FN void flush_lpc_ts(Node *p, float lpc, int ts) {
 // ======================================================================================================
 //  beam_cta_run: consume frames [0, Tb) of utterance b, leave the beam state in global memory.
 // ======================================================================================================
-template <int NT, bool SORTED, bool LM>
+// KPT: beam size rounded up to 32 as a compile-time constant (0 = taken from p.K at run time); with KPT > 0 every
+// slot-array address is an immediate offset.  TIMING: per-region cycle counters (tools/region_timing.py).
+template <int NT, bool SORTED, bool LM, int KPT = 0, bool TIMING = false>
 CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) {
   const int K = p.K, V = p.V, NP = p.NP, F = p.tile_frames;
-  const SmemLayout L = make_layout(K, V, NP, F, SORTED, NT, LM);
-  const int KP = L.KP, W = L.W, KP2 = 2 * L.KP;
+  const SmemLayout &L = p.L;  // computed by the host (plan.h): constant-bank reads, nothing to recompute per frame
+  constexpr int NW = NT / 32;
+  const int KP = KPT > 0 ? KPT : L.KP;
+  const int W = L.W, KP2 = 2 * KP, SEG = L.seg;
 
   Cta<SORTED, LM> c;
-  c.s_node = (int *)(smem + L.node);      c.s_chr = (int *)(smem + L.chr);
-  c.s_depth = (int *)(smem + L.depth);    c.s_bprev = (float *)(smem + L.bprev);
-  c.s_nbprev = (float *)(smem + L.nbprev);  c.s_score = (float *)(smem + L.score);
-  c.s_lpc = (float *)(smem + L.lpc);      c.s_ts = (int *)(smem + L.ts);
-  c.s_pslot = (int *)(smem + L.pslot);    c.s_anch = (int *)(smem + L.anch);
-  c.s_dstate = (int *)(smem + L.dstate);  c.s_lmsp = (float *)(smem + L.lmsp);
-  c.s_ddstate = (int *)(smem + L.ddstate);
-  c.s_bnew = (float *)(smem + L.bnew);    c.s_nbnew = (float *)(smem + L.nbnew);
-  c.s_snew = (float *)(smem + L.snew);    c.s_mask = (uint32_t *)(smem + L.mask);
-  c.s_rmask = (uint32_t *)(smem + L.rmask);  c.s_evict = (int *)(smem + L.evict);
-  c.s_sel = (int *)(smem + L.sel);        c.s_sel2 = (int *)(smem + L.sel2);
-  c.s_free = (int *)(smem + L.freel);     c.s_free2 = (int *)(smem + L.freel2);
-  c.s_newinfo = (int *)(smem + L.newinfo);  c.s_tie = (int *)(smem + L.tie);
-  c.s_dnode = (int *)(smem + L.dnode);    c.s_dchr = (int *)(smem + L.dchr);
-  c.s_dpslot = (int *)(smem + L.dpslot);  c.s_dlpc = (float *)(smem + L.dlpc);
-  c.s_dts = (int *)(smem + L.dts);        c.s_drev = (int *)(smem + L.drev);
-  c.s_cnt2 = (int *)(smem + L.cnt2);      c.s_amap = (int *)(smem + L.amap);
-  c.s_efree = (int *)(smem + L.efree);
-  c.s_rvwork = (int *)(smem + L.rvwork);  c.s_hist = (int *)(smem + L.hist);
-  c.s_rank = (int16_t *)(smem + L.rank);  c.s_ctl = (int *)(smem + L.ctl);
-  c.s_clk = (uint32_t *)(smem + L.clk);   c.s_cli = (int *)(smem + L.cli);
-  c.s_wcnt = (int *)(smem + L.wcnt);      c.s_evcnt = (int *)(smem + L.evcnt);
-  c.s_slot2q = (int *)(smem + L.slot2q);  c.s_stash = (int *)(smem + L.stash);
-  int *const pslot_base = (int *)(smem + L.pslot), *const anch_base = (int *)(smem + L.anch);
+#define CTC_SLOT(type, unit) ((type *)(smem + slot_off(unit, KP)))
+  c.s_node = CTC_SLOT(int, U_NODE);        c.s_chr = CTC_SLOT(int, U_CHR);
+  c.s_depth = CTC_SLOT(int, U_DEPTH);      c.s_bprev = CTC_SLOT(float, U_BPREV);
+  c.s_nbprev = CTC_SLOT(float, U_NBPREV);  c.s_score = CTC_SLOT(float, U_SCORE);
+  c.s_lpc = CTC_SLOT(float, U_LPC);        c.s_ts = CTC_SLOT(int, U_TS);
+  c.s_pslot = CTC_SLOT(int, U_PSLOT);      c.s_anch = CTC_SLOT(int, U_ANCH);
+  c.s_dstate = CTC_SLOT(int, U_DSTATE);    c.s_lmsp = CTC_SLOT(float, U_LMSP);
+  c.s_ddstate = CTC_SLOT(int, U_DDSTATE);
+  c.s_bnew = CTC_SLOT(float, U_BNEW);      c.s_nbnew = CTC_SLOT(float, U_NBNEW);
+  c.s_snew = CTC_SLOT(float, U_SNEW);      c.s_mask = (uint32_t *)(smem + L.mask);
+  c.s_rmask = (uint32_t *)(smem + L.rmask);  c.s_evict = CTC_SLOT(int, U_EVICT);
+  c.s_sel = CTC_SLOT(int, U_SEL);          c.s_sel2 = CTC_SLOT(int, U_SEL2);
+  c.s_free = CTC_SLOT(int, U_FREEL);       c.s_free2 = CTC_SLOT(int, U_FREEL2);
+  c.s_newinfo = CTC_SLOT(int, U_NEWINFO);  c.s_tie = CTC_SLOT(int, U_TIE);
+  c.s_dnode = CTC_SLOT(int, U_DNODE);      c.s_dchr = CTC_SLOT(int, U_DCHR);
+  c.s_dpslot = CTC_SLOT(int, U_DPSLOT);    c.s_dlpc = CTC_SLOT(float, U_DLPC);
+  c.s_dts = CTC_SLOT(int, U_DTS);          c.s_drev = CTC_SLOT(int, U_DREV);
+  c.s_cnt2 = CTC_SLOT(int, U_CNT2);        c.s_amap = CTC_SLOT(int, U_AMAP);
+  c.s_efree = CTC_SLOT(int, U_EFREE);
+  c.s_rvwork = CTC_SLOT(int, U_RVWORK);    c.s_hist = (int *)(smem + H_HIST);
+  c.s_rank = (int16_t *)(smem + L.rank);   c.s_ctl = (int *)(smem + H_CTL);
+  c.s_clk = (uint32_t *)(smem + L.clk);    c.s_cli = (int *)(smem + L.cli);
+  c.s_wcnt = (int *)(smem + H_WCNT);       c.s_evcnt = (int *)(smem + L.evcnt);
+  c.s_slot2q = CTC_SLOT(int, U_SLOT2Q);    c.s_stash = CTC_SLOT(int, U_STASH);
+  int *const pslot_base = CTC_SLOT(int, U_PSLOT), *const anch_base = CTC_SLOT(int, U_ANCH);
   int cur = 0;  // which half of the double-buffered link arrays describes the current beam
-  c.s_exptab = (uint64_t *)(smem + L.exptab);
-  c.s_logtab = (double *)(smem + L.logtab);
+  c.s_exptab = (uint64_t *)(smem + H_EXPTAB);
+  c.s_logtab = (double *)(smem + H_LOGTAB);
   c.K = K; c.KP = KP; c.V = V; c.NP = NP; c.W = W; c.blank = p.blank;
   c.s_dmask = (uint32_t *)(smem + L.dmask); c.WC = L.WC;
   c.dict_next = p.dict_next; c.space_id = p.space_id; c.beta = p.beta; c.lm_full = false; c.lm_cutoff = kNInf;
   int *const s_ctl = c.s_ctl;
 #if !defined(CTC_EMULATE)
-  long long *const s_tick = (long long *)(smem + L.ctl + 32 * 4);
-  if (p.timing && threadIdx.x == 0) {
+  long long *const s_tick = (long long *)(smem + H_CTL + 32 * 4);
+  if (TIMING && threadIdx.x == 0) {
     for (int x = 0; x < 15; ++x) s_tick[x] = 0;
     s_tick[15] = clock64();
   }
@@ -259,7 +264,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
   int *const dstate_arena = !LM ? nullptr : p.dstate_ptrs ? p.dstate_ptrs[b] : p.dstate_arena + (long long)b * p.arena_stride;
   int *const newlist = LM ? p.newlist + (long long)b * p.lm_nl_stride : nullptr;
   const int *const lm_upd = LM ? p.lm_upd + (long long)b * p.lm_up_stride : nullptr;
-  int *const s_upd = (int *)(smem + L.newinfo);  // staging for the host's answer (free outside R4c..R5: 10 * KP ints)
+  int *const s_upd = CTC_SLOT(int, U_NEWINFO);  // staging for the host's answer (free outside R4c..R5: 10 * KP ints)
   // Fetch the host's (node, LM term) pairs into s_upd; wait_for > 0: first poll the block's go flag until it
   // reaches wait_for.  One warp, whole 128-byte lines per request: the block lives in host memory and every
   // request is a PCIe round trip (tools/micro/sysmem_pingpong.cu: ~8 us per handshake for 64..148 CTAs).
@@ -376,7 +381,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
     }
   }
 #if !defined(CTC_EMULATE)
-  uint64_t *const mbar = (uint64_t *)(smem + L.mbar);
+  uint64_t *const mbar = (uint64_t *)(smem + H_MBAR);
   float *const tile_lp = (float *)(smem + L.tile_lp);
   uint16_t *const tile_idx = (uint16_t *)(smem + L.tile_idx);
   const float *const g_lp = p.lp + ((size_t)b * p.T + t0) * NP;
@@ -574,8 +579,8 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
     //      first radix histogram.  Everything after this region works on the list.
     CTC_WARPS {
       int cnt = 0;
-      uint32_t *const segk = c.s_clk + warp * L.seg;
-      int *const segi = c.s_cli + warp * L.seg;
+      uint32_t *const segk = c.s_clk + warp * SEG;
+      int *const segi = c.s_cli + warp * SEG;
       int *const hist0 = c.s_hist;
       if (!select_all) {
         CTC_LANES {
@@ -588,10 +593,10 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
       // rows (members) are tested 32 at a time: lane l looks at row base + warp + NW * l.  A row whose best
       // possible candidate (score + max non-blank log-prob) stays under lo32 contributes nothing; on config 2
       // that removes 80 % of the rows.
-      for (int base = 0; base < M; base += 32 * L.NW) {
+      for (int base = 0; base < M; base += 32 * NW) {
         CTC_LV(int, rowok);
         CTC_LANES {
-          const int i = base + warp + L.NW * lane;
+          const int i = base + warp + NW * lane;
           rowok[LX] = 0;
           if (i < M) {
             CTC_STAT(g_stats.rows++);
@@ -618,7 +623,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
           rows &= rows - 1u;
           const int rl2 = ctc_ffs(rows) - 1;
           rows &= rows - 1u;
-          const int i1 = base + warp + L.NW * rl1, i2 = base + warp + L.NW * rl2;
+          const int i1 = base + warp + NW * rl1, i2 = base + warp + NW * rl2;
           const float sc1 = c.s_score[i1], b1 = c.s_bprev[i1], sc2 = c.s_score[i2], b2 = c.s_bprev[i2];
           const int ch1 = c.s_chr[i1], ch2 = c.s_chr[i2];
           const uint32_t mw1 = c.s_mask[i1 * W], mw2 = c.s_mask[i2 * W];
@@ -648,11 +653,11 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
           CTC_LANES {
             if (pred1[LX]) {
               const int pos = cnt + ctc_popc(bal1 & ctc_lt_mask(lane));
-              if (pos < L.seg) { segk[pos] = kk1[LX]; segi[pos] = (i1 << 16) | lane; }
+              if (pos < SEG) { segk[pos] = kk1[LX]; segi[pos] = (i1 << 16) | lane; }
             }
             if (pred2[LX]) {
               const int pos = cnt + n1 + ctc_popc(bal2 & ctc_lt_mask(lane));
-              if (pos < L.seg) { segk[pos] = kk2[LX]; segi[pos] = (i2 << 16) | lane; }
+              if (pos < SEG) { segk[pos] = kk2[LX]; segi[pos] = (i2 << 16) | lane; }
             }
           }
           cnt += n1 + ctc_popc(bal2);
@@ -673,7 +678,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
           while (rows) {
             const int rl = ctc_ffs(rows) - 1;
             rows &= rows - 1u;
-            const int i = base + warp + L.NW * rl;
+            const int i = base + warp + NW * rl;
             const float sc_i = c.s_score[i], b_i = c.s_bprev[i];
             const int ch_i = c.s_chr[i];
             const uint32_t mwa = c.s_mask[i * W], mwb = c.s_mask[i * W + 1];
@@ -702,11 +707,11 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
             CTC_LANES {
               if (pred1[LX]) {
                 const int pos = cnt + ctc_popc(bal1 & ctc_lt_mask(lane));
-                if (pos < L.seg) { segk[pos] = kk1[LX]; segi[pos] = (i << 16) | lane; }
+                if (pos < SEG) { segk[pos] = kk1[LX]; segi[pos] = (i << 16) | lane; }
               }
               if (pred2[LX]) {
                 const int pos = cnt + n1 + ctc_popc(bal2 & ctc_lt_mask(lane));
-                if (pos < L.seg) { segk[pos] = kk2[LX]; segi[pos] = (i << 16) | (32 + lane); }
+                if (pos < SEG) { segk[pos] = kk2[LX]; segi[pos] = (i << 16) | (32 + lane); }
               }
             }
             cnt += n1 + ctc_popc(bal2);
@@ -716,7 +721,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
         while (rows) {
           const int rl = ctc_ffs(rows) - 1;
           rows &= rows - 1u;
-          const int i = base + warp + L.NW * rl;
+          const int i = base + warp + NW * rl;
           const float sc_i = c.s_score[i], b_i = c.s_bprev[i];
           const int ch_i = c.s_chr[i];
           for (int g = 0; g < G; ++g) {
@@ -755,7 +760,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
               CTC_LANES {
                 if (pred[LX]) {
                   const int pos = cnt + ctc_popc(bal & ctc_lt_mask(lane));
-                  if (pos < L.seg) { segk[pos] = kk[LX]; segi[pos] = (i << 16) | (g * 32 + lane); }
+                  if (pos < SEG) { segk[pos] = kk[LX]; segi[pos] = (i << 16) | (g * 32 + lane); }
                 }
               }
               cnt += ctc_popc(bal);
@@ -766,8 +771,8 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
       }
       CTC_LANES {
         if (lane == 0) {
-          if (cnt > L.seg) atom_or(&s_ctl[C_OVF], 1);
-          c.s_wcnt[warp] = cnt < L.seg ? cnt : L.seg;
+          if (cnt > SEG) atom_or(&s_ctl[C_OVF], 1);
+          c.s_wcnt[warp] = cnt < SEG ? cnt : SEG;
         }
       }
     }
@@ -778,7 +783,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
       // beam not full yet: do fewer than beam_size prefixes exist?  (lo32 == 0, so the lists hold every candidate)
       long long ncand = 0;
       if (!fallback) {
-        for (int w = 0; w < L.NW; ++w) ncand += c.s_wcnt[w];
+        for (int w = 0; w < NW; ++w) ncand += c.s_wcnt[w];
       } else {
         CTC_PAR {
           int mine = 0;
@@ -833,8 +838,8 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
             const int w = tid >> 5, ln = tid & 31;
             const int cn = c.s_wcnt[w];
             for (int e = ln; e < cn; e += 32) {
-              const int r = c.s_cli[w * L.seg + e] & 0xFFFF;
-              const uint64_t k = ((uint64_t)c.s_clk[w * L.seg + e] << 16) | (uint64_t)(0xFFFF - (c.chr_at(r) + 1));
+              const int r = c.s_cli[w * SEG + e] & 0xFFFF;
+              const uint64_t k = ((uint64_t)c.s_clk[w * SEG + e] << 16) | (uint64_t)(0xFFFF - (c.chr_at(r) + 1));
               if (k >= lo && k - lo < width) atom_add(&hist[(int)((k - lo) >> shift)], 1);
             }
           }
@@ -858,9 +863,9 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
             const int w = tid >> 5, ln = tid & 31;
             const int cn = c.s_wcnt[w];
             for (int e = ln; e < cn; e += 32) {
-              const int id = c.s_cli[w * L.seg + e];
+              const int id = c.s_cli[w * SEG + e];
               const int r = id & 0xFFFF;
-              const uint64_t k = ((uint64_t)c.s_clk[w * L.seg + e] << 16) | (uint64_t)(0xFFFF - (c.chr_at(r) + 1));
+              const uint64_t k = ((uint64_t)c.s_clk[w * SEG + e] << 16) | (uint64_t)(0xFFFF - (c.chr_at(r) + 1));
               if (k == thr) c.s_tie[atom_add(&s_ctl[C_NTIE], 1)] = K + (id >> 16) * NP + r;
             }
             if (tid == 0) s_ctl[C_FLAGS] |= FLAG_TIE_PRUNE;
@@ -944,7 +949,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
       CTC_WARPS {
         CTC_LANES { for (int j = warp * 32 + lane; j < K; j += NT) c.s_slot2q[j] = -1; }
         // members, in blocks of 32 slots
-        for (int blk = warp; blk * 32 < M; blk += L.NW) {
+        for (int blk = warp; blk * 32 < M; blk += NW) {
           CTC_LV(int, ev);
           CTC_LANES {
             const int j = blk * 32 + lane;
@@ -969,8 +974,8 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
         }
         // this warp's candidate-list segment, compacted in place
         const int cn = c.s_wcnt[warp];
-        uint32_t *const segk = c.s_clk + warp * L.seg;
-        int *const segi = c.s_cli + warp * L.seg;
+        uint32_t *const segk = c.s_clk + warp * SEG;
+        int *const segi = c.s_cli + warp * SEG;
         const unsigned thr_hi = (unsigned)(thr >> 16);
         int out = 0;
         for (int e0 = 0; e0 < cn; e0 += 32) {
@@ -1077,9 +1082,9 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
     auto sel_entry = [&](int q) -> int {
       if (fallback) return c.s_free2[q];
       int acc = 0;
-      for (int w = 0; w < L.NW; ++w) {
+      for (int w = 0; w < NW; ++w) {
         const int cw = c.s_wcnt[32 + w];
-        if (q < acc + cw) return c.s_cli[w * L.seg + (q - acc)];
+        if (q < acc + cw) return c.s_cli[w * SEG + (q - acc)];
         acc += cw;
       }
       return 0;
@@ -1421,7 +1426,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
     }
   }
 #if !defined(CTC_EMULATE)
-  if (p.timing && threadIdx.x == 0)
+  if (TIMING && p.timing && threadIdx.x == 0)
     for (int x = 0; x < 16; ++x) p.timing[(size_t)b * 16 + x] = s_tick[x];
 #endif
 }

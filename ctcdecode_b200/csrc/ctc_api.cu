@@ -25,12 +25,13 @@ namespace ctc {
 // ---------------------------------------------------------------------------------------------------
 //  kernels
 // ---------------------------------------------------------------------------------------------------
-// two co-resident CTAs per SM (one for NT = 1024): 128 registers per thread up to NT = 256, 64 at NT = 512.
+// two co-resident CTAs per SM (one for NT = 1024, four for NT = 128): 128 registers per thread up to NT = 256, 64 at NT = 512.
 // A config-2 batch of 256 utterances is 1.73 CTAs per SM, and the frame loop wants its registers.
-template <int NT, bool SORTED, bool LM>
-__global__ void __launch_bounds__(NT, (NT >= 1024 ? 1 : 2)) beam_kernel(const BeamParams p) {
+// KPT: beam size rounded up to 32 as a compile-time constant (0 = generic), TIMING: per-region cycle counters.
+template <int NT, bool SORTED, bool LM, int KPT, bool TIMING>
+__global__ void __launch_bounds__(NT, (NT >= 1024 ? 1 : NT <= 128 ? 4 : 2)) beam_kernel(const BeamParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
-  beam_cta_run<NT, SORTED, LM>(p, (int)blockIdx.x, smem);
+  beam_cta_run<NT, SORTED, LM, KPT, TIMING>(p, (int)blockIdx.x, smem);
 }
 
 template <int NT>
@@ -73,36 +74,81 @@ static int fail(int code, const char *fmt, ...) {
     if (e_ != cudaSuccess) return fail(CTCDEC_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
   } while (0)
 
+// utterances the calling thread is about to have in flight together (host entry point: all its groups)
+static thread_local int g_batch_in_flight = 0;
+
 static int make_plan(const ctcdec_config *cfg, int B, int T, Plan *pl) {
   char msg[256];
   int nt = 0;
   if (const char *e = getenv("CTCDEC_NT")) nt = atoi(e);  // tuning knob: threads per CTA of the beam kernel
-  const int rc = make_plan_core(cfg, B, T, pl, msg, sizeof(msg), nt);
+  const int rc = make_plan_core(cfg, B, T, pl, msg, sizeof(msg), nt, g_batch_in_flight);
   if (rc) return fail(rc, "%s", msg);
   return CTCDEC_OK;
 }
 
-template <int NT>
-static int launch_beam_nt(const BeamParams &bp, const Plan &pl, int B, cudaStream_t s) {
-  const bool lm = bp.dict_next != nullptr;
-#define CTC_LAUNCH(SORTED_, LM_)                                                                                      \
-  do {                                                                                                                \
-    CU(cudaFuncSetAttribute(beam_kernel<NT, SORTED_, LM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.L.total)); \
-    beam_kernel<NT, SORTED_, LM_><<<B, NT, pl.L.total, s>>>(bp);                                                      \
-  } while (0)
-  if (pl.sorted) { if (lm) CTC_LAUNCH(true, true); else CTC_LAUNCH(true, false); }
-  else { if (lm) CTC_LAUNCH(false, true); else CTC_LAUNCH(false, false); }
-#undef CTC_LAUNCH
+template <int NT, bool SORTED, bool LM, int KPT, bool TIMING>
+static int launch_beam_k(const BeamParams &bp, int B, cudaStream_t s) {
+  // raise the dynamic shared-memory limit once per device and size: cudaFuncSetAttribute on a kernel that is
+  // running waits for it, which would serialise the utterance groups the host entry point pipelines
+  static std::atomic<int> limit[64];
+  int dev = 0;
+  CU(cudaGetDevice(&dev));
+  if (bp.L.total > limit[dev & 63].load(std::memory_order_acquire)) {
+    CU(cudaFuncSetAttribute(beam_kernel<NT, SORTED, LM, KPT, TIMING>, cudaFuncAttributeMaxDynamicSharedMemorySize, bp.L.total));
+    limit[dev & 63].store(bp.L.total, std::memory_order_release);
+  }
+  beam_kernel<NT, SORTED, LM, KPT, TIMING><<<B, NT, bp.L.total, s>>>(bp);
   CU(cudaGetLastError());
   return CTCDEC_OK;
 }
 
-static int launch_beam(const BeamParams &bp, const Plan &pl, int B, cudaStream_t s) {
+// Instantiations: without a scorer the usual block sizes (128 / 256 threads) come specialised for beam sizes up to
+// 32 / 64 / 128 / 256 slots (every slot-array address an immediate) besides the generic kernel; the scorer path,
+// whose frame time is the host handshake, and the tuning-knob block sizes use the generic kernel only.  The
+// per-region cycle counters (diagnostic) exist for the 256-thread kernels of beam 65..256 and for the scorer path.
+template <int NT, bool SORTED>
+static int launch_beam_ns(const BeamParams &bp, int B, cudaStream_t s) {
+  const bool lm = bp.dict_next != nullptr, timing = bp.timing != nullptr;
+  const int KP = bp.L.KP;
+  if (lm) {
+    if (timing) {
+      if constexpr (NT <= 256) return launch_beam_k<NT, SORTED, true, 0, true>(bp, B, s);
+      else return fail(CTCDEC_E_UNSUPPORTED, "region timing is built for 128 / 256 threads only");
+    }
+    return launch_beam_k<NT, SORTED, true, 0, false>(bp, B, s);
+  }
+  if (timing) {
+    if constexpr (NT == 256) {
+      if (KP == 128) return launch_beam_k<NT, SORTED, false, 128, true>(bp, B, s);
+      if (KP == 256) return launch_beam_k<NT, SORTED, false, 256, true>(bp, B, s);
+    }
+    return fail(CTCDEC_E_UNSUPPORTED, "region timing is built for 256 threads and beam sizes 65..256 only");
+  }
+  if constexpr (NT <= 256) {
+    if (KP == 32) return launch_beam_k<NT, SORTED, false, 32, false>(bp, B, s);
+    if (KP == 64) return launch_beam_k<NT, SORTED, false, 64, false>(bp, B, s);
+    if (KP == 128) return launch_beam_k<NT, SORTED, false, 128, false>(bp, B, s);
+    if (KP == 256) return launch_beam_k<NT, SORTED, false, 256, false>(bp, B, s);
+  }
+  return launch_beam_k<NT, SORTED, false, 0, false>(bp, B, s);
+}
+
+static int launch_beam(const BeamParams &bp_in, const Plan &pl, int B, cudaStream_t s) {
+  BeamParams bp = bp_in;
+  bp.L = pl.L;
+  const bool generic = getenv("CTCDEC_GENERIC_KP") != nullptr;  // test knob: force the run-time-KP kernel
+  if (generic && !bp.timing && !bp.dict_next) {
+    switch (pl.NT) {
+      case 128: return pl.sorted ? launch_beam_k<128, true, false, 0, false>(bp, B, s) : launch_beam_k<128, false, false, 0, false>(bp, B, s);
+      case 256: return pl.sorted ? launch_beam_k<256, true, false, 0, false>(bp, B, s) : launch_beam_k<256, false, false, 0, false>(bp, B, s);
+      default: break;
+    }
+  }
   switch (pl.NT) {
-    case 128: return launch_beam_nt<128>(bp, pl, B, s);
-    case 256: return launch_beam_nt<256>(bp, pl, B, s);
-    case 1024: return launch_beam_nt<1024>(bp, pl, B, s);
-    default: return launch_beam_nt<512>(bp, pl, B, s);
+    case 128: return pl.sorted ? launch_beam_ns<128, true>(bp, B, s) : launch_beam_ns<128, false>(bp, B, s);
+    case 256: return pl.sorted ? launch_beam_ns<256, true>(bp, B, s) : launch_beam_ns<256, false>(bp, B, s);
+    case 1024: return pl.sorted ? launch_beam_ns<1024, true>(bp, B, s) : launch_beam_ns<1024, false>(bp, B, s);
+    default: return pl.sorted ? launch_beam_ns<512, true>(bp, B, s) : launch_beam_ns<512, false>(bp, B, s);
   }
 }
 
@@ -114,8 +160,15 @@ struct PruneInput {
 
 template <bool SORTED, int KPL, bool LOGITS>
 static int launch_prune_k(const PruneParams &pp, int grid, int threads, size_t smem, cudaStream_t s) {
-  if (smem > 48 * 1024)
-    CU(cudaFuncSetAttribute(prune_kernel<SORTED, KPL, LOGITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (smem > 48 * 1024) {
+    static std::atomic<int> limit[64];
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    if ((int)smem > limit[dev & 63].load(std::memory_order_acquire)) {
+      CU(cudaFuncSetAttribute(prune_kernel<SORTED, KPL, LOGITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      limit[dev & 63].store((int)smem, std::memory_order_release);
+    }
+  }
   prune_kernel<SORTED, KPL, LOGITS><<<grid, threads, smem, s>>>(pp);
   return CTCDEC_OK;
 }
@@ -184,8 +237,10 @@ static int check_device() {
 // ---------------------------------------------------------------------------------------------------
 //  per-device cache for the host-buffer entry points (stream + grow-only device buffers)
 // ---------------------------------------------------------------------------------------------------
+constexpr int kHostChunks = 8;  // utterance groups (streams) the host-buffer entry point pipelines over
 struct DevCache {
   cudaStream_t stream = nullptr;
+  cudaStream_t cs[kHostChunks] = {};
   void *buf[12] = {};
   size_t cap[12] = {};
   void *pin[4] = {};  // pinned host staging (scorer path: new-node lists, LM updates)
@@ -466,15 +521,28 @@ int ctcdec_decode_batch_host(const ctcdec_config *cfg, const float *probs, const
   if (B == 0) return CTCDEC_OK;
   std::lock_guard<std::mutex> lock(g_mu);
   DevCache &c = g_cache[device];
-  if (!c.stream) CU(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
   const int V = cfg->vocab_size, K = cfg->beam_size;
+  // The batch is cut into up to kHostChunks groups of utterances, each with its own stream: upload, kernels and
+  // download of different groups overlap (an utterance is T serial frames whatever the batch size, so a group's
+  // kernels take as long as the whole batch's would; only the PCIe legs of the first / last group stay exposed,
+  // and for batches of several waves the downloads hide under the next group's kernels).
+  int chunk = std::max(64, (B + kHostChunks - 1) / kHostChunks);
+  if (const char *e = getenv("CTCDEC_HOST_CHUNK")) chunk = std::max(1, atoi(e));  // tuning knob: utterances per group
+  const int C = std::min(kHostChunks, (B + chunk - 1) / chunk);
+  chunk = (B + C - 1) / C;
+  for (int i = 0; i < C; ++i)
+    if (!c.cs[i]) CU(cudaStreamCreateWithFlags(&c.cs[i], cudaStreamNonBlocking));
+  struct InFlight { InFlight(int n) { g_batch_in_flight = n; } ~InFlight() { g_batch_in_flight = 0; } } in_flight(B);
+  Plan plc;
+  if ((rc = make_plan(cfg, chunk, T, &plc))) return rc;
+  const size_t ws_stride = al256(plc.total + 512);
   const size_t n_probs = (size_t)B * T * V, n_out = (size_t)B * K * T, n_bk = (size_t)B * K;
   if ((rc = ensure(c, 0, n_probs * 4 + 256))) return rc;
   if ((rc = ensure(c, 1, (size_t)B * 4 + 256))) return rc;
   if ((rc = ensure(c, 2, n_out * 4 + 256))) return rc;
   if ((rc = ensure(c, 3, n_out * 4 + 256))) return rc;
   if ((rc = ensure(c, 4, n_bk * 4 * 2 + (size_t)B * 8 + 1024))) return rc;
-  if ((rc = ensure(c, 5, pl.total + 512))) return rc;
+  if ((rc = ensure(c, 5, ws_stride * C))) return rc;
   float *d_probs = (float *)c.buf[0];
   int *d_lens_in = seq_lens ? (int *)c.buf[1] : nullptr;
   int *d_tok = (int *)c.buf[2], *d_ts = (int *)c.buf[3];
@@ -482,34 +550,46 @@ int ctcdec_decode_batch_host(const ctcdec_config *cfg, const float *probs, const
   int *d_lens = (int *)((char *)c.buf[4] + al256(n_bk * 4));
   int *d_nres = (int *)((char *)d_lens + al256(n_bk * 4));
   int *d_flags = d_nres + B;
-  cudaStream_t s = c.stream;
-  if (n_probs) CU(cudaMemcpyAsync(d_probs, probs, n_probs * 4, cudaMemcpyHostToDevice, s));
-  if (seq_lens) CU(cudaMemcpyAsync(d_lens_in, seq_lens, (size_t)B * 4, cudaMemcpyHostToDevice, s));
-  rc = ctcdec_decode_batch_device(cfg, d_probs, d_lens_in, B, T, d_tok, d_ts, d_scores, d_lens, d_nres, d_flags,
-                                  c.buf[5], c.cap[5], s);
-  if (rc) return rc;
-  // small results first: lens tell how many columns of the big tensors carry data
   std::unique_ptr<int[]> h_nres(new int[(size_t)B * 2]);
-  CU(cudaMemcpyAsync(scores, d_scores, n_bk * 4, cudaMemcpyDeviceToHost, s));
-  CU(cudaMemcpyAsync(lens, d_lens, n_bk * 4, cudaMemcpyDeviceToHost, s));
-  CU(cudaMemcpyAsync(h_nres.get(), d_nres, (size_t)B * 8, cudaMemcpyDeviceToHost, s));
-  CU(cudaStreamSynchronize(s));
-  // The reference leaves rows p >= n_results and columns >= len untouched; lens of untouched rows are
-  // whatever the caller put there (the reference's Python zero-fills out_seq_len), so only trust rows
-  // below n_results when sizing the column window.
-  int max_len = 0;
-  for (int b = 0; b < B; ++b) {
-    const int nr = h_nres[b];
-    for (int p = 0; p < nr && p < K; ++p) max_len = std::max(max_len, lens[(size_t)b * K + p]);
+  int *const h_flags = h_nres.get() + B;
+  for (int i = 0; i < C; ++i) {
+    const int b0 = i * chunk, nb = std::min(chunk, B - b0);
+    cudaStream_t s = c.cs[i];
+    const size_t po = (size_t)b0 * T * V, oo = (size_t)b0 * K * T, ko = (size_t)b0 * K;
+    if (n_probs) CU(cudaMemcpyAsync(d_probs + po, probs + po, (size_t)nb * T * V * 4, cudaMemcpyHostToDevice, s));
+    if (seq_lens) CU(cudaMemcpyAsync(d_lens_in + b0, seq_lens + b0, (size_t)nb * 4, cudaMemcpyHostToDevice, s));
+    rc = ctcdec_decode_batch_device(cfg, d_probs + po, seq_lens ? d_lens_in + b0 : nullptr, nb, T, d_tok + oo, d_ts + oo,
+                                    d_scores + ko, d_lens + ko, d_nres + b0, d_flags + b0,
+                                    (char *)c.buf[5] + ws_stride * i, ws_stride, s);
+    if (rc) return rc;
+    // small results first: lens tell how many columns of the big tensors carry data
+    CU(cudaMemcpyAsync(scores + ko, d_scores + ko, (size_t)nb * K * 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(lens + ko, d_lens + ko, (size_t)nb * K * 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(h_nres.get() + b0, d_nres + b0, (size_t)nb * 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(h_flags + b0, d_flags + b0, (size_t)nb * 4, cudaMemcpyDeviceToHost, s));
   }
-  if (max_len > T) max_len = T;
-  if (max_len > 0) {
-    CU(cudaMemcpy2DAsync(tokens, (size_t)T * 4, d_tok, (size_t)T * 4, (size_t)max_len * 4, n_bk, cudaMemcpyDeviceToHost, s));
-    CU(cudaMemcpy2DAsync(timesteps, (size_t)T * 4, d_ts, (size_t)T * 4, (size_t)max_len * 4, n_bk, cudaMemcpyDeviceToHost, s));
+  for (int i = 0; i < C; ++i) {
+    const int b0 = i * chunk, nb = std::min(chunk, B - b0);
+    cudaStream_t s = c.cs[i];
+    CU(cudaStreamSynchronize(s));
+    // The reference leaves rows p >= n_results and columns >= len untouched; lens of untouched rows are
+    // whatever the caller put there (the reference's Python zero-fills out_seq_len), so only trust rows
+    // below n_results when sizing the column window.
+    int max_len = 0;
+    for (int b = b0; b < b0 + nb; ++b) {
+      const int nr = h_nres[b];
+      for (int p = 0; p < nr && p < K; ++p) max_len = std::max(max_len, lens[(size_t)b * K + p]);
+    }
+    if (max_len > T) max_len = T;
+    if (max_len > 0) {
+      const size_t oo = (size_t)b0 * K * T;
+      CU(cudaMemcpy2DAsync(tokens + oo, (size_t)T * 4, d_tok + oo, (size_t)T * 4, (size_t)max_len * 4, (size_t)nb * K, cudaMemcpyDeviceToHost, s));
+      CU(cudaMemcpy2DAsync(timesteps + oo, (size_t)T * 4, d_ts + oo, (size_t)T * 4, (size_t)max_len * 4, (size_t)nb * K, cudaMemcpyDeviceToHost, s));
+    }
   }
-  CU(cudaStreamSynchronize(s));
+  for (int i = 0; i < C; ++i) CU(cudaStreamSynchronize(c.cs[i]));
   if (n_results) memcpy(n_results, h_nres.get(), (size_t)B * 4);
-  if (flags) memcpy(flags, h_nres.get() + B, (size_t)B * 4);
+  if (flags) memcpy(flags, h_flags, (size_t)B * 4);
   return CTCDEC_OK;
 }
 

@@ -18,6 +18,7 @@ struct Plan {
   int P;          // next power of two >= V
   int F;          // frames per staged tile
   int NT;         // threads per CTA of the beam kernel
+  int budget_kb;  // shared-memory budget per CTA the layout was made for (make_layout)
   SmemLayout L;
   size_t off_lp, off_idx, off_arena, off_state, total;
   long long arena_stride, state_stride;
@@ -25,8 +26,10 @@ struct Plan {
 
 static inline size_t al256(size_t x) { return (x + 255) / 256 * 256; }
 
+// b_sched: the number of utterances that will be in flight on the device together (>= B when the caller runs
+// several groups of B concurrently); decides between the latency and the throughput shape of the beam kernel
 static inline int make_plan_core(const ctcdec_config *cfg, int B, int T, Plan *pl, char *msg, size_t msglen,
-                                 int nt_override = 0) {
+                                 int nt_override = 0, int b_sched = 0) {
 #define PLAN_FAIL(code, ...) do { snprintf(msg, msglen, __VA_ARGS__); return code; } while (0)
   if (!cfg) PLAN_FAIL(CTCDEC_E_INVALID, "cfg is NULL");
   const int V = cfg->vocab_size, K = cfg->beam_size;
@@ -50,10 +53,23 @@ static inline int make_plan_core(const ctcdec_config *cfg, int B, int T, Plan *p
   pl->P = P;
   pl->F = std::max(1, std::min(32, 4096 / (pl->NP * 4)));
   const long long grid = (long long)K * pl->n_max;
-  // measured on B200 (profiles/): 8 warps with 128 registers beat 16 warps with 64 on both config 2 and 4
+  // measured on B200 (profiles/): 8 warps with 128 registers beat 16 warps with 64 on both config 2 and 4 for a
+  // batch that fits the GPU in one go (an utterance is T serial frames: latency counts).  A batch of several
+  // waves is a throughput problem instead: 4 warps per utterance and as many CTAs per SM as shared memory allows
+  // (config 3, 2048 utterances on one GPU: +24 %).
   pl->NT = grid <= 512 ? 128 : 256;
+  int budget_kb = 111;
+  if (std::max(B, b_sched) > 2 * 148 && nt_override == 0) {
+    pl->NT = 128;
+    const int f_small = std::max(1, std::min(16, 2048 / (pl->NP * 4)));
+    for (int kb : {55, 74}) {
+      const SmemLayout t = make_layout(K, V, pl->NP, f_small, pl->sorted, 128, false, kb);
+      if (t.total <= kb * 1024 && t.seg * 8 * 4 >= 8 * 1024) { budget_kb = kb; pl->F = f_small; break; }
+    }
+  }
   if (nt_override == 128 || nt_override == 256 || nt_override == 512 || nt_override == 1024) pl->NT = nt_override;
-  pl->L = make_layout(K, V, pl->NP, pl->F, pl->sorted, pl->NT);
+  pl->budget_kb = budget_kb;
+  pl->L = make_layout(K, V, pl->NP, pl->F, pl->sorted, pl->NT, false, budget_kb);
   if (pl->L.total > 227 * 1024)
     PLAN_FAIL(CTCDEC_E_UNSUPPORTED, "beam_size %d x pruned vocab %d needs %d bytes of shared memory (> 227 KB)", K,
               pl->n_max, pl->L.total);

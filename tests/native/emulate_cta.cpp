@@ -93,13 +93,29 @@ static void prune_rows(const ctcdec_config &cfg, const Plan &pl, const float *pr
   }
 }
 
-template <int NT>
-static void run_beam(const BeamParams &bp, bool sorted, int B, unsigned char *smem) {
+template <int NT, int KPT>
+static void run_beam_k(const BeamParams &bp, bool sorted, int B, unsigned char *smem) {
   for (int b = 0; b < B; ++b) {
     const bool lm = bp.dict_next != nullptr;
-    if (sorted) { if (lm) beam_cta_run<NT, true, true>(bp, b, smem); else beam_cta_run<NT, true, false>(bp, b, smem); }
-    else { if (lm) beam_cta_run<NT, false, true>(bp, b, smem); else beam_cta_run<NT, false, false>(bp, b, smem); }
+    if (sorted) { if (lm) beam_cta_run<NT, true, true, 0>(bp, b, smem); else beam_cta_run<NT, true, false, KPT>(bp, b, smem); }
+    else { if (lm) beam_cta_run<NT, false, true, 0>(bp, b, smem); else beam_cta_run<NT, false, false, KPT>(bp, b, smem); }
   }
+}
+
+// like the launcher (ctc_api.cu launch_beam_ns): the compile-time-KP instantiation when there is one
+template <int NT>
+static void run_beam(const BeamParams &bp, bool sorted, int B, unsigned char *smem) {
+  const bool generic = getenv("CTC_EMU_GENERIC_KP") != nullptr;
+  if (!generic && NT <= 256) {
+    switch (bp.L.KP) {
+      case 32: return run_beam_k<NT, 32>(bp, sorted, B, smem);
+      case 64: return run_beam_k<NT, 64>(bp, sorted, B, smem);
+      case 128: return run_beam_k<NT, 128>(bp, sorted, B, smem);
+      case 256: return run_beam_k<NT, 256>(bp, sorted, B, smem);
+      default: break;
+    }
+  }
+  run_beam_k<NT, 0>(bp, sorted, B, smem);
 }
 
 extern "C" {
@@ -130,7 +146,7 @@ int emu_decode_batch(const float *probs, const int *seq_lens, int B, int T, int 
 
   BeamParams bp;
   memset(&bp, 0, sizeof(bp));
-  bp.V = V; bp.NP = pl.NP; bp.K = K; bp.blank = blank; bp.tile_frames = pl.F;
+  bp.V = V; bp.NP = pl.NP; bp.K = K; bp.blank = blank; bp.tile_frames = pl.F; bp.L = pl.L;
   bp.arena = arena.data(); bp.arena_stride = pl.arena_stride; bp.state = state.data();
   bp.state_stride = pl.state_stride; bp.arena_cap = (int)pl.arena_stride;
   bp.out_tokens = tokens; bp.out_timesteps = timesteps; bp.out_scores = scores; bp.out_lens = lens;
@@ -213,7 +229,7 @@ int emu_decode_batch_lm(const float *probs, const int *seq_lens, int B, int T, i
   BeamParams bp;
   memset(&bp, 0, sizeof(bp));
   bp.lp = lp.data(); bp.idx = pl.sorted ? idx.data() : nullptr; bp.seq_lens = seq_lens; bp.T = T;
-  bp.V = V; bp.NP = pl.NP; bp.K = K; bp.blank = blank; bp.tile_frames = pl.F;
+  bp.V = V; bp.NP = pl.NP; bp.K = K; bp.blank = blank; bp.tile_frames = pl.F; bp.L = pl.L;
   bp.arena = arena.data(); bp.arena_stride = pl.arena_stride; bp.state = state.data();
   bp.state_stride = pl.state_stride; bp.arena_cap = (int)pl.arena_stride;
   bp.out_tokens = tokens; bp.out_timesteps = timesteps; bp.out_scores = scores; bp.out_lens = lens;
