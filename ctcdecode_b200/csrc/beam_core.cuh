@@ -136,7 +136,7 @@ struct SmemLayout {
 };
 CTC_HD int align_up(int x, int a) { return (x + a - 1) / a * a; }
 // budget_kb: shared memory one CTA may take so that the intended number of CTAs fits an SM (227 KB, 1 KB reserved
-// per CTA): 111 = two per SM (default), 74 = three, 55 = four (plan.h picks it from the batch size).  Only the
+// per CTA): 111 = two per SM (default), 74 = three (plan.h picks it from the batch size).  Only the
 // candidate-list segments give way; a segment that overflows costs that frame the grid-walking fallback.
 CTC_HD SmemLayout make_layout(int K, int V, int NP, int tile_frames, bool sorted, int NT, bool lm = false,
                               int budget_kb = 111) {

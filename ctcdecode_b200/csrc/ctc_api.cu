@@ -25,11 +25,11 @@ namespace ctc {
 // ---------------------------------------------------------------------------------------------------
 //  kernels
 // ---------------------------------------------------------------------------------------------------
-// two co-resident CTAs per SM (one for NT = 1024, four for NT = 128): 128 registers per thread up to NT = 256, 64 at NT = 512.
+// two co-resident CTAs per SM (one for NT = 1024, three for NT = 128): 128 registers per thread up to NT = 256, 64 at NT = 512.
 // A config-2 batch of 256 utterances is 1.73 CTAs per SM, and the frame loop wants its registers.
 // KPT: beam size rounded up to 32 as a compile-time constant (0 = generic), TIMING: per-region cycle counters.
 template <int NT, bool SORTED, bool LM, int KPT, bool TIMING>
-__global__ void __launch_bounds__(NT, (NT >= 1024 ? 1 : NT <= 128 ? 4 : 2)) beam_kernel(const BeamParams p) {
+__global__ void __launch_bounds__(NT, (NT >= 1024 ? 1 : NT <= 128 ? 3 : 2)) beam_kernel(const BeamParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   beam_cta_run<NT, SORTED, LM, KPT, TIMING>(p, (int)blockIdx.x, smem);
 }
@@ -243,8 +243,8 @@ struct DevCache {
   cudaStream_t cs[kHostChunks] = {};
   void *buf[12] = {};
   size_t cap[12] = {};
-  void *pin[4] = {};  // pinned host staging (scorer path: new-node lists, LM updates)
-  size_t pcap[4] = {};
+  void *pin[6] = {};  // pinned host staging (scorer path: new-node lists, LM updates; [4]: n_results / flags)
+  size_t pcap[6] = {};
 };
 static DevCache g_cache[64];
 static std::mutex g_mu;
@@ -550,8 +550,12 @@ int ctcdec_decode_batch_host(const ctcdec_config *cfg, const float *probs, const
   int *d_lens = (int *)((char *)c.buf[4] + al256(n_bk * 4));
   int *d_nres = (int *)((char *)d_lens + al256(n_bk * 4));
   int *d_flags = d_nres + B;
-  std::unique_ptr<int[]> h_nres(new int[(size_t)B * 2]);
-  int *const h_flags = h_nres.get() + B;
+  // (pinned: a device-to-host copy into pageable memory would block this thread until the group has finished)
+  if ((rc = ensure_pinned(c, 4, (size_t)B * 8 + n_bk * 8))) return rc;
+  int *const h_nres = static_cast<int *>(c.pin[4]);
+  int *const h_flags = h_nres + B;
+  float *const h_scores = reinterpret_cast<float *>(h_flags + B);
+  int *const h_lens = reinterpret_cast<int *>(h_scores + n_bk);
   for (int i = 0; i < C; ++i) {
     const int b0 = i * chunk, nb = std::min(chunk, B - b0);
     cudaStream_t s = c.cs[i];
@@ -563,9 +567,9 @@ int ctcdec_decode_batch_host(const ctcdec_config *cfg, const float *probs, const
                                     (char *)c.buf[5] + ws_stride * i, ws_stride, s);
     if (rc) return rc;
     // small results first: lens tell how many columns of the big tensors carry data
-    CU(cudaMemcpyAsync(scores + ko, d_scores + ko, (size_t)nb * K * 4, cudaMemcpyDeviceToHost, s));
-    CU(cudaMemcpyAsync(lens + ko, d_lens + ko, (size_t)nb * K * 4, cudaMemcpyDeviceToHost, s));
-    CU(cudaMemcpyAsync(h_nres.get() + b0, d_nres + b0, (size_t)nb * 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(h_scores + ko, d_scores + ko, (size_t)nb * K * 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(h_lens + ko, d_lens + ko, (size_t)nb * K * 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(h_nres + b0, d_nres + b0, (size_t)nb * 4, cudaMemcpyDeviceToHost, s));
     CU(cudaMemcpyAsync(h_flags + b0, d_flags + b0, (size_t)nb * 4, cudaMemcpyDeviceToHost, s));
   }
   for (int i = 0; i < C; ++i) {
@@ -578,7 +582,7 @@ int ctcdec_decode_batch_host(const ctcdec_config *cfg, const float *probs, const
     int max_len = 0;
     for (int b = b0; b < b0 + nb; ++b) {
       const int nr = h_nres[b];
-      for (int p = 0; p < nr && p < K; ++p) max_len = std::max(max_len, lens[(size_t)b * K + p]);
+      for (int p = 0; p < nr && p < K; ++p) max_len = std::max(max_len, h_lens[(size_t)b * K + p]);
     }
     if (max_len > T) max_len = T;
     if (max_len > 0) {
@@ -587,8 +591,10 @@ int ctcdec_decode_batch_host(const ctcdec_config *cfg, const float *probs, const
       CU(cudaMemcpy2DAsync(timesteps + oo, (size_t)T * 4, d_ts + oo, (size_t)T * 4, (size_t)max_len * 4, (size_t)nb * K, cudaMemcpyDeviceToHost, s));
     }
   }
+  memcpy(scores, h_scores, n_bk * 4);
+  memcpy(lens, h_lens, n_bk * 4);
   for (int i = 0; i < C; ++i) CU(cudaStreamSynchronize(c.cs[i]));
-  if (n_results) memcpy(n_results, h_nres.get(), (size_t)B * 4);
+  if (n_results) memcpy(n_results, h_nres, (size_t)B * 4);
   if (flags) memcpy(flags, h_flags, (size_t)B * 4);
   return CTCDEC_OK;
 }

@@ -60,12 +60,11 @@ static inline int make_plan_core(const ctcdec_config *cfg, int B, int T, Plan *p
   pl->NT = grid <= 512 ? 128 : 256;
   int budget_kb = 111;
   if (std::max(B, b_sched) > 2 * 148 && nt_override == 0) {
+    // three CTAs per SM; a fourth (55 KB budget) was measured slower: 12 warps already saturate the SM's issue
+    // slots (0.62 utterances / ms / SM) and the coarser wave granularity costs more than it gains
     pl->NT = 128;
-    const int f_small = std::max(1, std::min(16, 2048 / (pl->NP * 4)));
-    for (int kb : {55, 74}) {
-      const SmemLayout t = make_layout(K, V, pl->NP, f_small, pl->sorted, 128, false, kb);
-      if (t.total <= kb * 1024 && t.seg * 8 * 4 >= 8 * 1024) { budget_kb = kb; pl->F = f_small; break; }
-    }
+    const SmemLayout t = make_layout(K, V, pl->NP, pl->F, pl->sorted, 128, false, 74);
+    if (t.total <= 74 * 1024 && t.seg * 8 * 4 >= 8 * 1024) budget_kb = 74;
   }
   if (nt_override == 128 || nt_override == 256 || nt_override == 512 || nt_override == 1024) pl->NT = nt_override;
   pl->budget_kb = budget_kb;
