@@ -72,6 +72,17 @@ def c5_inputs(B, T, seed):
 METRIC = "utterances/sec at beam_width=100, T=1000, V=29; HBM GB/s vs roofline"
 
 
+def traffic_of(config, kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture of this config (profiles/traffic.json, written
+    by tools/ncu_traffic.py from an `ncu --set full` report), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            e = json.load(f)[config][kernel]
+        return e["dram_read_bytes"] + e["dram_write_bytes"], e["source"]
+    except Exception:  # noqa: BLE001
+        return None, None
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -245,6 +256,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # keep stdout for the one JSON line: NCCL's version / debug lines go to stderr unless the caller chose a file
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     lib = _native.load()
     if cfg.get("lm"):
@@ -358,6 +371,8 @@ def main():
     n_max = min(V, max(1, cfg["cutoff_top_n"])) if is_sorted else V
     NP = (n_max + 3 + 7) // 8 * 8
     scan_bytes = alg_bytes + B * T * NP * (6 if is_sorted else 4)
+    beam_traffic, beam_traffic_src = traffic_of(args.config, "beam_kernel") if B == cfg["B"] else (None, None)
+    scan_traffic, _ = traffic_of(args.config, "prune_kernel") if B == cfg["B"] else (None, None)
     line = {
         "metric": METRIC, "value": value, "unit": "utterances/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
@@ -368,12 +383,14 @@ def main():
         "kernels_ms": {"prune_log_scan": scan_ms, "beam_search": beam_ms, "finalize": fin_ms,
                        "beam_share_of_step": beam_ms * K / total_ms},
         "roofline": {"kernel": "beam_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": beam_traffic, "traffic_source": beam_traffic_src,
+                     "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes,
                      "ns_per_frame_per_cta": beam_ms * 1e6 / T,
                      "note": "T-serial per utterance: latency bound, far below the HBM roofline by construction",
                      "scan": {"kernel": "prune_kernel", "bound": "fp64 issue (exact glibc log per element), then hbm",
-                              "bytes_per_launch": scan_bytes, "achieved": scan_bytes / (scan_ms * 1e-3) / 1e9,
+                              "bytes_per_launch": scan_bytes, "traffic": scan_traffic,
+                              "achieved": scan_bytes / (scan_ms * 1e-3) / 1e9,
                               "unit": "GB/s", "frac": scan_bytes / (scan_ms * 1e-3) / 1e9 / peak}},
         "clocks": clocks,
         "parity": {"arena_errors": int(t[2]), "tie_flagged_utterances_max_per_rank": int(t[3])},
@@ -390,7 +407,7 @@ def main():
         line["cpu_baseline"] = {"value": n * reps / spent, "unit": "utterances/s", "cores": cores if kind == "reference" else 1,
                                 "kind": kind,
                                 "sample": "%d x the first %d utterances of the same batch (one per host thread)" % (reps, n)}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

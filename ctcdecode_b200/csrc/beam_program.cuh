@@ -16,7 +16,16 @@ static EmuStats g_stats;
 
 #if defined(CTC_EMULATE)
 #define CTC_TICK(id) ((void)0)
+#define CTC_BARRIER_T(id) CTC_BARRIER()
 #else
+// a barrier that also accounts, per warp, the cycles between leaving the previous such barrier and arriving at
+// this one (TIMING instantiations only): shows which warp each region waits for
+#define CTC_BARRIER_T(id)                                                   \
+  do {                                                                      \
+    if (TIMING && (threadIdx.x & 31) == 0) s_wbusy[(id) * 32 + (threadIdx.x >> 5)] += clock64() - w_last; \
+    __syncthreads();                                                        \
+    if (TIMING) w_last = clock64();                                         \
+  } while (0)
 // per-region cycle accounting by thread 0 (TIMING instantiations only; tools/region_timing.py)
 #define CTC_TICK(id)                                                        \
   do {                                                                      \
@@ -253,6 +262,12 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
   if (TIMING && threadIdx.x == 0) {
     for (int x = 0; x < 15; ++x) s_tick[x] = 0;
     s_tick[15] = clock64();
+  }
+  long long *const s_wbusy = (long long *)(smem + L.total);  // [16][32], TIMING launches add 4 KB for it
+  long long w_last = 0;
+  if (TIMING) {
+    for (int x = threadIdx.x; x < 16 * 32; x += NT) s_wbusy[x] = 0;
+    w_last = clock64();
   }
 #endif
 
@@ -544,7 +559,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
       }
 #endif
     }
-    CTC_BARRIER();
+    CTC_BARRIER_T(2);
     CTC_TICK(2);  // R1
 
     const int n_nb = n - (rblank >= 0 ? 1 : 0);
@@ -776,7 +791,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
         }
       }
     }
-    CTC_BARRIER();
+    CTC_BARRIER_T(3);
     CTC_TICK(3);  // G
     const bool fallback = s_ctl[C_OVF] != 0 || p.force_fallback;  // a segment overflowed: redo on the grid
     if (LM && M < K) {
@@ -1018,7 +1033,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
           }
         }
       }
-      CTC_BARRIER();
+      CTC_BARRIER_T(5);
     } else {
       CTC_PAR {
         for (int j = tid; j < K; j += NT) {
@@ -1156,7 +1171,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
         c.s_slot2q[ni[3]] = q;
       }
     }
-    CTC_BARRIER();
+    CTC_BARRIER_T(6);
     CTC_TICK(6);  // R4c
     const int nrev = s_ctl[C_NREV];
 
@@ -1302,7 +1317,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
         s_ctl[C_NCAND] = 0;
       }
     }
-    CTC_BARRIER();
+    CTC_BARRIER_T(8);
     CTC_TICK(8);  // R5
     const int M_new = select_all ? (int)total : K;
     const bool anchors_active = nlive > 0 || nrev > 0 || s_ctl[C_ANYREF] != 0;
@@ -1426,8 +1441,13 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
     }
   }
 #if !defined(CTC_EMULATE)
-  if (TIMING && p.timing && threadIdx.x == 0)
-    for (int x = 0; x < 16; ++x) p.timing[(size_t)b * 16 + x] = s_tick[x];
+  if (TIMING && p.timing) {  // [B][16] region cycles of thread 0, then [B][16][32] busy cycles per region and warp
+    if (threadIdx.x == 0)
+      for (int x = 0; x < 16; ++x) p.timing[(size_t)b * 16 + x] = s_tick[x];
+    __syncthreads();
+    for (int x = threadIdx.x; x < 16 * 32; x += NT)
+      p.timing[(size_t)gridDim.x * 16 + (size_t)b * 16 * 32 + x] = s_wbusy[x];
+  }
 #endif
 }
 

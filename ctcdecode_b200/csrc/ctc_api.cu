@@ -93,11 +93,12 @@ static int launch_beam_k(const BeamParams &bp, int B, cudaStream_t s) {
   static std::atomic<int> limit[64];
   int dev = 0;
   CU(cudaGetDevice(&dev));
-  if (bp.L.total > limit[dev & 63].load(std::memory_order_acquire)) {
-    CU(cudaFuncSetAttribute(beam_kernel<NT, SORTED, LM, KPT, TIMING>, cudaFuncAttributeMaxDynamicSharedMemorySize, bp.L.total));
-    limit[dev & 63].store(bp.L.total, std::memory_order_release);
+  const int smem_bytes = bp.L.total + (TIMING ? 4096 : 0);  // TIMING: [16][32] per-warp counters behind the layout
+  if (smem_bytes > limit[dev & 63].load(std::memory_order_acquire)) {
+    CU(cudaFuncSetAttribute(beam_kernel<NT, SORTED, LM, KPT, TIMING>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    limit[dev & 63].store(smem_bytes, std::memory_order_release);
   }
-  beam_kernel<NT, SORTED, LM, KPT, TIMING><<<B, NT, bp.L.total, s>>>(bp);
+  beam_kernel<NT, SORTED, LM, KPT, TIMING><<<B, NT, bp.L.total + (TIMING ? 4096 : 0), s>>>(bp);
   CU(cudaGetLastError());
   return CTCDEC_OK;
 }
@@ -156,6 +157,7 @@ struct PruneInput {
   const void *data;   // probabilities / log-probabilities (kind IN_F32) or logits
   int kind;           // IN_F32, IN_LOGITS_F32, IN_LOGITS_F16, IN_LOGITS_BF16
   float *lsm_out;     // optional: the float32 log-softmax rows (logits kinds)
+  bool blank_prob = false;  // scorer path: also emit the row trailer [NP-3] (the reference's blank_prob)
 };
 
 template <bool SORTED, int KPL, bool LOGITS>
@@ -185,6 +187,7 @@ static int launch_prune(const ctcdec_config *cfg, const Plan &pl, const PruneInp
   pp.blank = cfg->blank_id; pp.log_input = logits ? 1 : cfg->log_input; pp.top_n = cfg->cutoff_top_n;
   pp.cp_active = pl.cp_active; pp.cutoff_prob = cfg->cutoff_prob; pp.P = pl.P; pp.lp = lp; pp.idx = idx;
   pp.flags = flags;
+  pp.want_blank_prob = in.blank_prob ? 1 : 0;
   const int V = cfg->vocab_size;
   pp.Vpad = (V + 3) / 4 * 4;
   const size_t row_bytes = logits ? (size_t)pp.Vpad * 4 : 0;  // per-warp staging row of the log-softmax
@@ -800,7 +803,7 @@ int ctcdec_decode_stream_host(const float *probs, const int32_t *seq_lens, int B
   ws = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(ws) + 255) / 256 * 256);
   float *lp = reinterpret_cast<float *>(ws + pl.off_lp);
   uint16_t *idx = pl.sorted ? reinterpret_cast<uint16_t *>(ws + pl.off_idx) : nullptr;
-  if (T > 0 && (rc = launch_prune(&cfg, pl, PruneInput{d_probs, IN_F32, nullptr}, d_lens_in, B, T, lp, idx, d_flags, s))) return rc;
+  if (T > 0 && (rc = launch_prune(&cfg, pl, PruneInput{d_probs, IN_F32, nullptr, sc != nullptr}, d_lens_in, B, T, lp, idx, d_flags, s))) return rc;
   BeamParams bp;
   memset(&bp, 0, sizeof(bp));
   bp.lp = lp; bp.idx = idx; bp.seq_lens = d_lens_in; bp.T = T; bp.V = V; bp.NP = pl.NP; bp.K = K;
@@ -994,7 +997,7 @@ int ctcdec_decode_batch_lm_host(const ctcdec_config *cfg, void *scorer, const fl
   unsigned char *ws = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(c.buf[5]) + 255) / 256 * 256);
   float *lp = reinterpret_cast<float *>(ws + pl.off_lp);
   uint16_t *idx = pl.sorted ? reinterpret_cast<uint16_t *>(ws + pl.off_idx) : nullptr;
-  if ((rc = launch_prune(cfg, pl, PruneInput{d_probs, IN_F32, nullptr}, d_lens_in, B, T, lp, idx, d_flags, s))) return rc;
+  if ((rc = launch_prune(cfg, pl, PruneInput{d_probs, IN_F32, nullptr, true}, d_lens_in, B, T, lp, idx, d_flags, s))) return rc;
 
   BeamParams bp;
   memset(&bp, 0, sizeof(bp));

@@ -46,6 +46,7 @@ struct PruneParams {
   float *lp;            // [B][T][NP]
   uint16_t *idx;        // [B][T][NP] (sorted mode)
   int *flags;           // [B]
+  int want_blank_prob;  // emit the row trailer [NP-3] (read by the scorer path only: one more fp64 log per frame)
 };
 
 #if !defined(CTC_EMULATE)
@@ -218,9 +219,11 @@ __global__ void __launch_bounds__(256) prune_kernel(const PruneParams p) {
         live[u] = false;
         v[u] = kNInf;
         if (f < nframes) {
-          const int b = (int)(f / p.T), t = (int)(f - (long long)b * p.T);
-          const int len = p.seq_lens ? p.seq_lens[b] : p.T;
-          live[u] = t < len;
+          live[u] = true;
+          if (p.seq_lens) {  // (the only use of the utterance index here: skip the 64-bit division otherwise)
+            const int b = (int)(f / p.T), t = (int)(f - (long long)b * p.T);
+            live[u] = t < p.seq_lens[b];
+          }
           if (live[u] && r < V) v[u] = p.probs[f * V + r];
         }
       }
@@ -246,7 +249,7 @@ __global__ void __launch_bounds__(256) prune_kernel(const PruneParams p) {
         }
         mx = __reduce_max_sync(0xffffffffu, mx);
         if (lane == 0) {
-          out[NP - 3] = blank_prob_value(p.probs + f * V, p.blank, V, p.log_input, logtab);
+          out[NP - 3] = p.want_blank_prob ? blank_prob_value(p.probs + f * V, p.blank, V, p.log_input, logtab) : kNInf;
           out[NP - 2] = bits_f((uint32_t)V | ((uint32_t)(rblank_unsorted + 1) << 16));
           out[NP - 1] = unord_f(mx);
         }
@@ -372,7 +375,7 @@ __global__ void __launch_bounds__(256) prune_kernel(const PruneParams p) {
     rb = __reduce_max_sync(0xffffffffu, rb);
     const float l0 = __shfl_sync(0xffffffffu, first_two, 0), l1 = __shfl_sync(0xffffffffu, first_two, 1);
     if (lane == 0) {
-      out[NP - 3] = blank_prob_value(row, p.blank, V, log_input, logtab);
+      out[NP - 3] = p.want_blank_prob ? blank_prob_value(row, p.blank, V, log_input, logtab) : kNInf;
       out[NP - 2] = bits_f((uint32_t)n | ((uint32_t)rb << 16));
       out[NP - 1] = (rb == 1) ? (n > 1 ? l1 : kNInf) : (n > 0 ? l0 : kNInf);
     }

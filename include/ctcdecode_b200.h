@@ -186,9 +186,11 @@ int ctcdec_decode_stream_host(const float *probs, const int32_t *seq_lens, int B
  * the device time in milliseconds of {prune/log scan, beam search, finalize}. */
 int ctcdec_profile_enable(int on);
 int ctcdec_profile_read(float *ms3);
-/* Diagnostic: if device_buffer (int64 [B][16], device memory) is non-NULL, every following
- * ctcdec_decode_batch_device call of this thread makes the beam kernel's thread 0 of each CTA record
- * the clock cycles it spent in each barrier-delimited region of the frame loop (tools/region_timing.py). */
+/* Diagnostic: if device_buffer (int64 [B][16] followed by int64 [B][16][32], device memory) is non-NULL, every
+ * following ctcdec_decode_batch_device call of this thread runs the instrumented build of the beam kernel:
+ * thread 0 of each CTA records the clock cycles it spent in each barrier-delimited region of the frame loop,
+ * and every warp the cycles it was busy before each of the main barriers (tools/region_timing.py).  Built for
+ * 256-thread launches with beam sizes 65..256 and for the scorer path; other shapes return CTCDEC_E_UNSUPPORTED. */
 int ctcdec_profile_region_cycles(void *device_buffer);
 
 /* ---- diagnostics used by the tests (device self-check of the bit-exact libm restatements) ----------- */

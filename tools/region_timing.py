@@ -23,14 +23,18 @@ for B in a.batch:
     probs = ctc_like_probs(B, cfg["T"], cfg["V"], seed=0).cuda()
     dec = CTCBeamDecoder([str(i) for i in range(cfg["V"])], beam_width=cfg["beam"], cutoff_top_n=cfg["cutoff_top_n"],
                          cutoff_prob=cfg["cutoff_prob"], device_outputs=True)
-    buf = torch.zeros(B, 16, dtype=torch.int64, device="cuda")
+    buf = torch.zeros(B * 16 + B * 16 * 32, dtype=torch.int64, device="cuda")  # [B][16] + [B][16][32]
     dec.decode(probs)
     lib.ctcdec_profile_region_cycles(buf.data_ptr())
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); dec.decode(probs); e1.record(); torch.cuda.synchronize()
     lib.ctcdec_profile_region_cycles(None)
-    t = buf.double().mean(0).cpu() / cfg["T"]
+    t = buf[:B * 16].view(B, 16).double().mean(0).cpu() / cfg["T"]
+    wb = buf[B * 16:].view(B, 16, 32).double().mean(0).cpu() / cfg["T"]
     tot = float(t[:12].sum())
     print(f"B={B}: step {e0.elapsed_time(e1):.2f} ms; cycles/frame (mean over CTAs) total {tot:.0f}")
     print("   " + "  ".join(f"{n}={float(v):.0f}" for n, v in zip(NAMES, t[:12])))
+    for rid, name in ((2, "R1"), (3, "G"), (5, "select+classify"), (6, "R4c"), (8, "R5")):
+        print("   busy cycles/frame per warp before the barrier closing %-16s " % name
+              + " ".join("%5.0f" % float(v) for v in wb[rid][:8]))
