@@ -122,8 +122,8 @@ enum : int {  // slot block, in units of KP ints
   U_DREV = U_DTS + 2,     // dead-anchor table: 2 units each
   U_CNT2 = U_DREV + 2,    // 3 units
   U_AMAP = U_CNT2 + 3, U_SLOT2Q,
-  U_STASH,                // 5 units
-  U_EFREE = U_STASH + 5,  // 2 units
+  U_STASH,                // 6 units: node, chr, lpc, ts, dstate, depth of the members evicted in this frame
+  U_EFREE = U_STASH + 6,  // 2 units
   U_RVWORK = U_EFREE + 2, // 3 units
   U_SLOT_UNITS = U_RVWORK + 3
 };
@@ -234,7 +234,8 @@ struct BeamParams {
 // control words: 32 ints in L.ctl
 enum {
   C_M = 0, C_NNODES, C_FLAGS, C_NSEL, C_NFREE, C_NTIE, C_NREV, C_NPAIRS, C_ABOVE, C_BIN, C_CNT, C_KMIN, C_KMAX,
-  C_SMAX, C_NEFREE, C_NETAKEN, C_NRVWORK, C_OVF, C_ANYREF, C_NLIVE, C_SMIN, C_NCAND
+  C_SMAX, C_NEFREE, C_NETAKEN, C_NRVWORK, C_OVF, C_ANYREF, C_NLIVE, C_SMIN, C_NCAND,
+  C_CMIN0, C_CMIN1, C_CMAX0, C_CMAX1  // min / max score key of the beam, double buffered by frame parity
 };
 
 // ---- small helpers --------------------------------------------------------------------------------

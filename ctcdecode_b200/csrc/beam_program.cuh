@@ -251,6 +251,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
   c.s_slot2q = CTC_SLOT(int, U_SLOT2Q);    c.s_stash = CTC_SLOT(int, U_STASH);
   int *const pslot_base = CTC_SLOT(int, U_PSLOT), *const anch_base = CTC_SLOT(int, U_ANCH);
   int cur = 0;  // which half of the double-buffered link arrays describes the current beam
+  int par = 0;  // frame parity: which C_CMIN / C_CMAX pair holds the current beam's score range
   c.s_exptab = (uint64_t *)(smem + H_EXPTAB);
   c.s_logtab = (double *)(smem + H_LOGTAB);
   c.K = K; c.KP = KP; c.V = V; c.NP = NP; c.W = W; c.blank = p.blank;
@@ -388,6 +389,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
       s_ctl[C_FLAGS] = fresh ? 0 : st[3];
       s_ctl[C_KMIN] = (int)0xFFFFFFFFu;
       s_ctl[C_SMIN] = (int)0xFFFFFFFFu;
+      s_ctl[C_CMIN0] = (int)0xFFFFFFFFu; s_ctl[C_CMIN0 + 1] = (int)0xFFFFFFFFu;
       if (fresh) {  // root node (reference path_trie.cpp:11-30)
         Node root; root.parent = -1; root.chr = -1; root.lpc = kNInf; root.ts = 0;
         store_node(&nodes[0], root);
@@ -421,11 +423,20 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
 #endif
 
   int M = s_ctl[C_M];
-  // number of dead anchors currently in the table (0 almost always: lets the frame loop skip their sweeps)
+  // number of dead anchors currently in the table (0 almost always: lets the frame loop skip their sweeps), and the
+  // score range of the beam (kept up to date by region R5: the radix range of a frame is known before region R1)
   CTC_PAR {
     int cntv = 0;
     for (int a = tid; a < KP2; a += NT) cntv += (c.s_dpslot[a] >= 0) ? 1 : 0;
     if (cntv) atom_add(&s_ctl[C_NLIVE], cntv);
+    unsigned smin = 0xFFFFFFFFu, smax = 0u;
+    for (int j = tid; j < M; j += NT) {
+      const unsigned o = ord_f(c.s_score[j]);
+      smin = o < smin ? o : smin;
+      smax = o > smax ? o : smax;
+    }
+    red_min_u32((unsigned *)&s_ctl[C_CMIN0], smin);
+    red_max_u32((unsigned *)&s_ctl[C_CMAX0], smax);
   }
   CTC_BARRIER();
   int nlive = s_ctl[C_NLIVE];
@@ -471,6 +482,35 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
       CTC_BARRIER();
       CTC_TICK(1);
     }
+    // score-key range [lo32, top32] of everything that can still be selected in this frame, and the shift that
+    // maps it onto the radix bins.  Without a scorer it follows from the beam as it stands and the frame's row, so
+    // members can bin themselves in region R1 and region G starts right after the barrier:
+    //   every new member score >= blank term = lp_blank + old score >= lp_blank + (lowest old score)   [beam full]
+    //   every key <= (highest old score) + (largest log-prob of the row) + 2 ln 2  (two nested log_sum_exp of at
+    //   most three such terms; 1.5 > 2 ln 2 + rounding)
+    unsigned lo32 = 0u, top32 = 0u;
+    int shift32 = 0;  // smallest shift with ((top32 - lo32) >> shift32) < kNBins
+    auto set_shift = [&]() {
+      const unsigned wm = top32 - lo32;
+#if defined(CTC_EMULATE)
+      const int bits = wm ? 32 - __builtin_clz(wm) : 0;
+#else
+      const int bits = 32 - __clz((int)wm);
+#endif
+      shift32 = bits > 8 ? bits - 8 : 0;
+    };
+    if (!LM) {
+      const float cmin = unord_f((unsigned)s_ctl[C_CMIN0 + par]), cmax = unord_f((unsigned)s_ctl[C_CMAX0 + par]);
+      float lpm = lpmax;
+      if (rblank >= 0) {
+        const float lpb = c.lp[rblank];
+        if (M == K) lo32 = ord_f(f_add(lpb, cmin));
+        lpm = lpb > lpm ? lpb : lpm;
+      }
+      top32 = ord_f(f_add(f_add(cmax, lpm), 1.5f));
+      if (top32 < lo32) top32 = lo32;
+      set_shift();
+    }
     if (LM) {
       // min_cutoff = worst beam score + blank_prob - max(0, beta); active once the beam is full
       // (reference ctc_beam_search_decoder.cpp:74-82: the sorted beam's last element is its minimum)
@@ -494,8 +534,11 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
     //      log_sum_exp; dead anchors take their lpc / timestep update.  All in shared memory.
     // (reference ctc_beam_search_decoder.cpp:97-118,138-139; path_trie.cpp:39-57,129-137)
     CTC_PAR {
-      for (int x = tid; x < 2 * kNBins; x += NT) c.s_hist[x] = 0;
-      if (tid == 0) s_ctl[C_NREV] = 0;  // (not with the other counters in R5: slow threads may still be reading it there)
+      if (tid == 0) {
+        s_ctl[C_NREV] = 0;  // (not with the other counters in R5: slow threads may still be reading it there)
+        s_ctl[C_CMIN0 + (par ^ 1)] = (int)0xFFFFFFFFu;  // the next frame's range: gathered by region R5
+        s_ctl[C_CMAX0 + (par ^ 1)] = 0;
+      }
       unsigned kmin = 0xFFFFFFFFu, kmax = 0u, smax = 0u;
       int npairs = 0;
       for (int j0 = 0; j0 < M; j0 += NT) {
@@ -527,10 +570,15 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
           const float sn = lse_smem(bnew, nb, c.s_exptab, c.s_logtab);
           c.s_bnew[j] = bnew; c.s_nbnew[j] = nb; c.s_snew[j] = sn;
           const unsigned o = ord_f(sn);
-          kmin = o < kmin ? o : kmin;
-          kmax = o > kmax ? o : kmax;
-          const unsigned os = ord_f(sc);
-          smax = os > smax ? os : smax;
+          if (!LM) {
+            // first radix pass: the member bins itself (the histograms were cleared by region R5)
+            if (o >= lo32) atom_add(&c.s_hist[(int)((o - lo32) >> shift32)], 1);
+          } else {
+            kmin = o < kmin ? o : kmin;
+            kmax = o > kmax ? o : kmax;
+            const unsigned os = ord_f(sc);
+            smax = os > smax ? os : smax;
+          }
         }
       }
       if (npairs) atom_add(&s_ctl[C_NPAIRS], npairs);
@@ -547,17 +595,19 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
           }
         }
       }
+      if (LM) {  // with a scorer the range is taken from the new member scores (the LM term is not bounded above)
 #if defined(CTC_EMULATE)
-      red_min_u32((unsigned *)&s_ctl[C_KMIN], kmin);
-      red_max_u32((unsigned *)&s_ctl[C_KMAX], kmax);
-      red_max_u32((unsigned *)&s_ctl[C_SMAX], smax);
-#else
-      if (tid < ((M + 31) & ~31)) {  // whole warps that own at least one member
         red_min_u32((unsigned *)&s_ctl[C_KMIN], kmin);
         red_max_u32((unsigned *)&s_ctl[C_KMAX], kmax);
         red_max_u32((unsigned *)&s_ctl[C_SMAX], smax);
-      }
+#else
+        if (tid < ((M + 31) & ~31)) {  // whole warps that own at least one member
+          red_min_u32((unsigned *)&s_ctl[C_KMIN], kmin);
+          red_max_u32((unsigned *)&s_ctl[C_KMAX], kmax);
+          red_max_u32((unsigned *)&s_ctl[C_SMAX], smax);
+        }
 #endif
+      }
     }
     CTC_BARRIER_T(2);
     CTC_TICK(2);  // R1
@@ -569,22 +619,12 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
     bool select_all = !LM && total <= (long long)K;  // reference :149 `prefixes.size() >= beam_size`
     const int G = (n + 31) >> 5;                     // 32-wide column groups of the candidate grid
 
-    // score-key range of everything that can still be selected: [lo32, top32]
-    const unsigned lo32 = (!select_all && M == K) ? (unsigned)s_ctl[C_KMIN] : 0u;
-    unsigned top32 = (unsigned)s_ctl[C_KMAX];
-    {
+    if (LM) {
+      lo32 = (!select_all && M == K) ? (unsigned)s_ctl[C_KMIN] : 0u;
+      top32 = (unsigned)s_ctl[C_KMAX];
       const unsigned o = ord_f(f_add(unord_f((unsigned)s_ctl[C_SMAX]), lpmax));
       top32 = o > top32 ? o : top32;
-    }
-    int shift32 = 0;  // smallest shift with ((top32 - lo32) >> shift32) < kNBins
-    {
-      const unsigned wm = top32 - lo32;
-#if defined(CTC_EMULATE)
-      const int bits = wm ? 32 - __builtin_clz(wm) : 0;
-#else
-      const int bits = 32 - __clz((int)wm);
-#endif
-      shift32 = bits > 8 ? bits - 8 : 0;
+      set_shift();
     }
 
     // ---- region G: the ONE walk over the beam x pruned-vocab grid.  A warp owns a beam member per
@@ -597,7 +637,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
       uint32_t *const segk = c.s_clk + warp * SEG;
       int *const segi = c.s_cli + warp * SEG;
       int *const hist0 = c.s_hist;
-      if (!select_all) {
+      if (LM && !select_all) {  // (without a scorer the members binned themselves in region R1)
         CTC_LANES {
           for (int j = warp * 32 + lane; j < M; j += NT) {
             const unsigned k = ord_f(c.s_snew[j]);
@@ -960,9 +1000,18 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
 
     // ---- region R4a: classify members (keep / evict) and candidates (selected); compact both with
     //      ballots so that slot assignment is deterministic without sorting
+    // FUSED (the common frame: no scorer, no dead anchors in the table, lists did not overflow): the selected
+    // candidates are turned into nodes by the owners of the slots they move into, inside region R5 -- region R4c
+    // and its barrier are skipped.  What R5 needs from members that are evicted right now (their node id / depth,
+    // as parents of new nodes) is stashed here, before the slots are overwritten.
+    const bool fused = !LM && !fallback && nlive == 0;
     if (!fallback) {
       CTC_WARPS {
-        CTC_LANES { for (int j = warp * 32 + lane; j < K; j += NT) c.s_slot2q[j] = -1; }
+        if (!fused) {
+          CTC_LANES { for (int j = warp * 32 + lane; j < K; j += NT) c.s_slot2q[j] = -1; }
+        } else {
+          CTC_LANES { if (warp == 0 && lane == 0) { s_ctl[C_NLIVE] = 0; s_ctl[C_ANYREF] = 0; } }  // (R4c's resets)
+        }
         // members, in blocks of 32 slots
         for (int blk = warp; blk * 32 < M; blk += NW) {
           CTC_LV(int, ev);
@@ -983,7 +1032,11 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
           }
           const unsigned bal = ctc_ballot(ev);
           CTC_LANES {
-            if (ev[LX]) c.s_free[blk * 32 + ctc_popc(bal & ctc_lt_mask(lane))] = blk * 32 + lane;
+            if (ev[LX]) {
+              const int j = blk * 32 + lane, rk = ctc_popc(bal & ctc_lt_mask(lane));
+              c.s_free[blk * 32 + rk] = j;
+              if (fused) { c.s_sel2[j] = rk; c.s_stash[j] = c.s_node[j]; c.s_stash[5 * KP + j] = c.s_depth[j]; }
+            }
             if (lane == 0) c.s_evcnt[blk] = ctc_popc(bal);
           }
         }
@@ -996,14 +1049,17 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
         for (int e0 = 0; e0 < cn; e0 += 32) {
           CTC_LV(int, sel);
           CTC_LV(int, idv);
+          CTC_LV(uint32_t, kv);
           CTC_LANES {
             const int e = e0 + lane;
             sel[LX] = 0;
             idv[LX] = 0;
+            kv[LX] = 0u;
             if (e < cn) {
               const unsigned k32 = segk[e];
               const int id = segi[e];
               idv[LX] = id;
+              kv[LX] = k32;
               bool s = k32 > thr_hi;
               if (k32 == thr_hi) {
                 const int r = id & 0xFFFF;
@@ -1022,7 +1078,11 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
           const unsigned bal = ctc_ballot(sel);
           CTC_SYNCWARP();  // in-place compaction: every lane has read its entry before any lane overwrites one
           CTC_LANES {
-            if (sel[LX]) segi[out + ctc_popc(bal & ctc_lt_mask(lane))] = idv[LX];
+            if (sel[LX]) {
+              const int pos = out + ctc_popc(bal & ctc_lt_mask(lane));
+              segi[pos] = idv[LX];
+              segk[pos] = kv[LX];  // the score key travels along: region R5 recovers the candidate's score from it
+            }
           }
           out += ctc_popc(bal);
         }
@@ -1121,6 +1181,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
 
     // ---- region R4c: selected candidates become trie nodes (or revive a dead anchor) -------------------
     // (reference path_trie.cpp:50-56 revive, :97-105 create).  Arena stores are fire-and-forget.
+    if (!fused) {
     CTC_PAR {
       if (tid == 0) {
         s_ctl[C_NLIVE] = 0; s_ctl[C_ANYREF] = 0;
@@ -1172,8 +1233,9 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
       }
     }
     CTC_BARRIER_T(6);
+    }
     CTC_TICK(6);  // R4c
-    const int nrev = s_ctl[C_NREV];
+    const int nrev = fused ? 0 : s_ctl[C_NREV];
 
     if (nrev > 0) {
       // ---- rare slow path: a dead anchor d came back to life.  Members that hung below d need the child
@@ -1241,13 +1303,18 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
     //      are double buffered: walks read the old beam's links while the new ones are written.
     int *const npslot = pslot_base + (cur ^ 1) * KP, *const nanch = anch_base + (cur ^ 1) * KP;
     CTC_PAR {
+      unsigned cmin = 0xFFFFFFFFu, cmax = 0u;  // score range of the new beam (read by the next frame before its R1)
       for (int j = tid; j < K; j += NT) {
         int start = 0, res = -1, newp = -1;
         bool have = false, resolved = false;
         if (j < M && !c.s_evict[j]) {
           c.s_bprev[j] = c.s_bnew[j];
           c.s_nbprev[j] = c.s_nbnew[j];
-          c.s_score[j] = c.s_snew[j];
+          const float sn = c.s_snew[j];
+          c.s_score[j] = sn;
+          const unsigned o = ord_f(sn);
+          cmin = o < cmin ? o : cmin;
+          cmax = o > cmax ? o : cmax;
           have = true;
           const int pq = c.s_pslot[j];
           if (pq >= 0) {
@@ -1263,25 +1330,70 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
             }
           }
         } else {
+          int q = -1;
           if (j < M) {  // evicted: write back, and remember what a dead anchor made of this node would need
             CTC_STAT(g_stats.evicted++);
             flush_lpc_ts(&nodes[c.s_node[j]], c.s_lpc[j], c.s_ts[j]);
-            c.s_stash[j] = c.s_node[j]; c.s_stash[KP + j] = c.s_chr[j];
+            if (!fused) c.s_stash[j] = c.s_node[j];  // (fused: stashed by the classification, others read it now)
+            c.s_stash[KP + j] = c.s_chr[j];
             c.s_stash[2 * KP + j] = (int)f_bits(c.s_lpc[j]); c.s_stash[3 * KP + j] = c.s_ts[j];
             c.s_stash[4 * KP + j] = c.s_dstate[j];
+            if (fused) {  // rank of this slot among the free slots: evicted slots in slot order ...
+              q = c.s_sel2[j];
+              for (int bb = 0; bb < (j >> 5); ++bb) q += c.s_evcnt[bb];
+            }
+          } else if (fused) {  // ... then the slots that were never used
+            q = j - M;
+            for (int bb = 0; bb * 32 < M; ++bb) q += c.s_evcnt[bb];
           }
-          const int q = c.s_slot2q[j];
+          if (!fused) q = c.s_slot2q[j];
+          else if (q >= nsel) q = -1;
           if (q >= 0) {  // a new member moves into this slot
-            const int *ni = c.s_newinfo + q * 10;
-            const float sc = bits_f((uint32_t)ni[2]);
-            c.s_node[j] = ni[0]; c.s_chr[j] = ni[1]; c.s_depth[j] = ni[8];
+            int nid, ch, ts, depth, dst, par_slot;
+            float sc, lpc;
+            if (fused) {
+              // the q-th selected candidate (reference path_trie.cpp:97-105 create); its score is the list key
+              int acc = 0, w = 0;
+              for (; w < NW - 1; ++w) {
+                const int cw = c.s_wcnt[32 + w];
+                if (q < acc + cw) break;
+                acc += cw;
+              }
+              const int id = c.s_cli[w * SEG + (q - acc)];
+              sc = unord_f(c.s_clk[w * SEG + (q - acc)]);
+              par_slot = id >> 16;
+              const int r = id & 0xFFFF;
+              ch = c.chr_at(r);
+              lpc = c.lp[r];
+              ts = t_abs;
+              dst = 0;
+              const bool pe = c.s_evict[par_slot] != 0;  // the parent was evicted in this very frame
+              const int pnode = pe ? c.s_stash[par_slot] : c.s_node[par_slot];
+              depth = (pe ? c.s_stash[5 * KP + par_slot] : c.s_depth[par_slot]) + 1;
+              nid = atom_add(&s_ctl[C_NNODES], 1);
+              CTC_STAT(g_stats.created++);
+              if (nid >= arena_cap) {  // cannot happen with capacity 1 + K * frames; never write out of bounds
+                s_ctl[C_FLAGS] |= FLAG_ERR_ARENA;
+                nid = arena_cap - 1;
+              }
+              Node nn; nn.parent = pnode; nn.chr = ch; nn.lpc = lpc; nn.ts = ts;
+              store_node(&nodes[nid], nn);
+            } else {
+              const int *ni = c.s_newinfo + q * 10;
+              nid = ni[0]; ch = ni[1]; sc = bits_f((uint32_t)ni[2]); par_slot = ni[4];
+              lpc = bits_f((uint32_t)ni[5]); ts = ni[6]; depth = ni[8]; dst = ni[9];
+            }
+            c.s_node[j] = nid; c.s_chr[j] = ch; c.s_depth[j] = depth;
             c.s_bprev[j] = kNInf; c.s_nbprev[j] = sc; c.s_score[j] = sc;  // score = lse(-inf, nb)
-            c.s_lpc[j] = bits_f((uint32_t)ni[5]); c.s_ts[j] = ni[6];
-            c.s_dstate[j] = ni[9];
-            if (LM) for (int w = 0; w < L.WC; ++w) c.s_dmask[j * L.WC + w] = p.dict_mask[(long long)ni[9] * L.WC + w];
+            const unsigned o = ord_f(sc);
+            cmin = o < cmin ? o : cmin;
+            cmax = o > cmax ? o : cmax;
+            c.s_lpc[j] = lpc; c.s_ts[j] = ts;
+            c.s_dstate[j] = dst;
+            if (LM) for (int w = 0; w < L.WC; ++w) c.s_dmask[j * L.WC + w] = p.dict_mask[(long long)dst * L.WC + w];
             c.s_lmsp[j] = 0.0f;  // supplied by the host's Scorer hook before the next launch
             have = true;
-            start = ni[4];
+            start = par_slot;
             if (c.s_evict[start] == 0) { newp = start; resolved = true; }
           }
         }
@@ -1308,7 +1420,12 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
           nanch[j] = res;
         }
       }
+      if (!LM) {
+        red_min_u32((unsigned *)&s_ctl[C_CMIN0 + (par ^ 1)], cmin);
+        red_max_u32((unsigned *)&s_ctl[C_CMAX0 + (par ^ 1)], cmax);
+      }
       for (int x = tid; x < KP * W; x += NT) { c.s_mask[x] = 0u; c.s_rmask[x] = 0u; }
+      for (int x = tid; x < 2 * kNBins; x += NT) c.s_hist[x] = 0;  // the select is over: clear both radix histograms
       if (SORTED) for (int r = tid; r < n; r += NT) c.s_rank[c.idx[r]] = (int16_t)-1;
       if (tid == 0) {  // (C_NLIVE / C_ANYREF are read below and reset in region R4c of the next frame)
         s_ctl[C_NSEL] = 0; s_ctl[C_NFREE] = 0; s_ctl[C_NTIE] = 0; s_ctl[C_NPAIRS] = 0;
@@ -1385,6 +1502,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
     }
     CTC_TICK(11);  // R5d
     cur ^= 1;
+    par ^= 1;
     c.s_pslot = pslot_base + cur * KP;
     c.s_anch = anch_base + cur * KP;
     nlive = nlive_next;
