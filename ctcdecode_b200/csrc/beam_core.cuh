@@ -106,7 +106,9 @@ CTC_HD long long state_ints(int K) { return kStateHeader + (long long)kSlotArray
 // shared-memory instruction -- and a tail whose sizes depend on the pruned vocabulary / tile / thread count.
 enum : int {  // head, bytes
   H_MBAR = 0, H_EXPTAB = 16, H_LOGTAB = H_EXPTAB + 32 * 8, H_HIST = H_LOGTAB + 32 * 8,
-  H_WCNT = H_HIST + 2 * 256 * 4, H_CTL = H_WCNT + 4 * 32 * 4, kSmemHead = H_CTL + 32 * 4 + 16 * 8
+  H_WCNT = H_HIST + 2 * 256 * 4,  // 8 x 32 ints: per-warp list counts [0,32) / selected counts [32,64), and from 128
+                                  // the per-warp score range of the new beam: [parity][min | max][warp]
+  H_CTL = H_WCNT + 8 * 32 * 4, kSmemHead = H_CTL + 32 * 4 + 16 * 8
 };
 static_assert(kSmemHead % 16 == 0, "slot block alignment");
 enum : int {  // slot block, in units of KP ints
@@ -234,8 +236,7 @@ struct BeamParams {
 // control words: 32 ints in L.ctl
 enum {
   C_M = 0, C_NNODES, C_FLAGS, C_NSEL, C_NFREE, C_NTIE, C_NREV, C_NPAIRS, C_ABOVE, C_BIN, C_CNT, C_KMIN, C_KMAX,
-  C_SMAX, C_NEFREE, C_NETAKEN, C_NRVWORK, C_OVF, C_ANYREF, C_NLIVE, C_SMIN, C_NCAND,
-  C_CMIN0, C_CMIN1, C_CMAX0, C_CMAX1  // min / max score key of the beam, double buffered by frame parity
+  C_SMAX, C_NEFREE, C_NETAKEN, C_NRVWORK, C_OVF, C_ANYREF, C_NLIVE, C_SMIN, C_NCAND
 };
 
 // ---- small helpers --------------------------------------------------------------------------------

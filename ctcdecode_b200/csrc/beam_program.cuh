@@ -132,39 +132,35 @@ CTC_FN void scan_bin_all(const int *hist, int need, int &bin, int &above, int &c
   }
   bin = 0; above = a - hist[0]; cnt = hist[0];  // unreachable when the invariants hold
 #else
-  // lane l reads bins l, l+32, ..., l+224 (bank-conflict free); rows of 32 bins are summed with the hardware
-  // warp reduction, the row holding the need-th key is located by a scalar walk over the 8 row sums, and a
-  // 5-step suffix scan inside that row finds the bin.
-  constexpr int ROWS = kNBins / 32;
+  // lane l owns the 8 consecutive bins [8 l, 8 l + 8) (two 16-byte loads): sums them, the 32 lane totals go through
+  // a 5-step suffix scan (lanes above = higher keys), a ballot finds the lane the need-th key falls into, that
+  // lane's 8 bins are walked from the top, and three shuffles broadcast the answer.
+  static_assert(kNBins == 256, "8 bins per lane");
   const int lane = (int)(threadIdx.x & 31);
-  int h[ROWS], rs[ROWS];
-#pragma unroll
-  for (int q = 0; q < ROWS; ++q) h[q] = hist[q * 32 + lane];
-#pragma unroll
-  for (int q = 0; q < ROWS; ++q) rs[q] = __reduce_add_sync(0xffffffffu, h[q]);
-  int a = 0, row = 0;
-  bool found = false;
-#pragma unroll
-  for (int q = ROWS - 1; q >= 0; --q) {
-    if (!found) {
-      if (a + rs[q] >= need) { row = q; found = true; }
-      else a += rs[q];
-    }
-  }
-  int hv = h[0];
-#pragma unroll
-  for (int q = 1; q < ROWS; ++q) hv = (row == q) ? h[q] : hv;
-  int sfx = hv;  // becomes the sum over lanes >= this lane
+  const int4 ha = *reinterpret_cast<const int4 *>(hist + 8 * lane), hb = *reinterpret_cast<const int4 *>(hist + 8 * lane + 4);
+  const int h[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
+  const int tot = ((h[0] + h[1]) + (h[2] + h[3])) + ((h[4] + h[5]) + (h[6] + h[7]));
+  int sfx = tot;  // becomes the sum over lanes >= this lane
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
     const int v = __shfl_down_sync(0xffffffffu, sfx, d);
     if (lane + d < 32) sfx += v;
   }
-  const unsigned ball = __ballot_sync(0xffffffffu, sfx >= need - a);  // lanes <= target
+  const unsigned ball = __ballot_sync(0xffffffffu, sfx >= need);  // lanes <= target
   const int target = ball ? 31 - __clz((int)ball) : 0;
-  bin = row * 32 + target;
-  cnt = __shfl_sync(0xffffffffu, hv, target);
-  above = a + __shfl_sync(0xffffffffu, sfx, target) - cnt;
+  // walk this lane's bins from the top (only the target lane's result is used)
+  int a = sfx - tot, q_hit = 0, a_hit = a, c_hit = h[0];
+  bool found = false;
+#pragma unroll
+  for (int q = 7; q >= 0; --q) {
+    const bool hit = !found && (a + h[q] >= need);
+    if (hit) { q_hit = q; a_hit = a; c_hit = h[q]; found = true; }
+    a += h[q];
+  }
+  if (!found) a_hit = a - h[0];  // unreachable when the invariants hold (mirrors the sequential version)
+  bin = __shfl_sync(0xffffffffu, 8 * lane + q_hit, target);
+  above = __shfl_sync(0xffffffffu, a_hit, target);
+  cnt = __shfl_sync(0xffffffffu, c_hit, target);
 #endif
 }
 
@@ -184,6 +180,35 @@ CTC_FN void red_min_u32(unsigned *dst, unsigned v) {
   v = __reduce_min_sync(0xffffffffu, v);
   if ((threadIdx.x & 31) == 0) atomicMin(dst, v);
 #endif
+}
+
+// Per-warp minimum / maximum of a key into dst[warp] / dst[32 + warp] (plain stores, no contention); whoever needs
+// the block-wide range reduces the NW pairs (warp_range_load).  Every thread of the CTA must call it.
+CTC_FN void warp_range_store(int *dst, unsigned mn, unsigned mx, int tid) {
+#if defined(CTC_EMULATE)
+  unsigned *d = (unsigned *)dst;
+  const int w = tid >> 5;
+  if ((tid & 31) == 0) { d[w] = 0xFFFFFFFFu; d[32 + w] = 0u; }
+  if (mn < d[w]) d[w] = mn;
+  if (mx > d[32 + w]) d[32 + w] = mx;
+#else
+  mn = __reduce_min_sync(0xffffffffu, mn);
+  mx = __reduce_max_sync(0xffffffffu, mx);
+  // every lane stores (same value, same word: one broadcast write).  Not `if (lane == 0)`: nvcc 12.9 folded
+  // (tid >> 5) * 4 into tid >> 3 under that predicate and then reused the address where all lanes run.
+  dst[tid >> 5] = (int)mn;
+  dst[32 + (tid >> 5)] = (int)mx;
+#endif
+}
+template <int NW>
+CTC_FN void warp_range_load(const int *src, unsigned &mn, unsigned &mx) {
+  mn = 0xFFFFFFFFu; mx = 0u;
+#pragma unroll
+  for (int w = 0; w < NW; ++w) {
+    const unsigned a = (unsigned)src[w], b = (unsigned)src[32 + w];
+    mn = a < mn ? a : mn;
+    mx = b > mx ? b : mx;
+  }
 }
 
 CTC_FN Node load_node(const Node *p) {
@@ -389,7 +414,6 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
       s_ctl[C_FLAGS] = fresh ? 0 : st[3];
       s_ctl[C_KMIN] = (int)0xFFFFFFFFu;
       s_ctl[C_SMIN] = (int)0xFFFFFFFFu;
-      s_ctl[C_CMIN0] = (int)0xFFFFFFFFu; s_ctl[C_CMIN0 + 1] = (int)0xFFFFFFFFu;
       if (fresh) {  // root node (reference path_trie.cpp:11-30)
         Node root; root.parent = -1; root.chr = -1; root.lpc = kNInf; root.ts = 0;
         store_node(&nodes[0], root);
@@ -435,8 +459,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
       smin = o < smin ? o : smin;
       smax = o > smax ? o : smax;
     }
-    red_min_u32((unsigned *)&s_ctl[C_CMIN0], smin);
-    red_max_u32((unsigned *)&s_ctl[C_CMAX0], smax);
+    warp_range_store(c.s_wcnt + 128, smin, smax, tid);
   }
   CTC_BARRIER();
   int nlive = s_ctl[C_NLIVE];
@@ -500,7 +523,9 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
       shift32 = bits > 8 ? bits - 8 : 0;
     };
     if (!LM) {
-      const float cmin = unord_f((unsigned)s_ctl[C_CMIN0 + par]), cmax = unord_f((unsigned)s_ctl[C_CMAX0 + par]);
+      unsigned cmin_o, cmax_o;
+      warp_range_load<NW>(c.s_wcnt + 128 + 64 * par, cmin_o, cmax_o);
+      const float cmin = unord_f(cmin_o), cmax = unord_f(cmax_o);
       float lpm = lpmax;
       if (rblank >= 0) {
         const float lpb = c.lp[rblank];
@@ -536,8 +561,6 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
     CTC_PAR {
       if (tid == 0) {
         s_ctl[C_NREV] = 0;  // (not with the other counters in R5: slow threads may still be reading it there)
-        s_ctl[C_CMIN0 + (par ^ 1)] = (int)0xFFFFFFFFu;  // the next frame's range: gathered by region R5
-        s_ctl[C_CMAX0 + (par ^ 1)] = 0;
       }
       unsigned kmin = 0xFFFFFFFFu, kmax = 0u, smax = 0u;
       int npairs = 0;
@@ -1046,45 +1069,56 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
         int *const segi = c.s_cli + warp * SEG;
         const unsigned thr_hi = (unsigned)(thr >> 16);
         int out = 0;
-        for (int e0 = 0; e0 < cn; e0 += 32) {
-          CTC_LV(int, sel);
-          CTC_LV(int, idv);
-          CTC_LV(uint32_t, kv);
-          CTC_LANES {
-            const int e = e0 + lane;
-            sel[LX] = 0;
-            idv[LX] = 0;
-            kv[LX] = 0u;
-            if (e < cn) {
-              const unsigned k32 = segk[e];
-              const int id = segi[e];
-              idv[LX] = id;
-              kv[LX] = k32;
-              bool s = k32 > thr_hi;
-              if (k32 == thr_hi) {
-                const int r = id & 0xFFFF;
-                const uint64_t k = ((uint64_t)k32 << 16) | (uint64_t)(0xFFFF - (c.chr_at(r) + 1));
-                s = k >= thr;
-                if (tie_m > 0 && k == thr) {
-                  const int tid_id = K + (id >> 16) * NP + r;
-                  int lower = 0;
-                  for (int x = 0; x < ntie; ++x) lower += (c.s_tie[x] < tid_id) ? 1 : 0;
-                  s = lower < tie_m;
-                }
+        // is list entry e selected?  (two entries per lane and iteration: two independent load -> compare chains)
+        auto classify_entry = [&](int e, int &sel, int &idv, uint32_t &kv) {
+          sel = 0; idv = 0; kv = 0u;
+          if (e < cn) {
+            const unsigned k32 = segk[e];
+            const int id = segi[e];
+            idv = id;
+            kv = k32;
+            bool s = k32 > thr_hi;
+            if (k32 == thr_hi) {
+              const int r = id & 0xFFFF;
+              const uint64_t k = ((uint64_t)k32 << 16) | (uint64_t)(0xFFFF - (c.chr_at(r) + 1));
+              s = k >= thr;
+              if (tie_m > 0 && k == thr) {
+                const int tid_id = K + (id >> 16) * NP + r;
+                int lower = 0;
+                for (int x = 0; x < ntie; ++x) lower += (c.s_tie[x] < tid_id) ? 1 : 0;
+                s = lower < tie_m;
               }
-              sel[LX] = s ? 1 : 0;
             }
+            sel = s ? 1 : 0;
           }
-          const unsigned bal = ctc_ballot(sel);
-          CTC_SYNCWARP();  // in-place compaction: every lane has read its entry before any lane overwrites one
+        };
+        for (int e0 = 0; e0 < cn; e0 += 64) {
+          CTC_LV(int, selA);
+          CTC_LV(int, selB);
+          CTC_LV(int, idA);
+          CTC_LV(int, idB);
+          CTC_LV(uint32_t, kA);
+          CTC_LV(uint32_t, kB);
           CTC_LANES {
-            if (sel[LX]) {
-              const int pos = out + ctc_popc(bal & ctc_lt_mask(lane));
-              segi[pos] = idv[LX];
-              segk[pos] = kv[LX];  // the score key travels along: region R5 recovers the candidate's score from it
+            classify_entry(e0 + lane, selA[LX], idA[LX], kA[LX]);
+            classify_entry(e0 + 32 + lane, selB[LX], idB[LX], kB[LX]);
+          }
+          const unsigned balA = ctc_ballot(selA), balB = ctc_ballot(selB);
+          const int nA = ctc_popc(balA);
+          CTC_SYNCWARP();  // in-place compaction: every lane has read its entries before any lane overwrites one
+          CTC_LANES {
+            if (selA[LX]) {
+              const int pos = out + ctc_popc(balA & ctc_lt_mask(lane));
+              segi[pos] = idA[LX];
+              segk[pos] = kA[LX];  // the score key travels along: region R5 recovers the candidate's score from it
+            }
+            if (selB[LX]) {
+              const int pos = out + nA + ctc_popc(balB & ctc_lt_mask(lane));
+              segi[pos] = idB[LX];
+              segk[pos] = kB[LX];
             }
           }
-          out += ctc_popc(bal);
+          out += nA + ctc_popc(balB);
         }
         CTC_LANES {
           if (lane == 0) {
@@ -1420,10 +1454,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
           nanch[j] = res;
         }
       }
-      if (!LM) {
-        red_min_u32((unsigned *)&s_ctl[C_CMIN0 + (par ^ 1)], cmin);
-        red_max_u32((unsigned *)&s_ctl[C_CMAX0 + (par ^ 1)], cmax);
-      }
+      if (!LM) warp_range_store(c.s_wcnt + 128 + 64 * (par ^ 1), cmin, cmax, tid);
       for (int x = tid; x < KP * W; x += NT) { c.s_mask[x] = 0u; c.s_rmask[x] = 0u; }
       for (int x = tid; x < 2 * kNBins; x += NT) c.s_hist[x] = 0;  // the select is over: clear both radix histograms
       if (SORTED) for (int r = tid; r < n; r += NT) c.s_rank[c.idx[r]] = (int16_t)-1;
