@@ -275,3 +275,37 @@ def test_pack_results_ragged_layout_and_string_helper():
     r = 24 * 100 - 1 - 37
     b, q = divmod(r, 100)
     assert torch.equal(ptok[offsets[r]:offsets[r + 1]], out[b, q, :int(offsets[r + 1] - offsets[r])])
+
+
+@pytest.mark.parametrize("on_device", [True, False])
+@pytest.mark.parametrize("cfg", [
+    dict(B=320, T=60, V=29, seed=21, beam=16),                      # > 2 x 148 utterances: the throughput plan
+    dict(B=320, T=40, V=64, seed=22, beam=24, cutoff_top_n=12),     #   (128-thread CTAs, three per SM), sorted too
+    dict(B=200, T=50, V=29, seed=23, beam=20),                      # host entry point: several utterance groups
+])
+def test_large_batches_match_oracle(cport, cfg, on_device):
+    """Batches of more than one wave (plan.h: 128 threads per utterance, smaller list segments) and the host entry
+    point's pipelined utterance groups (ctc_api.cu: ctcdec_decode_batch_host), ragged lengths included."""
+    cfg = dict(cfg)
+    B, T, V, seed = cfg.pop("B"), cfg.pop("T"), cfg.pop("V"), cfg.pop("seed")
+    probs = ctc_like_probs(B, T, V, seed).numpy()
+    rng = np.random.RandomState(seed)
+    seq_lens = rng.randint(0, T + 1, size=B).astype(np.int32)
+    seq_lens[:3] = [T, 0, 1]
+    ref = cport.decode(probs, seq_lens=seq_lens, **cfg)
+    got = _run(probs, seq_lens, on_device=on_device, **cfg)
+    compare(ref, got, ref["ties"], str(cfg))
+    assert np.array_equal(ref["ties"] != 0, (got["ties"] & 7) != 0)
+    assert not (got["ties"] & 256).any()
+
+
+def test_generic_kp_kernel_matches_specialised(monkeypatch):
+    """The beam kernel is instantiated with the beam size rounded up to 32 as a compile-time constant (32 / 64 / 128 /
+    256) and once with a run-time value (beam sizes above 256, tuning-knob block sizes): same results."""
+    probs = ctc_like_probs(6, 120, 29, seed=31).numpy()
+    a = _run(probs, beam=40)
+    monkeypatch.setenv("CTCDEC_GENERIC_KP", "1")
+    b = _run(probs, beam=40)
+    for k in ("tokens", "timesteps", "lens", "n_results", "ties"):
+        assert np.array_equal(a[k], b[k]), k
+    assert np.array_equal(a["scores"].view(np.uint32), b["scores"].view(np.uint32))
