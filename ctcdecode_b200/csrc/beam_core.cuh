@@ -96,7 +96,9 @@ struct alignas(16) Node {
 constexpr int kStateHeader = 4;
 constexpr int kSlotArrays = 11;
 constexpr int kAnchorArrays = 6;
-CTC_HD int kp_of(int K) { return (K + 31) / 32 * 32; }
+// KP: slots per slot array.  Beam sizes up to 256 round up to 32 / 64 / 128 / 256 -- the sizes the beam kernel is
+// instantiated for with KP as a compile-time constant -- larger ones to a multiple of 32.
+CTC_HD int kp_of(int K) { return K <= 32 ? 32 : K <= 64 ? 64 : K <= 128 ? 128 : K <= 256 ? 256 : (K + 31) / 32 * 32; }
 CTC_HD long long state_ints(int K) { return kStateHeader + (long long)kSlotArrays * K + (long long)kAnchorArrays * 2 * kp_of(K); }
 
 // ---- shared memory carve-up (bytes) ---------------------------------------------------------------
@@ -143,7 +145,7 @@ CTC_HD int align_up(int x, int a) { return (x + a - 1) / a * a; }
 CTC_HD SmemLayout make_layout(int K, int V, int NP, int tile_frames, bool sorted, int NT, bool lm = false,
                               int budget_kb = 111) {
   SmemLayout L;
-  const int KP = align_up(K, 32);
+  const int KP = kp_of(K);
   const int W = (NP + 31) / 32;
   const int NW = NT / 32;
   L.KP = KP;

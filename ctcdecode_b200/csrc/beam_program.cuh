@@ -7,7 +7,7 @@ namespace ctc {
 
 #if defined(CTC_EMULATE) && defined(CTC_STATS)
 struct EmuStats { long long frames, passes, walk_iters, anchors_live, evicted, anchors_new, rv_hops, created, revived,
-                  hist_adds, tie_frames, sel_all_frames, rv_frames, rows, rows_skipped, cl_entries; };
+                  hist_adds, tie_frames, sel_all_frames, rv_frames, rows, rows_skipped, cl_entries, rewalks; };
 static EmuStats g_stats;
 #define CTC_STAT(x) (x)
 #else
@@ -655,12 +655,19 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
     //      key reaches lo32 (the worst member's key once the beam is full) are appended to the warp's
     //      candidate-list segment -- ballot + popc, no atomics, deterministic -- and counted into the
     //      first radix histogram.  Everything after this region works on the list.
+    // If a list segment overflows (the beam is filling up, or most member scores collapsed because the blank /
+    // their own character was cut from the frame, so that lo32 filters nothing), every candidate has still been
+    // counted in the first histogram: the bin holding the K-th key is known, lo32 moves up to that bin's lower edge
+    // and the grid is walked ONCE more with lists that now only take what can still be selected.  Only if that
+    // overflows too does the frame take the grid-walking fallback.
+    bool rebin = LM;  // members are binned inside region G (scorer path; or the tightened second walk)
+    for (int attempt = 0;; ++attempt) {
     CTC_WARPS {
       int cnt = 0;
       uint32_t *const segk = c.s_clk + warp * SEG;
       int *const segi = c.s_cli + warp * SEG;
       int *const hist0 = c.s_hist;
-      if (LM && !select_all) {  // (without a scorer the members binned themselves in region R1)
+      if (rebin && !select_all) {  // (without a scorer the members binned themselves in region R1)
         CTC_LANES {
           for (int j = warp * 32 + lane; j < M; j += NT) {
             const unsigned k = ord_f(c.s_snew[j]);
@@ -855,8 +862,26 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
       }
     }
     CTC_BARRIER_T(3);
+    if (LM || attempt > 0 || select_all || s_ctl[C_OVF] == 0 || p.force_fallback) break;
+    {
+      int bin, above, cnt;
+      scan_bin_all(c.s_hist, K, bin, above, cnt);
+      const unsigned lo_new = lo32 + ((unsigned)bin << shift32);
+      if (lo_new == lo32 || above + cnt < K) break;  // nothing to gain: grid-walking fallback
+      CTC_BARRIER();  // every warp has scanned the histogram
+      CTC_PAR {
+        for (int x = tid; x < kNBins; x += NT) c.s_hist[x] = 0;
+        if (tid == 0) s_ctl[C_OVF] = 0;
+      }
+      CTC_BARRIER();
+      lo32 = lo_new;
+      set_shift();
+      rebin = true;
+      CTC_STAT(g_stats.rewalks++);
+    }
+    }
     CTC_TICK(3);  // G
-    const bool fallback = s_ctl[C_OVF] != 0 || p.force_fallback;  // a segment overflowed: redo on the grid
+    const bool fallback = s_ctl[C_OVF] != 0 || p.force_fallback;  // a segment overflowed (twice): redo on the grid
     if (LM && M < K) {
       // beam not full yet: do fewer than beam_size prefixes exist?  (lo32 == 0, so the lists hold every candidate)
       long long ncand = 0;

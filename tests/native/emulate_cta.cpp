@@ -136,6 +136,7 @@ int emu_decode_batch(const float *probs, const int *seq_lens, int B, int T, int 
   if (NT <= 0) NT = pl.NT;
   pl.NT = NT;
   pl.L = make_layout(K, V, pl.NP, pl.F, pl.sorted, NT);
+  if (const char *e = getenv("CTC_EMU_SEG")) pl.L.seg = std::max(1, std::min(pl.L.seg, atoi(e)));  // test knob: small list segments
   std::vector<float> lp((size_t)B * T * pl.NP + 8, 0.f);
   std::vector<uint16_t> idx(pl.sorted ? (size_t)B * T * pl.NP + 8 : 8, 0);
   std::vector<Node> arena((size_t)B * pl.arena_stride);

@@ -115,3 +115,15 @@ def test_emulation_segment_overflow_takes_fallback(cport):
     the list."""
     probs = ctc_like_probs(1, 12, 64, seed=42).numpy()
     _check(cport, probs, beam=512)
+
+
+@pytest.mark.parametrize("seg", [8, 40, 150])
+def test_emulation_list_overflow_rewalk(cport, monkeypatch, seg):
+    """A list segment that overflows makes the frame walk the grid once more with lo32 raised to the lower edge of
+    the K-th key's histogram bin (beam_program.cuh, region G); if that overflows too, the grid-walking fallback takes
+    over.  Tiny segments force both on ordinary inputs: results must not change."""
+    monkeypatch.setenv("CTC_EMU_SEG", str(seg))
+    _check(cport, ctc_like_probs(2, 150, 29, seed=50).numpy(), beam=60)
+    _check(cport, ctc_like_probs(1, 100, 256, seed=51).numpy(), beam=100, cutoff_prob=0.99)
+    _check(cport, ctc_like_probs(2, 80, 64, seed=52).numpy(), beam=32, cutoff_top_n=12)
+    _check(cport, flat_probs(2, 200, 4, seed=5, temp=1.0).numpy(), beam=16)

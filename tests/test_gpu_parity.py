@@ -306,6 +306,22 @@ def test_generic_kp_kernel_matches_specialised(monkeypatch):
     a = _run(probs, beam=40)
     monkeypatch.setenv("CTCDEC_GENERIC_KP", "1")
     b = _run(probs, beam=40)
-    for k in ("tokens", "timesteps", "lens", "n_results", "ties"):
-        assert np.array_equal(a[k], b[k]), k
-    assert np.array_equal(a["scores"].view(np.uint32), b["scores"].view(np.uint32))
+    assert np.array_equal(a["ties"], b["ties"]) and np.array_equal(a["n_results"], b["n_results"])
+    a["ties"] = b["ties"] = np.zeros_like(a["ties"])   # compare every utterance, tie-flagged or not: same program
+    checked, _ = compare(a, b, None, "generic KP")     # (only [:len] of a row is ever written)
+    assert checked == 6
+
+
+@pytest.mark.parametrize("seg", [8, 40, 150])
+def test_list_overflow_rewalk(cport, monkeypatch, seg):
+    """Overflowing candidate lists (forced by shrinking the per-warp segments): the tightened second grid walk and,
+    behind it, the grid-walking fallback give the same results as the oracle."""
+    monkeypatch.setenv("CTCDEC_SEG", str(seg))
+    for probs, kw in ((ctc_like_probs(4, 300, 29, seed=50).numpy(), dict(beam=100)),
+                      (ctc_like_probs(2, 200, 256, seed=51).numpy(), dict(beam=200, cutoff_prob=0.99)),
+                      (ctc_like_probs(2, 80, 64, seed=52).numpy(), dict(beam=32, cutoff_top_n=12)),
+                      (flat_probs(2, 200, 4, seed=5, temp=1.0).numpy(), dict(beam=16))):
+        ref = cport.decode(probs, **kw)
+        got = _run(probs, **kw)
+        compare(ref, got, ref["ties"], "seg %d %s" % (seg, kw))
+        assert not (got["ties"] & 256).any()
