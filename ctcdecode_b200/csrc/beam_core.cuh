@@ -197,6 +197,7 @@ struct BeamParams {
   int arena_cap;            // offline capacity per utterance
   int fresh;                // 1: start from the root state instead of loading `state`
   int force_fallback;       // test knob: run the grid-walking select path every frame
+  float heur_bias;          // test knob: added to the checked heuristic bound (> 0 makes it fail its check often)
   const unsigned char *finalize;  // [B] or nullptr (= finalize all)
   int *out_tokens, *out_timesteps;  // [B][K][out_T]
   float *out_scores;                // [B][K]

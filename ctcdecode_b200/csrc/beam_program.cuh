@@ -7,7 +7,7 @@ namespace ctc {
 
 #if defined(CTC_EMULATE) && defined(CTC_STATS)
 struct EmuStats { long long frames, passes, walk_iters, anchors_live, evicted, anchors_new, rv_hops, created, revived,
-                  hist_adds, tie_frames, sel_all_frames, rv_frames, rows, rows_skipped, cl_entries, rewalks; };
+                  hist_adds, tie_frames, sel_all_frames, rv_frames, rows, rows_skipped, cl_entries, rewalks, fb_frames, ovf_first, heur_fail; };
 static EmuStats g_stats;
 #define CTC_STAT(x) (x)
 #else
@@ -512,6 +512,8 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
     //   every key <= (highest old score) + (largest log-prob of the row) + 2 ln 2  (two nested log_sum_exp of at
     //   most three such terms; 1.5 > 2 ln 2 + rounding)
     unsigned lo32 = 0u, top32 = 0u;
+    unsigned lo_valid = 0u;   // the proven lower bound (lo32 may be the checked heuristic one, SORTED kernels)
+    bool heuristic = false;
     int shift32 = 0;  // smallest shift with ((top32 - lo32) >> shift32) < kNBins
     auto set_shift = [&]() {
       const unsigned wm = top32 - lo32;
@@ -533,6 +535,17 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
         lpm = lpb > lpm ? lpb : lpm;
       }
       top32 = ord_f(f_add(f_add(cmax, lpm), 1.5f));
+      lo_valid = lo32;
+      if (M == K && !p.force_fallback) {
+        // A second, usually much tighter bound (where the vocabulary is cut per frame the blank is often not among
+        // the kept characters and the bound above is void): every row's best candidate scores at least
+        // (lowest beam score) + (largest non-blank log-prob of the row), so normally K keys reach that value.
+        // Masked cells and the repeated-character rule can break the count, therefore this bound is CHECKED after
+        // the grid walk (histogram total >= K); if it fails, kernels for a cut vocabulary walk the grid again with
+        // the proven bound, index-order kernels (where that is a 3-in-1000-frames event) take the grid-walking select.
+        const unsigned lo_h = ord_f(f_add(f_add(cmin, lpmax), p.heur_bias));
+        if (lo_h > lo32 && lo_h <= top32) { lo32 = lo_h; heuristic = true; }
+      }
       if (top32 < lo32) top32 = lo32;
       set_shift();
     }
@@ -660,7 +673,9 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
     // counted in the first histogram: the bin holding the K-th key is known, lo32 moves up to that bin's lower edge
     // and the grid is walked ONCE more with lists that now only take what can still be selected.  Only if that
     // overflows too does the frame take the grid-walking fallback.
-    bool rebin = LM;  // members are binned inside region G (scorer path; or the tightened second walk)
+    bool rebin = LM;  // members are binned inside region G (scorer path; or the tightened second walk, SORTED only)
+    bool have_scan = false;  // the first histogram has already been scanned (pre_bin / pre_above / pre_cnt)
+    int pre_bin = 0, pre_above = 0, pre_cnt = 0;
     for (int attempt = 0;; ++attempt) {
     CTC_WARPS {
       int cnt = 0;
@@ -862,12 +877,24 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
       }
     }
     CTC_BARRIER_T(3);
-    if (LM || attempt > 0 || select_all || s_ctl[C_OVF] == 0 || p.force_fallback) break;
+    // (only where the vocabulary is cut per frame: there the blank / a member's character can drop out of a frame
+    // and take the lower bound with it; an index-order kernel keeps its single straight-line walk)
+    if (!SORTED || LM || attempt > 0 || select_all || p.force_fallback) break;
     {
-      int bin, above, cnt;
-      scan_bin_all(c.s_hist, K, bin, above, cnt);
-      const unsigned lo_new = lo32 + ((unsigned)bin << shift32);
-      if (lo_new == lo32 || above + cnt < K) break;  // nothing to gain: grid-walking fallback
+      const bool ovf = s_ctl[C_OVF] != 0;
+      if (!ovf && !heuristic) break;
+      scan_bin_all(c.s_hist, K, pre_bin, pre_above, pre_cnt);
+      unsigned lo_new;
+      if (pre_above + pre_cnt < K) {
+        lo_new = lo_valid;                 // the heuristic bound cut too deep: walk again with the proven one
+        CTC_STAT(g_stats.heur_fail++);
+      } else if (ovf) {
+        lo_new = lo32 + ((unsigned)pre_bin << shift32);
+        if (lo_new == lo32) break;         // nothing to gain: grid-walking fallback
+      } else {
+        have_scan = true;                  // bound holds, lists fit: the select continues from this scan
+        break;
+      }
       CTC_BARRIER();  // every warp has scanned the histogram
       CTC_PAR {
         for (int x = tid; x < kNBins; x += NT) c.s_hist[x] = 0;
@@ -875,13 +902,15 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
       }
       CTC_BARRIER();
       lo32 = lo_new;
+      heuristic = false;
       set_shift();
       rebin = true;
       CTC_STAT(g_stats.rewalks++);
     }
     }
     CTC_TICK(3);  // G
-    const bool fallback = s_ctl[C_OVF] != 0 || p.force_fallback;  // a segment overflowed (twice): redo on the grid
+    bool fallback = s_ctl[C_OVF] != 0 || p.force_fallback;  // a segment overflowed (twice): redo on the grid
+    CTC_STAT(g_stats.fb_frames += fallback);
     if (LM && M < K) {
       // beam not full yet: do fewer than beam_size prefixes exist?  (lo32 == 0, so the lists hold every candidate)
       long long ncand = 0;
@@ -916,10 +945,18 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
       // (replaces std::nth_element + prefix_compare, reference :149-154, decoder_utils.cpp:122-132).
       // Pass 0 (score bits only) was histogrammed during region G.
       CTC_STAT(g_stats.passes++);
-      int bin, above, cnt;
-      scan_bin_all(c.s_hist, K, bin, above, cnt);  // every warp, redundantly: no barrier, no broadcast
+      int bin = pre_bin, above = pre_above, cnt = pre_cnt;
+      if (!have_scan) scan_bin_all(c.s_hist, K, bin, above, cnt);  // every warp, redundantly: no barrier, no broadcast
       uint64_t lo = ((uint64_t)(lo32 + ((unsigned)bin << shift32))) << 16;
-      if (above + cnt == K) {
+      if (!SORTED && heuristic && above + cnt < K) {
+        // the checked bound cut too deep (index-order kernels: no second walk): grid-walking select from the
+        // proven bound.  Every warp sees the same histogram, so the decision is uniform.
+        CTC_STAT(g_stats.heur_fail++);
+        CTC_BARRIER();  // the fallback clears the histograms: every warp must have scanned first
+        lo32 = lo_valid;
+        set_shift();
+        fallback = true;
+      } else if (above + cnt == K) {
         thr = lo;
       } else {
         uint64_t width = 1ull << (shift32 + 16);
@@ -979,6 +1016,10 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
     }
     if (!select_all && fallback) {
       // ---- fallback: the same select with every pass walking the grid (48-bit keys from the start) -------
+      if (heuristic) {  // an overflow got here before the heuristic bound was checked: start from the proven one
+        lo32 = lo_valid;
+        set_shift();
+      }
       CTC_PAR {
         for (int x = tid; x < 2 * kNBins; x += NT) c.s_hist[x] = 0;
         if (tid == 0) { s_ctl[C_ABOVE] = 0; }

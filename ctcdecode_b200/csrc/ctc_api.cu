@@ -137,6 +137,7 @@ static int launch_beam_ns(const BeamParams &bp, int B, cudaStream_t s) {
 static int launch_beam(const BeamParams &bp_in, const Plan &pl, int B, cudaStream_t s) {
   BeamParams bp = bp_in;
   bp.L = pl.L;
+  if (const char *e = getenv("CTCDEC_HEUR_BIAS")) bp.heur_bias = (float)atof(e);  // test knob: make the checked bound fail
   if (const char *e = getenv("CTCDEC_SEG")) bp.L.seg = std::max(1, std::min(bp.L.seg, atoi(e)));  // test knob: small list segments
   const bool generic = getenv("CTCDEC_GENERIC_KP") != nullptr;  // test knob: force the run-time-KP kernel
   if (generic && !bp.timing && !bp.dict_next) {

@@ -153,6 +153,7 @@ int emu_decode_batch(const float *probs, const int *seq_lens, int B, int T, int 
   bp.out_tokens = tokens; bp.out_timesteps = timesteps; bp.out_scores = scores; bp.out_lens = lens;
   bp.n_results = n_results; bp.out_T = T; bp.flags = flags;
   bp.force_fallback = getenv("CTC_EMU_FORCE_FALLBACK") ? 1 : 0;
+  if (const char *e = getenv("CTC_EMU_HEUR_BIAS")) bp.heur_bias = (float)atof(e);  // test knob
 
   std::vector<int> chunk_lens(B);
   const int step = chunk > 0 ? chunk : (T > 0 ? T : 1);
@@ -236,6 +237,7 @@ int emu_decode_batch_lm(const float *probs, const int *seq_lens, int B, int T, i
   bp.out_tokens = tokens; bp.out_timesteps = timesteps; bp.out_scores = scores; bp.out_lens = lens;
   bp.n_results = n_results; bp.out_T = T; bp.flags = flags;
   bp.force_fallback = getenv("CTC_EMU_FORCE_FALLBACK") ? 1 : 0;
+  if (const char *e = getenv("CTC_EMU_HEUR_BIAS")) bp.heur_bias = (float)atof(e);  // test knob
   pack_dictionary(sc.dict, sc.space_id);
   bp.dict_next = sc.dict.packed.data(); bp.dict_mask = sc.dict.mask.data(); bp.dict_wc = sc.dict.wc;
   bp.dict_start = sc.dict.start;

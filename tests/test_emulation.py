@@ -123,7 +123,21 @@ def test_emulation_list_overflow_rewalk(cport, monkeypatch, seg):
     the K-th key's histogram bin (beam_program.cuh, region G); if that overflows too, the grid-walking fallback takes
     over.  Tiny segments force both on ordinary inputs: results must not change."""
     monkeypatch.setenv("CTC_EMU_SEG", str(seg))
+    monkeypatch.setenv("CTC_EMU_HEUR_BIAS", "0.7")  # and let the checked bound fail now and then on top of it
     _check(cport, ctc_like_probs(2, 150, 29, seed=50).numpy(), beam=60)
     _check(cport, ctc_like_probs(1, 100, 256, seed=51).numpy(), beam=100, cutoff_prob=0.99)
     _check(cport, ctc_like_probs(2, 80, 64, seed=52).numpy(), beam=32, cutoff_top_n=12)
     _check(cport, flat_probs(2, 200, 4, seed=5, temp=1.0).numpy(), beam=16)
+
+
+@pytest.mark.parametrize("bias", ["0.5", "3.0", "40.0"])
+def test_emulation_checked_bound_failure_is_redone(cport, monkeypatch, bias):
+    """Kernels for a per-frame vocabulary cut start the grid walk from a heuristic lower bound of the K-th key
+    (lowest beam score + largest non-blank log-prob) that is CHECKED against the histogram total; a bound that cuts
+    too deep (forced here by a bias) makes the frame walk again with the proven bound.  Results must not change."""
+    monkeypatch.setenv("CTC_EMU_HEUR_BIAS", bias)
+    _check(cport, ctc_like_probs(1, 100, 256, seed=51).numpy(), beam=100, cutoff_prob=0.99)
+    _check(cport, ctc_like_probs(2, 80, 64, seed=52).numpy(), beam=32, cutoff_top_n=12)
+    _check(cport, flat_probs(2, 120, 12, seed=6, temp=1.0).numpy(), beam=16, cutoff_top_n=5)
+    _check(cport, ctc_like_probs(2, 150, 29, seed=53).numpy(), beam=60)      # index-order kernel: grid-walking select
+    _check(cport, flat_probs(2, 150, 6, seed=7, temp=1.5).numpy(), beam=24)

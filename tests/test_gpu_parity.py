@@ -317,6 +317,7 @@ def test_list_overflow_rewalk(cport, monkeypatch, seg):
     """Overflowing candidate lists (forced by shrinking the per-warp segments): the tightened second grid walk and,
     behind it, the grid-walking fallback give the same results as the oracle."""
     monkeypatch.setenv("CTCDEC_SEG", str(seg))
+    monkeypatch.setenv("CTCDEC_HEUR_BIAS", "0.7")  # and let the checked bound fail now and then on top of it
     for probs, kw in ((ctc_like_probs(4, 300, 29, seed=50).numpy(), dict(beam=100)),
                       (ctc_like_probs(2, 200, 256, seed=51).numpy(), dict(beam=200, cutoff_prob=0.99)),
                       (ctc_like_probs(2, 80, 64, seed=52).numpy(), dict(beam=32, cutoff_top_n=12)),
@@ -324,4 +325,19 @@ def test_list_overflow_rewalk(cport, monkeypatch, seg):
         ref = cport.decode(probs, **kw)
         got = _run(probs, **kw)
         compare(ref, got, ref["ties"], "seg %d %s" % (seg, kw))
+        assert not (got["ties"] & 256).any()
+
+
+@pytest.mark.parametrize("bias", ["0.5", "3.0", "40.0"])
+def test_checked_bound_failure_is_redone(cport, monkeypatch, bias):
+    """The checked heuristic bound of the cut-vocabulary kernels, forced to fail (see tests/test_emulation.py)."""
+    monkeypatch.setenv("CTCDEC_HEUR_BIAS", bias)
+    for probs, kw in ((ctc_like_probs(2, 200, 256, seed=51).numpy(), dict(beam=200, cutoff_prob=0.99)),
+                      (ctc_like_probs(2, 80, 64, seed=52).numpy(), dict(beam=32, cutoff_top_n=12)),
+                      (flat_probs(2, 120, 12, seed=6, temp=1.0).numpy(), dict(beam=16, cutoff_top_n=5)),
+                      (ctc_like_probs(4, 300, 29, seed=53).numpy(), dict(beam=100)),   # index-order kernel
+                      (flat_probs(2, 150, 6, seed=7, temp=1.5).numpy(), dict(beam=24))):
+        ref = cport.decode(probs, **kw)
+        got = _run(probs, **kw)
+        compare(ref, got, ref["ties"], "bias %s %s" % (bias, kw))
         assert not (got["ties"] & 256).any()
