@@ -573,7 +573,8 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
     // (reference ctc_beam_search_decoder.cpp:97-118,138-139; path_trie.cpp:39-57,129-137)
     CTC_PAR {
       if (tid == 0) {
-        s_ctl[C_NREV] = 0;  // (not with the other counters in R5: slow threads may still be reading it there)
+        s_ctl[C_NREV] = 0;  // (not with the other counters in R5: slow threads may still be reading them there --
+        s_ctl[C_NSEL] = 0;  //  C_NSEL is read right after the classification's barrier, the last one before R5)
       }
       unsigned kmin = 0xFFFFFFFFu, kmax = 0u, smax = 0u;
       int npairs = 0;
@@ -1525,7 +1526,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
       for (int x = tid; x < 2 * kNBins; x += NT) c.s_hist[x] = 0;  // the select is over: clear both radix histograms
       if (SORTED) for (int r = tid; r < n; r += NT) c.s_rank[c.idx[r]] = (int16_t)-1;
       if (tid == 0) {  // (C_NLIVE / C_ANYREF are read below and reset in region R4c of the next frame)
-        s_ctl[C_NSEL] = 0; s_ctl[C_NFREE] = 0; s_ctl[C_NTIE] = 0; s_ctl[C_NPAIRS] = 0;
+        s_ctl[C_NFREE] = 0; s_ctl[C_NTIE] = 0; s_ctl[C_NPAIRS] = 0;
         s_ctl[C_ABOVE] = 0; s_ctl[C_KMIN] = (int)0xFFFFFFFFu; s_ctl[C_KMAX] = 0; s_ctl[C_SMAX] = 0;
         s_ctl[C_NEFREE] = 0; s_ctl[C_NETAKEN] = 0; s_ctl[C_OVF] = 0; s_ctl[C_SMIN] = (int)0xFFFFFFFFu;
         s_ctl[C_NCAND] = 0;
