@@ -11,7 +11,8 @@ BASELINE config 3: 2048 utterances over 8 GPUs).  Rank 0 prints ONE JSON line:
   value        whole-job utterances/s with inputs resident in HBM (device entry point of the C ABI), CUDA-event
                time of K steps, max over ranks; L2 is flushed between timed steps
   e2e          same metric through the host-buffer C-ABI call: pinned host probs -> H2D -> kernels -> D2H of the
-               results into pinned host tensors, wall clock around the call, max over ranks
+               results into pinned host tensors, wall clock around the call, max over ranks (the call pipelines
+               groups of utterances over streams: copies of one group overlap the kernels of the others)
   roofline     beam-search kernel: algorithmic bytes (B*T*V*4) / its CUDA-event duration,
                against MEASURED_PEAKS.json's HBM copy bandwidth.  The kernel is T-serial per utterance
                (latency bound), so the fraction is tiny by construction; `scan` reports the HBM-bound

@@ -106,7 +106,13 @@ int ctcdec_pack_results_device(const int32_t *tokens, const int32_t *timesteps, 
                                int32_t *packed_tokens, int32_t *packed_timesteps, size_t capacity, void *stream);
 
 /* Same operation with HOST buffers shaped exactly like the reference's CPU tensors
- * (reference __init__.py:77-86); copies in and out through pinned staging on `device`. */
+ * (reference __init__.py:77-86).  The batch is cut into up to 8 groups of utterances, each on its own stream, so
+ * that the upload, the kernels and the download of different groups overlap; small results are staged through
+ * pinned memory.  Pinned caller buffers keep every copy asynchronous (pageable ones work, more slowly).
+ * Environment (tuning / test knobs, all optional): CTCDEC_HOST_CHUNK=n utterances per group; CTCDEC_NT=128|256|512|
+ * 1024 threads per utterance; CTCDEC_GENERIC_KP=1 the run-time-beam-size kernel; CTCDEC_FORCE_FALLBACK=1 the
+ * grid-walking select on every frame; CTCDEC_SEG=n / CTCDEC_HEUR_BIAS=x small candidate lists / a failing heuristic
+ * bound (tests/test_gpu_parity.py drives every select path with them). */
 int ctcdec_decode_batch_host(const ctcdec_config *cfg, const float *probs, const int32_t *seq_lens, int B, int T,
                              int32_t *tokens, int32_t *timesteps, float *scores, int32_t *lens, int32_t *n_results,
                              int32_t *flags, int device);
