@@ -257,9 +257,19 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # keep stdout for the one JSON line: NCCL's version / debug lines go to stderr unless the caller chose a file
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=dev)
+        # keep stdout for the one JSON line: NCCL prints its version line (NCCL_DEBUG=WARN / VERSION) to stdout when the
+        # communicator comes up, so file descriptor 1 points at stderr until the first collective has run
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     lib = _native.load()
     if cfg.get("lm"):
         return bench_lm(args, cfg, config, rank, world, local_rank, dev, K, W, cores)
