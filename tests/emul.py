@@ -89,3 +89,15 @@ def decode_lm(probs, hook_lib, scorer_ptr, labels, words, max_order, alpha, beta
            ln.ctypes.data_as(_i32p), nres.ctypes.data_as(_i32p), flags.ctypes.data_as(_i32p))
     assert rc == 0, rc
     return dict(tokens=tok, timesteps=ts, scores=sc, lens=ln, n_results=nres, ties=flags)
+
+
+def plan(B, T, V, beam, cutoff_prob=1.0, cutoff_top_n=40):
+    """What plan.h decides: dict(NT, KP, budget_kb, seg, smem, F, NP, sorted), or the CTCDEC_E_* code."""
+    out = (ctypes.c_int * 8)()
+    l = lib()
+    l.emu_plan.restype = ctypes.c_int
+    l.emu_plan.argtypes = [ctypes.c_int] * 4 + [ctypes.c_double, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
+    rc = l.emu_plan(B, T, V, beam, cutoff_prob, cutoff_top_n, out)
+    if rc:
+        return rc
+    return dict(zip(("NT", "KP", "budget_kb", "seg", "smem", "F", "NP", "sorted"), list(out)))

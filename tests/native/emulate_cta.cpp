@@ -120,6 +120,20 @@ static void run_beam(const BeamParams &bp, bool sorted, int B, unsigned char *sm
 
 extern "C" {
 
+// What plan.h decides for a configuration: out[0..7] = NT, KP, budget_kb, seg, smem total, F, NP, sorted.
+int emu_plan(int B, int T, int V, int K, double cutoff_prob, int cutoff_top_n, int *out) {
+  ctcdec_config cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.vocab_size = V; cfg.beam_size = K; cfg.cutoff_top_n = cutoff_top_n; cfg.cutoff_prob = cutoff_prob;
+  Plan pl;
+  char msg[256];
+  const int rc = make_plan_core(&cfg, B, T, &pl, msg, sizeof(msg));
+  if (rc) return rc;
+  out[0] = pl.NT; out[1] = pl.L.KP; out[2] = pl.budget_kb; out[3] = pl.L.seg; out[4] = pl.L.total; out[5] = pl.F;
+  out[6] = pl.NP; out[7] = pl.sorted ? 1 : 0;
+  return 0;
+}
+
 // Offline batch decode through the emulated CTA program.  `chunk` > 0 feeds the frames in chunks of
 // that many frames through the streaming state path (state stored to / loaded from "global" memory
 // between chunks); chunk <= 0 decodes in one go.  Returns 0 or a CTCDEC_E_* code.

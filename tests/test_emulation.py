@@ -141,3 +141,27 @@ def test_emulation_checked_bound_failure_is_redone(cport, monkeypatch, bias):
     _check(cport, flat_probs(2, 120, 12, seed=6, temp=1.0).numpy(), beam=16, cutoff_top_n=5)
     _check(cport, ctc_like_probs(2, 150, 29, seed=53).numpy(), beam=60)      # index-order kernel: grid-walking select
     _check(cport, flat_probs(2, 150, 6, seed=7, temp=1.5).numpy(), beam=24)
+
+
+def test_plan_shapes():
+    """plan.h: block size / shared-memory budget by batch size (latency vs throughput shape), slot count rounded to
+    the sizes the beam kernel is specialised for, and every layout inside the 227 KB an SM offers."""
+    c2 = emul.plan(256, 1000, 29, 100)
+    assert (c2["NT"], c2["KP"], c2["budget_kb"], c2["sorted"]) == (256, 128, 111, 0)
+    assert 2 * (c2["smem"] + 1024) <= 227 * 1024            # two CTAs per SM
+    c3 = emul.plan(2048, 1000, 29, 100)
+    assert (c3["NT"], c3["KP"], c3["budget_kb"]) == (128, 128, 74)
+    assert 3 * (c3["smem"] + 1024) <= 227 * 1024            # three CTAs per SM
+    c4 = emul.plan(256, 2000, 256, 200, cutoff_prob=0.99)
+    assert (c4["NT"], c4["KP"], c4["sorted"], c4["NP"]) == (256, 256, 1, 48)
+    assert 2 * (c4["smem"] + 1024) <= 227 * 1024
+    assert emul.plan(1, 50, 6, 4)["KP"] == 32 and emul.plan(1, 50, 6, 4)["NT"] == 128
+    assert [emul.plan(4, 10, 29, k)["KP"] for k in (32, 33, 64, 65, 128, 129, 256, 257, 300)] == \
+        [32, 64, 64, 128, 128, 256, 256, 288, 320]
+    for k in (1, 16, 100, 256, 512, 1024, 2048):
+        for v in (2, 29, 256, 5000):
+            pl = emul.plan(8, 20, v, k)
+            assert isinstance(pl, int) or pl["smem"] <= 227 * 1024, (k, v, pl)
+            if not isinstance(pl, int):
+                assert pl["seg"] >= 32
+    assert isinstance(emul.plan(8, 20, 29, 5000), int)      # beam size out of range -> an error code, not a layout
