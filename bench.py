@@ -303,12 +303,12 @@ def main():
             ctypes.byref(ccfg), probs_dev.data_ptr(), None, B, T, d_tok.data_ptr(), d_ts.data_ptr(), d_sc.data_ptr(),
             d_len.data_ptr(), d_nres.data_ptr(), d_flags.data_ptr(), ws.data_ptr(), ws.numel(), stream))
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()  # (before the warm-up: a 10-step timed region is only ~50 ms, a sample every 100 ms)
     for _ in range(W):
         device_step()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     barrier()
     step_ms, kern_ms = [], []
     for _ in range(K):
