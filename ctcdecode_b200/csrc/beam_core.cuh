@@ -283,6 +283,16 @@ CTC_FN int ctc_popc(unsigned x) { return __popc(x); }
 CTC_FN int ctc_ffs(unsigned x) { return __ffs((int)x); }
 #endif
 CTC_FN unsigned ctc_lt_mask(int lane) { return (1u << lane) - 1u; }
+// warp-wide maximum of one value per lane
+#if defined(CTC_EMULATE)
+static inline unsigned ctc_warp_max(const unsigned (&v)[kLW]) {
+  unsigned m = 0;
+  for (int l = 0; l < 32; ++l) m = v[l] > m ? v[l] : m;
+  return m;
+}
+#else
+CTC_FN unsigned ctc_warp_max(const unsigned (&v)[kLW]) { return __reduce_max_sync(0xffffffffu, v[0]); }
+#endif
 
 // log_sum_exp<float> (reference decoder_utils.h:47-54) with the 32-entry expf / 16-entry logf tables
 // staged in shared memory (a __constant__ table indexed per thread would serialise divergent reads).

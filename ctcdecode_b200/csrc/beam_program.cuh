@@ -691,6 +691,70 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
           }
         }
       }
+      // ---- the dominant column first.  In a frame with one likely non-blank character (log-prob lpmax, runner-up
+      //      lpmax2 at least 1 below) that column is walked column-wise -- lane = row, 32 rows per step -- and left
+      //      out of the row walk, whose skip test then uses lpmax2: in such frames EVERY row passes the lpmax test
+      //      (each row's extension by the likely character is a candidate that counts) but only the top rows have
+      //      anything else to offer.
+      int rstar = -1;         // rank of the most likely non-blank kept character (column-first frames only)
+      float lp_rows = lpmax;  // largest log-prob the row walk can still meet
+      if (!LM && n > 0) {
+        float lp2 = kNInf;
+        int r1 = -1;
+        if (SORTED) {  // rows are sorted by probability: the first two non-blank ranks
+          r1 = (rblank == 0) ? 1 : 0;
+          int r2 = r1 + 1;
+          if (r2 == rblank) ++r2;
+          if (r1 >= n) r1 = -1;
+          else if (r2 < n) lp2 = c.lp[r2];
+        } else if (n <= 32) {
+          CTC_LV(unsigned, key);
+          CTC_LV(unsigned, key2);
+          CTC_LANES { key[LX] = (lane < n && lane != rblank) ? ord_f(c.lp[lane]) : 0u; }
+          const unsigned m1 = ctc_warp_max(key);
+          CTC_LV(int, ism);
+          CTC_LANES { ism[LX] = (key[LX] == m1 && m1 != 0u) ? 1 : 0; }
+          const unsigned bm = ctc_ballot(ism);
+          r1 = bm ? ctc_ffs(bm) - 1 : -1;
+          CTC_LANES { key2[LX] = (lane == r1) ? 0u : key[LX]; }
+          const unsigned m2 = ctc_warp_max(key2);
+          if (m2 != 0u) lp2 = unord_f(m2);
+        }
+        if (r1 >= 0 && f_add(c.lp[r1], -lp2) >= 1.0f) { rstar = r1; lp_rows = lp2; }
+      }
+      if (rstar >= 0) {
+        const int chs = c.chr_at(rstar);
+        const float ls = c.lp[rstar];
+        for (int i0 = warp * 32; i0 < M; i0 += NT) {
+          CTC_LV(int, pred);
+          CTC_LV(uint32_t, kk);
+          CTC_LANES {
+            const int i = i0 + lane;
+            pred[LX] = 0;
+            kk[LX] = 0u;
+            if (i < M) {
+              const bool rep = (chs == c.s_chr[i]);
+              const float b = c.s_bprev[i];
+              float sc = f_add(ls, rep ? b : c.s_score[i]);
+              if (rep && !(b > kNInf)) sc = kNInf;
+              const unsigned k = ord_f(sc);
+              const bool ok = !((c.s_mask[i * W + (rstar >> 5)] >> (rstar & 31)) & 1u) && (k >= lo32);
+              pred[LX] = ok ? 1 : 0;
+              kk[LX] = k;
+              if (ok && !select_all) atom_add(&hist0[(int)((k - lo32) >> shift32)], 1);
+            }
+          }
+          const unsigned bal = ctc_ballot(pred);
+          CTC_LANES {
+            if (pred[LX]) {
+              const int pos = cnt + ctc_popc(bal & ctc_lt_mask(lane));
+              if (pos < SEG) { segk[pos] = kk[LX]; segi[pos] = ((i0 + lane) << 16) | rstar; }
+            }
+          }
+          cnt += ctc_popc(bal);
+          CTC_STAT(g_stats.cl_entries += ctc_popc(bal));
+        }
+      }
       // rows (members) are tested 32 at a time: lane l looks at row base + warp + NW * l.  A row whose best
       // possible candidate (score + max non-blank log-prob) stays under lo32 contributes nothing; on config 2
       // that removes 80 % of the rows.
@@ -701,7 +765,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
           rowok[LX] = 0;
           if (i < M) {
             CTC_STAT(g_stats.rows++);
-            rowok[LX] = (LM || ord_f(f_add(c.s_score[i], lpmax)) >= lo32) ? 1 : 0;
+            rowok[LX] = (LM || ord_f(f_add(c.s_score[i], lp_rows)) >= lo32) ? 1 : 0;
             CTC_STAT(g_stats.rows_skipped += !rowok[LX]);
           }
         }
@@ -712,7 +776,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
         CTC_LANES {
           colc[LX] = -2;  // not a candidate column (beyond n, or the blank)
           colv[LX] = 0.0f;
-          if (rows && lane < n) {
+          if (rows && lane < n && lane != rstar) {  // (the dominant column has been walked already)
             const int ch = c.chr_at(lane);
             if (ch != c.blank) { colc[LX] = ch; colv[LX] = c.lp[lane]; }
           }
