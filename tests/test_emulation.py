@@ -165,3 +165,35 @@ def test_plan_shapes():
             if not isinstance(pl, int):
                 assert pl["seg"] >= 32
     assert isinstance(emul.plan(8, 20, 29, 5000), int)      # beam size out of range -> an error code, not a layout
+
+
+@pytest.mark.parametrize("knob", [None, ("CTC_EMU_SEG", "16"), ("CTC_EMU_HEUR_BIAS", "1.5"), ("CTC_EMU_FORCE_FALLBACK", "1")])
+def test_emulation_random_configs(cport, monkeypatch, knob):
+    """Seeded random walk over vocabulary / beam / length / pruning mode / input kind / ragged lengths / streaming
+    chunk size, with the test knobs that force the rare select paths: the CTA program must agree with the oracle."""
+    if knob:
+        monkeypatch.setenv(*knob)
+    rng = np.random.RandomState(1234 + (0 if knob is None else len(knob[0])))
+    for _ in range(60):
+        V = int(rng.choice([2, 3, 5, 8, 12, 29, 33, 64, 100, 256]))
+        beam = int(rng.choice([1, 2, 4, 8, 16, 31, 32, 33, 60, 100, 128, 200]))
+        T, B = int(rng.randint(1, 60)), int(rng.randint(1, 4))
+        kw = dict(beam=beam)
+        mode = rng.randint(0, 4)
+        if mode in (1, 3):
+            kw["cutoff_top_n"] = int(rng.randint(1, V + 1))
+        if mode in (2, 3):
+            kw["cutoff_prob"] = float(rng.choice([0.3, 0.9, 0.99, 0.999]))
+        blank = int(rng.choice([0, V - 1]))
+        kw["blank_id"] = blank
+        kind, seed = rng.randint(0, 3), int(rng.randint(0, 10000))
+        if kind == 0:
+            probs = ctc_like_probs(B, T, V, seed, peak=float(rng.choice([1.0, 3.0, 8.0])), blank_id=blank).numpy()
+        elif kind == 1:
+            probs = flat_probs(B, T, V, seed, temp=float(rng.choice([0.5, 1.0, 3.0]))).numpy()
+        else:
+            probs = ctc_like_probs(B, T, V, seed, peak=8.0, blank_id=blank, log=True).numpy()
+            kw["log_input"] = True
+        sl = rng.randint(0, T + 1, size=B).astype(np.int32) if rng.rand() < 0.5 else None
+        chunk = int(rng.choice([0, 0, 1, 7, 16]))
+        _check(cport, probs, sl, chunk=chunk, **kw)
