@@ -41,18 +41,30 @@
 //     cross a warp collective (ballot) live in CTC_LV arrays indexed by LX (one element per lane in the
 //     emulation, a single register on the device).
 #if defined(CTC_EMULATE)
-#define CTC_PAR for (int tid = 0; tid < NT; ++tid)
-#define CTC_WARPS for (int warp = 0; warp < NT / 32; ++warp)
-#define CTC_LANES for (int lane = 0, LX = 0; lane < 32; ++lane, ++LX)
+// The emulation runs the "threads" of a region one after the other.  A region is only correct on the device if its
+// result does not depend on that order, so the order is a test knob (ctc::g_emu_order, CTC_EMU_ORDER): bit 0 walks the
+// warps of a region from the last to the first, bit 1 the lanes of a CTC_LANES block, bit 2 swaps the two halves of a
+// CTC_HALVES region (two pieces of work that run concurrently on different warps of the device).
+namespace ctc { static int g_emu_order = 0; constexpr int kLW = 32; }
+#define CTC_PAR                                                                                                  \
+  for (int tid_i_ = 0, tid = (::ctc::g_emu_order & 1) ? NT - 32 : 0; tid_i_ < NT;                                 \
+       ++tid_i_, tid = (::ctc::g_emu_order & 1) ? ((NT / 32 - 1 - tid_i_ / 32) * 32 + (tid_i_ & 31)) : tid_i_)
+#define CTC_WARPS                                                                                                \
+  for (int warp_i_ = 0, warp = (::ctc::g_emu_order & 1) ? NT / 32 - 1 : 0; warp_i_ < NT / 32;                     \
+       ++warp_i_, warp = (::ctc::g_emu_order & 1) ? NT / 32 - 1 - warp_i_ : warp_i_)
+#define CTC_LANES                                                                                                \
+  for (int lane_i_ = 0, lane = (::ctc::g_emu_order & 2) ? 31 : 0, LX = lane; lane_i_ < 32;                        \
+       ++lane_i_, lane = (::ctc::g_emu_order & 2) ? 31 - lane_i_ : lane_i_, LX = lane)
+#define CTC_HALVES for (int half_i_ = 0, half = (::ctc::g_emu_order & 4) ? 1 : 0; half_i_ < 2; ++half_i_, half ^= 1)
 #define CTC_BARRIER() ((void)0)
 #define CTC_SYNCWARP() ((void)0)
 #define CTC_FN static inline
 #define CTC_MFN inline
-namespace ctc { constexpr int kLW = 32; }
 #else
 #define CTC_PAR for (int tid = (int)threadIdx.x, once_ = 1; once_; once_ = 0)
 #define CTC_WARPS for (int warp = (int)(threadIdx.x >> 5), once_w_ = 1; once_w_; once_w_ = 0)
 #define CTC_LANES for (int lane = (int)(threadIdx.x & 31), LX = 0, once_l_ = 1; once_l_; once_l_ = 0)
+#define CTC_HALVES for (int half = 0; half < 2; ++half)
 #define CTC_BARRIER() __syncthreads()
 #define CTC_SYNCWARP() __syncwarp()
 #define CTC_FN __device__ __forceinline__
@@ -129,12 +141,14 @@ enum : int {  // slot block, in units of KP ints
   U_STASH,                // 6 units: node, chr, lpc, ts, dstate, depth of the members evicted in this frame
   U_EFREE = U_STASH + 6,  // 2 units
   U_RVWORK = U_EFREE + 2, // 3 units
-  U_SLOT_UNITS = U_RVWORK + 3
+  U_NODEN = U_RVWORK + 3, // node id / depth of a member committed by the barrier-free back half of a frame, installed
+  U_DEPTHN,               // into U_NODE / U_DEPTH by the slot owner at the start of the next frame (-1 = nothing pending)
+  U_SLOT_UNITS
 };
 CTC_HD int slot_off(int unit, int KP) { return kSmemHead + unit * KP * 4; }
 
 struct SmemLayout {
-  int evcnt, mask, rmask, dmask, rank, tile_lp, tile_idx, clk, cli;  // tail offsets
+  int evcnt, mask, mask2, rmask, dmask, rank, tile_lp, tile_idx, clk, cli;  // tail offsets
   int total;
   int KP, W, WC, NW, seg;
 };
@@ -155,6 +169,7 @@ CTC_HD SmemLayout make_layout(int K, int V, int NP, int tile_frames, bool sorted
   int o = slot_off(U_SLOT_UNITS, KP);
   L.evcnt = o;     o += (KP / 32) * 4;
   L.mask = o;      o += KP * W * 4;    // [KP][W] bitmasks over pruned ranks
+  L.mask2 = o;     o += KP * W * 4;    // (index-order kernels: the masks of frame t+1 are built while frame t commits)
   L.rmask = o;     o += KP * W * 4;
   L.dmask = o;     o += lm ? KP * L.WC * 4 : 0;   // scorer path: [KP][WC] dictionary arc bits
   L.rank = o;      o += sorted ? align_up(V * 2, 16) : 0;
@@ -197,6 +212,7 @@ struct BeamParams {
   int arena_cap;            // offline capacity per utterance
   int fresh;                // 1: start from the root state instead of loading `state`
   int force_fallback;       // test knob: run the grid-walking select path every frame
+  int no_fast;              // test knob: never take the barrier-free back half of a frame
   float heur_bias;          // test knob: added to the checked heuristic bound (> 0 makes it fail its check often)
   const unsigned char *finalize;  // [B] or nullptr (= finalize all)
   int *out_tokens, *out_timesteps;  // [B][K][out_T]
@@ -239,7 +255,10 @@ struct BeamParams {
 // control words: 32 ints in L.ctl
 enum {
   C_M = 0, C_NNODES, C_FLAGS, C_NSEL, C_NFREE, C_NTIE, C_NREV, C_NPAIRS, C_ABOVE, C_BIN, C_CNT, C_KMIN, C_KMAX,
-  C_SMAX, C_NEFREE, C_NETAKEN, C_NRVWORK, C_OVF, C_ANYREF, C_NLIVE, C_SMIN, C_NCAND
+  C_SMAX, C_NEFREE, C_NETAKEN, C_NRVWORK, C_OVF, C_ANYREF, C_NLIVE, C_SMIN, C_NCAND,
+  // second copies, used by frames of odd parity in kernels whose frames have no barrier between reading and
+  // resetting these words (beam_program.cuh, "merged front / barrier-free back half")
+  C_OVF_B, C_ANYREF_B, C_NPAIRS_B
 };
 
 // ---- small helpers --------------------------------------------------------------------------------
@@ -283,6 +302,16 @@ CTC_FN int ctc_popc(unsigned x) { return __popc(x); }
 CTC_FN int ctc_ffs(unsigned x) { return __ffs((int)x); }
 #endif
 CTC_FN unsigned ctc_lt_mask(int lane) { return (1u << lane) - 1u; }
+// position of the q-th (0-based) set bit of x; x has more than q bits set
+CTC_FN int ctc_nth_bit(unsigned x, int q) {
+#if defined(CTC_EMULATE)
+  for (int b = 0; b < 32; ++b)
+    if ((x >> b) & 1u) { if (q == 0) return b; --q; }
+  return 0;
+#else
+  return (int)__fns(x, 0, q + 1);
+#endif
+}
 // warp-wide maximum of one value per lane
 #if defined(CTC_EMULATE)
 static inline unsigned ctc_warp_max(const unsigned (&v)[kLW]) {
@@ -290,8 +319,14 @@ static inline unsigned ctc_warp_max(const unsigned (&v)[kLW]) {
   for (int l = 0; l < 32; ++l) m = v[l] > m ? v[l] : m;
   return m;
 }
+static inline unsigned ctc_warp_min(const unsigned (&v)[kLW]) {
+  unsigned m = 0xFFFFFFFFu;
+  for (int l = 0; l < 32; ++l) m = v[l] < m ? v[l] : m;
+  return m;
+}
 #else
 CTC_FN unsigned ctc_warp_max(const unsigned (&v)[kLW]) { return __reduce_max_sync(0xffffffffu, v[0]); }
+CTC_FN unsigned ctc_warp_min(const unsigned (&v)[kLW]) { return __reduce_min_sync(0xffffffffu, v[0]); }
 #endif
 
 // log_sum_exp<float> (reference decoder_utils.h:47-54) with the 32-entry expf / 16-entry logf tables

@@ -7,7 +7,8 @@ namespace ctc {
 
 #if defined(CTC_EMULATE) && defined(CTC_STATS)
 struct EmuStats { long long frames, passes, walk_iters, anchors_live, evicted, anchors_new, rv_hops, created, revived,
-                  hist_adds, tie_frames, sel_all_frames, rv_frames, rows, rows_skipped, cl_entries, rewalks, fb_frames, ovf_first, heur_fail; };
+                  hist_adds, tie_frames, sel_all_frames, rv_frames, rows, rows_skipped, cl_entries, rewalks, fb_frames, ovf_first, heur_fail,
+                  fast_frames, nf_anchor, nf_notfull, nf_seg, nf_pass, nf_pass_cnt; };
 static EmuStats g_stats;
 #define CTC_STAT(x) (x)
 #else
@@ -248,6 +249,22 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
   constexpr int NW = NT / 32;
   const int KP = KPT > 0 ? KPT : L.KP;
   const int W = L.W, KP2 = 2 * KP, SEG = L.seg;
+  // MERGED (index-order kernels without a scorer): a frame is TWO barrier-separated regions on the common path.
+  //   front: the members' terms (region R1) and the grid walk (region G) run side by side -- on different warps where
+  //          the CTA has more warps than the beam has 32-slot blocks (WB0 = first grid-walking warp, NB of them),
+  //          one after the other inside each warp otherwise.  That needs the "existing child" masks before the frame
+  //          starts: they depend on the beam's links only (rank == character here), so the commit of frame t-1
+  //          builds them (double buffered by frame parity, like the first radix histogram and the words of s_ctl
+  //          that are read right after a barrier and reset in the same region).
+  //   back:  FASTB -- every warp redundantly finds the K-th key and classifies ALL members / list entries into
+  //          ballot words it keeps in registers, so the slot owners commit the new beam without another barrier.
+  //          Frames that need more (dead anchors in the table, beam not full, a second radix pass, ties, list
+  //          overflow) take the general back half below, unchanged.
+  constexpr bool MERGED = !LM && !SORTED;
+  constexpr int KPW = KPT / 32;
+  constexpr bool FASTB = MERGED && KPT > 0 && KPT <= NT && KPW <= 8;
+  constexpr int WB0 = (MERGED && KPT > 0 && KPW < NW) ? KPW : 0;
+  constexpr int NB = NW - WB0;
 
   Cta<SORTED, LM> c;
 #define CTC_SLOT(type, unit) ((type *)(smem + slot_off(unit, KP)))
@@ -275,6 +292,8 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
   c.s_wcnt = (int *)(smem + H_WCNT);       c.s_evcnt = (int *)(smem + L.evcnt);
   c.s_slot2q = CTC_SLOT(int, U_SLOT2Q);    c.s_stash = CTC_SLOT(int, U_STASH);
   int *const pslot_base = CTC_SLOT(int, U_PSLOT), *const anch_base = CTC_SLOT(int, U_ANCH);
+  int *const s_nodeN = CTC_SLOT(int, U_NODEN), *const s_depthN = CTC_SLOT(int, U_DEPTHN);
+  uint32_t *const mask_buf0 = (uint32_t *)(smem + L.mask), *const mask_buf1 = (uint32_t *)(smem + L.mask2);
   int cur = 0;  // which half of the double-buffered link arrays describes the current beam
   int par = 0;  // frame parity: which C_CMIN / C_CMAX pair holds the current beam's score range
   c.s_exptab = (uint64_t *)(smem + H_EXPTAB);
@@ -390,6 +409,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
       if (LM) for (int w = 0; w < L.WC; ++w) c.s_dmask[j * L.WC + w] = p.dict_mask[(long long)dstate * L.WC + w];
       c.s_lmsp[j] = (LM && !fresh && j < st[0]) ? ld_cg(&lm_arena[node]) : 0.0f;
       c.s_evict[j] = 0;
+      s_nodeN[j] = -1;
     }
     for (int a = tid; a < KP2; a += NT) {
       int dnode = 0, dchr = 0, dpslot = -1, dts = 0, ddstate = 0;
@@ -404,7 +424,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
       c.s_drev[a] = 0;
     }
     for (int x = tid; x < 3 * KP; x += NT) c.s_cnt2[x] = 0;
-    for (int x = tid; x < KP * W; x += NT) { c.s_mask[x] = 0u; c.s_rmask[x] = 0u; }
+    for (int x = tid; x < KP * W; x += NT) { mask_buf0[x] = 0u; mask_buf1[x] = 0u; c.s_rmask[x] = 0u; }
     for (int x = tid; x < 2 * kNBins; x += NT) c.s_hist[x] = 0;
     if (SORTED) for (int v = tid; v < V; v += NT) c.s_rank[v] = (int16_t)-1;
     if (tid == 0) {
@@ -460,9 +480,21 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
       smax = o > smax ? o : smax;
     }
     warp_range_store(c.s_wcnt + 128, smin, smax, tid);
+    if (MERGED) {
+      // "existing child" masks of the first frame (afterwards every commit builds those of the next frame): member j
+      // whose parent sits in beam slot i masks grid cell (i, chr[j])  (reference path_trie.cpp:39-57)
+      int np = 0;
+      for (int j = tid; j < M; j += NT) {
+        const int i = c.s_pslot[j], ch = c.s_chr[j];
+        if (i >= 0 && ch >= 0) { atom_or(&mask_buf0[i * W + (ch >> 5)], 1u << (ch & 31)); ++np; }
+      }
+      if (np) atom_add(&s_ctl[C_NPAIRS], np);
+    }
   }
   CTC_BARRIER();
   int nlive = s_ctl[C_NLIVE];
+  int nnodes = s_ctl[C_NNODES];  // MERGED: the node count travels in a register across barrier-free commits;
+  bool nn_stale = false;         // s_ctl[C_NNODES] is brought up to date before a general back half needs it
   CTC_BARRIER();
 
   // "is the parent designation q (a beam slot, possibly tagged kNewFlag) alive after this frame?"
@@ -568,19 +600,46 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
       c.lm_cutoff = (float)d_add((double)f_add(worst, c.lp[NP - 3]), -mx0);
     }
 
+    // ---- frame-parity views (MERGED kernels; parity 0 everywhere else) and what is known before the frame starts
+    const int hpar = MERGED ? par : 0;
+    int *const hist0 = c.s_hist + hpar * kNBins;  // first radix histogram of this frame
+    const int ovf_w = (MERGED && par) ? C_OVF_B : C_OVF, ovf_nx = (MERGED && !par) ? C_OVF_B : C_OVF;
+    const int anyref_w = (MERGED && par) ? C_ANYREF_B : C_ANYREF, anyref_nx = (MERGED && !par) ? C_ANYREF_B : C_ANYREF;
+    const int npairs_w = (MERGED && par) ? C_NPAIRS_B : C_NPAIRS, npairs_nx = (MERGED && !par) ? C_NPAIRS_B : C_NPAIRS;
+    uint32_t *const mask_next = par ? mask_buf0 : mask_buf1;  // MERGED: "existing child" masks of frame t + 1
+    if (MERGED) c.s_mask = par ? mask_buf1 : mask_buf0;
+    (void)ovf_nx; (void)anyref_nx; (void)mask_next;
+    const int n_nb = n - (rblank >= 0 ? 1 : 0);
+    // how many prefixes exist after this frame: the members plus every grid cell that is a new candidate.  With a
+    // scorer the dictionary / cutoff decide that per cell, so the count is taken after the grid walk instead.
+    // (MERGED: the pair count came with the beam; otherwise region R1 counts it, see below)
+    long long total = MERGED ? (long long)M * (n_nb + 1) - s_ctl[npairs_w] : 0;
+    bool select_all = MERGED && total <= (long long)K;  // reference :149 `prefixes.size() >= beam_size`
+    const int G = (n + 31) >> 5;                        // 32-wide column groups of the candidate grid
+
     // ---- region R1: every member's blank / repeat / extension-from-parent terms, merged with
     //      log_sum_exp; dead anchors take their lpc / timestep update.  All in shared memory.
     // (reference ctc_beam_search_decoder.cpp:97-118,138-139; path_trie.cpp:39-57,129-137)
-    CTC_PAR {
+    auto members_region = [&](const int tid) {
       if (tid == 0) {
         s_ctl[C_NREV] = 0;  // (not with the other counters in R5: slow threads may still be reading them there --
         s_ctl[C_NSEL] = 0;  //  C_NSEL is read right after the classification's barrier, the last one before R5)
+        if (MERGED) {
+          s_ctl[npairs_nx] = 0;  // (the commit of this frame counts the pairs of the next one into it)
+          if (nn_stale) s_ctl[C_NNODES] = nnodes;
+        }
       }
+      if (MERGED)  // the other histogram: scanned by the previous frame, first used again by the next one
+        for (int x = tid; x < kNBins; x += NT) c.s_hist[(hpar ^ 1) * kNBins + x] = 0;
       unsigned kmin = 0xFFFFFFFFu, kmax = 0u, smax = 0u;
       int npairs = 0;
       for (int j0 = 0; j0 < M; j0 += NT) {
         const int j = j0 + tid;
         if (j < M) {
+          if (FASTB) {  // a member committed by the barrier-free back half of the previous frame moves in
+            const int pn = s_nodeN[j];
+            if (pn >= 0) { c.s_node[j] = pn; c.s_depth[j] = s_depthN[j]; s_nodeN[j] = -1; }
+          }
           const float sc = c.s_score[j];
           const int ch = c.s_chr[j];
           const float bnew = (rblank >= 0 && !c.lm_cut(c.lp[rblank], sc)) ? f_add(c.lp[rblank], sc) : kNInf;
@@ -599,8 +658,10 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
                 ext = f_add(l, c.s_score[i]);
               }
               if (LM && ch == c.space_id) ext = c.lm_apply(ext, i);
-              atom_or(&c.s_mask[i * W + (rr >> 5)], 1u << (rr & 31));
-              ++npairs;
+              if (!MERGED) {  // (MERGED: the mask bit and the pair count were set when the beam was committed)
+                atom_or(&c.s_mask[i * W + (rr >> 5)], 1u << (rr & 31));
+                ++npairs;
+              }
             }
           }
           const float nb = lse_smem(rep, ext, c.s_exptab, c.s_logtab);
@@ -609,7 +670,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
           const unsigned o = ord_f(sn);
           if (!LM) {
             // first radix pass: the member bins itself (the histograms were cleared by region R5)
-            if (o >= lo32) atom_add(&c.s_hist[(int)((o - lo32) >> shift32)], 1);
+            if (o >= lo32) atom_add(&hist0[(int)((o - lo32) >> shift32)], 1);
           } else {
             kmin = o < kmin ? o : kmin;
             kmax = o > kmax ? o : kmax;
@@ -645,25 +706,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
         }
 #endif
       }
-    }
-    CTC_BARRIER_T(2);
-    CTC_TICK(2);  // R1
-
-    const int n_nb = n - (rblank >= 0 ? 1 : 0);
-    // how many prefixes exist after this frame: the members plus every grid cell that is a new candidate.  With a
-    // scorer the dictionary / cutoff decide that per cell, so the count is taken after the grid walk instead.
-    long long total = (long long)M * (n_nb + 1) - s_ctl[C_NPAIRS];
-    bool select_all = !LM && total <= (long long)K;  // reference :149 `prefixes.size() >= beam_size`
-    const int G = (n + 31) >> 5;                     // 32-wide column groups of the candidate grid
-
-    if (LM) {
-      lo32 = (!select_all && M == K) ? (unsigned)s_ctl[C_KMIN] : 0u;
-      top32 = (unsigned)s_ctl[C_KMAX];
-      const unsigned o = ord_f(f_add(unord_f((unsigned)s_ctl[C_SMAX]), lpmax));
-      top32 = o > top32 ? o : top32;
-      set_shift();
-    }
-
+    };
     // ---- region G: the ONE walk over the beam x pruned-vocab grid.  A warp owns a beam member per
     //      iteration (member values are warp-broadcast), lanes own the characters.  Candidates whose score
     //      key reaches lo32 (the worst member's key once the beam is full) are appended to the warp's
@@ -677,12 +720,10 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
     bool rebin = LM;  // members are binned inside region G (scorer path; or the tightened second walk, SORTED only)
     bool have_scan = false;  // the first histogram has already been scanned (pre_bin / pre_above / pre_cnt)
     int pre_bin = 0, pre_above = 0, pre_cnt = 0;
-    for (int attempt = 0;; ++attempt) {
-    CTC_WARPS {
+    auto grid_walk = [&](const int warp, const bool rebin) {
       int cnt = 0;
       uint32_t *const segk = c.s_clk + warp * SEG;
       int *const segi = c.s_cli + warp * SEG;
-      int *const hist0 = c.s_hist;
       if (rebin && !select_all) {  // (without a scorer the members binned themselves in region R1)
         CTC_LANES {
           for (int j = warp * 32 + lane; j < M; j += NT) {
@@ -725,7 +766,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
       if (rstar >= 0) {
         const int chs = c.chr_at(rstar);
         const float ls = c.lp[rstar];
-        for (int i0 = warp * 32; i0 < M; i0 += NT) {
+        for (int i0 = (warp - WB0) * 32; i0 < M; i0 += NB * 32) {
           CTC_LV(int, pred);
           CTC_LV(uint32_t, kk);
           CTC_LANES {
@@ -755,13 +796,13 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
           CTC_STAT(g_stats.cl_entries += ctc_popc(bal));
         }
       }
-      // rows (members) are tested 32 at a time: lane l looks at row base + warp + NW * l.  A row whose best
+      // rows (members) are tested 32 at a time: lane l of the w-th grid-walking warp looks at row base + w + NB * l.  A row whose best
       // possible candidate (score + max non-blank log-prob) stays under lo32 contributes nothing; on config 2
       // that removes 80 % of the rows.
-      for (int base = 0; base < M; base += 32 * NW) {
+      for (int base = 0; base < M; base += 32 * NB) {
         CTC_LV(int, rowok);
         CTC_LANES {
-          const int i = base + warp + NW * lane;
+          const int i = base + (warp - WB0) + NB * lane;
           rowok[LX] = 0;
           if (i < M) {
             CTC_STAT(g_stats.rows++);
@@ -788,7 +829,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
           rows &= rows - 1u;
           const int rl2 = ctc_ffs(rows) - 1;
           rows &= rows - 1u;
-          const int i1 = base + warp + NW * rl1, i2 = base + warp + NW * rl2;
+          const int i1 = base + (warp - WB0) + NB * rl1, i2 = base + (warp - WB0) + NB * rl2;
           const float sc1 = c.s_score[i1], b1 = c.s_bprev[i1], sc2 = c.s_score[i2], b2 = c.s_bprev[i2];
           const int ch1 = c.s_chr[i1], ch2 = c.s_chr[i2];
           const uint32_t mw1 = c.s_mask[i1 * W], mw2 = c.s_mask[i2 * W];
@@ -843,7 +884,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
           while (rows) {
             const int rl = ctc_ffs(rows) - 1;
             rows &= rows - 1u;
-            const int i = base + warp + NW * rl;
+            const int i = base + (warp - WB0) + NB * rl;
             const float sc_i = c.s_score[i], b_i = c.s_bprev[i];
             const int ch_i = c.s_chr[i];
             const uint32_t mwa = c.s_mask[i * W], mwb = c.s_mask[i * W + 1];
@@ -886,7 +927,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
         while (rows) {
           const int rl = ctc_ffs(rows) - 1;
           rows &= rows - 1u;
-          const int i = base + warp + NW * rl;
+          const int i = base + (warp - WB0) + NB * rl;
           const float sc_i = c.s_score[i], b_i = c.s_bprev[i];
           const int ch_i = c.s_chr[i];
           for (int g = 0; g < G; ++g) {
@@ -936,11 +977,42 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
       }
       CTC_LANES {
         if (lane == 0) {
-          if (cnt > SEG) atom_or(&s_ctl[C_OVF], 1);
+          if (cnt > SEG) atom_or(&s_ctl[ovf_w], 1);
           c.s_wcnt[warp] = cnt < SEG ? cnt : SEG;
         }
       }
+    };
+    if (MERGED) {
+      // ---- the front of the frame: members (R1) and grid walk (G) in ONE region; nothing the one writes is read by
+      //      the other.  (The emulation runs the halves in either order, CTC_EMU_ORDER bit 2.)
+      CTC_HALVES {
+        if (half == 0) {
+          CTC_PAR { members_region(tid); }
+        } else {
+          CTC_WARPS {
+            if (warp >= WB0) grid_walk(warp, false);
+            else { CTC_LANES { if (lane == 0) c.s_wcnt[warp] = 0; } }
+          }
+        }
+      }
+      CTC_BARRIER_T(3);
+      CTC_TICK(2);  // front: R1 | G
+    } else {
+    CTC_PAR { members_region(tid); }
+    CTC_BARRIER_T(2);
+    CTC_TICK(2);  // R1
+    total = (long long)M * (n_nb + 1) - s_ctl[C_NPAIRS];
+    select_all = !LM && total <= (long long)K;
+
+    if (LM) {
+      lo32 = (!select_all && M == K) ? (unsigned)s_ctl[C_KMIN] : 0u;
+      top32 = (unsigned)s_ctl[C_KMAX];
+      const unsigned o = ord_f(f_add(unord_f((unsigned)s_ctl[C_SMAX]), lpmax));
+      top32 = o > top32 ? o : top32;
+      set_shift();
     }
+    for (int attempt = 0;; ++attempt) {
+    CTC_WARPS { grid_walk(warp, rebin); }
     CTC_BARRIER_T(3);
     // (only where the vocabulary is cut per frame: there the blank / a member's character can drop out of a frame
     // and take the lower bound with it; an index-order kernel keeps its single straight-line walk)
@@ -973,9 +1045,216 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
       CTC_STAT(g_stats.rewalks++);
     }
     }
+    }  // !MERGED
     CTC_TICK(3);  // G
-    bool fallback = s_ctl[C_OVF] != 0 || p.force_fallback;  // a segment overflowed (twice): redo on the grid
+    bool fallback = s_ctl[ovf_w] != 0 || p.force_fallback;  // a segment overflowed (twice): redo on the grid
     CTC_STAT(g_stats.fb_frames += fallback);
+
+    // ================= the barrier-free back half (FASTB kernels, common frame) ===========================
+    // Taken when: the beam is full, no dead anchor is in the table, no list overflowed and every list segment fits
+    // one ballot, and ONE radix pass settles the cut (the bin of the K-th key holds selected keys only -- which also
+    // checks the heuristic bound).  Every warp scans the histogram, then classifies ALL members and ALL list
+    // entries itself: evw[] / selw[] end up identical in every warp's registers, so slot owners can rank their slot
+    // among the evicted ones and pick their candidate without any exchange.  What a slot owner reads of OTHER
+    // slots in this region is not written in it: new scores (s_snew), list entries, the old beam's links, and
+    // node id / depth of a parent -- a new member's own node id / depth therefore wait in s_nodeN / s_depthN until
+    // the next frame's region R1.
+    int *const npslot = pslot_base + (cur ^ 1) * KP, *const nanch = anch_base + (cur ^ 1) * KP;
+    int nrev = 0;
+    bool fastb = false;
+    if (FASTB) {
+      fastb = !p.no_fast && !fallback && nlive == 0 && M == K && !select_all;
+      CTC_STAT(g_stats.nf_anchor += (nlive != 0));
+      CTC_STAT(g_stats.nf_notfull += (M != K || select_all));
+      if (fastb) {
+#pragma unroll
+        for (int q = 0; q < NB; ++q) fastb = fastb && c.s_wcnt[WB0 + q] <= 32;
+        CTC_STAT(g_stats.nf_seg += !fastb);
+      }
+      if (fastb) {
+        scan_bin_all(hist0, K, pre_bin, pre_above, pre_cnt);
+        have_scan = true;
+        fastb = (pre_above + pre_cnt == K);
+        CTC_STAT(g_stats.nf_pass += !fastb);
+        CTC_STAT(g_stats.nf_pass_cnt += fastb ? 0 : pre_cnt);
+      }
+    }
+    if (FASTB && fastb) {
+      CTC_STAT(g_stats.passes++);
+      CTC_STAT(g_stats.fast_frames++);
+      const unsigned thr_hi = lo32 + ((unsigned)pre_bin << shift32);  // selected <=> score key >= thr_hi
+      int nsel_f = 0;
+      CTC_WARPS {
+        unsigned evw[KPW > 0 ? KPW : 1];
+#pragma unroll
+        for (int blk = 0; blk < KPW; ++blk) {
+          CTC_LV(int, ev);
+          CTC_LANES {
+            const int j = blk * 32 + lane;
+            ev[LX] = (j < K && ord_f(c.s_snew[j]) < thr_hi) ? 1 : 0;
+          }
+          evw[blk] = ctc_ballot(ev);
+        }
+        // this warp's word of the evicted-slot bitmap, the number of evicted slots below its first slot, and the total
+        // (= the number of selected candidates: the beam is full)
+        unsigned mine = evw[0];
+        int base_w = 0, nsel = 0;
+#pragma unroll
+        for (int bq = 0; bq < KPW; ++bq) {
+          mine = (bq == warp) ? evw[bq] : mine;
+          base_w += (bq < warp) ? ctc_popc(evw[bq]) : 0;
+          nsel += ctc_popc(evw[bq]);
+        }
+        if (warp >= KPW) mine = 0u;
+        const int cnt_w = ctc_popc(mine);
+        // The r-th selected list entry (segments in warp order, entries in list order) moves into the r-th evicted
+        // slot.  Each slot-owning warp copies the entries its own slots take -- ranks [base_w, base_w + cnt_w) -- into
+        // a scratch row of its own, so nothing but a __syncwarp lies between classification and commit.
+        int *const scr = c.s_newinfo + (warp < KPW ? warp : 0) * 64;
+        if (cnt_w > 0) {
+          int acc = 0;
+#pragma unroll
+          for (int q = 0; q < NB; ++q) {
+            const int cn = c.s_wcnt[WB0 + q];
+            CTC_LV(int, sl);
+            CTC_LV(uint32_t, kv);
+            CTC_LANES {
+              kv[LX] = lane < cn ? c.s_clk[(WB0 + q) * SEG + lane] : 0u;
+              sl[LX] = (lane < cn && kv[LX] >= thr_hi) ? 1 : 0;
+            }
+            const unsigned sb = ctc_ballot(sl);
+            CTC_LANES {
+              if (sl[LX]) {
+                const int rk = acc + ctc_popc(sb & ctc_lt_mask(lane)) - base_w;
+                if (rk >= 0 && rk < cnt_w) { scr[2 * rk] = c.s_cli[(WB0 + q) * SEG + lane]; scr[2 * rk + 1] = (int)kv[LX]; }
+              }
+            }
+            acc += ctc_popc(sb);
+          }
+          if (acc != nsel) { CTC_LANES { if (lane == 0) s_ctl[C_FLAGS] |= FLAG_ERR_ARENA; } }  // cannot happen
+          CTC_SYNCWARP();
+        }
+        // is beam slot x evicted in this frame?  (x < KP.  The bitmap is packed into 64-bit scalars and picked by
+        // selects on the bits of x: an indexed evw[x >> 5] would put the array into local memory)
+        const uint64_t w01 = (uint64_t)evw[0] | (KPW > 1 ? (uint64_t)evw[KPW > 1 ? 1 : 0] << 32 : 0ull);
+        const uint64_t w23 = KPW > 2 ? ((uint64_t)evw[KPW > 2 ? 2 : 0] | (KPW > 3 ? (uint64_t)evw[KPW > 3 ? 3 : 0] << 32 : 0ull)) : 0ull;
+        const uint64_t w45 = KPW > 4 ? ((uint64_t)evw[KPW > 4 ? 4 : 0] | (KPW > 5 ? (uint64_t)evw[KPW > 5 ? 5 : 0] << 32 : 0ull)) : 0ull;
+        const uint64_t w67 = KPW > 6 ? ((uint64_t)evw[KPW > 6 ? 6 : 0] | (KPW > 7 ? (uint64_t)evw[KPW > 7 ? 7 : 0] << 32 : 0ull)) : 0ull;
+        auto evbit = [&](int x) -> bool {
+          uint64_t a = (KPW > 2 && (x & 64)) ? w23 : w01;
+          if (KPW > 4) {
+            const uint64_t b = (x & 64) ? w67 : w45;
+            a = (x & 128) ? b : a;
+          }
+          return (a >> (x & 63)) & 1ull;
+        };
+        CTC_LV(unsigned, cmin);
+        CTC_LV(unsigned, cmax);
+        CTC_LV(int, pair);
+        CTC_LANES {
+          cmin[LX] = 0xFFFFFFFFu; cmax[LX] = 0u; pair[LX] = 0;
+          const int j = warp * 32 + lane;
+          if (warp < KPW && j < K) {
+            int newp = -1, res = -1, start = 0, ch_mine;
+            bool resolved = false;
+            const bool ev = (mine >> lane) & 1u;
+            if (!ev) {
+              // the member stays: roll cur -> prev (reference path_trie.cpp:129-137)
+              c.s_bprev[j] = c.s_bnew[j];
+              c.s_nbprev[j] = c.s_nbnew[j];
+              const float sn = c.s_snew[j];
+              c.s_score[j] = sn;
+              cmin[LX] = cmax[LX] = ord_f(sn);
+              ch_mine = c.s_chr[j];
+              const int pq = c.s_pslot[j];
+              if (pq >= 0) {
+                if (!evbit(pq)) { newp = pq; resolved = true; }
+                start = pq;
+              } else {
+                const int a = c.s_anch[j];
+                if (a < 0) { resolved = true; }
+                else {
+                  const int q = c.s_dpslot[a];
+                  if (!evbit(q)) { res = a; resolved = true; }
+                  start = q;
+                }
+              }
+            } else {
+              // evicted: write back lpc / timestep, remember what a dead anchor made of this node would need ...
+              CTC_STAT(g_stats.evicted++);
+              flush_lpc_ts(&nodes[c.s_node[j]], c.s_lpc[j], c.s_ts[j]);
+              c.s_stash[j] = c.s_node[j]; c.s_stash[KP + j] = c.s_chr[j];
+              c.s_stash[2 * KP + j] = (int)f_bits(c.s_lpc[j]); c.s_stash[3 * KP + j] = c.s_ts[j];
+              c.s_stash[4 * KP + j] = 0;
+              // ... and take the q-th selected candidate, q = rank of this slot among the evicted ones
+              // (reference path_trie.cpp:97-105 create); its score is the list key
+              const int qloc = ctc_popc(mine & ctc_lt_mask(lane));  // rank among this warp's evicted slots
+              const int id = scr[2 * qloc];
+              const float sc = unord_f((uint32_t)scr[2 * qloc + 1]);
+              const int par_slot = id >> 16, r = id & 0xFFFF;
+              const int ch = c.chr_at(r);
+              const float lpc = c.lp[r];
+              CTC_STAT(g_stats.created++);
+              // node ids follow the rank of the slot among the evicted slots: no atomic, and the arena is filled the
+              // same way on every run
+              int nid = nnodes + base_w + qloc;
+              if (nid >= arena_cap) {  // cannot happen with capacity 1 + K * frames; never write out of bounds
+                s_ctl[C_FLAGS] |= FLAG_ERR_ARENA;
+                nid = arena_cap - 1;
+              }
+              Node nn; nn.parent = c.s_node[par_slot]; nn.chr = ch; nn.lpc = lpc; nn.ts = t_abs;
+              store_node(&nodes[nid], nn);
+              s_nodeN[j] = nid; s_depthN[j] = c.s_depth[par_slot] + 1;
+              c.s_chr[j] = ch;
+              c.s_bprev[j] = kNInf; c.s_nbprev[j] = sc; c.s_score[j] = sc;  // score = lse(-inf, nb)
+              cmin[LX] = cmax[LX] = ord_f(sc);
+              c.s_lpc[j] = lpc; c.s_ts[j] = t_abs;
+              ch_mine = ch;
+              start = par_slot;
+              if (!evbit(start)) { newp = start; resolved = true; }
+            }
+            if (!resolved) {
+              int cs = start;  // an old slot evicted in this frame
+              while (true) {
+                CTC_STAT(g_stats.walk_iters++);
+                const int pq = c.s_pslot[cs];
+                if (pq >= 0) {
+                  if (!evbit(pq)) { res = KP2 + cs; break; }
+                  cs = pq;
+                  continue;
+                }
+                const int a = c.s_anch[cs];
+                if (a < 0) { res = -1; break; }
+                const int q = c.s_dpslot[a];
+                if (!evbit(q)) { res = a; break; }
+                cs = q;
+              }
+            }
+            if (res >= 0) { atom_add(&c.s_cnt2[res], 1); s_ctl[anyref_w] = 1; }
+            npslot[j] = newp;
+            nanch[j] = res;
+            c.s_evict[j] = ev ? 1 : 0;
+            if (newp >= 0) {  // the "existing child" mask of the next frame (ch_mine >= 0: only the root has none)
+              atom_or(&mask_next[newp * W + (ch_mine >> 5)], 1u << (ch_mine & 31));
+              pair[LX] = 1;
+            }
+          }
+        }
+        // what the next frame needs before its first region: pair count, score range of the new beam
+        const unsigned pb = ctc_ballot(pair), mn = ctc_warp_min(cmin), mx = ctc_warp_max(cmax);
+        CTC_LANES {
+          if (lane == 0 && pb) atom_add(&s_ctl[npairs_nx], ctc_popc(pb));
+          c.s_wcnt[128 + 64 * (par ^ 1) + warp] = (int)mn;        // (every lane stores the same word, see
+          c.s_wcnt[128 + 64 * (par ^ 1) + 32 + warp] = (int)mx;   //  warp_range_store)
+          for (int x = warp * 32 + lane; x < KP * W; x += NT) c.s_mask[x] = 0u;  // this frame's masks: used up
+          if (warp == NW - 1 && lane == 0) { s_ctl[ovf_nx] = 0; s_ctl[anyref_nx] = 0; }
+        }
+        nsel_f = nsel;  // (the same in every warp)
+      }
+      nnodes += nsel_f;
+      nn_stale = true;
+    } else {
+    // ================= the general back half ===============================================================
     if (LM && M < K) {
       // beam not full yet: do fewer than beam_size prefixes exist?  (lo32 == 0, so the lists hold every candidate)
       long long ncand = 0;
@@ -1011,7 +1290,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
       // Pass 0 (score bits only) was histogrammed during region G.
       CTC_STAT(g_stats.passes++);
       int bin = pre_bin, above = pre_above, cnt = pre_cnt;
-      if (!have_scan) scan_bin_all(c.s_hist, K, bin, above, cnt);  // every warp, redundantly: no barrier, no broadcast
+      if (!have_scan) scan_bin_all(hist0, K, bin, above, cnt);  // every warp, redundantly: no barrier, no broadcast
       uint64_t lo = ((uint64_t)(lo32 + ((unsigned)bin << shift32))) << 16;
       if (!SORTED && heuristic && above + cnt < K) {
         // the checked bound cut too deep (index-order kernels: no second walk): grid-walking select from the
@@ -1029,7 +1308,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
         int pass = 1;
         while (true) {
           CTC_STAT(g_stats.passes++);
-          int *const hist = c.s_hist + (pass & 1) * kNBins;
+          int *const hist = c.s_hist + ((hpar + pass) & 1) * kNBins;
           CTC_BARRIER();  // every warp is done scanning the previous histogram
           if (pass >= 2) {
             CTC_PAR { for (int x = tid; x < kNBins; x += NT) hist[x] = 0; }
@@ -1150,6 +1429,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
       }
     }
     const int ntie = s_ctl[C_NTIE];
+    CTC_STAT(g_stats.tie_frames += tie_m > 0);
     CTC_TICK(4);  // select
 
     // ---- region R4a: classify members (keep / evict) and candidates (selected); compact both with
@@ -1164,7 +1444,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
         if (!fused) {
           CTC_LANES { for (int j = warp * 32 + lane; j < K; j += NT) c.s_slot2q[j] = -1; }
         } else {
-          CTC_LANES { if (warp == 0 && lane == 0) { s_ctl[C_NLIVE] = 0; s_ctl[C_ANYREF] = 0; } }  // (R4c's resets)
+          CTC_LANES { if (warp == 0 && lane == 0) { s_ctl[C_NLIVE] = 0; s_ctl[C_ANYREF] = 0; s_ctl[C_ANYREF_B] = 0; } }  // (R4c's resets)
         }
         // members, in blocks of 32 slots
         for (int blk = warp; blk * 32 < M; blk += NW) {
@@ -1349,7 +1629,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
     if (!fused) {
     CTC_PAR {
       if (tid == 0) {
-        s_ctl[C_NLIVE] = 0; s_ctl[C_ANYREF] = 0;
+        s_ctl[C_NLIVE] = 0; s_ctl[C_ANYREF] = 0; s_ctl[C_ANYREF_B] = 0;
         if (LM) newlist[0] = nsel;
       }
       for (int q = tid; q < nsel; q += NT) {
@@ -1400,7 +1680,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
     CTC_BARRIER_T(6);
     }
     CTC_TICK(6);  // R4c
-    const int nrev = fused ? 0 : s_ctl[C_NREV];
+    nrev = fused ? 0 : s_ctl[C_NREV];
 
     if (nrev > 0) {
       // ---- rare slow path: a dead anchor d came back to life.  Members that hung below d need the child
@@ -1466,9 +1746,9 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
     //      parent stays (provisional code 2KP + slot), or nothing (-1).  This replaces the reference's removal
     //      cascade (path_trie.cpp:144-163); the walk only crosses members evicted in this very frame.  Links
     //      are double buffered: walks read the old beam's links while the new ones are written.
-    int *const npslot = pslot_base + (cur ^ 1) * KP, *const nanch = anch_base + (cur ^ 1) * KP;
     CTC_PAR {
       unsigned cmin = 0xFFFFFFFFu, cmax = 0u;  // score range of the new beam (read by the next frame before its R1)
+      int npair_next = 0;
       for (int j = tid; j < K; j += NT) {
         int start = 0, res = -1, newp = -1;
         bool have = false, resolved = false;
@@ -1580,26 +1860,36 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
               cs = q;
             }
           }
-          if (res >= 0) { atom_add(&c.s_cnt2[res], 1); s_ctl[C_ANYREF] = 1; }
+          if (res >= 0) { atom_add(&c.s_cnt2[res], 1); s_ctl[anyref_w] = 1; }
           npslot[j] = newp;
           nanch[j] = res;
+          if (MERGED && newp >= 0) {  // the "existing child" mask of the next frame
+            const int ch_mine = c.s_chr[j];
+            atom_or(&mask_next[newp * W + (ch_mine >> 5)], 1u << (ch_mine & 31));
+            ++npair_next;
+          }
         }
       }
+      if (MERGED && npair_next) atom_add(&s_ctl[npairs_nx], npair_next);
       if (!LM) warp_range_store(c.s_wcnt + 128 + 64 * (par ^ 1), cmin, cmax, tid);
       for (int x = tid; x < KP * W; x += NT) { c.s_mask[x] = 0u; c.s_rmask[x] = 0u; }
       for (int x = tid; x < 2 * kNBins; x += NT) c.s_hist[x] = 0;  // the select is over: clear both radix histograms
       if (SORTED) for (int r = tid; r < n; r += NT) c.s_rank[c.idx[r]] = (int16_t)-1;
       if (tid == 0) {  // (C_NLIVE / C_ANYREF are read below and reset in region R4c of the next frame)
-        s_ctl[C_NFREE] = 0; s_ctl[C_NTIE] = 0; s_ctl[C_NPAIRS] = 0;
+        s_ctl[C_NFREE] = 0; s_ctl[C_NTIE] = 0;
+        if (!MERGED) s_ctl[C_NPAIRS] = 0;  // (MERGED: the pair count of the next frame is being accumulated)
+        else s_ctl[C_OVF_B] = 0;
         s_ctl[C_ABOVE] = 0; s_ctl[C_KMIN] = (int)0xFFFFFFFFu; s_ctl[C_KMAX] = 0; s_ctl[C_SMAX] = 0;
         s_ctl[C_NEFREE] = 0; s_ctl[C_NETAKEN] = 0; s_ctl[C_OVF] = 0; s_ctl[C_SMIN] = (int)0xFFFFFFFFu;
         s_ctl[C_NCAND] = 0;
       }
     }
+    }  // general back half
     CTC_BARRIER_T(8);
     CTC_TICK(8);  // R5
+    if (MERGED && !fastb) { nnodes = s_ctl[C_NNODES]; nn_stale = false; }
     const int M_new = select_all ? (int)total : K;
-    const bool anchors_active = nlive > 0 || nrev > 0 || s_ctl[C_ANYREF] != 0;
+    const bool anchors_active = nlive > 0 || nrev > 0 || s_ctl[anyref_w] != 0;
     int nlive_next = 0;
 
     if (anchors_active) {
@@ -1694,7 +1984,6 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
       CTC_TICK(13);  // LM terms in
     }
     CTC_STAT(g_stats.frames++);
-    CTC_STAT(g_stats.tie_frames += tie_m > 0);
     CTC_STAT(g_stats.sel_all_frames += select_all);
   }
 #undef CTC_PARENT_ALIVE
@@ -1704,6 +1993,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
   CTC_PAR {
     int *s = st_slots;
     for (int j = tid; j < K; j += NT) {
+      if (FASTB && s_nodeN[j] >= 0) { c.s_node[j] = s_nodeN[j]; c.s_depth[j] = s_depthN[j]; s_nodeN[j] = -1; }
       s[j] = c.s_node[j]; s[K + j] = c.s_chr[j]; s[2 * K + j] = c.s_depth[j];
       s[3 * K + j] = (int)f_bits(c.s_bprev[j]); s[4 * K + j] = (int)f_bits(c.s_nbprev[j]);
       s[5 * K + j] = (int)f_bits(c.s_score[j]); s[6 * K + j] = (int)f_bits(c.s_lpc[j]); s[7 * K + j] = c.s_ts[j];
@@ -1717,7 +2007,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
       if (c.s_dpslot[a] >= 0) flush_lpc_ts(&nodes[c.s_dnode[a]], c.s_dlpc[a], c.s_dts[a]);
     }
     if (tid == 0) {
-      st[0] = M; st[1] = s_ctl[C_NNODES]; st[2] = abs_t0 + Tb; st[3] = s_ctl[C_FLAGS];
+      st[0] = M; st[1] = MERGED ? nnodes : s_ctl[C_NNODES]; st[2] = abs_t0 + Tb; st[3] = s_ctl[C_FLAGS];
     }
   }
 #if !defined(CTC_EMULATE)

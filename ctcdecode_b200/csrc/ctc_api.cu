@@ -138,6 +138,7 @@ static int launch_beam(const BeamParams &bp_in, const Plan &pl, int B, cudaStrea
   BeamParams bp = bp_in;
   bp.L = pl.L;
   if (const char *e = getenv("CTCDEC_HEUR_BIAS")) bp.heur_bias = (float)atof(e);  // test knob: make the checked bound fail
+  bp.no_fast = getenv("CTCDEC_NO_FAST") ? 1 : 0;  // test knob: general back half in every frame
   if (const char *e = getenv("CTCDEC_SEG")) bp.L.seg = std::max(1, std::min(bp.L.seg, atoi(e)));  // test knob: small list segments
   const bool generic = getenv("CTCDEC_GENERIC_KP") != nullptr;  // test knob: force the run-time-KP kernel
   if (generic && !bp.timing && !bp.dict_next) {

@@ -167,6 +167,8 @@ int emu_decode_batch(const float *probs, const int *seq_lens, int B, int T, int 
   bp.out_tokens = tokens; bp.out_timesteps = timesteps; bp.out_scores = scores; bp.out_lens = lens;
   bp.n_results = n_results; bp.out_T = T; bp.flags = flags;
   bp.force_fallback = getenv("CTC_EMU_FORCE_FALLBACK") ? 1 : 0;
+  bp.no_fast = getenv("CTC_EMU_NO_FAST") ? 1 : 0;
+  g_emu_order = getenv("CTC_EMU_ORDER") ? atoi(getenv("CTC_EMU_ORDER")) : 0;  // test knob: order of the emulated threads
   if (const char *e = getenv("CTC_EMU_HEUR_BIAS")) bp.heur_bias = (float)atof(e);  // test knob
 
   std::vector<int> chunk_lens(B);
@@ -251,6 +253,8 @@ int emu_decode_batch_lm(const float *probs, const int *seq_lens, int B, int T, i
   bp.out_tokens = tokens; bp.out_timesteps = timesteps; bp.out_scores = scores; bp.out_lens = lens;
   bp.n_results = n_results; bp.out_T = T; bp.flags = flags;
   bp.force_fallback = getenv("CTC_EMU_FORCE_FALLBACK") ? 1 : 0;
+  bp.no_fast = getenv("CTC_EMU_NO_FAST") ? 1 : 0;
+  g_emu_order = getenv("CTC_EMU_ORDER") ? atoi(getenv("CTC_EMU_ORDER")) : 0;  // test knob: order of the emulated threads
   if (const char *e = getenv("CTC_EMU_HEUR_BIAS")) bp.heur_bias = (float)atof(e);  // test knob
   pack_dictionary(sc.dict, sc.space_id);
   bp.dict_next = sc.dict.packed.data(); bp.dict_mask = sc.dict.mask.data(); bp.dict_wc = sc.dict.wc;
