@@ -45,22 +45,23 @@ CONFIGS = {
                name="config3: [2048 x T=1000 x V=29] in total, split over the GPUs, beam 100, cutoff_top_n 40, cutoff_prob 1.0, no LM"),
     "c4": dict(B=256, T=2000, V=256, beam=200, cutoff_top_n=40, cutoff_prob=0.99,
                name="config4: [256 x T=2000 x V=256] per GPU, beam 200, cutoff_top_n 40, cutoff_prob 0.99, no LM"),
-    # BASELINE config 5: KenLM scorer path.  The reference's tests/test.arpa is not on the GPU box, so the model is
-    # tests/data/tiny_lm.arpa (authored for this repo) and the posteriors spell sentences over its vocabulary.
+    # BASELINE config 5: KenLM scorer path with the reference's own test LM (its tests/test.arpa, kept as the fixture
+    # tests/golden/test.arpa); the posteriors noisily spell sentences over that model's vocabulary.
     "c5": dict(B=64, T=1000, V=29, beam=100, cutoff_top_n=40, cutoff_prob=1.0, lm=True, alpha=2.0, beta=1.0,
-               name="config5: [64 x T=1000 x V=29], beam 100, KenLM scorer hook (tests/data/tiny_lm.arpa, alpha 2.0, beta 1.0)"),
+               name="config5: [64 x T=1000 x V=29], beam 100, KenLM scorer hook (tests/test.arpa, alpha 2.0, beta 1.0)"),
 }
 L29 = ["_"] + [chr(ord("a") + i) for i in range(26)] + [" ", "'"]
-TINY_LM = os.path.join(ROOT, "tests", "data", "tiny_lm.arpa")
-PROVIDER = os.path.join(ROOT, "oracle", "_ref", "libctcref.so")
+TINY_LM = os.path.join(ROOT, "tests", "golden", "test.arpa")  # (name kept: tools/ import it) the reference's test LM
+PROVIDER = os.path.join(ROOT, "providers", "_build", "libkenlm_provider.so")
 
 
 def c5_inputs(B, T, seed):
-    """Random sentences over the tiny LM's vocabulary, ~T/5 characters each."""
+    """Random sentences over the vocabulary of the reference's test.arpa, ~T/5 characters each."""
     import random
     from ctcdecode_b200.synth import text_probs
     rng = random.Random(seed)
-    words = ["the", "a", "cat", "dog", "sat", "ran", "on", "mat", "fast"]
+    words = ["a", "also", "beyond", "call", "concerns", "consider", "for", "higher", "however", "i", "in", "is", "little",
+             "loin", "look", "looking", "more", "on", "screening", "small", "the", "to", "watch", "what", "would"]
     texts = []
     for _ in range(B):
         s = ""
@@ -159,6 +160,16 @@ def reference_cpu(probs_np, cfg, n_utts, threads):
     return time.perf_counter() - t0, "port"
 
 
+def reference_outputs(probs_np, cfg, n_utts, threads):
+    """The reference's results for the first n_utts utterances (no-LM configurations).  Returns (outputs, kind)."""
+    from oracle import oracle as orc
+    sample = probs_np[:n_utts]
+    kw = dict(beam=cfg["beam"], cutoff_prob=cfg["cutoff_prob"], cutoff_top_n=cfg["cutoff_top_n"])
+    if orc.reference_available():
+        return orc.Reference([str(i) for i in range(cfg["V"])]).decode(sample, num_processes=threads, **kw), "reference"
+    return orc.CPort().decode(sample, **kw), "port"
+
+
 def bench_lm(args, cfg, config, rank, world, local_rank, dev, K, W, cores):
     """Config 5: the scorer path is a host-buffer API (the LM hook lives on the host), so value == e2e."""
     import torch
@@ -208,6 +219,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-strong", action="store_true", help="skip the fixed-2048 (BASELINE config 3) leg")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     rank = int(os.environ.get("RANK", "0"))
@@ -273,19 +285,113 @@ def main():
     lib = _native.load()
     if cfg.get("lm"):
         return bench_lm(args, cfg, config, rank, world, local_rank, dev, K, W, cores)
-    probs_cpu = ctc_like_probs(B, T, V, seed=rank)  # every rank its own shard of the global batch
-    probs_dev = probs_cpu.to(dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    _native.check(lib.ctcdec_profile_enable(1))
-    ms3 = (ctypes.c_float * 3)()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- value: inputs resident in HBM, the C ABI's device entry point on torch's current stream -----------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()  # (before the warm-up: a 10-step timed region is only ~50 ms, a sample every 100 ms)
+    m = measure(lib, dev, local_rank, cfg, B, rank, K, W, barrier)
+    clocks = sampler.stop() if rank == 0 else None
+    # BASELINE config 3 beside it: a FIXED total of 2048 utterances split over the ranks, so that the
+    # driver's N = 1, 2, 4, 8 runs carry the strong-scaling curve next to the weak one
+    strong = None
+    if args.config == "c2" and not args.no_strong:
+        c3 = CONFIGS["c3"]
+        strong = measure(lib, dev, local_rank, c3, c3["B"] // world, 1000 + rank, min(K, 5), 3, barrier)
+
+    # ---- reduce over ranks (max time) ----------------------------------------------------------------------------
+    vals = [m["total_ms"], m["e2e_ms"], float(m["n_err"]), float(m["n_tie"]), 0.0 if m["same"] else 1.0]
+    if strong:
+        vals += [strong["total_ms"], strong["e2e_ms"], float(strong["n_err"]), 0.0 if strong["same"] else 1.0]
+    t = torch.tensor(vals, device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max, e2e_ms_max = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    kern_ms, total_ms = m["kern_ms"], m["total_ms"]
     Kb = cfg["beam"]
+    value = B * world * K / (total_ms_max / 1e3)
+    e2e_val = B * world * K / (e2e_ms_max / 1e3)
+    peak, peak_src = peaks()
+    beam_ms = statistics.mean(k[1] for k in kern_ms)
+    scan_ms = statistics.mean(k[0] for k in kern_ms)
+    fin_ms = statistics.mean(k[2] for k in kern_ms)
+    alg_bytes = B * T * V * 4
+    achieved = alg_bytes / (beam_ms * 1e-3) / 1e9
+    # the scan reads the [B,T,V] input once and writes the pruned rows (NP floats, + NP uint16 when the
+    # vocabulary is cut): its bytes per launch
+    is_sorted = cfg["cutoff_prob"] < 1.0 or cfg["cutoff_top_n"] < V
+    n_max = min(V, max(1, cfg["cutoff_top_n"])) if is_sorted else V
+    NP = (n_max + 3 + 7) // 8 * 8
+    scan_bytes = alg_bytes + B * T * NP * (6 if is_sorted else 4)
+    beam_traffic, beam_traffic_src = traffic_of(args.config, "beam_kernel") if B == cfg["B"] else (None, None)
+    scan_traffic, _ = traffic_of(args.config, "prune_kernel") if B == cfg["B"] else (None, None)
+    line = {
+        "metric": METRIC, "value": value, "unit": "utterances/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": config,
+        "e2e": {"value": e2e_val, "unit": "utterances/s", "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": m["d2h"],
+                "ms_per_step": e2e_ms_max / K, "host_equals_device": bool(float(t[4]) == 0.0)},
+        "gpu_launches": 3 * K,
+        "kernels_ms": {"prune_log_scan": scan_ms, "beam_search": beam_ms, "finalize": fin_ms,
+                       "beam_share_of_step": beam_ms * K / total_ms},
+        "roofline": {"kernel": "beam_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": beam_traffic, "traffic_source": beam_traffic_src,
+                     "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": alg_bytes,
+                     "ns_per_frame_per_cta": beam_ms * 1e6 / T,
+                     "note": "T-serial per utterance: latency bound, far below the HBM roofline by construction",
+                     "scan": {"kernel": "prune_kernel", "bound": "fp64 issue (exact glibc log per element), then hbm",
+                              "bytes_per_launch": scan_bytes, "traffic": scan_traffic,
+                              "achieved": scan_bytes / (scan_ms * 1e-3) / 1e9,
+                              "unit": "GB/s", "frac": scan_bytes / (scan_ms * 1e-3) / 1e9 / peak}},
+        "clocks": clocks,
+        "parity": {"arena_errors": int(t[2]), "tie_flagged_utterances_max_per_rank": int(t[3])},
+    }
+    if strong:
+        gb = CONFIGS["c3"]["B"] // world * world
+        ks = min(K, 5)
+        line["strong_c3"] = {
+            "workload": CONFIGS["c3"]["name"], "global_batch": gb, "batch_per_gpu": gb // world, "steps": ks,
+            "value": gb * ks / (float(t[5]) / 1e3), "unit": "utterances/s", "ms_per_step": float(t[5]) / ks,
+            "e2e": {"value": gb * ks / (float(t[6]) / 1e3), "unit": "utterances/s", "ms_per_step": float(t[6]) / ks,
+                    "h2d_bytes_per_step": strong["h2d"], "d2h_bytes_per_step": strong["d2h"],
+                    "host_equals_device": bool(float(t[8]) == 0.0)},
+            "arena_errors": int(t[7]),
+            "kernels_ms": {"prune_log_scan": statistics.mean(k[0] for k in strong["kern_ms"]),
+                           "beam_search": statistics.mean(k[1] for k in strong["kern_ms"]),
+                           "finalize": statistics.mean(k[2] for k in strong["kern_ms"])},
+            "note": "fixed total of 2048 utterances split over the ranks (strong scaling); time = max over ranks"}
+    if world == 1 and not args.no_cpu_baseline:
+        line.update(cpu_legs(m, cfg, cores))
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def measure(lib, dev, local_rank, cfg, B, seed, K, W, barrier):
+    """W warm-up + K timed steps of one workload on this rank, device-resident (CUDA events, L2 flushed between steps)
+    and end to end through the host entry point (pinned host buffers, wall clock).  Returns the raw times and the
+    tensors of the last step."""
+    import torch
+    from ctcdecode_b200 import _native
+    from ctcdecode_b200.synth import ctc_like_probs
+    T, V, Kb = cfg["T"], cfg["V"], cfg["beam"]
+    probs_cpu = ctc_like_probs(B, T, V, seed=seed)  # every rank its own shard of the global batch
+    probs_dev = probs_cpu.to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    _native.check(lib.ctcdec_profile_enable(1))
+    ms3 = (ctypes.c_float * 3)()
+
+    # ---- value: inputs resident in HBM, the C ABI's device entry point on torch's current stream -----------------
     ccfg = _native.Config(V, Kb, 0, 0, cfg["cutoff_top_n"], float(cfg["cutoff_prob"]))
     ws_bytes = ctypes.c_size_t(0)
     _native.check(lib.ctcdec_workspace_bytes(ctypes.byref(ccfg), B, T, ctypes.byref(ws_bytes)))
@@ -303,9 +409,6 @@ def main():
             ctypes.byref(ccfg), probs_dev.data_ptr(), None, B, T, d_tok.data_ptr(), d_ts.data_ptr(), d_sc.data_ptr(),
             d_len.data_ptr(), d_nres.data_ptr(), d_flags.data_ptr(), ws.data_ptr(), ws.numel(), stream))
 
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()  # (before the warm-up: a 10-step timed region is only ~50 ms, a sample every 100 ms)
     for _ in range(W):
         device_step()
     torch.cuda.synchronize()
@@ -322,11 +425,9 @@ def main():
         _native.check(lib.ctcdec_profile_read(ms3))
         kern_ms.append(list(ms3))
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
     total_ms = sum(step_ms)
     n_err = int((d_flags & 256).sum())
     n_tie = int(((d_flags & 7) != 0).sum())
-    out = (d_tok, d_sc, d_ts, d_len)
 
     # ---- e2e: host buffers through the C-ABI host entry point -------------------------------------------------
     h_probs = probs_cpu.pin_memory()
@@ -355,72 +456,43 @@ def main():
     h2d = B * T * V * 4
     d2h = 2 * B * Kb * max_len * 4 + 2 * B * Kb * 4 + 2 * B * 4
     # sanity: host path and device path agree
-    same = bool(torch.equal(h_sc, out[1].cpu()) and torch.equal(h_len, out[3].cpu()))
+    same = bool(torch.equal(h_sc, d_sc.cpu()) and torch.equal(h_len, d_len.cpu()))
+    return dict(total_ms=total_ms, e2e_ms=e2e_s * 1e3, kern_ms=kern_ms, n_err=n_err, n_tie=n_tie, same=same, h2d=h2d,
+                d2h=d2h, probs_cpu=probs_cpu,
+                host=dict(tokens=h_tok.numpy(), timesteps=h_ts.numpy(), scores=h_sc.numpy(), lens=h_len.numpy(),
+                          n_results=h_nres.numpy(), ties=h_flags.numpy()))
 
-    # ---- reduce over ranks (max time) ----------------------------------------------------------------------------
-    t = torch.tensor([total_ms, e2e_s * 1e3, float(n_err), float(n_tie), 0.0 if same else 1.0], device=dev,
-                     dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms_max, e2e_ms_max = float(t[0]), float(t[1])
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
 
-    value = B * world * K / (total_ms_max / 1e3)
-    e2e_val = B * world * K / (e2e_ms_max / 1e3)
-    peak, peak_src = peaks()
-    beam_ms = statistics.mean(k[1] for k in kern_ms)
-    scan_ms = statistics.mean(k[0] for k in kern_ms)
-    fin_ms = statistics.mean(k[2] for k in kern_ms)
-    alg_bytes = B * T * V * 4
-    achieved = alg_bytes / (beam_ms * 1e-3) / 1e9
-    # the scan reads the [B,T,V] input once and writes the pruned rows (NP floats, + NP uint16 when the
-    # vocabulary is cut): its bytes per launch
-    is_sorted = cfg["cutoff_prob"] < 1.0 or cfg["cutoff_top_n"] < V
-    n_max = min(V, max(1, cfg["cutoff_top_n"])) if is_sorted else V
-    NP = (n_max + 3 + 7) // 8 * 8
-    scan_bytes = alg_bytes + B * T * NP * (6 if is_sorted else 4)
-    beam_traffic, beam_traffic_src = traffic_of(args.config, "beam_kernel") if B == cfg["B"] else (None, None)
-    scan_traffic, _ = traffic_of(args.config, "prune_kernel") if B == cfg["B"] else (None, None)
-    line = {
-        "metric": METRIC, "value": value, "unit": "utterances/s", "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": config,
-        "e2e": {"value": e2e_val, "unit": "utterances/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_ms_max / K, "host_equals_device": same},
-        "gpu_launches": 3 * K,
-        "kernels_ms": {"prune_log_scan": scan_ms, "beam_search": beam_ms, "finalize": fin_ms,
-                       "beam_share_of_step": beam_ms * K / total_ms},
-        "roofline": {"kernel": "beam_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": beam_traffic, "traffic_source": beam_traffic_src,
-                     "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": alg_bytes,
-                     "ns_per_frame_per_cta": beam_ms * 1e6 / T,
-                     "note": "T-serial per utterance: latency bound, far below the HBM roofline by construction",
-                     "scan": {"kernel": "prune_kernel", "bound": "fp64 issue (exact glibc log per element), then hbm",
-                              "bytes_per_launch": scan_bytes, "traffic": scan_traffic,
-                              "achieved": scan_bytes / (scan_ms * 1e-3) / 1e9,
-                              "unit": "GB/s", "frac": scan_bytes / (scan_ms * 1e-3) / 1e9 / peak}},
-        "clocks": clocks,
-        "parity": {"arena_errors": int(t[2]), "tie_flagged_utterances_max_per_rank": int(t[3])},
-    }
-    if world == 1 and not args.no_cpu_baseline:
-        # bounded sample: one utterance per host thread, repeated until ~10 s of CPU work
-        n = max(1, min(B, cores))
-        dt, kind = reference_cpu(probs_cpu.numpy(), cfg, n, cores)
-        reps, spent = 1, dt
-        while spent < 10.0 and reps < 8:
-            d2, _ = reference_cpu(probs_cpu.numpy(), cfg, n, cores)
-            spent += d2
-            reps += 1
-        line["cpu_baseline"] = {"value": n * reps / spent, "unit": "utterances/s", "cores": cores if kind == "reference" else 1,
-                                "kind": kind,
-                                "sample": "%d x the first %d utterances of the same batch (one per host thread)" % (reps, n)}
-    print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+def cpu_legs(m, cfg, cores):
+    """cpu_baseline (the reference's CPU path on a bounded sample of the same batch, all host threads; plus one thread
+    and a mid-size pool, so that the CPU's best is on record) and the parity block: the reference outputs of that
+    sample against what the CUDA path returned for the same utterances (host entry point), through tests/parity."""
+    from tests import parity
+    probs = m["probs_cpu"].numpy()
+    B = probs.shape[0]
+    n = max(1, min(B, max(cores, 128)))  # at least 128 utterances go through the comparison
+    t0 = time.perf_counter()
+    ref, kind = reference_outputs(probs, cfg, n, cores)
+    spent, reps = time.perf_counter() - t0, 1
+    while spent < 10.0 and reps < 8:
+        d2, _ = reference_cpu(probs, cfg, n, cores)
+        spent += d2
+        reps += 1
+    out = {"cpu_baseline": {"value": n * reps / spent, "unit": "utterances/s", "cores": cores if kind == "reference" else 1,
+                            "kind": kind, "threads": cores if kind == "reference" else 1,
+                            "sample": "%d x the first %d utterances of the same batch, ThreadPool of %d" % (reps, n, cores)}}
+    if kind == "reference":
+        alt = []
+        for th, nu in ((1, 2), (max(2, min(32, cores // 4)), max(2, min(32, cores // 4)))):
+            d, _ = reference_cpu(probs, cfg, nu, th)
+            alt.append({"threads": th, "utterances": nu, "value": nu / d})
+        out["cpu_baseline"]["other_pool_sizes"] = alt
+        best = max([out["cpu_baseline"]["value"]] + [a["value"] for a in alt])
+        out["cpu_baseline"]["best_pool_value"] = best
+    cnt = parity.count(ref, m["host"], None, n)
+    cnt["against"] = "oracle/_ref (unmodified reference build)" if kind == "reference" else "oracle C port"
+    cnt["utterances"] = n
+    return {"cpu_baseline": out["cpu_baseline"], "parity_vs_reference": cnt}
 
 
 if __name__ == "__main__":

@@ -141,11 +141,23 @@ CTC_FN void scan_bin_all(const int *hist, int need, int &bin, int &above, int &c
   const int4 ha = *reinterpret_cast<const int4 *>(hist + 8 * lane), hb = *reinterpret_cast<const int4 *>(hist + 8 * lane + 4);
   const int h[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
   const int tot = ((h[0] + h[1]) + (h[2] + h[3])) + ((h[4] + h[5]) + (h[6] + h[7]));
-  int sfx = tot;  // becomes the sum over lanes >= this lane
+  // sfx = the sum of tot over lanes >= this lane.  The lane totals are small (a beam plus a few candidates over 256
+  // bins), so the suffix sums are assembled from eight INDEPENDENT ballots, one per bit of tot, instead of a chain of
+  // five dependent shuffles; a lane total above 255 (degenerate key distributions) takes the shuffle scan.
+  int sfx;
+  if (__ballot_sync(0xffffffffu, tot > 255) == 0u) {
+    const unsigned ge = 0xFFFFFFFFu << lane;
+    sfx = 0;
 #pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const int v = __shfl_down_sync(0xffffffffu, sfx, d);
-    if (lane + d < 32) sfx += v;
+    for (int pbit = 0; pbit < 8; ++pbit)
+      sfx += __popc(__ballot_sync(0xffffffffu, (tot >> pbit) & 1) & ge) << pbit;
+  } else {
+    sfx = tot;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int v = __shfl_down_sync(0xffffffffu, sfx, d);
+      if (lane + d < 32) sfx += v;
+    }
   }
   const unsigned ball = __ballot_sync(0xffffffffu, sfx >= need);  // lanes <= target
   const int target = ball ? 31 - __clz((int)ball) : 0;
@@ -265,6 +277,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
   constexpr bool FASTB = MERGED && KPT > 0 && KPT <= NT && KPW <= 8;
   constexpr int WB0 = (MERGED && KPT > 0 && KPW < NW) ? KPW : 0;
   constexpr int NB = NW - WB0;
+  constexpr int CH = NB <= 2 ? 2 : 1;  // 32-entry chunks of a list segment the barrier-free back half looks at
 
   Cta<SORTED, LM> c;
 #define CTC_SLOT(type, unit) ((type *)(smem + slot_off(unit, KP)))
@@ -353,6 +366,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
           }
         }
       }
+      if (wait_for > 0) __threadfence_system();  // acquire: the payload loads below stay behind the flag load
       const int v = blk[lane];  // read (again) after the flag: the host writes the pairs first, the flag last
       int cnt = __shfl_sync(0xffffffffu, v, 1);
       if (cnt > K) cnt = K;
@@ -493,6 +507,8 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
   }
   CTC_BARRIER();
   int nlive = s_ctl[C_NLIVE];
+  const bool head_offload = WB0 > 0 && !(p.no_fast & 2);  // (test knob bit 1: every warp computes the head itself)
+  bool head_ready = false;       // FASTB: the head block of the coming frame has been written (see the fast back half)
   int nnodes = s_ctl[C_NNODES];  // MERGED: the node count travels in a register across barrier-free commits;
   bool nn_stale = false;         // s_ctl[C_NNODES] is brought up to date before a general back half needs it
   CTC_BARRIER();
@@ -556,29 +572,45 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
 #endif
       shift32 = bits > 8 ? bits - 8 : 0;
     };
-    if (!LM) {
-      unsigned cmin_o, cmax_o;
-      warp_range_load<NW>(c.s_wcnt + 128 + 64 * par, cmin_o, cmax_o);
+    // the range of a frame from its row and the score range [cmin_o, cmax_o] (monotone keys) of the beam it starts from
+    auto head_of = [&](const float *row, unsigned cmin_o, unsigned cmax_o, bool full, unsigned &lo, unsigned &top,
+                       unsigned &lov, bool &heur) {
+      const uint32_t meta_r = f_bits(row[NP - 2]);
+      const int rblank_r = (int)(meta_r >> 16) - 1;
+      const float lpmax_r = row[NP - 1];
       const float cmin = unord_f(cmin_o), cmax = unord_f(cmax_o);
-      float lpm = lpmax;
-      if (rblank >= 0) {
-        const float lpb = c.lp[rblank];
-        if (M == K) lo32 = ord_f(f_add(lpb, cmin));
+      float lpm = lpmax_r;
+      lo = 0u; heur = false;
+      if (rblank_r >= 0) {
+        const float lpb = row[rblank_r];
+        if (full) lo = ord_f(f_add(lpb, cmin));
         lpm = lpb > lpm ? lpb : lpm;
       }
-      top32 = ord_f(f_add(f_add(cmax, lpm), 1.5f));
-      lo_valid = lo32;
-      if (M == K && !p.force_fallback) {
+      top = ord_f(f_add(f_add(cmax, lpm), 1.5f));
+      lov = lo;
+      if (full && !p.force_fallback) {
         // A second, usually much tighter bound (where the vocabulary is cut per frame the blank is often not among
         // the kept characters and the bound above is void): every row's best candidate scores at least
         // (lowest beam score) + (largest non-blank log-prob of the row), so normally K keys reach that value.
         // Masked cells and the repeated-character rule can break the count, therefore this bound is CHECKED after
         // the grid walk (histogram total >= K); if it fails, kernels for a cut vocabulary walk the grid again with
         // the proven bound, index-order kernels (where that is a 3-in-1000-frames event) take the grid-walking select.
-        const unsigned lo_h = ord_f(f_add(f_add(cmin, lpmax), p.heur_bias));
-        if (lo_h > lo32 && lo_h <= top32) { lo32 = lo_h; heuristic = true; }
+        const unsigned lo_h = ord_f(f_add(f_add(cmin, lpmax_r), p.heur_bias));
+        if (lo_h > lo && lo_h <= top) { lo = lo_h; heur = true; }
       }
-      if (top32 < lo32) top32 = lo32;
+      if (top < lo) top = lo;
+    };
+    if (!LM) {
+      if (FASTB && head_ready) {
+        // left behind by a grid-walking warp of the previous frame while the slot owners committed the beam
+        const int *hb = c.s_wcnt + 64 + 8 * par;
+        lo32 = (unsigned)hb[0]; top32 = (unsigned)hb[1]; lo_valid = (unsigned)hb[2]; heuristic = hb[3] != 0;
+      } else {
+        unsigned cmin_o, cmax_o;
+        warp_range_load<NW>(c.s_wcnt + 128 + 64 * par, cmin_o, cmax_o);
+        head_of(c.lp, cmin_o, cmax_o, M == K, lo32, top32, lo_valid, heuristic);
+      }
+      head_ready = false;
       set_shift();
     }
     if (LM) {
@@ -664,8 +696,10 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
               }
             }
           }
+          CTC_TICK(12);  // members: loads and terms
           const float nb = lse_smem(rep, ext, c.s_exptab, c.s_logtab);
           const float sn = lse_smem(bnew, nb, c.s_exptab, c.s_logtab);
+          CTC_TICK(13);  // members: two log_sum_exp
           c.s_bnew[j] = bnew; c.s_nbnew[j] = nb; c.s_snew[j] = sn;
           const unsigned o = ord_f(sn);
           if (!LM) {
@@ -982,6 +1016,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
         }
       }
     };
+    CTC_TICK(1);  // head (SORTED kernels: + rank table)
     if (MERGED) {
       // ---- the front of the frame: members (R1) and grid walk (G) in ONE region; nothing the one writes is read by
       //      the other.  (The emulation runs the halves in either order, CTC_EMU_ORDER bit 2.)
@@ -1063,12 +1098,12 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
     int nrev = 0;
     bool fastb = false;
     if (FASTB) {
-      fastb = !p.no_fast && !fallback && nlive == 0 && M == K && !select_all;
+      fastb = !(p.no_fast & 1) && !fallback && nlive == 0 && M == K && !select_all;
       CTC_STAT(g_stats.nf_anchor += (nlive != 0));
       CTC_STAT(g_stats.nf_notfull += (M != K || select_all));
       if (fastb) {
 #pragma unroll
-        for (int q = 0; q < NB; ++q) fastb = fastb && c.s_wcnt[WB0 + q] <= 32;
+        for (int q = 0; q < NB; ++q) fastb = fastb && c.s_wcnt[WB0 + q] <= 32 * CH;
         CTC_STAT(g_stats.nf_seg += !fastb);
       }
       if (fastb) {
@@ -1083,6 +1118,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
       CTC_STAT(g_stats.passes++);
       CTC_STAT(g_stats.fast_frames++);
       const unsigned thr_hi = lo32 + ((unsigned)pre_bin << shift32);  // selected <=> score key >= thr_hi
+      CTC_TICK(14);  // fast back half: checks + histogram scan
       int nsel_f = 0;
       CTC_WARPS {
         unsigned evw[KPW > 0 ? KPW : 1];
@@ -1116,24 +1152,79 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
 #pragma unroll
           for (int q = 0; q < NB; ++q) {
             const int cn = c.s_wcnt[WB0 + q];
-            CTC_LV(int, sl);
-            CTC_LV(uint32_t, kv);
-            CTC_LANES {
-              kv[LX] = lane < cn ? c.s_clk[(WB0 + q) * SEG + lane] : 0u;
-              sl[LX] = (lane < cn && kv[LX] >= thr_hi) ? 1 : 0;
-            }
-            const unsigned sb = ctc_ballot(sl);
-            CTC_LANES {
-              if (sl[LX]) {
-                const int rk = acc + ctc_popc(sb & ctc_lt_mask(lane)) - base_w;
-                if (rk >= 0 && rk < cnt_w) { scr[2 * rk] = c.s_cli[(WB0 + q) * SEG + lane]; scr[2 * rk + 1] = (int)kv[LX]; }
+#pragma unroll
+            for (int h = 0; h < CH; ++h) {
+              if (h > 0 && cn <= 32 * h) break;  // (warp-uniform)
+              CTC_LV(int, sl);
+              CTC_LV(uint32_t, kv);
+              CTC_LANES {
+                const int e = 32 * h + lane;
+                kv[LX] = e < cn ? c.s_clk[(WB0 + q) * SEG + e] : 0u;
+                sl[LX] = (e < cn && kv[LX] >= thr_hi) ? 1 : 0;
               }
+              const unsigned sb = ctc_ballot(sl);
+              CTC_LANES {
+                if (sl[LX]) {
+                  const int rk = acc + ctc_popc(sb & ctc_lt_mask(lane)) - base_w;
+                  if (rk >= 0 && rk < cnt_w) {
+                    scr[2 * rk] = c.s_cli[(WB0 + q) * SEG + 32 * h + lane];
+                    scr[2 * rk + 1] = (int)kv[LX];
+                  }
+                }
+              }
+              acc += ctc_popc(sb);
             }
-            acc += ctc_popc(sb);
           }
           if (acc != nsel) { CTC_LANES { if (lane == 0) s_ctl[C_FLAGS] |= FLAG_ERR_ARENA; } }  // cannot happen
           CTC_SYNCWARP();
         }
+        if (head_offload && warp == WB0 && t + 1 < Tb) {
+          // ---- this warp owns no slots: while the owners commit, it works out the NEXT frame's key range.  The
+          //      new beam's score range follows from what was just classified (kept members' new scores, selected
+          //      candidates' keys), the next row is already staged (at a tile boundary the tile was requested a
+          //      whole tile ago) -- so the head of frame t + 1 costs the slot owners nothing.
+          CTC_LV(unsigned, kmn);
+          CTC_LV(unsigned, kmx);
+          CTC_LANES {
+            kmn[LX] = 0xFFFFFFFFu; kmx[LX] = 0u;
+#pragma unroll
+            for (int blk = 0; blk < KPW; ++blk) {
+              const int j = blk * 32 + lane;
+              if (j < K) {
+                const unsigned k = ord_f(c.s_snew[j]);
+                if (k >= thr_hi) { kmn[LX] = k < kmn[LX] ? k : kmn[LX]; kmx[LX] = k > kmx[LX] ? k : kmx[LX]; }
+              }
+            }
+#pragma unroll
+            for (int q = 0; q < NB; ++q) {
+#pragma unroll
+              for (int h = 0; h < CH; ++h) {
+                if (32 * h + lane < c.s_wcnt[WB0 + q]) {
+                  const unsigned k = c.s_clk[(WB0 + q) * SEG + 32 * h + lane];
+                  if (k >= thr_hi) { kmn[LX] = k < kmn[LX] ? k : kmn[LX]; kmx[LX] = k > kmx[LX] ? k : kmx[LX]; }
+                }
+              }
+            }
+          }
+          const unsigned nmin = ctc_warp_min(kmn), nmax = ctc_warp_max(kmx);
+#if defined(CTC_EMULATE)
+          const float *nrow = p.lp + ((size_t)b * p.T + t0 + t + 1) * NP;
+#else
+          int ft2 = ft, tile2 = tile;
+          if (ft2 == F) { ft2 = 0; ++tile2; mbar_wait(&mbar[tile2 & 1], (uint32_t)((tile2 >> 1) & 1)); }
+          const float *nrow = tile_lp + ((size_t)(tile2 & 1) * F + ft2) * NP;
+#endif
+          unsigned hlo, htop, hlov;
+          bool hheur;
+          head_of(nrow, nmin, nmax, true, hlo, htop, hlov, hheur);
+          CTC_LANES {
+            if (lane == 0) {
+              int *hb = c.s_wcnt + 64 + 8 * (par ^ 1);
+              hb[0] = (int)hlo; hb[1] = (int)htop; hb[2] = (int)hlov; hb[3] = hheur ? 1 : 0;
+            }
+          }
+        }
+        CTC_TICK(6);  // fast back half: evicted / selected ballots, scratch rows
         // is beam slot x evicted in this frame?  (x < KP.  The bitmap is packed into 64-bit scalars and picked by
         // selects on the bits of x: an indexed evw[x >> 5] would put the array into local memory)
         const uint64_t w01 = (uint64_t)evw[0] | (KPW > 1 ? (uint64_t)evw[KPW > 1 ? 1 : 0] << 32 : 0ull);
@@ -1240,12 +1331,18 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
             }
           }
         }
+        CTC_TICK(7);  // fast back half: slot owners commit
         // what the next frame needs before its first region: pair count, score range of the new beam
-        const unsigned pb = ctc_ballot(pair), mn = ctc_warp_min(cmin), mx = ctc_warp_max(cmax);
+        const unsigned pb = ctc_ballot(pair);
+        if (!(head_offload && t + 1 < Tb)) {  // (otherwise a grid-walking warp has the next frame's range from the ballots)
+          const unsigned mn = ctc_warp_min(cmin), mx = ctc_warp_max(cmax);
+          CTC_LANES {
+            c.s_wcnt[128 + 64 * (par ^ 1) + warp] = (int)mn;        // (every lane stores the same word, see
+            c.s_wcnt[128 + 64 * (par ^ 1) + 32 + warp] = (int)mx;   //  warp_range_store)
+          }
+        }
         CTC_LANES {
           if (lane == 0 && pb) atom_add(&s_ctl[npairs_nx], ctc_popc(pb));
-          c.s_wcnt[128 + 64 * (par ^ 1) + warp] = (int)mn;        // (every lane stores the same word, see
-          c.s_wcnt[128 + 64 * (par ^ 1) + 32 + warp] = (int)mx;   //  warp_range_store)
           for (int x = warp * 32 + lane; x < KP * W; x += NT) c.s_mask[x] = 0u;  // this frame's masks: used up
           if (warp == NW - 1 && lane == 0) { s_ctl[ovf_nx] = 0; s_ctl[anyref_nx] = 0; }
         }
@@ -1253,6 +1350,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
       }
       nnodes += nsel_f;
       nn_stale = true;
+      head_ready = head_offload && t + 1 < Tb;
     } else {
     // ================= the general back half ===============================================================
     if (LM && M < K) {

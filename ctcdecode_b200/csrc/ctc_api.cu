@@ -77,6 +77,16 @@ static int fail(int code, const char *fmt, ...) {
 // utterances the calling thread is about to have in flight together (host entry point: all its groups)
 static thread_local int g_batch_in_flight = 0;
 
+// the kernels raise CTCDEC_FLAG_ERR_ARENA for an utterance whose node arena / anchor table ran out or whose scorer
+// handshake was abandoned: its results are not valid, so the host entry points fail instead of returning them
+static int check_error_flags(const int *flags, int B) {
+  for (int b = 0; b < B; ++b)
+    if (flags[b] & FLAG_ERR_ARENA)
+      return fail(CTCDEC_E_INTERNAL, "utterance %d: the beam kernel reported an internal error (node arena / anchor table "
+                  "exhausted or scorer handshake abandoned); results are not valid", b);
+  return CTCDEC_OK;
+}
+
 static int make_plan(const ctcdec_config *cfg, int B, int T, Plan *pl) {
   char msg[256];
   int nt = 0;
@@ -91,12 +101,16 @@ static int launch_beam_k(const BeamParams &bp, int B, cudaStream_t s) {
   // raise the dynamic shared-memory limit once per device and size: cudaFuncSetAttribute on a kernel that is
   // running waits for it, which would serialise the utterance groups the host entry point pipelines
   static std::atomic<int> limit[64];
+  static std::mutex limit_mu;
   int dev = 0;
   CU(cudaGetDevice(&dev));
   const int smem_bytes = bp.L.total + (TIMING ? 4096 : 0);  // TIMING: [16][32] per-warp counters behind the layout
   if (smem_bytes > limit[dev & 63].load(std::memory_order_acquire)) {
-    CU(cudaFuncSetAttribute(beam_kernel<NT, SORTED, LM, KPT, TIMING>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    limit[dev & 63].store(smem_bytes, std::memory_order_release);
+    std::lock_guard<std::mutex> lk(limit_mu);  // (check again under the lock: two host threads, same device)
+    if (smem_bytes > limit[dev & 63].load(std::memory_order_acquire)) {
+      CU(cudaFuncSetAttribute(beam_kernel<NT, SORTED, LM, KPT, TIMING>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+      limit[dev & 63].store(smem_bytes, std::memory_order_release);
+    }
   }
   beam_kernel<NT, SORTED, LM, KPT, TIMING><<<B, NT, bp.L.total + (TIMING ? 4096 : 0), s>>>(bp);
   CU(cudaGetLastError());
@@ -138,7 +152,7 @@ static int launch_beam(const BeamParams &bp_in, const Plan &pl, int B, cudaStrea
   BeamParams bp = bp_in;
   bp.L = pl.L;
   if (const char *e = getenv("CTCDEC_HEUR_BIAS")) bp.heur_bias = (float)atof(e);  // test knob: make the checked bound fail
-  bp.no_fast = getenv("CTCDEC_NO_FAST") ? 1 : 0;  // test knob: general back half in every frame
+  if (const char *e = getenv("CTCDEC_NO_FAST")) bp.no_fast = atoi(e);  // test knob: 1 = general back half in every frame, 2 = no head offload
   if (const char *e = getenv("CTCDEC_SEG")) bp.L.seg = std::max(1, std::min(bp.L.seg, atoi(e)));  // test knob: small list segments
   const bool generic = getenv("CTCDEC_GENERIC_KP") != nullptr;  // test knob: force the run-time-KP kernel
   if (generic && !bp.timing && !bp.dict_next) {
@@ -150,6 +164,8 @@ static int launch_beam(const BeamParams &bp_in, const Plan &pl, int B, cudaStrea
   }
   switch (pl.NT) {
     case 128: return pl.sorted ? launch_beam_ns<128, true>(bp, B, s) : launch_beam_ns<128, false>(bp, B, s);
+    case 160: return pl.sorted ? launch_beam_ns<160, true>(bp, B, s) : launch_beam_ns<160, false>(bp, B, s);
+    case 192: return pl.sorted ? launch_beam_ns<192, true>(bp, B, s) : launch_beam_ns<192, false>(bp, B, s);
     case 256: return pl.sorted ? launch_beam_ns<256, true>(bp, B, s) : launch_beam_ns<256, false>(bp, B, s);
     case 1024: return pl.sorted ? launch_beam_ns<1024, true>(bp, B, s) : launch_beam_ns<1024, false>(bp, B, s);
     default: return pl.sorted ? launch_beam_ns<512, true>(bp, B, s) : launch_beam_ns<512, false>(bp, B, s);
@@ -167,11 +183,15 @@ template <bool SORTED, int KPL, bool LOGITS>
 static int launch_prune_k(const PruneParams &pp, int grid, int threads, size_t smem, cudaStream_t s) {
   if (smem > 48 * 1024) {
     static std::atomic<int> limit[64];
+    static std::mutex limit_mu;
     int dev = 0;
     CU(cudaGetDevice(&dev));
     if ((int)smem > limit[dev & 63].load(std::memory_order_acquire)) {
-      CU(cudaFuncSetAttribute(prune_kernel<SORTED, KPL, LOGITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      limit[dev & 63].store((int)smem, std::memory_order_release);
+      std::lock_guard<std::mutex> lk(limit_mu);
+      if ((int)smem > limit[dev & 63].load(std::memory_order_acquire)) {
+        CU(cudaFuncSetAttribute(prune_kernel<SORTED, KPL, LOGITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        limit[dev & 63].store((int)smem, std::memory_order_release);
+      }
     }
   }
   prune_kernel<SORTED, KPL, LOGITS><<<grid, threads, smem, s>>>(pp);
@@ -188,7 +208,11 @@ static int launch_prune(const ctcdec_config *cfg, const Plan &pl, const PruneInp
   pp.in_kind = in.kind; pp.lsm_out = logits ? in.lsm_out : nullptr;
   pp.seq_lens = seq_lens; pp.B = B; pp.T = T; pp.V = cfg->vocab_size; pp.NP = pl.NP;
   pp.blank = cfg->blank_id; pp.log_input = logits ? 1 : cfg->log_input; pp.top_n = cfg->cutoff_top_n;
-  pp.cp_active = pl.cp_active; pp.cutoff_prob = cfg->cutoff_prob; pp.P = pl.P; pp.lp = lp; pp.idx = idx;
+  pp.cp_active = pl.cp_active; pp.cutoff_prob = cfg->cutoff_prob; pp.P = pl.P;
+  {
+    const double cp = cfg->cutoff_prob, band = 1e-9 * (1.0 + std::fabs(cp));
+    pp.cp_s_fire = std::expm1(cp); pp.cp_s_lo = std::expm1(cp - band); pp.cp_s_hi = std::expm1(cp + band);
+  } pp.lp = lp; pp.idx = idx;
   pp.flags = flags;
   pp.want_blank_prob = in.blank_prob ? 1 : 0;
   const int V = cfg->vocab_size;
@@ -253,7 +277,7 @@ struct DevCache {
   size_t pcap[6] = {};
 };
 static DevCache g_cache[64];
-static std::mutex g_mu;
+static std::mutex g_mu[64];  // one per device: threads driving different GPUs from one process do not serialise
 
 static int ensure(DevCache &c, int slot, size_t bytes) {
   if (bytes <= c.cap[slot]) return CTCDEC_OK;
@@ -525,7 +549,7 @@ int ctcdec_decode_batch_host(const ctcdec_config *cfg, const float *probs, const
   if (cudaSetDevice(device) != cudaSuccess) return fail(CTCDEC_E_NO_DEVICE, "cudaSetDevice(%d) failed (this library has no CPU fallback)", device);
   if ((rc = check_device())) return rc;
   if (B == 0) return CTCDEC_OK;
-  std::lock_guard<std::mutex> lock(g_mu);
+  std::lock_guard<std::mutex> lock(g_mu[device]);
   DevCache &c = g_cache[device];
   const int V = cfg->vocab_size, K = cfg->beam_size;
   // The batch is cut into up to kHostChunks groups of utterances, each with its own stream: upload, kernels and
@@ -597,12 +621,17 @@ int ctcdec_decode_batch_host(const ctcdec_config *cfg, const float *probs, const
       CU(cudaMemcpy2DAsync(timesteps + oo, (size_t)T * 4, d_ts + oo, (size_t)T * 4, (size_t)max_len * 4, (size_t)nb * K, cudaMemcpyDeviceToHost, s));
     }
   }
-  memcpy(scores, h_scores, n_bk * 4);
-  memcpy(lens, h_lens, n_bk * 4);
+  // rows p >= n_results[b] stay as the caller left them (the finalize kernel does not write them, and the
+  // device buffers are reused between calls; reference: binding.cpp:79-99 writes results.size() rows)
+  for (int b = 0; b < B; ++b) {
+    const size_t nr = (size_t)std::max(0, std::min(h_nres[b], K));
+    memcpy(scores + (size_t)b * K, h_scores + (size_t)b * K, nr * 4);
+    memcpy(lens + (size_t)b * K, h_lens + (size_t)b * K, nr * 4);
+  }
   for (int i = 0; i < C; ++i) CU(cudaStreamSynchronize(c.cs[i]));
   if (n_results) memcpy(n_results, h_nres, (size_t)B * 4);
   if (flags) memcpy(flags, h_flags, (size_t)B * 4);
-  return CTCDEC_OK;
+  return check_error_flags(h_flags, B);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -720,7 +749,7 @@ int ctcdec_decode_stream_host(const float *probs, const int32_t *seq_lens, int B
   const int device = s0->device;
   if (cudaSetDevice(device) != cudaSuccess) return fail(CTCDEC_E_NO_DEVICE, "cudaSetDevice(%d) failed", device);
   if ((rc = check_device())) return rc;
-  std::lock_guard<std::mutex> lock(g_mu);
+  std::lock_guard<std::mutex> lock(g_mu[device]);
   DevCache &c = g_cache[device];
   if (!c.stream) CU(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
   cudaStream_t s = c.stream;
@@ -891,6 +920,7 @@ int ctcdec_decode_stream_host(const float *probs, const int32_t *seq_lens, int B
     }
     if (n_results) memcpy(n_results, h_nres.get(), (size_t)B * 4);
     if (flags) memcpy(flags, h_nres.get() + B, (size_t)B * 4);
+    if ((rc = check_error_flags(h_nres.get() + B, B))) return rc;
   } else {
     CU(cudaStreamSynchronize(s));
     if (n_results) memset(n_results, 0, (size_t)B * 4);
@@ -941,8 +971,8 @@ int ctcdec_scorer_dict_size(const void *scorer) { return scorer ? static_cast<co
 int ctcdec_scorer_reset_params(void *scorer, double alpha, double beta) {
   if (!scorer) return fail(CTCDEC_E_INVALID, "scorer is NULL");
   HostScorer *sc = static_cast<HostScorer *>(scorer);
-  sc->alpha = alpha;  // reference Scorer::reset_params takes floats (scorer.cpp:122-125)
-  sc->beta = beta;
+  sc->alpha = (double)(float)alpha;  // reference Scorer::reset_params(float, float) (scorer.cpp:122-125): both values
+  sc->beta = (double)(float)beta;    // pass through float32 (the constructor takes doubles)
   return CTCDEC_OK;
 }
 
@@ -959,7 +989,7 @@ int ctcdec_decode_batch_lm_host(const ctcdec_config *cfg, void *scorer, const fl
   if (cudaSetDevice(device) != cudaSuccess) return fail(CTCDEC_E_NO_DEVICE, "cudaSetDevice(%d) failed (this library has no CPU fallback)", device);
   if ((rc = check_device())) return rc;
   if (B == 0) return CTCDEC_OK;
-  std::lock_guard<std::mutex> lock(g_mu);
+  std::lock_guard<std::mutex> lock(g_mu[device]);
   DevCache &c = g_cache[device];
   if (!c.stream) CU(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
   cudaStream_t s = c.stream;
@@ -1079,11 +1109,18 @@ int ctcdec_decode_batch_lm_host(const ctcdec_config *cfg, void *scorer, const fl
   }
   if ((rc = launch_finalize(bp, B, s))) return rc;
   std::unique_ptr<int[]> h_nres(new int[(size_t)B * 2]);
-  CU(cudaMemcpyAsync(scores, d_scores, n_bk * 4, cudaMemcpyDeviceToHost, s));
-  CU(cudaMemcpyAsync(lens, d_lens, n_bk * 4, cudaMemcpyDeviceToHost, s));
+  std::unique_ptr<float[]> h_scores(new float[n_bk]);
+  std::unique_ptr<int[]> h_lens(new int[n_bk]);
+  CU(cudaMemcpyAsync(h_scores.get(), d_scores, n_bk * 4, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(h_lens.get(), d_lens, n_bk * 4, cudaMemcpyDeviceToHost, s));
   CU(cudaMemcpyAsync(h_nres.get(), d_nres, (size_t)B * 8, cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
   int max_len = 0;
+  for (int b = 0; b < B; ++b) {  // rows p >= n_results[b] stay as the caller left them
+    const size_t nr = (size_t)std::max(0, std::min(h_nres[b], K));
+    memcpy(scores + (size_t)b * K, h_scores.get() + (size_t)b * K, nr * 4);
+    memcpy(lens + (size_t)b * K, h_lens.get() + (size_t)b * K, nr * 4);
+  }
   for (int b = 0; b < B; ++b)
     for (int p = 0; p < h_nres[b] && p < K; ++p) max_len = std::max(max_len, lens[(size_t)b * K + p]);
   if (max_len > T) max_len = T;
@@ -1095,7 +1132,7 @@ int ctcdec_decode_batch_lm_host(const ctcdec_config *cfg, void *scorer, const fl
   lm_rescore_batch(*sc, B, K, T, h_nres.get(), tokens, lens, scores);  // reported scores: approx_ctc (reference :194-208)
   if (n_results) memcpy(n_results, h_nres.get(), (size_t)B * 4);
   if (flags) memcpy(flags, h_nres.get() + B, (size_t)B * 4);
-  return CTCDEC_OK;
+  return check_error_flags(h_nres.get() + B, B);
 }
 
 int ctcdec_selftest_math(int which, const float *x, const float *x2, float *y, size_t n, int device) {

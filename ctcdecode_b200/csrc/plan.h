@@ -48,7 +48,7 @@ static inline int make_plan_core(const ctcdec_config *cfg, int B, int T, Plan *p
   else if (pl->cp_active) pl->n_max = std::min(V, std::max(1, cfg->cutoff_top_n));
   else pl->n_max = std::min(V, cfg->cutoff_top_n);
   pl->NP = align_up(pl->n_max + kRowTrailer, 8);
-  int P = 1;
+  int P = 64;  // (at least 64 sort words per warp: the partial top-n selection sorts up to 64 survivors)
   while (P < V) P <<= 1;
   pl->P = P;
   pl->F = std::max(1, std::min(32, 4096 / (pl->NP * 4)));
@@ -66,7 +66,7 @@ static inline int make_plan_core(const ctcdec_config *cfg, int B, int T, Plan *p
     const SmemLayout t = make_layout(K, V, pl->NP, pl->F, pl->sorted, 128, false, 74);
     if (t.total <= 74 * 1024 && t.seg * 8 * 4 >= 8 * 1024) budget_kb = 74;
   }
-  if (nt_override == 128 || nt_override == 256 || nt_override == 512 || nt_override == 1024) pl->NT = nt_override;
+  if (nt_override == 128 || nt_override == 160 || nt_override == 192 || nt_override == 256 || nt_override == 512 || nt_override == 1024) pl->NT = nt_override;
   pl->budget_kb = budget_kb;
   pl->L = make_layout(K, V, pl->NP, pl->F, pl->sorted, pl->NT, false, budget_kb);
   if (pl->L.total > 227 * 1024)

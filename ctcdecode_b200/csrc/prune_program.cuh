@@ -42,6 +42,7 @@ struct PruneParams {
   int top_n;            // cutoff_top_n
   int cp_active;        // log(cutoff_prob) < 0
   double cutoff_prob;
+  double cp_s_fire, cp_s_lo, cp_s_hi;  // expm1(cutoff_prob), expm1(cutoff_prob -+ 1e-9 (1 + |cutoff_prob|))
   int P;                // next power of two >= V (sorted mode)
   float *lp;            // [B][T][NP]
   uint16_t *idx;        // [B][T][NP] (sorted mode)
@@ -98,10 +99,13 @@ __device__ __forceinline__ void lsm_row(const void *logits, int kind, long long 
 }
 
 // Top-`lim` of a frame without sorting all of it (lim <= 64, V <= 32 * KPL): every lane keeps KPL ordered
-// float keys in registers; a 32-step bitwise search (compare + hardware warp add per step) finds the lim-th
-// largest key; elements above it, then the needed number of equal ones in index order, are ballot-compacted into
-// shared memory as 64-bit (key, ~index) words and only those <= 64 words are bitonic-sorted.  Same order as the
-// full sort: probability descending, index ascending.  Returns whether an unselected element ties with the last
+// float keys in registers; a bitwise search from the top bit (compare + hardware warp add per step) raises a threshold
+// while at least lim keys reach it and STOPS as soon as at most 64 do -- typically after the exponent and two or three
+// mantissa bits, 11 to 13 steps instead of 32.  Those <= 64 survivors are ballot-compacted into shared memory as
+// 64-bit (key, ~index) words, sorted in registers (two per lane, bitonic network over shuffles) and written back:
+// the first lim of them are the answer, in the order of the full sort (probability descending, index ascending).
+// Only if more than 64 keys share the lim-th value does the search run all 32 steps; then the keys above it and the
+// needed number of equal ones, in index order, are taken.  Returns whether an unselected element ties with the last
 // selected probability (the reference's std::sort leaves that order unspecified).
 template <int KPL>
 __device__ __forceinline__ bool top_select(const float *row, int V, int lim, uint64_t *keys, int lane) {
@@ -112,51 +116,90 @@ __device__ __forceinline__ bool top_select(const float *row, int V, int lim, uin
     kr[q] = e < V ? ord_f(row[e]) : 0u;
   }
   uint32_t thr = 0u;
+  int cnt_thr = 32 * KPL;  // keys >= thr
 #pragma unroll 1
-  for (int bit = 31; bit >= 0; --bit) {
+  for (int bit = 31; bit >= 0 && cnt_thr > 64; --bit) {
     const uint32_t cand = thr | (1u << bit);
     int cnt = 0;
 #pragma unroll
     for (int q = 0; q < KPL; ++q) cnt += (kr[q] >= cand) ? 1 : 0;
     cnt = __reduce_add_sync(0xffffffffu, cnt);
-    if (cnt >= lim) thr = cand;
+    if (cnt >= lim) { thr = cand; cnt_thr = cnt; }
   }
-  int base = 0;
+  bool more_equal = false;
+  int nsurv;
+  if (cnt_thr <= 64) {
+    // everything >= thr survives (thr > 0 here, so the zero keys of lanes beyond V stay out)
+    int base = 0;
 #pragma unroll
-  for (int q = 0; q < KPL; ++q) {
-    const bool pr = kr[q] > thr;
-    const unsigned bal = __ballot_sync(0xffffffffu, pr);
-    if (pr) keys[base + __popc(bal & ((1u << lane) - 1u))] = ((uint64_t)kr[q] << 32) | (uint64_t)(0xFFFFFFFFu - (unsigned)(q * 32 + lane));
-    base += __popc(bal);
-  }
-  const int need = lim - base;
-  int taken = 0;
+    for (int q = 0; q < KPL; ++q) {
+      const bool pr = kr[q] >= thr;
+      const unsigned bal = __ballot_sync(0xffffffffu, pr);
+      if (pr) keys[base + __popc(bal & ((1u << lane) - 1u))] = ((uint64_t)kr[q] << 32) | (uint64_t)(0xFFFFFFFFu - (unsigned)(q * 32 + lane));
+      base += __popc(bal);
+    }
+    nsurv = base;
+  } else {
+    // more than 64 keys reach the lim-th value: thr IS that value (the search ran to the last bit)
+    int base = 0;
 #pragma unroll
-  for (int q = 0; q < KPL; ++q) {
-    const bool pr = (kr[q] == thr) && (q * 32 + lane < V);
-    const unsigned bal = __ballot_sync(0xffffffffu, pr);
-    const int rk = taken + __popc(bal & ((1u << lane) - 1u));
-    if (pr && rk < need) keys[base + rk] = ((uint64_t)kr[q] << 32) | (uint64_t)(0xFFFFFFFFu - (unsigned)(q * 32 + lane));
-    taken += __popc(bal);
+    for (int q = 0; q < KPL; ++q) {
+      const bool pr = kr[q] > thr;
+      const unsigned bal = __ballot_sync(0xffffffffu, pr);
+      if (pr) keys[base + __popc(bal & ((1u << lane) - 1u))] = ((uint64_t)kr[q] << 32) | (uint64_t)(0xFFFFFFFFu - (unsigned)(q * 32 + lane));
+      base += __popc(bal);
+    }
+    const int need = lim - base;
+    int taken = 0;
+#pragma unroll
+    for (int q = 0; q < KPL; ++q) {
+      const bool pr = (kr[q] == thr) && (q * 32 + lane < V);
+      const unsigned bal = __ballot_sync(0xffffffffu, pr);
+      const int rk = taken + __popc(bal & ((1u << lane) - 1u));
+      if (pr && rk < need) keys[base + rk] = ((uint64_t)kr[q] << 32) | (uint64_t)(0xFFFFFFFFu - (unsigned)(q * 32 + lane));
+      taken += __popc(bal);
+    }
+    more_equal = taken > need;
+    nsurv = lim;
   }
-  int pn = 1;
-  while (pn < lim) pn <<= 1;
-  for (int i = lim + lane; i < pn; i += 32) keys[i] = 0ull;
+  for (int i = nsurv + lane; i < 64; i += 32) keys[i] = 0ull;
   __syncwarp();
-  for (int k = 2; k <= pn; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = lane; i < pn; i += 32) {
-        const int l = i ^ j;
-        if (l > i) {
-          const uint64_t a = keys[i], bb = keys[l];
-          const bool desc_block = (i & k) == 0;
-          if (desc_block ? (a < bb) : (a > bb)) { keys[i] = bb; keys[l] = a; }
+  // ---- sort the <= 64 words, descending: element i = lane + 32 h lives in register a[h]
+  uint64_t a0 = keys[lane], a1 = keys[lane + 32];
+  if (nsurv > 32) {
+#pragma unroll
+    for (int k = 2; k <= 64; k <<= 1) {
+#pragma unroll
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        if (j == 32) {  // (k == 64) partner of element lane is element lane + 32: inside the lane, descending block
+          const uint64_t hi = a0 > a1 ? a0 : a1, lo = a0 > a1 ? a1 : a0;
+          a0 = hi; a1 = lo;
+        } else {
+          const uint64_t o0 = __shfl_xor_sync(0xffffffffu, a0, j), o1 = __shfl_xor_sync(0xffffffffu, a1, j);
+          const bool lower = (lane & j) == 0;
+          const bool desc0 = (lane & k) == 0, desc1 = ((lane + 32) & k) == 0;  // descending block?
+          const bool max0 = lower == desc0, max1 = lower == desc1;
+          a0 = max0 ? (a0 > o0 ? a0 : o0) : (a0 < o0 ? a0 : o0);
+          a1 = max1 ? (a1 > o1 ? a1 : o1) : (a1 < o1 ? a1 : o1);
         }
       }
-      __syncwarp();
     }
+    keys[lane] = a0; keys[lane + 32] = a1;
+  } else {
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        const uint64_t o0 = __shfl_xor_sync(0xffffffffu, a0, j);
+        const bool max0 = ((lane & j) == 0) == ((lane & k) == 0);
+        a0 = max0 ? (a0 > o0 ? a0 : o0) : (a0 < o0 ? a0 : o0);
+      }
+    }
+    keys[lane] = a0;
   }
-  return taken > need;
+  __syncwarp();
+  if (cnt_thr <= 64) more_equal = nsurv > lim && (keys[lim - 1] >> 32) == (keys[lim] >> 32);
+  return more_equal;
 }
 
 // KPL: keys per lane of the partial top-n selection (0 = always sort the whole vocabulary)
@@ -320,10 +363,11 @@ __global__ void __launch_bounds__(256) prune_kernel(const PruneParams p) {
           if (lane >= d) s += o;
         }
         s += carry;
-        const double approx = log1p(s);
+        // log(1 + s) >= cutoff_prob  <=>  s >= expm1(cutoff_prob): the thresholds (and those of the +-1e-9 band that
+        // hands the frame to the serial replay below) come from the host in double, so no log1p per element here
         const bool in = i < lim;
-        const bool fire = in && approx >= p.cutoff_prob;
-        const bool unc = in && fabs(approx - p.cutoff_prob) <= 1e-9 * (1.0 + fabs(p.cutoff_prob));
+        const bool fire = in && s >= p.cp_s_fire;
+        const bool unc = in && s >= p.cp_s_lo && s <= p.cp_s_hi;
         const unsigned fb = __ballot_sync(0xffffffffu, fire);
         const unsigned ub = __ballot_sync(0xffffffffu, unc);
         if (fb) {

@@ -13,12 +13,17 @@ small stub of INTEGRATION.md section 6 -- that owns the real ``Scorer`` (KenLM) 
     double ref_scorer_sent_from_labels(void *, const int *labels, int n)   # get_sent_log_prob(split_labels(prefix))
     size_t ref_lm_vocabulary(const char *lm_path, char *buf, size_t cap)   # '\\n'-separated LM vocabulary
 
-Pass its path as ``scorer_provider=`` or in the environment variable CTCDECODE_B200_SCORER_PROVIDER.
+providers/ in this repository holds exactly that stub (kenlm_provider.cpp) and the recipe (Makefile) that builds it
+from the reference's sources where they lie: providers/_build/libkenlm_provider.so, used when present.  Another
+provider is chosen with ``scorer_provider=`` or the environment variable CTCDECODE_B200_SCORER_PROVIDER.
 """
 import ctypes
 import os
 
 from . import _native
+
+DEFAULT_PROVIDER = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "providers", "_build",
+                                "libkenlm_provider.so")
 
 
 class ProviderScorer(object):
@@ -26,6 +31,8 @@ class ProviderScorer(object):
 
     def __init__(self, labels, model_path, alpha, beta, provider=None):
         provider = provider or os.environ.get("CTCDECODE_B200_SCORER_PROVIDER")
+        if not provider and os.path.exists(DEFAULT_PROVIDER):
+            provider = DEFAULT_PROVIDER  # providers/Makefile: the reference's Scorer + KenLM behind the C-ABI stub
         if not provider:
             raise RuntimeError(
                 "ctcdecode_b200: model_path needs a scorer provider library (scorer_provider=... or "

@@ -45,6 +45,7 @@ extern "C" {
 #define CTCDEC_E_CUDA (-3)      /* a CUDA runtime call failed                                         */
 #define CTCDEC_E_WORKSPACE (-4) /* workspace too small                                                */
 #define CTCDEC_E_NO_DEVICE (-5) /* no CUDA device / wrong architecture: there is NO CPU fallback      */
+#define CTCDEC_E_INTERNAL (-6)  /* a kernel raised CTCDEC_FLAG_ERR_ARENA: results are not valid (host entry points) */
 
 #define CTCDEC_FLAG_TIE_PRUNE 1
 #define CTCDEC_FLAG_TIE_FINAL 2

@@ -11,7 +11,7 @@
  * the file is compiled with -ffp-contract=off like the reference's plain -O3 x86-64 build
  * (setup.py:57), so float32 scores are bit-identical to the reference on the same machine.
  *
- * Parity pinning: tests/test_oracle_vs_reference.py compares this file against oracle/_ref
+ * Parity pinning: tests/test_oracle.py compares this file against oracle/_ref
  * (the unmodified reference sources compiled by oracle/Makefile) bit-for-bit, and
  * tests/golden/ holds outputs of that reference build for the reference's own fixtures
  * (tests/test_decode.py:13-32) and for seeded synthetic inputs.
@@ -232,6 +232,9 @@ typedef struct {
   Node root;
   NodeVec prefixes;
   int tie_flags;
+  /* what kind of ties straddled the beam cut (tools/tie_report.py): frames where the tied prefixes are -FLT_MAX
+   * "junk"  / carry a finite score, and the first such frame */
+  int tie_junk_frames, tie_finite_frames, tie_first_frame;
   /* scratch */
   ProbIdx *work;
   int *pr_idx;
@@ -313,7 +316,12 @@ void ctc_oracle_state_next(void *h, const float *probs, int num_time_steps) {
       merge_sort_nodes(s->prefixes.v, s->tmp, s->prefixes.n);
       if (s->prefixes.n > s->beam_size) {
         Node *a = s->prefixes.v[s->beam_size - 1], *b = s->prefixes.v[s->beam_size];
-        if (!prefix_compare(a, b) && !prefix_compare(b, a)) s->tie_flags |= TIE_PRUNE;
+        if (!prefix_compare(a, b) && !prefix_compare(b, a)) {
+          if (!(s->tie_flags & TIE_PRUNE)) s->tie_first_frame = s->abs_time_step;
+          s->tie_flags |= TIE_PRUNE;
+          if (a->score <= -NUM_FLT_INF) s->tie_junk_frames++;
+          else s->tie_finite_frames++;
+        }
       }
       for (int i = s->beam_size; i < s->prefixes.n; ++i) node_remove(s->prefixes.v[i]);
       s->prefixes.n = s->beam_size;
@@ -351,6 +359,14 @@ int ctc_oracle_state_decode(void *h, int row_stride, int *out_tokens, int *out_t
   free(copy);
   free(tmp);
   return n;
+}
+
+/* out[0..2] = frames with a -FLT_MAX tie at the beam cut, frames with a finite-score tie, first tie frame (or -1) */
+void ctc_oracle_state_tie_stats(void *h, int *out) {
+  OracleState *s = (OracleState *)h;
+  out[0] = s->tie_junk_frames;
+  out[1] = s->tie_finite_frames;
+  out[2] = (s->tie_flags & TIE_PRUNE) ? s->tie_first_frame : -1;
 }
 
 /* ctc_beam_search_decoder_batch, serial  (ctc_beam_search_decoder.cpp:213-227, 245-285) with the

@@ -167,7 +167,7 @@ int emu_decode_batch(const float *probs, const int *seq_lens, int B, int T, int 
   bp.out_tokens = tokens; bp.out_timesteps = timesteps; bp.out_scores = scores; bp.out_lens = lens;
   bp.n_results = n_results; bp.out_T = T; bp.flags = flags;
   bp.force_fallback = getenv("CTC_EMU_FORCE_FALLBACK") ? 1 : 0;
-  bp.no_fast = getenv("CTC_EMU_NO_FAST") ? 1 : 0;
+  bp.no_fast = getenv("CTC_EMU_NO_FAST") ? atoi(getenv("CTC_EMU_NO_FAST")) : 0;
   g_emu_order = getenv("CTC_EMU_ORDER") ? atoi(getenv("CTC_EMU_ORDER")) : 0;  // test knob: order of the emulated threads
   if (const char *e = getenv("CTC_EMU_HEUR_BIAS")) bp.heur_bias = (float)atof(e);  // test knob
 
@@ -192,6 +192,8 @@ int emu_decode_batch(const float *probs, const int *seq_lens, int B, int T, int 
       case 32: run_beam<32>(bp, pl.sorted, B, smem.data()); break;
       case 64: run_beam<64>(bp, pl.sorted, B, smem.data()); break;
       case 128: run_beam<128>(bp, pl.sorted, B, smem.data()); break;
+      case 160: run_beam<160>(bp, pl.sorted, B, smem.data()); break;
+      case 192: run_beam<192>(bp, pl.sorted, B, smem.data()); break;
       case 256: run_beam<256>(bp, pl.sorted, B, smem.data()); break;
       case 1024: run_beam<1024>(bp, pl.sorted, B, smem.data()); break;
       default: run_beam<512>(bp, pl.sorted, B, smem.data()); break;
@@ -253,7 +255,7 @@ int emu_decode_batch_lm(const float *probs, const int *seq_lens, int B, int T, i
   bp.out_tokens = tokens; bp.out_timesteps = timesteps; bp.out_scores = scores; bp.out_lens = lens;
   bp.n_results = n_results; bp.out_T = T; bp.flags = flags;
   bp.force_fallback = getenv("CTC_EMU_FORCE_FALLBACK") ? 1 : 0;
-  bp.no_fast = getenv("CTC_EMU_NO_FAST") ? 1 : 0;
+  bp.no_fast = getenv("CTC_EMU_NO_FAST") ? atoi(getenv("CTC_EMU_NO_FAST")) : 0;
   g_emu_order = getenv("CTC_EMU_ORDER") ? atoi(getenv("CTC_EMU_ORDER")) : 0;  // test knob: order of the emulated threads
   if (const char *e = getenv("CTC_EMU_HEUR_BIAS")) bp.heur_bias = (float)atof(e);  // test knob
   pack_dictionary(sc.dict, sc.space_id);

@@ -73,3 +73,28 @@ def compare(ref, got, ref_ties=None, name=""):
             assert np.array_equal(ref["timesteps"][b, p, :L], got["timesteps"][b, p, :L]), \
                 f"{name} utt {b} beam {p}: timesteps differ\n{ref['timesteps'][b, p, :L]}\n{got['timesteps'][b, p, :L]}"
     return checked, skipped
+
+
+def count(ref, got, ties=None, n=None):
+    """Like compare(), but counts instead of asserting: over the first n utterances returns dict(checked, mismatches,
+    skipped, tie_prune, tie_vocab, tie_final).  `ties`: flags of either side (the CUDA path's own flags will do: it
+    flags exactly the utterances the oracle flags, which the tests assert)."""
+    B = ref["lens"].shape[0] if n is None else n
+    out = dict(checked=0, mismatches=0, skipped=0, tie_prune=0, tie_vocab=0, tie_final=0)
+    for b in range(B):
+        tie = int(ties[b]) & 7 if ties is not None else 0
+        if "ties" in got:
+            tie |= int(got["ties"][b]) & 7
+        out["tie_prune"] += 1 if tie & 1 else 0
+        out["tie_vocab"] += 1 if tie & 4 else 0
+        out["tie_final"] += 1 if tie & 2 else 0
+        one_ref = {k: v[b:b + 1] for k, v in ref.items() if hasattr(v, "shape") and v.shape[:1] == ref["lens"].shape[:1]}
+        one_got = {k: v[b:b + 1] for k, v in got.items() if hasattr(v, "shape") and v.shape[:1] == got["lens"].shape[:1]}
+        try:
+            c, s = compare(one_ref, one_got, [tie], "utt %d" % b)
+            out["checked"] += c
+            out["skipped"] += s
+        except AssertionError:
+            out["checked"] += 1
+            out["mismatches"] += 1
+    return out

@@ -77,7 +77,9 @@ def test_product_never_imports_the_oracle():
 
 def test_lm_path_needs_a_provider(monkeypatch):
     import ctcdecode_b200
+    from ctcdecode_b200 import scorer
     monkeypatch.delenv("CTCDECODE_B200_SCORER_PROVIDER", raising=False)
+    monkeypatch.setattr(scorer, "DEFAULT_PROVIDER", "/nonexistent/libkenlm_provider.so")  # (the in-tree build, if any)
     with pytest.raises(RuntimeError, match="scorer provider"):
         ctcdecode_b200.CTCBeamDecoder(list("_abc "), model_path="/nonexistent.arpa")
     with pytest.raises(RuntimeError, match="scorer provider"):

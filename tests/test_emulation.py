@@ -66,10 +66,11 @@ def test_emulation_matches_oracle(cport, cfg):
     _check(cport, probs, **cfg)
 
 
-@pytest.mark.parametrize("nt", [32, 64, 128, 256, 512, 1024])
+@pytest.mark.parametrize("nt", [32, 64, 128, 160, 192, 256, 512, 1024])
 def test_emulation_any_block_size(cport, nt):
     probs = ctc_like_probs(2, 80, 29, seed=20).numpy()
     _check(cport, probs, nt=nt, beam=40)
+    _check(cport, ctc_like_probs(1, 300, 29, seed=24).numpy(), nt=nt, beam=100)
 
 
 def test_emulation_ragged_and_empty(cport):

@@ -157,6 +157,10 @@ def test_full_size_config2_properties(cport):
     out, scores, ts, lens = dec.decode(d)
     flags, nres = dec.last_flags.clone(), dec.last_n_results.clone()
     assert int((flags & 256).sum()) == 0 and bool((nres == K).all())
+    # parity skips utterances with a comparator-equal pair at the beam cut (reference: unspecified); on this batch that
+    # is 7 of 256, each with one such frame, and 6 of the 7 still equal the reference build (tools/tie_report.py,
+    # DESIGN.md section 8).  Ties that only permute equal-key rows of the final order (10 more) are compared.
+    assert int(((flags & 5) != 0).sum()) <= 12
     # determinism
     out2, scores2, ts2, lens2 = dec.decode(d)
     assert torch.equal(scores, scores2) and torch.equal(lens, lens2)

@@ -16,10 +16,10 @@ from tests.parity import compare
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 TINY = os.path.join(ROOT, "tests", "data", "tiny_lm.arpa")
-REF_ARPA = "/root/reference/tests/test.arpa"
+REF_ARPA = os.path.join(ROOT, "tests", "golden", "test.arpa")  # the reference's own test LM (its tests/test.arpa), a fixture
 L29 = ["_"] + [chr(ord("a") + i) for i in range(26)] + [" ", "'"]
 TEXTS = ["the cat sat on the mat", "a dog ran fast", "the dog sat on a mat the cat ran"]
-PROVIDER = os.path.join(ROOT, "oracle", "_ref", "libctcref.so")
+PROVIDER = os.path.join(ROOT, "providers", "_build", "libkenlm_provider.so")
 
 needs_ref = pytest.mark.skipif(not orc.reference_available(), reason="oracle/_ref not built (needs /root/reference)")
 
@@ -79,7 +79,7 @@ def test_emulation_lm_matches_reference(cfg):
 @pytest.mark.skipif(not os.path.exists(REF_ARPA), reason="reference test LM not present")
 def test_emulation_lm_reference_unit_test_and_config5_shape():
     """reference tests/test_decode.py:55-64 ("a a", 7 results) and a BASELINE config-5 shaped batch (test.arpa,
-    alpha 2.0, beta 1.0, beam 100) -- with the reference's own LM file, which exists only in the build container."""
+    alpha 2.0, beta 1.0, beam 100) -- with the reference's own LM file (tests/golden/test.arpa)."""
     vocab = ["'", " ", "a", "b", "c", "d", "_"]
     kat, _, _, _ = golden_util.load("ref_kat_beam20")
     ref = orc.Reference(vocab, model_path=REF_ARPA, alpha=0.0, beta=0.0)
@@ -117,7 +117,7 @@ def test_scorer_accessors_match_reference():
 
 # ---------------------------------------------------------------------------------------------------------------
 @pytest.mark.gpu
-@pytest.mark.skipif(not os.path.exists(PROVIDER), reason="scorer provider (oracle/_ref/libctcref.so) not shipped")
+@pytest.mark.skipif(not os.path.exists(PROVIDER), reason="scorer provider (providers/_build/libkenlm_provider.so) not built")
 @pytest.mark.parametrize("per_frame", [False, True], ids=["persistent", "per_frame_launch"])
 @pytest.mark.parametrize("name", golden_util.names(lm=True))
 def test_cuda_lm_matches_reference_golden(name, per_frame, monkeypatch):
@@ -138,7 +138,7 @@ def test_cuda_lm_matches_reference_golden(name, per_frame, monkeypatch):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(not os.path.exists(PROVIDER), reason="scorer provider (oracle/_ref/libctcref.so) not shipped")
+@pytest.mark.skipif(not os.path.exists(PROVIDER), reason="scorer provider (providers/_build/libkenlm_provider.so) not built")
 def test_cuda_lm_matches_live_reference_and_reset_params():
     """BASELINE config-5 shape on the tiny LM: 8 utterances x T=400, beam 100, alpha 2.0, beta 1.0, against the
     reference Scorer path run on the same box; then reset_params (reference __init__.py:134-136)."""
@@ -164,7 +164,7 @@ def test_cuda_lm_matches_live_reference_and_reset_params():
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(not os.path.exists(PROVIDER), reason="scorer provider (oracle/_ref/libctcref.so) not shipped")
+@pytest.mark.skipif(not os.path.exists(PROVIDER), reason="scorer provider (providers/_build/libkenlm_provider.so) not built")
 def test_cuda_online_decoder_with_scorer_matches_reference_online_path():
     """reference tests/test_decode.py:93-115,141-159 shape (OnlineCTCBeamDecoder with a language model, one call and
     several calls), on the tiny LM: chunked decoding through device-resident DecoderStates against the reference's
@@ -208,3 +208,52 @@ def test_cuda_online_decoder_with_scorer_matches_reference_online_path():
     plain = ctcdecode_b200.OnlineCTCBeamDecoder(L29, beam_width=32)
     with pytest.raises(Exception):
         dec.decode(probs[:2, :4], [ctcdecode_b200.DecoderState(dec), ctcdecode_b200.DecoderState(plain)], [False] * 2)
+
+
+def c5_text_probs(B, T, seed):
+    """Posteriors that noisily spell sentences over the words of the reference's test.arpa (BASELINE config 5)."""
+    import random
+    rng = random.Random(seed)
+    words = ["a", "also", "beyond", "call", "concerns", "consider", "for", "higher", "however", "i", "in", "is", "little",
+             "loin", "look", "looking", "more", "on", "screening", "small", "the", "to", "watch", "what", "would"]
+    texts = []
+    for _ in range(B):
+        s = ""
+        while len(s) < T // 5:
+            s += (" " if s else "") + rng.choice(words)
+        texts.append(s[: T // 4])
+    return text_probs(texts, L29, T, seed=seed), texts
+
+
+@pytest.mark.gpu
+@needs_ref
+@pytest.mark.skipif(not os.path.exists(PROVIDER), reason="scorer provider (providers/_build/libkenlm_provider.so) not built")
+def test_cuda_config5_as_stated_matches_reference():
+    """BASELINE config 5 as BASELINE.json states it: the reference's tests/test.arpa, alpha 2.0, beta 1.0, beam 100,
+    T = 1000 (12 utterances here; bench.py --config c5 runs the 64), against the reference's own Scorer path on the same
+    box: tokens, timesteps, lens identical, float32 scores bit-exact; plus alpha / beta that are NOT exact in float32
+    after reset_params (reference Scorer::reset_params takes floats, scorer.cpp:122-125)."""
+    import torch
+    import ctcdecode_b200
+    probs, texts = c5_text_probs(12, 1000, seed=7)
+    noise = ctc_like_probs(4, 1000, 29, seed=8)
+    probs = torch.cat([probs, noise], 0)
+    ref = orc.Reference(L29, model_path=REF_ARPA, alpha=2.0, beta=1.0)
+    want = ref.decode(probs.numpy(), beam=100)
+    dec = ctcdecode_b200.CTCBeamDecoder(L29, model_path=REF_ARPA, alpha=2.0, beta=1.0, beam_width=100,
+                                        scorer_provider=PROVIDER)
+    assert dec.dict_size() == ref.dict_size() and dec.max_order() == ref.max_order() == 5
+    out, scores, ts, lens = dec.decode(probs)
+    got = dict(tokens=out.numpy(), timesteps=ts.numpy(), scores=scores.numpy(), lens=lens.numpy(),
+               n_results=dec.last_n_results.numpy(), ties=dec.last_flags.numpy())
+    checked, skipped = compare(want, got, None, "config 5 (test.arpa)")
+    assert checked >= 12
+    hits = sum("".join(L29[x] for x in out[b, 0, :lens[b, 0]]) == texts[b] for b in range(12))
+    assert hits >= 9, hits  # the posteriors are noisy; most utterances still decode to their sentence
+    dec.reset_params(0.3, 0.1)
+    ref.lib.ref_scorer_reset_params(ref.scorer, 0.3, 0.1)
+    want = ref.decode(probs[:6].numpy(), beam=100)
+    out, scores, ts, lens = dec.decode(probs[:6])
+    got = dict(tokens=out.numpy(), timesteps=ts.numpy(), scores=scores.numpy(), lens=lens.numpy(),
+               n_results=dec.last_n_results.numpy(), ties=dec.last_flags.numpy())
+    compare(want, got, None, "after reset_params(0.3, 0.1)")

@@ -11,8 +11,11 @@ from bench import CONFIGS  # noqa: E402
 from ctcdecode_b200 import CTCBeamDecoder, _native  # noqa: E402
 from ctcdecode_b200.synth import ctc_like_probs  # noqa: E402
 
-NAMES = ["tile_wait", "R0_rank", "R1_members", "G_gridwalk", "select_scan", "classify", "R4c_nodes", "RV_revive",
-         "R5_commit", "R5b_sweep", "R5c_newanchor", "R5d_fixup"]
+# (index-order kernels: "front" = members | grid walk in one region; ids 12..14 / 6 / 7 split thread 0's way through the
+#  members' region and the barrier-free back half; frames that take the general back half book into 4..8 as before)
+NAMES = ["tile_wait", "head", "front_rest+barrier", "G_gridwalk", "select_scan", "classify", "R4c_nodes|fast:ballots+rows",
+         "RV_revive|fast:commit", "R5_commit|fast:tail+barrier", "R5b_sweep", "R5c_newanchor", "R5d_fixup",
+         "members:loads+terms", "members:2xlse", "fast:checks+scan"]
 ap = argparse.ArgumentParser()
 ap.add_argument("--config", default="c2")
 ap.add_argument("--batch", type=int, nargs="*", default=[1, 148, 256])
@@ -32,9 +35,9 @@ for B in a.batch:
     lib.ctcdec_profile_region_cycles(None)
     t = buf[:B * 16].view(B, 16).double().mean(0).cpu() / cfg["T"]
     wb = buf[B * 16:].view(B, 16, 32).double().mean(0).cpu() / cfg["T"]
-    tot = float(t[:12].sum())
+    tot = float(t[:15].sum())
     print(f"B={B}: step {e0.elapsed_time(e1):.2f} ms; cycles/frame (mean over CTAs) total {tot:.0f}")
-    print("   " + "  ".join(f"{n}={float(v):.0f}" for n, v in zip(NAMES, t[:12])))
+    print("   " + "  ".join(f"{n}={float(v):.0f}" for n, v in zip(NAMES, t[:15])))
     for rid, name in ((2, "R1"), (3, "G"), (5, "select+classify"), (6, "R4c"), (8, "R5")):
         print("   busy cycles/frame per warp before the barrier closing %-16s " % name
               + " ".join("%5.0f" % float(v) for v in wb[rid][:8]))

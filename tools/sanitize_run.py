@@ -23,7 +23,7 @@ torch.cuda.synchronize()
 print("sanitize_run done")
 # scorer path (both host/kernel protocols), when the provider library travelled with the snapshot
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-PROVIDER = os.path.join(ROOT, "oracle", "_ref", "libctcref.so")
+PROVIDER = os.path.join(ROOT, "providers", "_build", "libkenlm_provider.so")
 if os.path.exists(PROVIDER):
     from ctcdecode_b200.synth import text_probs  # noqa: E402
     LBL = ["_"] + [chr(ord("a") + i) for i in range(26)] + [" ", "'"]
