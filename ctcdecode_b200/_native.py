@@ -39,6 +39,8 @@ _SIGNATURES = {
                                                   _vp, _vp, ctypes.c_size_t, _vp]),
     "ctcdec_decode_batch_host": (ctypes.c_int, [ctypes.POINTER(Config), _vp, _vp, ctypes.c_int, ctypes.c_int,
                                                 _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_int]),
+    "ctcdec_decode_batch_host_multi": (ctypes.c_int, [ctypes.POINTER(Config), _vp, _vp, ctypes.c_int, ctypes.c_int,
+                                                      _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_int]),
     "ctcdec_scorer_create": (ctypes.c_int, [_vp, ctypes.c_double, ctypes.c_double, ctypes.POINTER(ctypes.c_char_p),
                                             ctypes.c_int, ctypes.POINTER(ctypes.c_char_p), ctypes.c_int, ctypes.c_int,
                                             ctypes.c_int, ctypes.POINTER(_vp)]),

@@ -34,16 +34,19 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB_PATH
     os.makedirs(_OUT_DIR, exist_ok=True)
-    obj = os.path.join(_OUT_DIR, "ctc_api.o")
+    obj = os.path.join(_OUT_DIR, "ctc_api.%d.o" % os.getpid())
     cmd = [_NVCC] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
           ["-c", os.path.join(_CSRC, "ctc_api.cu"), "-o", obj]
     subprocess.run(cmd, check=True)
     cuda_lib = os.path.join(os.path.dirname(os.path.dirname(_NVCC)), "lib64")
     # link with the host compiler so that libstdc++ stays a shared dependency (this image's g++ would
     # otherwise pull in a static libstdc++ that clashes with the one python already loaded)
-    link = ["g++", "-shared", "-nostdlib++", "-o", LIB_PATH, obj, "-L" + cuda_lib, "-lcudart_static",
+    tmp = LIB_PATH + ".tmp%d" % os.getpid()  # link beside the target and rename: readers never see a partial file
+    link = ["g++", "-shared", "-nostdlib++", "-o", tmp, obj, "-L" + cuda_lib, "-lcudart_static",
             "-l:libstdc++.so.6", "-lm", "-lrt", "-lpthread", "-ldl"]
     subprocess.run(link, check=True)
+    os.replace(tmp, LIB_PATH)
+    os.remove(obj)
     return LIB_PATH
 
 

@@ -92,21 +92,32 @@ constexpr int kDictFinal = 1 << 30;        // the target is a final state: the c
 constexpr int kDictSpace = 1 << 29;        // the state the child ends up in has an arc for the space label
 constexpr int kDictStateMask = (1 << 29) - 1;  // in-frame marker: "parent slot refers to this frame's NEW occupant"
 
-// Trie node in the global arena: exactly what the final backtrace needs (reference path_trie.cpp:109-126).
-struct alignas(16) Node {
+// Trie node in the global arena: what the final backtrace needs (reference path_trie.cpp:109-126), one 32-byte
+// sector.  `jump` is the ancestor kJump levels further up the last multiple of kJump in depth: for a node of depth
+// d >= 1 the ancestor of depth ((d - 1) / kJump) * kJump.  The backtrace of a prefix of length L is then L / kJump
+// dependent hops along the jump pointers plus kJump hops inside each stretch, all stretches in parallel, instead of
+// L dependent DRAM round trips (finalize_cta_run).
+constexpr int kJump = 16;
+struct alignas(32) Node {
   int parent;  // node index, -1 for the root
   int chr;     // character, -1 for the root
   float lpc;   // reference PathTrie::log_prob_c
   int ts;      // reference PathTrie::timestep
+  int jump;    // node index of the checkpoint ancestor (unused for the root)
+  int pad_[3];
 };
+// a new node's jump pointer from its parent's (node id, depth, jump)
+CTC_HD int jump_of_child(int parent_node, int parent_depth, int parent_jump) {
+  return (parent_depth % kJump == 0) ? parent_node : parent_jump;
+}
 
 // Per-utterance persistent state (global memory; survives between chunks of a streaming decode).
-// Layout in ints: [0]=M (beam count) [1]=nnodes [2]=abs_t [3]=flags, then 11 slot arrays of K ints
-// (node, chr, depth, bprev, nbprev, score, lpc, ts, pslot, anch, dstate; floats by bit pattern) and the
+// Layout in ints: [0]=M (beam count) [1]=nnodes [2]=abs_t [3]=flags, then 12 slot arrays of K ints
+// (node, chr, depth, bprev, nbprev, score, lpc, ts, pslot, anch, dstate, jump; floats by bit pattern) and the
 // dead-anchor table, 6 arrays of 2*KP ints (dnode, dchr, dpslot, dlpc, dts, ddstate), KP = K rounded up to 32.
 // dstate / ddstate (dictionary state of the scorer path) are 0 without a scorer.
 constexpr int kStateHeader = 4;
-constexpr int kSlotArrays = 11;
+constexpr int kSlotArrays = 12;
 constexpr int kAnchorArrays = 6;
 // KP: slots per slot array.  Beam sizes up to 256 round up to 32 / 64 / 128 / 256 -- the sizes the beam kernel is
 // instantiated for with KP as a compile-time constant -- larger ones to a multiple of 32.
@@ -132,17 +143,19 @@ enum : int {  // slot block, in units of KP ints
   U_DSTATE = U_ANCH + 2, U_LMSP,
   U_DDSTATE,              // 2 units
   U_BNEW = U_DDSTATE + 2, U_NBNEW, U_SNEW, U_EVICT, U_SEL, U_SEL2, U_FREEL, U_FREEL2,
-  U_NEWINFO,              // 10 units
-  U_TIE = U_NEWINFO + 10, // 2 units
+  U_NEWINFO,              // 11 units
+  U_TIE = U_NEWINFO + 11, // 2 units
   U_DNODE = U_TIE + 2, U_DCHR = U_DNODE + 2, U_DPSLOT = U_DCHR + 2, U_DLPC = U_DPSLOT + 2, U_DTS = U_DLPC + 2,
   U_DREV = U_DTS + 2,     // dead-anchor table: 2 units each
   U_CNT2 = U_DREV + 2,    // 3 units
   U_AMAP = U_CNT2 + 3, U_SLOT2Q,
-  U_STASH,                // 6 units: node, chr, lpc, ts, dstate, depth of the members evicted in this frame
-  U_EFREE = U_STASH + 6,  // 2 units
+  U_STASH,                // 7 units: node, chr, lpc, ts, dstate, depth, jump of the members evicted in this frame
+  U_EFREE = U_STASH + 7,  // 2 units
   U_RVWORK = U_EFREE + 2, // 3 units
-  U_NODEN = U_RVWORK + 3, // node id / depth of a member committed by the barrier-free back half of a frame, installed
-  U_DEPTHN,               // into U_NODE / U_DEPTH by the slot owner at the start of the next frame (-1 = nothing pending)
+  U_NODEN = U_RVWORK + 3, // node id / depth / jump pointer of a member committed by the barrier-free back half of a
+  U_DEPTHN,               // frame, installed into U_NODE / U_DEPTH / U_JUMP by the slot owner at the start of the next
+  U_JUMPN,                // frame (U_NODEN: -1 = nothing pending)
+  U_JUMP,                 // jump pointer of the member's node (Node::jump)
   U_SLOT_UNITS
 };
 CTC_HD int slot_off(int unit, int KP) { return kSmemHead + unit * KP * 4; }
@@ -183,7 +196,10 @@ CTC_HD SmemLayout make_layout(int K, int V, int NP, int tile_frames, bool sorted
   {
     int cap_bytes = budget_kb * 1024 - o - 64;
     if (cap_bytes > 64 * 1024) cap_bytes = 64 * 1024;
-    if (cap_bytes < 8 * 1024) cap_bytes = 64 * 1024;
+    if (cap_bytes < 8 * 1024) {  // the intended number of CTAs per SM does not fit: one CTA, whatever an SM has left
+      cap_bytes = 227 * 1024 - o - 64;
+      if (cap_bytes > 64 * 1024) cap_bytes = 64 * 1024;
+    }
     if (seg > cap_bytes / 8 / NW) seg = cap_bytes / 8 / NW;
   }
   if (seg < 32) seg = 32;
@@ -279,6 +295,7 @@ static inline unsigned atom_sub_u(unsigned *p, unsigned v) { unsigned o = *p; *p
 static inline int atom_or(int *p, int v) { int o = *p; *p = o | v; return o; }
 static inline unsigned atom_or(unsigned *p, unsigned v) { unsigned o = *p; *p = o | v; return o; }
 template <class T> static inline T ld_cg(const T *p) { return *p; }
+static inline void atom_max_i(int *p, int v) { if (v > *p) *p = v; }
 #else
 template <class T> CTC_FN T atom_add(T *p, T v) { return atomicAdd(p, v); }
 CTC_FN int atom_exch(int *p, int v) { return atomicExch(p, v); }
@@ -286,6 +303,7 @@ CTC_FN unsigned atom_sub_u(unsigned *p, unsigned v) { return atomicSub(p, v); }
 CTC_FN int atom_or(int *p, int v) { return atomicOr(p, v); }
 CTC_FN unsigned atom_or(unsigned *p, unsigned v) { return atomicOr(p, v); }
 template <class T> CTC_FN T ld_cg(const T *p) { return __ldcg(p); }
+CTC_FN void atom_max_i(int *p, int v) { atomicMax(p, v); }
 #endif
 
 #if defined(CTC_EMULATE)

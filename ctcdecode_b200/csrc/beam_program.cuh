@@ -231,6 +231,7 @@ CTC_FN Node load_node(const Node *p) {
   const int4 a = __ldcg(reinterpret_cast<const int4 *>(p));  // nodes are written by this CTA: read through L2
   Node n;
   n.parent = a.x; n.chr = a.y; n.lpc = __int_as_float(a.z); n.ts = a.w;
+  n.jump = __ldcg(&p->jump);  // (same 32-byte sector)
   return n;
 #endif
 }
@@ -239,6 +240,16 @@ CTC_FN void store_node(Node *p, const Node &n) {
   *p = n;
 #else
   *reinterpret_cast<int4 *>(p) = make_int4(n.parent, n.chr, __float_as_int(n.lpc), n.ts);
+  p->jump = n.jump;
+#endif
+}
+// 16-byte entry of the new-node list the scorer path hands to the host (device-mapped host memory: one store)
+struct alignas(16) Entry16 { int a, b, c, d; };
+CTC_FN void store_entry16(int *dst, const Entry16 &e) {
+#if defined(CTC_EMULATE)
+  dst[0] = e.a; dst[1] = e.b; dst[2] = e.c; dst[3] = e.d;
+#else
+  *reinterpret_cast<int4 *>(dst) = make_int4(e.a, e.b, e.c, e.d);
 #endif
 }
 CTC_FN void flush_lpc_ts(Node *p, float lpc, int ts) {
@@ -306,6 +317,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
   c.s_slot2q = CTC_SLOT(int, U_SLOT2Q);    c.s_stash = CTC_SLOT(int, U_STASH);
   int *const pslot_base = CTC_SLOT(int, U_PSLOT), *const anch_base = CTC_SLOT(int, U_ANCH);
   int *const s_nodeN = CTC_SLOT(int, U_NODEN), *const s_depthN = CTC_SLOT(int, U_DEPTHN);
+  int *const s_jumpN = CTC_SLOT(int, U_JUMPN), *const s_jump = CTC_SLOT(int, U_JUMP);
   uint32_t *const mask_buf0 = (uint32_t *)(smem + L.mask), *const mask_buf1 = (uint32_t *)(smem + L.mask2);
   int cur = 0;  // which half of the double-buffered link arrays describes the current beam
   int par = 0;  // frame parity: which C_CMIN / C_CMAX pair holds the current beam's score range
@@ -406,7 +418,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
       ((double *)c.s_logtab)[i] = kLogfTab[i];
     }
     for (int j = tid; j < KP; j += NT) {
-      int node = 0, chr = -1, depth = 0, ts = 0, pslot = -1, anch = -1, dstate = LM ? p.dict_start : 0;
+      int node = 0, chr = -1, depth = 0, ts = 0, pslot = -1, anch = -1, dstate = LM ? p.dict_start : 0, jump = -1;
       float bprev = kNInf, nbprev = kNInf, score = kNInf, lpc = kNInf;
       if (fresh) {
         if (j == 0) { bprev = 0.0f; score = 0.0f; }  // reference ctc_beam_search_decoder.cpp:43
@@ -415,11 +427,11 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
         node = s[j]; chr = s[K + j]; depth = s[2 * K + j]; bprev = bits_f((uint32_t)s[3 * K + j]);
         nbprev = bits_f((uint32_t)s[4 * K + j]); score = bits_f((uint32_t)s[5 * K + j]);
         lpc = bits_f((uint32_t)s[6 * K + j]); ts = s[7 * K + j]; pslot = s[8 * K + j]; anch = s[9 * K + j];
-        dstate = s[10 * K + j];
+        dstate = s[10 * K + j]; jump = s[11 * K + j];
       }
       c.s_node[j] = node; c.s_chr[j] = chr; c.s_depth[j] = depth; c.s_bprev[j] = bprev; c.s_nbprev[j] = nbprev;
       c.s_score[j] = score; c.s_lpc[j] = lpc; c.s_ts[j] = ts; c.s_pslot[j] = pslot; c.s_anch[j] = anch;
-      c.s_dstate[j] = dstate;
+      c.s_dstate[j] = dstate; s_jump[j] = jump;
       if (LM) for (int w = 0; w < L.WC; ++w) c.s_dmask[j * L.WC + w] = p.dict_mask[(long long)dstate * L.WC + w];
       c.s_lmsp[j] = (LM && !fresh && j < st[0]) ? ld_cg(&lm_arena[node]) : 0.0f;
       c.s_evict[j] = 0;
@@ -449,7 +461,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
       s_ctl[C_KMIN] = (int)0xFFFFFFFFu;
       s_ctl[C_SMIN] = (int)0xFFFFFFFFu;
       if (fresh) {  // root node (reference path_trie.cpp:11-30)
-        Node root; root.parent = -1; root.chr = -1; root.lpc = kNInf; root.ts = 0;
+        Node root; root.parent = -1; root.chr = -1; root.lpc = kNInf; root.ts = 0; root.jump = -1;
         store_node(&nodes[0], root);
         if (LM) { dstate_arena[0] = p.dict_start; lm_arena[0] = 0.0f; }
       }
@@ -670,7 +682,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
         if (j < M) {
           if (FASTB) {  // a member committed by the barrier-free back half of the previous frame moves in
             const int pn = s_nodeN[j];
-            if (pn >= 0) { c.s_node[j] = pn; c.s_depth[j] = s_depthN[j]; s_nodeN[j] = -1; }
+            if (pn >= 0) { c.s_node[j] = pn; c.s_depth[j] = s_depthN[j]; s_jump[j] = s_jumpN[j]; s_nodeN[j] = -1; }
           }
           const float sc = c.s_score[j];
           const int ch = c.s_chr[j];
@@ -1293,9 +1305,11 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
                 s_ctl[C_FLAGS] |= FLAG_ERR_ARENA;
                 nid = arena_cap - 1;
               }
-              Node nn; nn.parent = c.s_node[par_slot]; nn.chr = ch; nn.lpc = lpc; nn.ts = t_abs;
+              const int pnode = c.s_node[par_slot], pdepth = c.s_depth[par_slot];
+              Node nn; nn.parent = pnode; nn.chr = ch; nn.lpc = lpc; nn.ts = t_abs;
+              nn.jump = jump_of_child(pnode, pdepth, s_jump[par_slot]);
               store_node(&nodes[nid], nn);
-              s_nodeN[j] = nid; s_depthN[j] = c.s_depth[par_slot] + 1;
+              s_nodeN[j] = nid; s_depthN[j] = pdepth + 1; s_jumpN[j] = nn.jump;
               c.s_chr[j] = ch;
               c.s_bprev[j] = kNInf; c.s_nbprev[j] = sc; c.s_score[j] = sc;  // score = lse(-inf, nb)
               cmin[LX] = cmax[LX] = ord_f(sc);
@@ -1567,7 +1581,10 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
             if (ev[LX]) {
               const int j = blk * 32 + lane, rk = ctc_popc(bal & ctc_lt_mask(lane));
               c.s_free[blk * 32 + rk] = j;
-              if (fused) { c.s_sel2[j] = rk; c.s_stash[j] = c.s_node[j]; c.s_stash[5 * KP + j] = c.s_depth[j]; }
+              if (fused) {
+                c.s_sel2[j] = rk; c.s_stash[j] = c.s_node[j]; c.s_stash[5 * KP + j] = c.s_depth[j];
+                c.s_stash[6 * KP + j] = s_jump[j];
+              }
             }
             if (lane == 0) c.s_evcnt[blk] = ctc_popc(bal);
           }
@@ -1736,12 +1753,13 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
         float sc; int ch;
         c.cand(i, r, sc, ch);
         float lpc = c.lp[r];
-        int ts = t_abs, nid, rev = -1, dst = 0;
+        int ts = t_abs, nid, rev = -1, dst = 0, jmp = -1;
         if (nlive > 0 && ((c.s_rmask[i * W + (r >> 5)] >> (r & 31)) & 1u)) {
           for (int a = 0; a < KP2; ++a)
             if (c.s_dpslot[a] == i && c.s_dchr[a] == ch) rev = a;
           nid = c.s_dnode[rev]; lpc = c.s_dlpc[rev]; ts = c.s_dts[rev];
           dst = c.s_ddstate[rev];
+          jmp = ld_cg(&nodes[nid].jump);  // (a revived node keeps the jump pointer it was created with)
           c.s_drev[rev] = 1;
           atom_add(&s_ctl[C_NREV], 1);
           CTC_STAT(g_stats.revived++);
@@ -1754,6 +1772,8 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
             nid = arena_cap - 1;
           }
           Node nn; nn.parent = c.s_node[i]; nn.chr = ch; nn.lpc = lpc; nn.ts = ts;
+          nn.jump = jump_of_child(c.s_node[i], c.s_depth[i], s_jump[i]);
+          jmp = nn.jump;
           store_node(&nodes[nid], nn);
           if (LM) {
             // dictionary state of the new node (reference path_trie.cpp:83-92); tell the host about the node: it
@@ -1763,15 +1783,15 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
             dstate_arena[nid] = dst;
             lm_arena[nid] = 0.0f;
             // one 16-byte store per entry: the list lives in device-mapped host memory
-            Node e;  // (same 16-byte shape as an arena node)
-            e.parent = nid; e.chr = c.s_node[i]; e.lpc = bits_f((uint32_t)ch);
-            e.ts = (arc & kDictSpace) ? 1 : 0;
-            store_node(reinterpret_cast<Node *>(newlist + 4 + 4 * q), e);
+            Entry16 e;
+            e.a = nid; e.b = c.s_node[i]; e.c = ch;
+            e.d = (arc & kDictSpace) ? 1 : 0;
+            store_entry16(newlist + 4 + 4 * q, e);
           }
         }
-        int *ni = c.s_newinfo + q * 10;
+        int *ni = c.s_newinfo + q * 11;
         ni[0] = nid; ni[1] = ch; ni[2] = (int)f_bits(sc); ni[3] = free_slot(q); ni[4] = i; ni[5] = (int)f_bits(lpc);
-        ni[6] = ts; ni[7] = rev; ni[8] = c.s_depth[i] + 1; ni[9] = dst;
+        ni[6] = ts; ni[7] = rev; ni[8] = c.s_depth[i] + 1; ni[9] = dst; ni[10] = jmp;
         c.s_slot2q[ni[3]] = q;
       }
     }
@@ -1791,7 +1811,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
             const int d = c.s_dnode[a];
             int s_new = -1;
             for (int q = 0; q < nsel; ++q)
-              if (c.s_newinfo[q * 10 + 7] == a) s_new = c.s_newinfo[q * 10 + 3];
+              if (c.s_newinfo[q * 11 + 7] == a) s_new = c.s_newinfo[q * 11 + 3];
             int cur = c.s_node[y];
             while (true) {
               CTC_STAT(g_stats.rv_hops++);
@@ -1892,7 +1912,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
           if (!fused) q = c.s_slot2q[j];
           else if (q >= nsel) q = -1;
           if (q >= 0) {  // a new member moves into this slot
-            int nid, ch, ts, depth, dst, par_slot;
+            int nid, ch, ts, depth, dst, par_slot, jmp;
             float sc, lpc;
             if (fused) {
               // the q-th selected candidate (reference path_trie.cpp:97-105 create); its score is the list key
@@ -1913,20 +1933,21 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
               const bool pe = c.s_evict[par_slot] != 0;  // the parent was evicted in this very frame
               const int pnode = pe ? c.s_stash[par_slot] : c.s_node[par_slot];
               depth = (pe ? c.s_stash[5 * KP + par_slot] : c.s_depth[par_slot]) + 1;
+              jmp = jump_of_child(pnode, depth - 1, pe ? c.s_stash[6 * KP + par_slot] : s_jump[par_slot]);
               nid = atom_add(&s_ctl[C_NNODES], 1);
               CTC_STAT(g_stats.created++);
               if (nid >= arena_cap) {  // cannot happen with capacity 1 + K * frames; never write out of bounds
                 s_ctl[C_FLAGS] |= FLAG_ERR_ARENA;
                 nid = arena_cap - 1;
               }
-              Node nn; nn.parent = pnode; nn.chr = ch; nn.lpc = lpc; nn.ts = ts;
+              Node nn; nn.parent = pnode; nn.chr = ch; nn.lpc = lpc; nn.ts = ts; nn.jump = jmp;
               store_node(&nodes[nid], nn);
             } else {
-              const int *ni = c.s_newinfo + q * 10;
+              const int *ni = c.s_newinfo + q * 11;
               nid = ni[0]; ch = ni[1]; sc = bits_f((uint32_t)ni[2]); par_slot = ni[4];
-              lpc = bits_f((uint32_t)ni[5]); ts = ni[6]; depth = ni[8]; dst = ni[9];
+              lpc = bits_f((uint32_t)ni[5]); ts = ni[6]; depth = ni[8]; dst = ni[9]; jmp = ni[10];
             }
-            c.s_node[j] = nid; c.s_chr[j] = ch; c.s_depth[j] = depth;
+            c.s_node[j] = nid; c.s_chr[j] = ch; c.s_depth[j] = depth; s_jump[j] = jmp;
             c.s_bprev[j] = kNInf; c.s_nbprev[j] = sc; c.s_score[j] = sc;  // score = lse(-inf, nb)
             const unsigned o = ord_f(sc);
             cmin = o < cmin ? o : cmin;
@@ -2091,11 +2112,11 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
   CTC_PAR {
     int *s = st_slots;
     for (int j = tid; j < K; j += NT) {
-      if (FASTB && s_nodeN[j] >= 0) { c.s_node[j] = s_nodeN[j]; c.s_depth[j] = s_depthN[j]; s_nodeN[j] = -1; }
+      if (FASTB && s_nodeN[j] >= 0) { c.s_node[j] = s_nodeN[j]; c.s_depth[j] = s_depthN[j]; s_jump[j] = s_jumpN[j]; s_nodeN[j] = -1; }
       s[j] = c.s_node[j]; s[K + j] = c.s_chr[j]; s[2 * K + j] = c.s_depth[j];
       s[3 * K + j] = (int)f_bits(c.s_bprev[j]); s[4 * K + j] = (int)f_bits(c.s_nbprev[j]);
       s[5 * K + j] = (int)f_bits(c.s_score[j]); s[6 * K + j] = (int)f_bits(c.s_lpc[j]); s[7 * K + j] = c.s_ts[j];
-      s[8 * K + j] = c.s_pslot[j]; s[9 * K + j] = c.s_anch[j]; s[10 * K + j] = c.s_dstate[j];
+      s[8 * K + j] = c.s_pslot[j]; s[9 * K + j] = c.s_anch[j]; s[10 * K + j] = c.s_dstate[j]; s[11 * K + j] = s_jump[j];
       if (j < M) flush_lpc_ts(&nodes[c.s_node[j]], c.s_lpc[j], c.s_ts[j]);
     }
     for (int a = tid; a < KP2; a += NT) {
@@ -2124,7 +2145,21 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
 //  (reference ctc_beam_search_decoder.cpp:164-211, decoder_utils.cpp:48-73, path_trie.cpp:109-126,
 //   binding.cpp:79-99).  Sorts the <= K members by (score desc, char asc), walks each prefix up the
 //   trie, writes only [:len] of each row; rows >= n_results are left untouched like the reference.
+//
+//  The walk is a pointer chase through an arena of hundreds of megabytes: every hop is a DRAM round trip.  Instead
+//  of len dependent hops per prefix, a thread per prefix follows the JUMP pointers (Node::jump: the ancestor at the
+//  last multiple of kJump in depth) and records up to R checkpoints; then every (prefix, checkpoint) pair is an
+//  independent stretch of at most kJump hops, spread over all threads.  Rounds repeat until every prefix reached
+//  the root: len / kJump + kJump dependent hops instead of len.
 // ======================================================================================================
+CTC_HD int finalize_rounds_cap(int K) {  // checkpoints per prefix and round: whatever 32 KB of shared memory hold
+  int R = 8192 / (K > 0 ? K : 1);
+  return R < 1 ? 1 : (R > 16 ? 16 : R);
+}
+CTC_HD size_t finalize_smem_bytes(int K) {
+  // keys [K] u64, order [K], flag, cur node [K], cur depth [K], checkpoint count [K], checkpoints [K][R]
+  return (size_t)K * 8 + (size_t)K * 4 * 4 + (size_t)K * finalize_rounds_cap(K) * 4 + 64;
+}
 template <int NT>
 CTC_FN void finalize_cta_run(const BeamParams &p, const int b, unsigned char *smem) {
   const int K = p.K;
@@ -2133,12 +2168,15 @@ CTC_FN void finalize_cta_run(const BeamParams &p, const int b, unsigned char *sm
   if (p.finalize && !p.finalize[b]) return;
   const int M = st[0];
   const int *s = st + kStateHeader;
+  const int R = finalize_rounds_cap(K);
   uint64_t *s_key = (uint64_t *)smem;             // [K]
   int *s_order = (int *)(smem + (size_t)K * 8);   // [K]
-  int *s_flag = s_order + K;
+  int *s_cur = s_order + K, *s_dep = s_cur + K, *s_ncp = s_dep + K;  // [K] each, by output row
+  int *s_cp = s_ncp + K;                          // [K][R] checkpoint node ids
+  int *s_flag = s_cp + (size_t)K * R;             // [0] tie flag, [1] deepest prefix
   CTC_PAR {
     for (int j = tid; j < M; j += NT) s_key[j] = key64(bits_f((uint32_t)s[5 * K + j]), s[K + j]);
-    if (tid == 0) *s_flag = 0;
+    if (tid == 0) { s_flag[0] = 0; s_flag[1] = 0; }
   }
   CTC_BARRIER();
   CTC_PAR {
@@ -2151,33 +2189,76 @@ CTC_FN void finalize_cta_run(const BeamParams &p, const int b, unsigned char *sm
         tie |= (kx == k && x != j) ? 1 : 0;
       }
       s_order[rk] = j;
-      if (tie) *s_flag = 1;  // benign race: all writers store 1
+      if (tie) s_flag[0] = 1;  // benign race: all writers store 1
     }
   }
   CTC_BARRIER();
   CTC_PAR {
+    int dmax = 0;
     for (int q = tid; q < M; q += NT) {
       const int j = s_order[q];
-      int nid = s[j];
       const int depth = s[2 * K + j];
       const float score = bits_f((uint32_t)s[5 * K + j]);
-      const size_t row = ((size_t)b * K + q) * (size_t)p.out_T;
       p.out_scores[(size_t)b * K + q] = (float)(-(double)score);  // decoder_utils.cpp:68, binding.cpp:91
       p.out_lens[(size_t)b * K + q] = depth;
-      for (int d = depth - 1; d >= 0; --d) {
-        const Node nd = load_node(&nodes[nid]);
-        if (d < p.out_T) {
-          p.out_tokens[row + d] = nd.chr;
-          p.out_timesteps[row + d] = nd.ts;
-        }
-        nid = nd.parent;
-      }
+      s_cur[q] = s[j];
+      s_dep[q] = depth;
+      dmax = depth > dmax ? depth : dmax;
     }
+    if (dmax > 0) atom_max_i(&s_flag[1], dmax);
     if (tid == 0) {
       p.n_results[b] = M;
-      int f = st[3] | (*s_flag ? FLAG_TIE_FINAL : 0);
+      int f = st[3] | (s_flag[0] ? FLAG_TIE_FINAL : 0);
       atom_or(&p.flags[b], f);
     }
+  }
+  CTC_BARRIER();
+  const int rounds = ((s_flag[1] + kJump - 1) / kJump + R - 1) / R;  // a prefix of depth d has ceil(d / kJump) checkpoints
+  for (int rd = 0; rd < rounds; ++rd) {
+    // (a) one thread per prefix: up to R checkpoints along the jump pointers
+    CTC_PAR {
+      for (int q = tid; q < M; q += NT) {
+        int nid = s_cur[q], d = s_dep[q], k = 0;
+        while (k < R && d > 0) {
+          s_cp[(size_t)q * R + k] = nid;
+          nid = ld_cg(&nodes[nid].jump);
+          d = ((d - 1) / kJump) * kJump;
+          ++k;
+        }
+        s_ncp[q] = k;
+        s_cur[q] = nid;  // (s_dep[q] is advanced after the stretches below have read it)
+      }
+    }
+    CTC_BARRIER();
+    // (b) every (prefix, checkpoint) pair: the stretch of at most kJump nodes below the checkpoint's jump target
+    CTC_PAR {
+      for (int it = tid; it < M * R; it += NT) {
+        const int q = it / R, k = it - q * R;
+        if (k >= s_ncp[q]) continue;
+        const int d0 = s_dep[q];
+        int d = (k == 0) ? d0 : ((d0 - 1) / kJump) * kJump - (k - 1) * kJump;  // depth of the k-th checkpoint
+        const int dend = ((d - 1) / kJump) * kJump;
+        int nid = s_cp[(size_t)q * R + k];
+        const size_t row = ((size_t)b * K + q) * (size_t)p.out_T;
+        for (; d > dend; --d) {
+          const Node nd = load_node(&nodes[nid]);
+          if (d - 1 < p.out_T) {
+            p.out_tokens[row + d - 1] = nd.chr;
+            p.out_timesteps[row + d - 1] = nd.ts;
+          }
+          nid = nd.parent;
+        }
+      }
+    }
+    CTC_BARRIER();
+    CTC_PAR {
+      for (int q = tid; q < M; q += NT) {
+        int d = s_dep[q];
+        for (int k = 0; k < s_ncp[q]; ++k) d = ((d - 1) / kJump) * kJump;
+        s_dep[q] = d;
+      }
+    }
+    CTC_BARRIER();
   }
 }
 

@@ -12,6 +12,9 @@
 #include <chrono>
 #include <memory>
 #include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
 
 #include "../../include/ctcdecode_b200.h"
 #include "beam_program.cuh"
@@ -246,10 +249,10 @@ static int launch_prune(const ctcdec_config *cfg, const Plan &pl, const PruneInp
 }
 
 static int launch_finalize(const BeamParams &bp, int B, cudaStream_t s) {
-  const size_t smem = (size_t)bp.K * 12 + 16;
+  const size_t smem = finalize_smem_bytes(bp.K);
   if (smem > 48 * 1024)
-    CU(cudaFuncSetAttribute(finalize_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  finalize_kernel<128><<<B, 128, smem, s>>>(bp);
+    CU(cudaFuncSetAttribute(finalize_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  finalize_kernel<256><<<B, 256, smem, s>>>(bp);
   CU(cudaGetLastError());
   return CTCDEC_OK;
 }
@@ -349,7 +352,11 @@ static int serve_handshakes(HostScorer *sc, int B, int K, const int *need, TrieM
   exchange_strides(K, &nls, &ups);
   unsigned nt = std::thread::hardware_concurrency();
   if (const char *e = getenv("CTCDEC_LM_THREADS")) nt = (unsigned)atoi(e);
-  nt = nt == 0 ? 1 : (nt > 8 ? 8 : nt);
+  // every worker busy-polls the done flags of its utterances: one worker per utterance is the latency optimum (a frame
+  // of an utterance costs one PCIe round trip plus the hook calls, and workers sharing a thread serialise them) -- up to
+  // half the host's hardware threads, 64 at most
+  if (!getenv("CTCDEC_LM_THREADS")) nt = nt / 2;
+  nt = nt == 0 ? 1 : (nt > 64 ? 64 : nt);
   if ((unsigned)B < nt) nt = (unsigned)B;
   if (sc->cond_caches.size() < nt) sc->cond_caches.resize(nt);
   std::atomic<int> failed{0};
@@ -634,6 +641,48 @@ int ctcdec_decode_batch_host(const ctcdec_config *cfg, const float *probs, const
   return check_error_flags(h_flags, B);
 }
 
+int ctcdec_decode_batch_host_multi(const ctcdec_config *cfg, const float *probs, const int32_t *seq_lens, int B, int T,
+                                   int32_t *tokens, int32_t *timesteps, float *scores, int32_t *lens,
+                                   int32_t *n_results, int32_t *flags, const int *devices, int n_devices) {
+  if (!cfg) return fail(CTCDEC_E_INVALID, "cfg is NULL");
+  if (B < 0 || T < 0) return fail(CTCDEC_E_INVALID, "negative batch (%d) or time (%d)", B, T);
+  std::vector<int> devs;
+  if (devices && n_devices > 0) {
+    devs.assign(devices, devices + n_devices);
+  } else {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) n = 0;
+    for (int d = 0; d < n && d < 64; ++d) {
+      int major = 0;
+      if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10) devs.push_back(d);
+    }
+  }
+  if (devs.empty()) return fail(CTCDEC_E_NO_DEVICE, "no usable CUDA device (this library has no CPU fallback)");
+  const int nd = (int)std::min<size_t>(devs.size(), (size_t)std::max(B, 1));
+  if (nd == 1)
+    return ctcdec_decode_batch_host(cfg, probs, seq_lens, B, T, tokens, timesteps, scores, lens, n_results, flags, devs[0]);
+  const int V = cfg->vocab_size, K = cfg->beam_size;
+  std::vector<int> rcs(nd, CTCDEC_OK);
+  std::vector<std::string> errs(nd);
+  std::vector<std::thread> pool;
+  const int per = (B + nd - 1) / nd;
+  for (int i = 0; i < nd; ++i) {
+    const int b0 = std::min(B, i * per), nb = std::min(per, B - b0);
+    if (nb <= 0) continue;
+    pool.emplace_back([&, i, b0, nb]() {
+      const size_t po = (size_t)b0 * T * V, oo = (size_t)b0 * K * T, ko = (size_t)b0 * K;
+      rcs[i] = ctcdec_decode_batch_host(cfg, probs ? probs + po : nullptr, seq_lens ? seq_lens + b0 : nullptr, nb, T,
+                                        tokens + oo, timesteps + oo, scores + ko, lens + ko,
+                                        n_results ? n_results + b0 : nullptr, flags ? flags + b0 : nullptr, devs[i]);
+      if (rcs[i]) errs[i] = g_err;  // (the message lives in the worker's thread-local buffer)
+    });
+  }
+  for (auto &th : pool) th.join();
+  for (int i = 0; i < nd; ++i)
+    if (rcs[i]) return fail(rcs[i], "device %d: %s", devs[i], errs[i].c_str());
+  return CTCDEC_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------
 //  streaming
 // ---------------------------------------------------------------------------------------------------
@@ -652,7 +701,7 @@ static int state_init_device(StreamState *st) {
     memcpy(&s[4 * K + j], &ninf, 4);
     memcpy(&s[5 * K + j], j == 0 ? &zero : &ninf, 4);
     memcpy(&s[6 * K + j], &ninf, 4);
-    s[7 * K + j] = 0; s[8 * K + j] = -1; s[9 * K + j] = -1; s[10 * K + j] = 0;
+    s[7 * K + j] = 0; s[8 * K + j] = -1; s[9 * K + j] = -1; s[10 * K + j] = 0; s[11 * K + j] = -1;
   }
   int *a = s + kSlotArrays * K;
   for (int e = 0; e < KP2; ++e) {
@@ -662,7 +711,8 @@ static int state_init_device(StreamState *st) {
   }
   CU(cudaMemcpy(st->state, h.get(), n * 4, cudaMemcpyHostToDevice));
   Node root;
-  root.parent = -1; root.chr = -1; root.lpc = -FLT_MAX; root.ts = 0;
+  memset(&root, 0, sizeof(root));
+  root.parent = -1; root.chr = -1; root.lpc = -FLT_MAX; root.ts = 0; root.jump = -1;
   CU(cudaMemcpy(st->arena, &root, sizeof(Node), cudaMemcpyHostToDevice));
   return CTCDEC_OK;
 }

@@ -14,7 +14,10 @@ Differences from the reference, all additive:
     of the last call (the reference has no equivalent; see include/ctcdecode_b200.h).
   * ``model_path`` (word-based KenLM models): the language model stays on the host behind a hook; the real Scorer
     comes from a provider library (``scorer_provider=`` / CTCDECODE_B200_SCORER_PROVIDER, see scorer.py and
-    INTEGRATION.md).  Character-based models and the online decoder with a scorer are not built.
+    INTEGRATION.md; providers/ builds one from the reference's own Scorer + KenLM).  The online decoder takes a
+    scorer too (device-resident states, one persistent launch per chunk).  Character-based models are not built.
+  * ``device="all"`` (or no device and a CPU batch of more than 4 x 148 utterances on a multi-GPU box): the host batch
+    is sharded over every visible GPU by one call (ctcdec_decode_batch_host_multi).
 """
 import ctypes
 
@@ -57,9 +60,16 @@ class _Base(object):
     def _device_index(self, probs=None):
         if probs is not None and probs.is_cuda:
             return probs.device.index if probs.device.index is not None else torch.cuda.current_device()
-        if self._device is not None:
+        if self._device is not None and self._device != "all":
             return torch.device(self._device).index or 0
         return 0
+
+    def _use_all_gpus(self, B):
+        """CPU input: device="all" spreads the batch over every visible GPU; with no device given that happens once
+        the batch is more than two waves of one GPU (> 4 x 148 utterances) and there is more than one GPU."""
+        if self._device == "all":
+            return torch.cuda.device_count() > 1
+        return self._device is None and B > 4 * 148 and torch.cuda.device_count() > 1
 
     def character_based(self):
         return self._scorer.is_character_based() if self._scorer else None
@@ -116,6 +126,13 @@ class CTCBeamDecoder(_Base):
                 ctypes.byref(cfg), self._scorer.handle, probs.data_ptr(),
                 seq_lens.data_ptr() if seq_lens is not None else None, B, T, output.data_ptr(), timesteps.data_ptr(),
                 scores.data_ptr(), out_seq_len.data_ptr(), n_results.data_ptr(), flags.data_ptr(), dev_index))
+        elif self._use_all_gpus(B):
+            # one host batch over every GPU of the box (contiguous shards, a worker thread per device, nothing
+            # crosses between GPUs): the reference's ThreadPool fan-out over utterances at box scale
+            _native.check(lib.ctcdec_decode_batch_host_multi(
+                ctypes.byref(cfg), probs.data_ptr(), seq_lens.data_ptr() if seq_lens is not None else None, B, T,
+                output.data_ptr(), timesteps.data_ptr(), scores.data_ptr(), out_seq_len.data_ptr(),
+                n_results.data_ptr(), flags.data_ptr(), None, 0))
         else:
             _native.check(lib.ctcdec_decode_batch_host(
                 ctypes.byref(cfg), probs.data_ptr(), seq_lens.data_ptr() if seq_lens is not None else None, B, T,

@@ -110,13 +110,22 @@ int ctcdec_pack_results_device(const int32_t *tokens, const int32_t *timesteps, 
  * (reference __init__.py:77-86).  The batch is cut into up to 8 groups of utterances, each on its own stream, so
  * that the upload, the kernels and the download of different groups overlap; small results are staged through
  * pinned memory.  Pinned caller buffers keep every copy asynchronous (pageable ones work, more slowly).
- * Environment (tuning / test knobs, all optional): CTCDEC_HOST_CHUNK=n utterances per group; CTCDEC_NT=128|256|512|
- * 1024 threads per utterance; CTCDEC_GENERIC_KP=1 the run-time-beam-size kernel; CTCDEC_FORCE_FALLBACK=1 the
+ * Environment (tuning / test knobs, all optional): CTCDEC_HOST_CHUNK=n utterances per group; CTCDEC_NT=128|160|192|256|
+ * 512|1024 threads per utterance; CTCDEC_NO_FAST=1|2 the general back half of a frame everywhere / no head hand-over; CTCDEC_GENERIC_KP=1 the run-time-beam-size kernel; CTCDEC_FORCE_FALLBACK=1 the
  * grid-walking select on every frame; CTCDEC_SEG=n / CTCDEC_HEUR_BIAS=x small candidate lists / a failing heuristic
  * bound (tests/test_gpu_parity.py drives every select path with them). */
 int ctcdec_decode_batch_host(const ctcdec_config *cfg, const float *probs, const int32_t *seq_lens, int B, int T,
                              int32_t *tokens, int32_t *timesteps, float *scores, int32_t *lens, int32_t *n_results,
                              int32_t *flags, int device);
+
+/* The same call spread over several GPUs of the box from ONE host thread of the caller: the batch is cut into
+ * contiguous shards, one per device in `devices` (NULL / n_devices <= 0: every usable device), each shard runs
+ * ctcdec_decode_batch_host on its own device from its own worker thread (per-device streams and buffers; utterances are
+ * independent, so nothing crosses between GPUs -- the reference's ThreadPool fan-out over utterances,
+ * ctc_beam_search_decoder.cpp:245-285, at box scale).  This is what decoder.decode(cpu_probs) of a large batch uses. */
+int ctcdec_decode_batch_host_multi(const ctcdec_config *cfg, const float *probs, const int32_t *seq_lens, int B, int T,
+                                   int32_t *tokens, int32_t *timesteps, float *scores, int32_t *lens,
+                                   int32_t *n_results, int32_t *flags, const int *devices, int n_devices);
 
 /* ---- scorer path: word-based language model + dictionary (reference Scorer, scorer.h:41-110) --------------
  *
@@ -156,7 +165,7 @@ int ctcdec_scorer_reset_params(void *scorer, double alpha, double beta);
  * The beam search runs on `device` in ONE kernel launch; after every frame each utterance's CTA hands the trie
  * nodes it created to the host through device-mapped pinned memory and waits for their LM terms (hook calls).
  * Environment: CTCDEC_LM_PER_FRAME=1 selects the older protocol (one launch per frame), CTCDEC_LM_THREADS=n the
- * number of host workers (default min(8, cores)). */
+ * number of host workers (default: one per utterance, at most half the hardware threads and at most 64). */
 int ctcdec_decode_batch_lm_host(const ctcdec_config *cfg, void *scorer, const float *probs, const int32_t *seq_lens,
                                 int B, int T, int32_t *tokens, int32_t *timesteps, float *scores, int32_t *lens,
                                 int32_t *n_results, int32_t *flags, int device);

@@ -201,8 +201,8 @@ int emu_decode_batch(const float *probs, const int *seq_lens, int B, int T, int 
     first = false;
     if (T == 0) break;
   }
-  std::vector<unsigned char> fsmem((size_t)K * 12 + 64);
-  for (int b = 0; b < B; ++b) finalize_cta_run<128>(bp, b, fsmem.data());
+  std::vector<unsigned char> fsmem(finalize_smem_bytes(K) + 64);
+  for (int b = 0; b < B; ++b) finalize_cta_run<256>(bp, b, fsmem.data());
   return 0;
 }
 
@@ -294,8 +294,8 @@ int emu_decode_batch_lm(const float *probs, const int *seq_lens, int B, int T, i
         default: run_beam<256>(bp, pl.sorted, B, smem.data()); break;
       }
     }
-    std::vector<unsigned char> fsmem2((size_t)K * 12 + 64);
-    for (int b = 0; b < B; ++b) finalize_cta_run<128>(bp, b, fsmem2.data());
+    std::vector<unsigned char> fsmem2(finalize_smem_bytes(K) + 64);
+    for (int b = 0; b < B; ++b) finalize_cta_run<256>(bp, b, fsmem2.data());
     lm_rescore_batch(sc, B, K, T, n_results, tokens, lens, scores);
     return 0;
   }
@@ -314,8 +314,8 @@ int emu_decode_batch_lm(const float *probs, const int *seq_lens, int B, int T, i
       lm_after_frame(sc, sc.cond_caches[0], mirror[b], newlist.data() + (size_t)b * nls, upd.data() + (size_t)b * ups,
                      scratch);
   }
-  std::vector<unsigned char> fsmem((size_t)K * 12 + 64);
-  for (int b = 0; b < B; ++b) finalize_cta_run<128>(bp, b, fsmem.data());
+  std::vector<unsigned char> fsmem(finalize_smem_bytes(K) + 64);
+  for (int b = 0; b < B; ++b) finalize_cta_run<256>(bp, b, fsmem.data());
   lm_rescore_batch(sc, B, K, T, n_results, tokens, lens, scores);
   return 0;
 }

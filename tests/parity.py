@@ -3,8 +3,9 @@ oracle.oracle / tests.emul / the CUDA path), honouring the reference's "unspecif
 
 Integer outputs (tokens, timesteps, lens, n_results) must be identical on [:len]; scores must be identical
 as float32 bit patterns (stronger than the 1e-4 the spec asks for).  Utterances whose tie flags are set
-by either side are handled as follows: a tie at a CUT (beam prune, vocabulary prune) can change everything after
-it, so those utterances are skipped and counted; a tie only in the FINAL order (two result rows with the same
+by either side are handled as follows: a tie at a CUT (beam prune, vocabulary prune) can change which of two equally
+scored prefixes lives on, so for those utterances only what cannot depend on that choice is compared (number of
+results, multiset of score bits, the best beam when its score is unique) and they are counted as "skipped"; a tie only in the FINAL order (two result rows with the same
 score and the same last character, which std::sort may emit in either order) is compared row-set-wise inside
 each tied group -- everything else about the utterance must still match exactly.  Beams with score == FLT_MAX are -FLT_MAX "junk" prefixes
  whose relative order is a tie by construction.
@@ -45,7 +46,13 @@ def compare(ref, got, ref_ties=None, name=""):
         if "ties" in got:
             tie |= int(got["ties"][b]) & 7
         if tie & 5:  # FLAG_TIE_PRUNE | FLAG_TIE_VOCAB
+            # the reference's own choice between comparator-equal prefixes is unspecified here: rows may name different
+            # (equally scored) prefixes, and -- the two can split their score differently into blank / non-blank parts
+            # -- later scores may differ too.  Only the number of results is asserted; count() below reports how often
+            # the multiset of scores and the best beam still agree (tools/tie_report.py: always, on BASELINE configs 2
+            # and 4 against oracle/_ref).
             skipped += 1
+            assert int(got["n_results"][b]) == int(ref["n_results"][b]), f"{name} utt {b} (tie-flagged): n_results differ"
             continue
         if tie & 2:  # FLAG_TIE_FINAL only: canonical order inside groups of equal (score, last char)
             ref = dict(ref)
@@ -80,7 +87,8 @@ def count(ref, got, ties=None, n=None):
     skipped, tie_prune, tie_vocab, tie_final).  `ties`: flags of either side (the CUDA path's own flags will do: it
     flags exactly the utterances the oracle flags, which the tests assert)."""
     B = ref["lens"].shape[0] if n is None else n
-    out = dict(checked=0, mismatches=0, skipped=0, tie_prune=0, tie_vocab=0, tie_final=0)
+    out = dict(checked=0, mismatches=0, skipped=0, tie_prune=0, tie_vocab=0, tie_final=0, skipped_same_scores=0,
+               skipped_same_best_beam=0)
     for b in range(B):
         tie = int(ties[b]) & 7 if ties is not None else 0
         if "ties" in got:
@@ -90,6 +98,14 @@ def count(ref, got, ties=None, n=None):
         out["tie_final"] += 1 if tie & 2 else 0
         one_ref = {k: v[b:b + 1] for k, v in ref.items() if hasattr(v, "shape") and v.shape[:1] == ref["lens"].shape[:1]}
         one_got = {k: v[b:b + 1] for k, v in got.items() if hasattr(v, "shape") and v.shape[:1] == got["lens"].shape[:1]}
+        if tie & 5:  # what the skipped utterances still have in common with the reference
+            nr = int(ref["n_results"][b])
+            if int(got["n_results"][b]) == nr:
+                rs, gs = ref["scores"][b, :nr].view(np.int32), got["scores"][b, :nr].view(np.int32)
+                out["skipped_same_scores"] += int(np.array_equal(np.sort(rs), np.sort(gs)))
+                L = int(ref["lens"][b, 0]) if nr else 0
+                out["skipped_same_best_beam"] += int(nr > 0 and int(got["lens"][b, 0]) == L and
+                                                     np.array_equal(ref["tokens"][b, 0, :L], got["tokens"][b, 0, :L]))
         try:
             c, s = compare(one_ref, one_got, [tie], "utt %d" % b)
             out["checked"] += c
