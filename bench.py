@@ -85,6 +85,31 @@ def traffic_of(config, kernel):
         return None, None
 
 
+def pin_to_gpu_numa_node(index):
+    """One process per GPU, N of them on one host: run this rank on the cores of the NUMA node its GPU hangs off, so
+    that its pinned host buffers (first touch) and the threads that fill them are local to the GPU's PCIe root --
+    what a production launcher does with numactl.  Best effort: any failure leaves the affinity as it was."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(index).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(index), "pci_domain_id", 0)
+        dev_id = torch.cuda.get_device_properties(index).pci_device_id
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/numa_node" % (dom, bus, dev_id)
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -268,6 +293,8 @@ def main():
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    if world > 1:
+        pin_to_gpu_numa_node(local_rank)  # before any pinned allocation: first touch puts the buffers next to the GPU
     if world > 1:
         # keep stdout for the one JSON line: NCCL prints its version line (NCCL_DEBUG=WARN / VERSION) to stdout when the
         # communicator comes up, so file descriptor 1 points at stderr until the first collective has run

@@ -347,6 +347,16 @@ CTC_FN unsigned ctc_warp_max(const unsigned (&v)[kLW]) { return __reduce_max_syn
 CTC_FN unsigned ctc_warp_min(const unsigned (&v)[kLW]) { return __reduce_min_sync(0xffffffffu, v[0]); }
 #endif
 
+// one lane's 64-bit value to the whole warp
+#if defined(CTC_EMULATE)
+static inline uint64_t ctc_shfl64(const uint64_t (&v)[kLW], int src) { return v[src]; }
+#else
+CTC_FN uint64_t ctc_shfl64(const uint64_t (&v)[kLW], int src) {
+  const unsigned lo = __shfl_sync(0xffffffffu, (unsigned)v[0], src), hi = __shfl_sync(0xffffffffu, (unsigned)(v[0] >> 32), src);
+  return ((uint64_t)hi << 32) | lo;
+}
+#endif
+
 // log_sum_exp<float> (reference decoder_utils.h:47-54) with the 32-entry expf / 16-entry logf tables
 // staged in shared memory (a __constant__ table indexed per thread would serialise divergent reads).
 CTC_FN float lse_smem(float x, float y, const uint64_t *exptab, const double *logtab) {

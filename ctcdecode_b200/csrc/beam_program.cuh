@@ -8,7 +8,7 @@ namespace ctc {
 #if defined(CTC_EMULATE) && defined(CTC_STATS)
 struct EmuStats { long long frames, passes, walk_iters, anchors_live, evicted, anchors_new, rv_hops, created, revived,
                   hist_adds, tie_frames, sel_all_frames, rv_frames, rows, rows_skipped, cl_entries, rewalks, fb_frames, ovf_first, heur_fail,
-                  fast_frames, nf_anchor, nf_notfull, nf_seg, nf_pass, nf_pass_cnt; };
+                  fast_frames, nf_anchor, nf_notfull, nf_seg, nf_pass, nf_pass_cnt, fast2_frames; };
 static EmuStats g_stats;
 #define CTC_STAT(x) (x)
 #else
@@ -289,6 +289,10 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
   constexpr int WB0 = (MERGED && KPT > 0 && KPW < NW) ? KPW : 0;
   constexpr int NB = NW - WB0;
   constexpr int CH = NB <= 2 ? 2 : 1;  // 32-entry chunks of a list segment the barrier-free back half looks at
+  // FAST2: a frame whose K-th key shares its histogram bin with other keys stays in the barrier-free back half when
+  // that bin holds at most 32 keys: every warp ranks them among themselves (64 scratch words per warp: the
+  // general path's selection lists, unused in such a frame)
+  constexpr bool FAST2 = FASTB && 4 * KPT >= NW * 64;
 
   Cta<SORTED, LM> c;
 #define CTC_SLOT(type, unit) ((type *)(smem + slot_off(unit, KP)))
@@ -1109,6 +1113,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
     int *const npslot = pslot_base + (cur ^ 1) * KP, *const nanch = anch_base + (cur ^ 1) * KP;
     int nrev = 0;
     bool fastb = false;
+    unsigned thr_hi = 0u, thr_code = 0u;
     if (FASTB) {
       fastb = !(p.no_fast & 1) && !fallback && nlive == 0 && M == K && !select_all;
       CTC_STAT(g_stats.nf_anchor += (nlive != 0));
@@ -1118,18 +1123,108 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
         for (int q = 0; q < NB; ++q) fastb = fastb && c.s_wcnt[WB0 + q] <= 32 * CH;
         CTC_STAT(g_stats.nf_seg += !fastb);
       }
+      bool inbin = false;  // the K-th key shares its bin: rank the bin's keys (FAST2)
       if (fastb) {
         scan_bin_all(hist0, K, pre_bin, pre_above, pre_cnt);
         have_scan = true;
         fastb = (pre_above + pre_cnt == K);
+        if (FAST2 && !fastb && pre_above + pre_cnt > K && pre_cnt <= 32 && !(p.no_fast & 4)) { fastb = true; inbin = true; }
         CTC_STAT(g_stats.nf_pass += !fastb);
         CTC_STAT(g_stats.nf_pass_cnt += fastb ? 0 : pre_cnt);
+      }
+      // selected <=> 48-bit key >= (thr_hi, thr_code): score key, then smaller character first.  One radix pass:
+      // the lower edge of the K-th key's bin, any character.
+      thr_hi = lo32 + ((unsigned)pre_bin << shift32);
+      thr_code = 0u;
+      if (FAST2 && fastb && inbin) {
+        // ---- the bin [thr_hi, thr_hi + 2^shift32) holds pre_cnt <= 32 keys of which K - pre_above are selected: every
+        //      warp gathers them (members' keys need their character, list entries the character of their column)
+        //      into a scratch row of its own and ranks them by counting; the key of rank K - pre_above - 1 is the
+        //      threshold.  Two equal keys there (comparator-equal prefixes at the cut: the reference's choice is
+        //      unspecified) leave the frame to the general back half and its tie handling.
+        const int need = K - pre_above;
+        const unsigned bw = 1u << shift32;
+        bool ok2 = true;
+        unsigned t_hi = thr_hi, t_code = 0u;
+        CTC_WARPS {
+          uint64_t *const scr2 = reinterpret_cast<uint64_t *>(c.s_sel) + warp * 32;
+          int n = 0;
+#pragma unroll
+          for (int blk = 0; blk < KPW; ++blk) {
+            CTC_LV(int, inb);
+            CTC_LV(uint64_t, kk);
+            CTC_LANES {
+              const int j = blk * 32 + lane;
+              inb[LX] = 0; kk[LX] = 0ull;
+              if (j < K) {
+                const unsigned k = ord_f(c.s_snew[j]);
+                if (k >= thr_hi && k - thr_hi < bw) { inb[LX] = 1; kk[LX] = ((uint64_t)k << 16) | (uint64_t)(0xFFFF - (c.s_chr[j] + 1)); }
+              }
+            }
+            const unsigned bl = ctc_ballot(inb);
+            CTC_LANES { if (inb[LX]) { const int pos = n + ctc_popc(bl & ctc_lt_mask(lane)); if (pos < 32) scr2[pos] = kk[LX]; } }
+            n += ctc_popc(bl);
+          }
+#pragma unroll
+          for (int q = 0; q < NB; ++q) {
+            const int cn = c.s_wcnt[WB0 + q];
+#pragma unroll
+            for (int h = 0; h < CH; ++h) {
+              if (h > 0 && cn <= 32 * h) break;
+              CTC_LV(int, inb);
+              CTC_LV(uint64_t, kk);
+              CTC_LANES {
+                const int e = 32 * h + lane;
+                inb[LX] = 0; kk[LX] = 0ull;
+                if (e < cn) {
+                  const unsigned k = c.s_clk[(WB0 + q) * SEG + e];
+                  if (k >= thr_hi && k - thr_hi < bw) {
+                    const int r = c.s_cli[(WB0 + q) * SEG + e] & 0xFFFF;
+                    inb[LX] = 1; kk[LX] = ((uint64_t)k << 16) | (uint64_t)(0xFFFF - (c.chr_at(r) + 1));
+                  }
+                }
+              }
+              const unsigned bl = ctc_ballot(inb);
+              CTC_LANES { if (inb[LX]) { const int pos = n + ctc_popc(bl & ctc_lt_mask(lane)); if (pos < 32) scr2[pos] = kk[LX]; } }
+              n += ctc_popc(bl);
+            }
+          }
+          CTC_SYNCWARP();
+          CTC_LV(int, hit);
+          CTC_LV(uint64_t, mykey);
+          CTC_LANES {
+            hit[LX] = 0; mykey[LX] = 0ull;
+            if (n == pre_cnt && lane < n) {
+              const uint64_t mk = scr2[lane];
+              int rank = 0, eq = 0;
+              for (int i = 0; i < n; ++i) {
+                const uint64_t o = scr2[i];
+                rank += (o > mk) ? 1 : 0;
+                eq += (o == mk) ? 1 : 0;
+              }
+              mykey[LX] = mk;
+              hit[LX] = (rank == need - 1 && eq == 1) ? 1 : 0;
+            }
+          }
+          const unsigned hb = ctc_ballot(hit);
+          if (ctc_popc(hb) != 1) {
+            ok2 = false;
+          } else {
+            const uint64_t tk = ctc_shfl64(mykey, ctc_ffs(hb) - 1);
+            t_hi = (unsigned)(tk >> 16); t_code = (unsigned)(tk & 0xFFFFull);
+          }
+          CTC_SYNCWARP();  // (the scratch rows alias the general path's lists: every lane is done reading)
+        }
+        if (ok2) { thr_hi = t_hi; thr_code = t_code; }
+        else { fastb = false; CTC_STAT(g_stats.nf_pass++); }
+        CTC_STAT(g_stats.fast2_frames += ok2);
       }
     }
     if (FASTB && fastb) {
       CTC_STAT(g_stats.passes++);
       CTC_STAT(g_stats.fast_frames++);
-      const unsigned thr_hi = lo32 + ((unsigned)pre_bin << shift32);  // selected <=> score key >= thr_hi
+      // is the key (k, character ch) selected?  (the character is only looked at for a key equal to the threshold's)
+      auto sel48 = [&](unsigned k, int ch) -> bool { return k > thr_hi || (k == thr_hi && (unsigned)(0xFFFF - (ch + 1)) >= thr_code); };
       CTC_TICK(14);  // fast back half: checks + histogram scan
       int nsel_f = 0;
       CTC_WARPS {
@@ -1139,7 +1234,11 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
           CTC_LV(int, ev);
           CTC_LANES {
             const int j = blk * 32 + lane;
-            ev[LX] = (j < K && ord_f(c.s_snew[j]) < thr_hi) ? 1 : 0;
+            ev[LX] = 0;
+            if (j < K) {
+              const unsigned k = ord_f(c.s_snew[j]);
+              ev[LX] = (k > thr_hi || (k == thr_hi && sel48(k, c.s_chr[j]))) ? 0 : 1;
+            }
           }
           evw[blk] = ctc_ballot(ev);
         }
@@ -1172,7 +1271,10 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
               CTC_LANES {
                 const int e = 32 * h + lane;
                 kv[LX] = e < cn ? c.s_clk[(WB0 + q) * SEG + e] : 0u;
-                sl[LX] = (e < cn && kv[LX] >= thr_hi) ? 1 : 0;
+                sl[LX] = 0;
+                if (e < cn)
+                  sl[LX] = (kv[LX] > thr_hi ||
+                            (kv[LX] == thr_hi && sel48(kv[LX], c.chr_at(c.s_cli[(WB0 + q) * SEG + e] & 0xFFFF)))) ? 1 : 0;
               }
               const unsigned sb = ctc_ballot(sl);
               CTC_LANES {
@@ -1204,7 +1306,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
               const int j = blk * 32 + lane;
               if (j < K) {
                 const unsigned k = ord_f(c.s_snew[j]);
-                if (k >= thr_hi) { kmn[LX] = k < kmn[LX] ? k : kmn[LX]; kmx[LX] = k > kmx[LX] ? k : kmx[LX]; }
+                if (k > thr_hi || (k == thr_hi && sel48(k, c.s_chr[j]))) { kmn[LX] = k < kmn[LX] ? k : kmn[LX]; kmx[LX] = k > kmx[LX] ? k : kmx[LX]; }
               }
             }
 #pragma unroll
@@ -1213,7 +1315,9 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
               for (int h = 0; h < CH; ++h) {
                 if (32 * h + lane < c.s_wcnt[WB0 + q]) {
                   const unsigned k = c.s_clk[(WB0 + q) * SEG + 32 * h + lane];
-                  if (k >= thr_hi) { kmn[LX] = k < kmn[LX] ? k : kmn[LX]; kmx[LX] = k > kmx[LX] ? k : kmx[LX]; }
+                  if (k > thr_hi || (k == thr_hi && sel48(k, c.chr_at(c.s_cli[(WB0 + q) * SEG + 32 * h + lane] & 0xFFFF)))) {
+                    kmn[LX] = k < kmn[LX] ? k : kmn[LX]; kmx[LX] = k > kmx[LX] ? k : kmx[LX];
+                  }
                 }
               }
             }

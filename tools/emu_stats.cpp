@@ -30,6 +30,6 @@ int main(int argc, char **argv) {
   printf("rc %d frames %lld passes %lld heur_fail %lld rewalks %lld fb_frames %lld sel_all %lld cl_entries/frame %.1f rows/frame %.1f skipped %.1f created/frame %.2f\n", rc, g_stats.frames, g_stats.passes, g_stats.heur_fail, g_stats.rewalks,
          g_stats.fb_frames, g_stats.sel_all_frames, (double)g_stats.cl_entries / g_stats.frames, (double)g_stats.rows / g_stats.frames, (double)g_stats.rows_skipped / g_stats.frames, (double)g_stats.created / g_stats.frames);
   printf("fast back halves %lld of %lld frames; not taken because: dead anchors in the table %lld, beam not full %lld, a list segment > 32 entries %lld, "
-         "second radix pass needed %lld (keys in the K-th key's bin: %.1f on average)\n", g_stats.fast_frames, g_stats.frames, g_stats.nf_anchor,
-         g_stats.nf_notfull, g_stats.nf_seg, g_stats.nf_pass, g_stats.nf_pass ? (double)g_stats.nf_pass_cnt / g_stats.nf_pass : 0.0);
+         "second radix pass needed %lld (keys in the K-th key's bin: %.1f on average); %lld of the fast ones ranked a shared bin\n", g_stats.fast_frames, g_stats.frames, g_stats.nf_anchor,
+         g_stats.nf_notfull, g_stats.nf_seg, g_stats.nf_pass, g_stats.nf_pass ? (double)g_stats.nf_pass_cnt / g_stats.nf_pass : 0.0, g_stats.fast2_frames);
 }
