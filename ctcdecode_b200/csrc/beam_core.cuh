@@ -156,6 +156,8 @@ enum : int {  // slot block, in units of KP ints
   U_DEPTHN,               // frame, installed into U_NODE / U_DEPTH / U_JUMP by the slot owner at the start of the next
   U_JUMPN,                // frame (U_NODEN: -1 = nothing pending)
   U_JUMP,                 // jump pointer of the member's node (Node::jump)
+  U_CODE,                 // 0xFFFF - (chr + 1) of the member as the frame started: the tie-break half of its 48-bit key,
+                          // read by the barrier-free back half while slot owners already overwrite U_CHR
   U_SLOT_UNITS
 };
 CTC_HD int slot_off(int unit, int KP) { return kSmemHead + unit * KP * 4; }

@@ -322,6 +322,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
   int *const pslot_base = CTC_SLOT(int, U_PSLOT), *const anch_base = CTC_SLOT(int, U_ANCH);
   int *const s_nodeN = CTC_SLOT(int, U_NODEN), *const s_depthN = CTC_SLOT(int, U_DEPTHN);
   int *const s_jumpN = CTC_SLOT(int, U_JUMPN), *const s_jump = CTC_SLOT(int, U_JUMP);
+  int *const s_code = CTC_SLOT(int, U_CODE);
   uint32_t *const mask_buf0 = (uint32_t *)(smem + L.mask), *const mask_buf1 = (uint32_t *)(smem + L.mask2);
   int cur = 0;  // which half of the double-buffered link arrays describes the current beam
   int par = 0;  // frame parity: which C_CMIN / C_CMAX pair holds the current beam's score range
@@ -690,6 +691,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
           }
           const float sc = c.s_score[j];
           const int ch = c.s_chr[j];
+          if (FASTB) s_code[j] = 0xFFFF - (ch + 1);
           const float bnew = (rblank >= 0 && !c.lm_cut(c.lp[rblank], sc)) ? f_add(c.lp[rblank], sc) : kNInf;
           float rep = kNInf, ext = kNInf;
           const int rr = (ch >= 0) ? c.rank_of(ch) : -1;
@@ -1158,7 +1160,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
               inb[LX] = 0; kk[LX] = 0ull;
               if (j < K) {
                 const unsigned k = ord_f(c.s_snew[j]);
-                if (k >= thr_hi && k - thr_hi < bw) { inb[LX] = 1; kk[LX] = ((uint64_t)k << 16) | (uint64_t)(0xFFFF - (c.s_chr[j] + 1)); }
+                if (k >= thr_hi && k - thr_hi < bw) { inb[LX] = 1; kk[LX] = ((uint64_t)k << 16) | (uint64_t)(unsigned)s_code[j]; }
               }
             }
             const unsigned bl = ctc_ballot(inb);
@@ -1224,7 +1226,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
       CTC_STAT(g_stats.passes++);
       CTC_STAT(g_stats.fast_frames++);
       // is the key (k, character ch) selected?  (the character is only looked at for a key equal to the threshold's)
-      auto sel48 = [&](unsigned k, int ch) -> bool { return k > thr_hi || (k == thr_hi && (unsigned)(0xFFFF - (ch + 1)) >= thr_code); };
+      auto sel48 = [&](unsigned k, int code) -> bool { return k > thr_hi || (k == thr_hi && (unsigned)code >= thr_code); };
       CTC_TICK(14);  // fast back half: checks + histogram scan
       int nsel_f = 0;
       CTC_WARPS {
@@ -1237,7 +1239,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
             ev[LX] = 0;
             if (j < K) {
               const unsigned k = ord_f(c.s_snew[j]);
-              ev[LX] = (k > thr_hi || (k == thr_hi && sel48(k, c.s_chr[j]))) ? 0 : 1;
+              ev[LX] = (k > thr_hi || (k == thr_hi && sel48(k, s_code[j]))) ? 0 : 1;
             }
           }
           evw[blk] = ctc_ballot(ev);
@@ -1274,7 +1276,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
                 sl[LX] = 0;
                 if (e < cn)
                   sl[LX] = (kv[LX] > thr_hi ||
-                            (kv[LX] == thr_hi && sel48(kv[LX], c.chr_at(c.s_cli[(WB0 + q) * SEG + e] & 0xFFFF)))) ? 1 : 0;
+                            (kv[LX] == thr_hi && sel48(kv[LX], 0xFFFF - (c.chr_at(c.s_cli[(WB0 + q) * SEG + e] & 0xFFFF) + 1)))) ? 1 : 0;
               }
               const unsigned sb = ctc_ballot(sl);
               CTC_LANES {
@@ -1306,7 +1308,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
               const int j = blk * 32 + lane;
               if (j < K) {
                 const unsigned k = ord_f(c.s_snew[j]);
-                if (k > thr_hi || (k == thr_hi && sel48(k, c.s_chr[j]))) { kmn[LX] = k < kmn[LX] ? k : kmn[LX]; kmx[LX] = k > kmx[LX] ? k : kmx[LX]; }
+                if (k > thr_hi || (k == thr_hi && sel48(k, s_code[j]))) { kmn[LX] = k < kmn[LX] ? k : kmn[LX]; kmx[LX] = k > kmx[LX] ? k : kmx[LX]; }
               }
             }
 #pragma unroll
@@ -1315,7 +1317,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
               for (int h = 0; h < CH; ++h) {
                 if (32 * h + lane < c.s_wcnt[WB0 + q]) {
                   const unsigned k = c.s_clk[(WB0 + q) * SEG + 32 * h + lane];
-                  if (k > thr_hi || (k == thr_hi && sel48(k, c.chr_at(c.s_cli[(WB0 + q) * SEG + 32 * h + lane] & 0xFFFF)))) {
+                  if (k > thr_hi || (k == thr_hi && sel48(k, 0xFFFF - (c.chr_at(c.s_cli[(WB0 + q) * SEG + 32 * h + lane] & 0xFFFF) + 1)))) {
                     kmn[LX] = k < kmn[LX] ? k : kmn[LX]; kmx[LX] = k > kmx[LX] ? k : kmx[LX];
                   }
                 }

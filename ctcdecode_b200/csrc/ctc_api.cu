@@ -251,8 +251,9 @@ static int launch_prune(const ctcdec_config *cfg, const Plan &pl, const PruneInp
 static int launch_finalize(const BeamParams &bp, int B, cudaStream_t s) {
   const size_t smem = finalize_smem_bytes(bp.K);
   if (smem > 48 * 1024)
-    CU(cudaFuncSetAttribute(finalize_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  finalize_kernel<256><<<B, 256, smem, s>>>(bp);
+    CU(cudaFuncSetAttribute(finalize_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // 1024 threads: the backtrace is a latency-bound pointer chase, its only resource is chains in flight
+  finalize_kernel<1024><<<B, 1024, smem, s>>>(bp);
   CU(cudaGetLastError());
   return CTCDEC_OK;
 }
@@ -383,6 +384,11 @@ static int serve_handshakes(HostScorer *sc, int B, int K, const int *need, TrieM
         served[b] = d;
         if (d >= need[b]) --remaining;
         progress = true;
+      }
+      if (!progress) {
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();  // (a spinning worker must not starve the hyper-thread that runs another worker's hooks)
+#endif
       }
       if (progress) { idle = 0; last_progress = std::chrono::steady_clock::now(); }
       else if ((++idle & 0xFFFF) == 0 &&
