@@ -183,11 +183,14 @@ CTC_HD SmemLayout make_layout(int K, int V, int NP, int tile_frames, bool sorted
   L.WC = (V + 31) / 32;
   int o = slot_off(U_SLOT_UNITS, KP);
   L.evcnt = o;     o += (KP / 32) * 4;
-  L.mask = o;      o += KP * W * 4;    // [KP][W] bitmasks over pruned ranks
-  L.mask2 = o;     o += KP * W * 4;    // (index-order kernels: the masks of frame t+1 are built while frame t commits)
+  // "existing child" masks: [KP][W] bits over pruned ranks (scorer path), [KP][WC] bits over CHARACTERS otherwise (the
+  // masks of frame t+1 are built while frame t commits, when the frame's ranks are not known yet); rmask: ranks
+  const int MWd = lm ? W : (L.WC > W ? L.WC : W);
+  L.mask = o;      o += KP * MWd * 4;
+  L.mask2 = o;     o += KP * MWd * 4;
   L.rmask = o;     o += KP * W * 4;
   L.dmask = o;     o += lm ? KP * L.WC * 4 : 0;   // scorer path: [KP][WC] dictionary arc bits
-  L.rank = o;      o += sorted ? align_up(V * 2, 16) : 0;
+  L.rank = o;      o += sorted ? 2 * align_up(V * 2, 16) : 0;   // two rank tables: frame t+1's is built during frame t
   o = align_up(o, 128);
   L.tile_lp = o;   o += 2 * tile_frames * NP * 4;
   L.tile_idx = o;  o += sorted ? 2 * tile_frames * NP * 2 : 0;
@@ -198,7 +201,7 @@ CTC_HD SmemLayout make_layout(int K, int V, int NP, int tile_frames, bool sorted
   {
     int cap_bytes = budget_kb * 1024 - o - 64;
     if (cap_bytes > 64 * 1024) cap_bytes = 64 * 1024;
-    if (cap_bytes < 8 * 1024) {  // the intended number of CTAs per SM does not fit: one CTA, whatever an SM has left
+    if (cap_bytes < NW * 32 * 8) {  // not even minimal segments fit beside the intended number of CTAs per SM: one CTA
       cap_bytes = 227 * 1024 - o - 64;
       if (cap_bytes > 64 * 1024) cap_bytes = 64 * 1024;
     }
@@ -394,6 +397,8 @@ struct Cta {
   // global
   Node *nodes;
   int K, KP, V, NP, W, blank;
+  int WS;      // words per member of s_mask
+  bool mch;    // s_mask is indexed by character (kernels without a scorer), not by pruned rank
   // scorer path, per frame: prune everything under min_cutoff once the beam is full (reference :74-82,93-95)
   const int *dict_next;
   uint32_t *s_dmask;    // [KP][WC]: which characters the dictionary lets follow each member
@@ -419,7 +424,10 @@ struct Cta {
   CTC_MFN bool cand(int i, int r, float &sc, int &c) const {
     c = chr_at(r);
     if (c == blank) return false;
-    if ((s_mask[i * W + (r >> 5)] >> (r & 31)) & 1u) return false;  // that child is itself a beam member
+    {  // that child is itself a beam member
+      const int mb = mch ? c : r;
+      if ((s_mask[i * WS + (mb >> 5)] >> (mb & 31)) & 1u) return false;
+    }
     const float l = lp[r];
     if (LM) {
       if (lm_cut(l, s_score[i])) return false;

@@ -272,18 +272,18 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
   constexpr int NW = NT / 32;
   const int KP = KPT > 0 ? KPT : L.KP;
   const int W = L.W, KP2 = 2 * KP, SEG = L.seg;
-  // MERGED (index-order kernels without a scorer): a frame is TWO barrier-separated regions on the common path.
+  // MERGED (kernels without a scorer): a frame is TWO barrier-separated regions on the common path.
   //   front: the members' terms (region R1) and the grid walk (region G) run side by side -- on different warps where
   //          the CTA has more warps than the beam has 32-slot blocks (WB0 = first grid-walking warp, NB of them),
   //          one after the other inside each warp otherwise.  That needs the "existing child" masks before the frame
-  //          starts: they depend on the beam's links only (rank == character here), so the commit of frame t-1
+  //          starts: indexed by CHARACTER they depend on the beam's links only, so the commit of frame t-1
   //          builds them (double buffered by frame parity, like the first radix histogram and the words of s_ctl
   //          that are read right after a barrier and reset in the same region).
   //   back:  FASTB -- every warp redundantly finds the K-th key and classifies ALL members / list entries into
   //          ballot words it keeps in registers, so the slot owners commit the new beam without another barrier.
   //          Frames that need more (dead anchors in the table, beam not full, a second radix pass, ties, list
   //          overflow) take the general back half below, unchanged.
-  constexpr bool MERGED = !LM && !SORTED;
+  constexpr bool MERGED = !LM;
   constexpr int KPW = KPT / 32;
   constexpr bool FASTB = MERGED && KPT > 0 && KPT <= NT && KPW <= 8;
   constexpr int WB0 = (MERGED && KPT > 0 && KPW < NW) ? KPW : 0;
@@ -323,12 +323,16 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
   int *const s_nodeN = CTC_SLOT(int, U_NODEN), *const s_depthN = CTC_SLOT(int, U_DEPTHN);
   int *const s_jumpN = CTC_SLOT(int, U_JUMPN), *const s_jump = CTC_SLOT(int, U_JUMP);
   int *const s_code = CTC_SLOT(int, U_CODE);
+  const int WS = MERGED ? (L.WC > W ? L.WC : W) : W;  // words per member of the "existing child" masks
+  const int VR = SORTED ? align_up(V * 2, 16) / 2 : 0;  // entries of one rank table
+  int16_t *const rank_base = (int16_t *)(smem + L.rank);
   uint32_t *const mask_buf0 = (uint32_t *)(smem + L.mask), *const mask_buf1 = (uint32_t *)(smem + L.mask2);
   int cur = 0;  // which half of the double-buffered link arrays describes the current beam
   int par = 0;  // frame parity: which C_CMIN / C_CMAX pair holds the current beam's score range
   c.s_exptab = (uint64_t *)(smem + H_EXPTAB);
   c.s_logtab = (double *)(smem + H_LOGTAB);
   c.K = K; c.KP = KP; c.V = V; c.NP = NP; c.W = W; c.blank = p.blank;
+  c.WS = WS; c.mch = MERGED;
   c.s_dmask = (uint32_t *)(smem + L.dmask); c.WC = L.WC;
   c.dict_next = p.dict_next; c.space_id = p.space_id; c.beta = p.beta; c.lm_full = false; c.lm_cutoff = kNInf;
   int *const s_ctl = c.s_ctl;
@@ -455,9 +459,10 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
       c.s_drev[a] = 0;
     }
     for (int x = tid; x < 3 * KP; x += NT) c.s_cnt2[x] = 0;
-    for (int x = tid; x < KP * W; x += NT) { mask_buf0[x] = 0u; mask_buf1[x] = 0u; c.s_rmask[x] = 0u; }
+    for (int x = tid; x < KP * WS; x += NT) { mask_buf0[x] = 0u; mask_buf1[x] = 0u; }
+    for (int x = tid; x < KP * W; x += NT) c.s_rmask[x] = 0u;
     for (int x = tid; x < 2 * kNBins; x += NT) c.s_hist[x] = 0;
-    if (SORTED) for (int v = tid; v < V; v += NT) c.s_rank[v] = (int16_t)-1;
+    if (SORTED) for (int v = tid; v < 2 * VR; v += NT) rank_base[v] = (int16_t)-1;
     if (tid == 0) {
       for (int x = 0; x < 32; ++x) s_ctl[x] = 0;
       s_ctl[C_M] = fresh ? 1 : st[0];
@@ -517,9 +522,11 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
       int np = 0;
       for (int j = tid; j < M; j += NT) {
         const int i = c.s_pslot[j], ch = c.s_chr[j];
-        if (i >= 0 && ch >= 0) { atom_or(&mask_buf0[i * W + (ch >> 5)], 1u << (ch & 31)); ++np; }
+        if (i >= 0 && ch >= 0) { atom_or(&mask_buf0[i * WS + (ch >> 5)], 1u << (ch & 31)); ++np; }
       }
-      if (np) atom_add(&s_ctl[C_NPAIRS], np);
+      // (the pair count: with a per-frame vocabulary cut only children whose character the frame keeps count, so
+      //  those kernels count in region R1)
+      if (np && !SORTED) atom_add(&s_ctl[C_NPAIRS], np);
     }
   }
   CTC_BARRIER();
@@ -563,7 +570,10 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
     const int rblank = (int)(meta >> 16) - 1;
     const float lpmax = c.lp[NP - 1];
 
-    if (SORTED) {
+    if (SORTED) c.s_rank = rank_base + (MERGED ? par : 0) * VR;
+    if (SORTED && (!MERGED || t == 0)) {
+      // rank of every kept character.  MERGED kernels build the table of frame t + 1 during frame t (below); only
+      // the first frame of a launch builds its own.
       CTC_PAR {
         for (int r = tid; r < n; r += NT) c.s_rank[c.idx[r]] = (int16_t)r;
       }
@@ -662,8 +672,10 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
     // how many prefixes exist after this frame: the members plus every grid cell that is a new candidate.  With a
     // scorer the dictionary / cutoff decide that per cell, so the count is taken after the grid walk instead.
     // (MERGED: the pair count came with the beam; otherwise region R1 counts it, see below)
-    long long total = MERGED ? (long long)M * (n_nb + 1) - s_ctl[npairs_w] : 0;
-    bool select_all = MERGED && total <= (long long)K;  // reference :149 `prefixes.size() >= beam_size`
+    // (cut-vocabulary kernels: only children whose character the frame keeps are pairs, region R1 counts them and
+    //  select_all is known after the front; the grid walk bins its candidates regardless)
+    long long total = (MERGED && !SORTED) ? (long long)M * (n_nb + 1) - s_ctl[npairs_w] : 0;
+    bool select_all = MERGED && !SORTED && total <= (long long)K;  // reference :149 `prefixes.size() >= beam_size`
     const int G = (n + 31) >> 5;                        // 32-wide column groups of the candidate grid
 
     // ---- region R1: every member's blank / repeat / extension-from-parent terms, merged with
@@ -680,6 +692,10 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
       }
       if (MERGED)  // the other histogram: scanned by the previous frame, first used again by the next one
         for (int x = tid; x < kNBins; x += NT) c.s_hist[(hpar ^ 1) * kNBins + x] = 0;
+      if (MERGED && SORTED) {  // the other rank table (last read by the previous frame's members): the back half refills it
+        int *const rn = reinterpret_cast<int *>(rank_base + (par ^ 1) * VR);
+        for (int x = tid; x < VR / 2; x += NT) rn[x] = -1;
+      }
       unsigned kmin = 0xFFFFFFFFu, kmax = 0u, smax = 0u;
       int npairs = 0;
       for (int j0 = 0; j0 < M; j0 += NT) {
@@ -708,10 +724,9 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
                 ext = f_add(l, c.s_score[i]);
               }
               if (LM && ch == c.space_id) ext = c.lm_apply(ext, i);
-              if (!MERGED) {  // (MERGED: the mask bit and the pair count were set when the beam was committed)
-                atom_or(&c.s_mask[i * W + (rr >> 5)], 1u << (rr & 31));
-                ++npairs;
-              }
+              // (MERGED: the mask bit -- and in index order the pair count -- were set when the beam was committed)
+              if (!MERGED) atom_or(&c.s_mask[i * W + (rr >> 5)], 1u << (rr & 31));
+              if (!MERGED || SORTED) ++npairs;
             }
           }
           CTC_TICK(12);  // members: loads and terms
@@ -731,7 +746,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
           }
         }
       }
-      if (npairs) atom_add(&s_ctl[C_NPAIRS], npairs);
+      if (npairs) atom_add(&s_ctl[MERGED ? npairs_w : (int)C_NPAIRS], npairs);
       if (nlive > 0) {
         for (int a = tid; a < KP2; a += NT) {
           const int i = c.s_dpslot[a];
@@ -772,6 +787,9 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
     bool rebin = LM;  // members are binned inside region G (scorer path; or the tightened second walk, SORTED only)
     bool have_scan = false;  // the first histogram has already been scanned (pre_bin / pre_above / pre_cnt)
     int pre_bin = 0, pre_above = 0, pre_cnt = 0;
+    // "does member i already have a child by character ch in the beam?" for masks indexed by character (ch >= 0)
+    auto mbit = [&](int i, int ch) -> bool { return (c.s_mask[i * WS + (ch >> 5)] >> (ch & 31)) & 1u; };
+    constexpr bool MCS = MERGED && SORTED;  // the lanes of a column group hold arbitrary characters: per-lane mask words
     auto grid_walk = [&](const int warp, const bool rebin) {
       int cnt = 0;
       uint32_t *const segk = c.s_clk + warp * SEG;
@@ -831,7 +849,8 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
               float sc = f_add(ls, rep ? b : c.s_score[i]);
               if (rep && !(b > kNInf)) sc = kNInf;
               const unsigned k = ord_f(sc);
-              const bool ok = !((c.s_mask[i * W + (rstar >> 5)] >> (rstar & 31)) & 1u) && (k >= lo32);
+              const int mb = MERGED ? chs : rstar;  // (masks by character / by rank)
+              const bool ok = !((c.s_mask[i * WS + (mb >> 5)] >> (mb & 31)) & 1u) && (k >= lo32);
               pred[LX] = ok ? 1 : 0;
               kk[LX] = k;
               if (ok && !select_all) atom_add(&hist0[(int)((k - lo32) >> shift32)], 1);
@@ -884,7 +903,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
           const int i1 = base + (warp - WB0) + NB * rl1, i2 = base + (warp - WB0) + NB * rl2;
           const float sc1 = c.s_score[i1], b1 = c.s_bprev[i1], sc2 = c.s_score[i2], b2 = c.s_bprev[i2];
           const int ch1 = c.s_chr[i1], ch2 = c.s_chr[i2];
-          const uint32_t mw1 = c.s_mask[i1 * W], mw2 = c.s_mask[i2 * W];
+          const uint32_t mw1 = MCS ? 0u : c.s_mask[i1 * WS], mw2 = MCS ? 0u : c.s_mask[i2 * WS];
           CTC_LV(int, pred1);
           CTC_LV(int, pred2);
           CTC_LV(uint32_t, kk1);
@@ -897,8 +916,10 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
             if (rep1 && !(b1 > kNInf)) s1 = kNInf;
             if (rep2 && !(b2 > kNInf)) s2 = kNInf;
             const unsigned k1 = ord_f(s1), k2 = ord_f(s2);
-            const bool ok1 = (ch >= 0) && !((mw1 >> lane) & 1u) && (k1 >= lo32);
-            const bool ok2 = (ch >= 0) && !((mw2 >> lane) & 1u) && (k2 >= lo32);
+            const bool m1 = MCS ? (ch >= 0 && mbit(i1, ch)) : (((mw1 >> lane) & 1u) != 0u);
+            const bool m2 = MCS ? (ch >= 0 && mbit(i2, ch)) : (((mw2 >> lane) & 1u) != 0u);
+            const bool ok1 = (ch >= 0) && !m1 && (k1 >= lo32);
+            const bool ok2 = (ch >= 0) && !m2 && (k2 >= lo32);
             pred1[LX] = ok1 ? 1 : 0; kk1[LX] = k1;
             pred2[LX] = ok2 ? 1 : 0; kk2[LX] = k2;
             if (!select_all) {
@@ -939,7 +960,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
             const int i = base + (warp - WB0) + NB * rl;
             const float sc_i = c.s_score[i], b_i = c.s_bprev[i];
             const int ch_i = c.s_chr[i];
-            const uint32_t mwa = c.s_mask[i * W], mwb = c.s_mask[i * W + 1];
+            const uint32_t mwa = MCS ? 0u : c.s_mask[i * WS], mwb = MCS ? 0u : c.s_mask[i * WS + 1];
             CTC_LV(int, pred1);
             CTC_LV(int, pred2);
             CTC_LV(uint32_t, kk1);
@@ -951,8 +972,10 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
               if (repa && !(b_i > kNInf)) s1 = kNInf;
               if (repb && !(b_i > kNInf)) s2 = kNInf;
               const unsigned k1 = ord_f(s1), k2 = ord_f(s2);
-              const bool ok1 = (cha >= 0) && !((mwa >> lane) & 1u) && (k1 >= lo32);
-              const bool ok2 = (chb >= 0) && !((mwb >> lane) & 1u) && (k2 >= lo32);
+              const bool ma = MCS ? (cha >= 0 && mbit(i, cha)) : (((mwa >> lane) & 1u) != 0u);
+              const bool mb2 = MCS ? (chb >= 0 && mbit(i, chb)) : (((mwb >> lane) & 1u) != 0u);
+              const bool ok1 = (cha >= 0) && !ma && (k1 >= lo32);
+              const bool ok2 = (chb >= 0) && !mb2 && (k2 >= lo32);
               pred1[LX] = ok1 ? 1 : 0; kk1[LX] = k1;
               pred2[LX] = ok2 ? 1 : 0; kk2[LX] = k2;
               if (!select_all) {
@@ -983,7 +1006,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
           const float sc_i = c.s_score[i], b_i = c.s_bprev[i];
           const int ch_i = c.s_chr[i];
           for (int g = 0; g < G; ++g) {
-            const uint32_t mw = c.s_mask[i * W + g];
+            const uint32_t mw = MCS ? 0u : c.s_mask[i * WS + g];
             const uint32_t rmw = LM ? c.s_rmask[i * W + g] : 0u;
             CTC_LV(int, pred);
             CTC_LV(uint32_t, kk);
@@ -1008,7 +1031,8 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
                 if (ch == c.space_id) sc = c.lm_apply(sc, i);
               }
               const unsigned k = ord_f(sc);
-              const bool ok = (ch >= 0) && !((mw >> lane) & 1u) && (k >= lo32) && okl;
+              const bool mk = MCS ? (ch >= 0 && mbit(i, ch)) : (((mw >> lane) & 1u) != 0u);
+              const bool ok = (ch >= 0) && !mk && (k >= lo32) && okl;
               pred[LX] = ok ? 1 : 0;
               kk[LX] = k;
               if (ok && !select_all) atom_add(&hist0[(int)((k - lo32) >> shift32)], 1);
@@ -1035,70 +1059,107 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
       }
     };
     CTC_TICK(1);  // head (SORTED kernels: + rank table)
-    if (MERGED) {
-      // ---- the front of the frame: members (R1) and grid walk (G) in ONE region; nothing the one writes is read by
-      //      the other.  (The emulation runs the halves in either order, CTC_EMU_ORDER bit 2.)
-      CTC_HALVES {
-        if (half == 0) {
-          CTC_PAR { members_region(tid); }
-        } else {
-          CTC_WARPS {
-            if (warp >= WB0) grid_walk(warp, false);
-            else { CTC_LANES { if (lane == 0) c.s_wcnt[warp] = 0; } }
-          }
-        }
+    if (!MERGED) {
+      CTC_PAR { members_region(tid); }
+      CTC_BARRIER_T(2);
+      CTC_TICK(2);  // R1
+      total = (long long)M * (n_nb + 1) - s_ctl[C_NPAIRS];
+      select_all = !LM && total <= (long long)K;
+      if (LM) {
+        lo32 = (!select_all && M == K) ? (unsigned)s_ctl[C_KMIN] : 0u;
+        top32 = (unsigned)s_ctl[C_KMAX];
+        const unsigned o = ord_f(f_add(unord_f((unsigned)s_ctl[C_SMAX]), lpmax));
+        top32 = o > top32 ? o : top32;
+        set_shift();
       }
-      CTC_BARRIER_T(3);
-      CTC_TICK(2);  // front: R1 | G
-    } else {
-    CTC_PAR { members_region(tid); }
-    CTC_BARRIER_T(2);
-    CTC_TICK(2);  // R1
-    total = (long long)M * (n_nb + 1) - s_ctl[C_NPAIRS];
-    select_all = !LM && total <= (long long)K;
-
-    if (LM) {
-      lo32 = (!select_all && M == K) ? (unsigned)s_ctl[C_KMIN] : 0u;
-      top32 = (unsigned)s_ctl[C_KMAX];
-      const unsigned o = ord_f(f_add(unord_f((unsigned)s_ctl[C_SMAX]), lpmax));
-      top32 = o > top32 ? o : top32;
-      set_shift();
     }
     for (int attempt = 0;; ++attempt) {
-    CTC_WARPS { grid_walk(warp, rebin); }
-    CTC_BARRIER_T(3);
-    // (only where the vocabulary is cut per frame: there the blank / a member's character can drop out of a frame
-    // and take the lower bound with it; an index-order kernel keeps its single straight-line walk)
-    if (!SORTED || LM || attempt > 0 || select_all || p.force_fallback) break;
-    {
-      const bool ovf = s_ctl[C_OVF] != 0;
-      if (!ovf && !heuristic) break;
-      scan_bin_all(c.s_hist, K, pre_bin, pre_above, pre_cnt);
-      unsigned lo_new;
-      if (pre_above + pre_cnt < K) {
-        lo_new = lo_valid;                 // the heuristic bound cut too deep: walk again with the proven one
-        CTC_STAT(g_stats.heur_fail++);
-      } else if (ovf) {
-        lo_new = lo32 + ((unsigned)pre_bin << shift32);
-        if (lo_new == lo32) break;         // nothing to gain: grid-walking fallback
+      if (MERGED && attempt == 0) {
+        // ---- the front of the frame: members (R1) and grid walk (G) in ONE region; nothing the one writes is read
+        //      by the other.  (The emulation runs the halves in either order, CTC_EMU_ORDER bit 2.)
+        CTC_HALVES {
+          if (half == 0) {
+            CTC_PAR { members_region(tid); }
+          } else {
+            CTC_WARPS {
+              if (warp >= WB0) grid_walk(warp, false);
+              else { CTC_LANES { if (lane == 0) c.s_wcnt[warp] = 0; } }
+            }
+          }
+        }
+        CTC_BARRIER_T(3);
+        CTC_TICK(2);  // front: R1 | G
+        if (SORTED) {  // (the pairs of this frame were counted by the members' region)
+          total = (long long)M * (n_nb + 1) - s_ctl[npairs_w];
+          select_all = total <= (long long)K;
+        }
       } else {
-        have_scan = true;                  // bound holds, lists fit: the select continues from this scan
-        break;
+        if (MERGED) {
+          // the tightened second walk of a MERGED kernel: the members re-bin themselves (every thread), the
+          // grid-walking warps walk
+          CTC_PAR {
+            if (!select_all)
+              for (int j = tid; j < M; j += NT) {
+                const unsigned k = ord_f(c.s_snew[j]);
+                if (k >= lo32) atom_add(&hist0[(int)((k - lo32) >> shift32)], 1);
+              }
+          }
+        }
+        CTC_WARPS {
+          if (warp >= WB0) grid_walk(warp, MERGED ? false : rebin);
+          else { CTC_LANES { if (lane == 0) c.s_wcnt[warp] = 0; } }
+        }
+        CTC_BARRIER_T(3);
       }
-      CTC_BARRIER();  // every warp has scanned the histogram
+      // (only where the vocabulary is cut per frame: there the blank / a member's character can drop out of a frame
+      // and take the lower bound with it; an index-order kernel keeps its single straight-line walk)
+      if (!SORTED || LM || attempt > 0 || select_all || p.force_fallback) break;
+      {
+        const bool ovf = s_ctl[ovf_w] != 0;
+        if (!ovf && !heuristic) break;
+        scan_bin_all(hist0, K, pre_bin, pre_above, pre_cnt);
+        unsigned lo_new;
+        if (pre_above + pre_cnt < K) {
+          lo_new = lo_valid;                 // the heuristic bound cut too deep: walk again with the proven one
+          CTC_STAT(g_stats.heur_fail++);
+        } else if (ovf) {
+          lo_new = lo32 + ((unsigned)pre_bin << shift32);
+          if (lo_new == lo32) break;         // nothing to gain: grid-walking fallback
+        } else {
+          have_scan = true;                  // bound holds, lists fit: the select continues from this scan
+          break;
+        }
+        CTC_BARRIER();  // every warp has scanned the histogram
+        CTC_PAR {
+          for (int x = tid; x < kNBins; x += NT) hist0[x] = 0;
+          if (tid == 0) s_ctl[ovf_w] = 0;
+        }
+        CTC_BARRIER();
+        lo32 = lo_new;
+        heuristic = false;
+        set_shift();
+        rebin = true;
+        CTC_STAT(g_stats.rewalks++);
+      }
+    }
+    // ---- cut-vocabulary MERGED kernels: the rank table of frame t + 1 (its row is already staged; at a tile boundary
+    //      the tile was requested a whole tile ago), into the table the members' region of this frame cleared
+    if (MERGED && SORTED && t + 1 < Tb) {
+#if defined(CTC_EMULATE)
+      const float *nrow = p.lp + ((size_t)b * p.T + t0 + t + 1) * NP;
+      const uint16_t *nidx = p.idx + ((size_t)b * p.T + t0 + t + 1) * NP;
+#else
+      int ft2 = ft, tile2 = tile;
+      if (ft2 == F) { ft2 = 0; ++tile2; mbar_wait(&mbar[tile2 & 1], (uint32_t)((tile2 >> 1) & 1)); }
+      const float *nrow = tile_lp + ((size_t)(tile2 & 1) * F + ft2) * NP;
+      const uint16_t *nidx = tile_idx + ((size_t)(tile2 & 1) * F + ft2) * NP;
+#endif
+      const int n_next = (int)(f_bits(nrow[NP - 2]) & 0xFFFFu);
+      int16_t *const rn = rank_base + (par ^ 1) * VR;
       CTC_PAR {
-        for (int x = tid; x < kNBins; x += NT) c.s_hist[x] = 0;
-        if (tid == 0) s_ctl[C_OVF] = 0;
+        for (int r = tid; r < n_next; r += NT) rn[nidx[r]] = (int16_t)r;
       }
-      CTC_BARRIER();
-      lo32 = lo_new;
-      heuristic = false;
-      set_shift();
-      rebin = true;
-      CTC_STAT(g_stats.rewalks++);
     }
-    }
-    }  // !MERGED
     CTC_TICK(3);  // G
     bool fallback = s_ctl[ovf_w] != 0 || p.force_fallback;  // a segment overflowed (twice): redo on the grid
     CTC_STAT(g_stats.fb_frames += fallback);
@@ -1446,8 +1507,8 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
             nanch[j] = res;
             c.s_evict[j] = ev ? 1 : 0;
             if (newp >= 0) {  // the "existing child" mask of the next frame (ch_mine >= 0: only the root has none)
-              atom_or(&mask_next[newp * W + (ch_mine >> 5)], 1u << (ch_mine & 31));
-              pair[LX] = 1;
+              atom_or(&mask_next[newp * WS + (ch_mine >> 5)], 1u << (ch_mine & 31));
+              pair[LX] = SORTED ? 0 : 1;  // (cut-vocabulary kernels count pairs per frame, in region R1)
             }
           }
         }
@@ -1463,7 +1524,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
         }
         CTC_LANES {
           if (lane == 0 && pb) atom_add(&s_ctl[npairs_nx], ctc_popc(pb));
-          for (int x = warp * 32 + lane; x < KP * W; x += NT) c.s_mask[x] = 0u;  // this frame's masks: used up
+          for (int x = warp * 32 + lane; x < KP * WS; x += NT) c.s_mask[x] = 0u;  // this frame's masks: used up
           if (warp == NW - 1 && lane == 0) { s_ctl[ovf_nx] = 0; s_ctl[anyref_nx] = 0; }
         }
         nsel_f = nsel;  // (the same in every warp)
@@ -2090,16 +2151,17 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
           nanch[j] = res;
           if (MERGED && newp >= 0) {  // the "existing child" mask of the next frame
             const int ch_mine = c.s_chr[j];
-            atom_or(&mask_next[newp * W + (ch_mine >> 5)], 1u << (ch_mine & 31));
-            ++npair_next;
+            atom_or(&mask_next[newp * WS + (ch_mine >> 5)], 1u << (ch_mine & 31));
+            if (!SORTED) ++npair_next;
           }
         }
       }
       if (MERGED && npair_next) atom_add(&s_ctl[npairs_nx], npair_next);
       if (!LM) warp_range_store(c.s_wcnt + 128 + 64 * (par ^ 1), cmin, cmax, tid);
-      for (int x = tid; x < KP * W; x += NT) { c.s_mask[x] = 0u; c.s_rmask[x] = 0u; }
+      for (int x = tid; x < KP * WS; x += NT) c.s_mask[x] = 0u;
+      for (int x = tid; x < KP * W; x += NT) c.s_rmask[x] = 0u;
       for (int x = tid; x < 2 * kNBins; x += NT) c.s_hist[x] = 0;  // the select is over: clear both radix histograms
-      if (SORTED) for (int r = tid; r < n; r += NT) c.s_rank[c.idx[r]] = (int16_t)-1;
+      if (SORTED && !MERGED) for (int r = tid; r < n; r += NT) c.s_rank[c.idx[r]] = (int16_t)-1;
       if (tid == 0) {  // (C_NLIVE / C_ANYREF are read below and reset in region R4c of the next frame)
         s_ctl[C_NFREE] = 0; s_ctl[C_NTIE] = 0;
         if (!MERGED) s_ctl[C_NPAIRS] = 0;  // (MERGED: the pair count of the next frame is being accumulated)
