@@ -288,7 +288,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
   constexpr bool FASTB = MERGED && KPT > 0 && KPT <= NT && KPW <= 8;
   constexpr int WB0 = (MERGED && KPT > 0 && KPW < NW) ? KPW : 0;
   constexpr int NB = NW - WB0;
-  constexpr int CH = NB <= 2 ? 2 : 1;  // 32-entry chunks of a list segment the barrier-free back half looks at
+  constexpr int CH = 2;  // 32-entry chunks of a list segment the barrier-free back half looks at (the second one rarely)
   // FAST2: a frame whose K-th key shares its histogram bin with other keys stays in the barrier-free back half when
   // that bin holds at most 32 keys: every warp ranks them among themselves (64 scratch words per warp: the
   // general path's selection lists, unused in such a frame)
