@@ -3,7 +3,8 @@ import ctypes
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "_lib", "libctcdecode_b200.so")
+# (CTCDECODE_B200_LIB: another build of the same ABI, for A/B measurements of kernel variants)
+LIB_PATH = os.environ.get("CTCDECODE_B200_LIB") or os.path.join(_PKG, "_lib", "libctcdecode_b200.so")
 
 OK = 0
 FLAG_TIE_PRUNE, FLAG_TIE_FINAL, FLAG_TIE_VOCAB, FLAG_ERR_ARENA = 1, 2, 4, 256
@@ -78,6 +79,8 @@ def load():
             "(nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
     lib = ctypes.CDLL(LIB_PATH)
     for name, (res, args) in _SIGNATURES.items():
+        if os.environ.get("CTCDECODE_B200_LIB") and not hasattr(lib, name):
+            continue  # (an older build of the ABI, loaded for an A/B measurement)
         fn = getattr(lib, name)  # AttributeError here = header / library out of sync
         fn.restype = res
         fn.argtypes = args

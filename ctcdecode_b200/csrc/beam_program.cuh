@@ -1287,7 +1287,8 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
       CTC_STAT(g_stats.passes++);
       CTC_STAT(g_stats.fast_frames++);
       // is the key (k, character ch) selected?  (the character is only looked at for a key equal to the threshold's)
-      auto sel48 = [&](unsigned k, int code) -> bool { return k > thr_hi || (k == thr_hi && (unsigned)code >= thr_code); };
+      // (thr_code != 0 only in a frame that ranked a shared bin -- uniform, so the code is not even loaded otherwise)
+      const bool two = thr_code != 0u;
       CTC_TICK(14);  // fast back half: checks + histogram scan
       int nsel_f = 0;
       CTC_WARPS {
@@ -1300,7 +1301,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
             ev[LX] = 0;
             if (j < K) {
               const unsigned k = ord_f(c.s_snew[j]);
-              ev[LX] = (k > thr_hi || (k == thr_hi && sel48(k, s_code[j]))) ? 0 : 1;
+              ev[LX] = (k > thr_hi || (k == thr_hi && (!two || (unsigned)s_code[j] >= thr_code))) ? 0 : 1;
             }
           }
           evw[blk] = ctc_ballot(ev);
@@ -1337,7 +1338,8 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
                 sl[LX] = 0;
                 if (e < cn)
                   sl[LX] = (kv[LX] > thr_hi ||
-                            (kv[LX] == thr_hi && sel48(kv[LX], 0xFFFF - (c.chr_at(c.s_cli[(WB0 + q) * SEG + e] & 0xFFFF) + 1)))) ? 1 : 0;
+                            (kv[LX] == thr_hi &&
+                             (!two || (unsigned)(0xFFFF - (c.chr_at(c.s_cli[(WB0 + q) * SEG + e] & 0xFFFF) + 1)) >= thr_code))) ? 1 : 0;
               }
               const unsigned sb = ctc_ballot(sl);
               CTC_LANES {
@@ -1369,7 +1371,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
               const int j = blk * 32 + lane;
               if (j < K) {
                 const unsigned k = ord_f(c.s_snew[j]);
-                if (k > thr_hi || (k == thr_hi && sel48(k, s_code[j]))) { kmn[LX] = k < kmn[LX] ? k : kmn[LX]; kmx[LX] = k > kmx[LX] ? k : kmx[LX]; }
+                if (k > thr_hi || (k == thr_hi && (!two || (unsigned)s_code[j] >= thr_code))) { kmn[LX] = k < kmn[LX] ? k : kmn[LX]; kmx[LX] = k > kmx[LX] ? k : kmx[LX]; }
               }
             }
 #pragma unroll
@@ -1378,7 +1380,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
               for (int h = 0; h < CH; ++h) {
                 if (32 * h + lane < c.s_wcnt[WB0 + q]) {
                   const unsigned k = c.s_clk[(WB0 + q) * SEG + 32 * h + lane];
-                  if (k > thr_hi || (k == thr_hi && sel48(k, 0xFFFF - (c.chr_at(c.s_cli[(WB0 + q) * SEG + 32 * h + lane] & 0xFFFF) + 1)))) {
+                  if (k > thr_hi || (k == thr_hi && (!two || (unsigned)(0xFFFF - (c.chr_at(c.s_cli[(WB0 + q) * SEG + 32 * h + lane] & 0xFFFF) + 1)) >= thr_code))) {
                     kmn[LX] = k < kmn[LX] ? k : kmn[LX]; kmx[LX] = k > kmx[LX] ? k : kmx[LX];
                   }
                 }

@@ -165,7 +165,7 @@ int ctcdec_scorer_reset_params(void *scorer, double alpha, double beta);
  * The beam search runs on `device` in ONE kernel launch; after every frame each utterance's CTA hands the trie
  * nodes it created to the host through device-mapped pinned memory and waits for their LM terms (hook calls).
  * Environment: CTCDEC_LM_PER_FRAME=1 selects the older protocol (one launch per frame), CTCDEC_LM_THREADS=n the
- * number of host workers (default: one per utterance, at most half the hardware threads and at most 64). */
+ * number of host workers (default min(8, cores): more do not help, the frame is bound by the PCIe round trip). */
 int ctcdec_decode_batch_lm_host(const ctcdec_config *cfg, void *scorer, const float *probs, const int32_t *seq_lens,
                                 int B, int T, int32_t *tokens, int32_t *timesteps, float *scores, int32_t *lens,
                                 int32_t *n_results, int32_t *flags, int device);

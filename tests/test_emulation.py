@@ -198,3 +198,16 @@ def test_emulation_random_configs(cport, monkeypatch, knob):
         sl = rng.randint(0, T + 1, size=B).astype(np.int32) if rng.rand() < 0.5 else None
         chunk = int(rng.choice([0, 0, 1, 7, 16]))
         _check(cport, probs, sl, chunk=chunk, **kw)
+
+
+@pytest.mark.parametrize("knob", ["1", "2", "4"], ids=["general_back_half", "no_head_offload", "no_shared_bin_ranking"])
+@pytest.mark.parametrize("order", ["0", "7"])
+def test_emulation_frame_structure_knobs(cport, monkeypatch, knob, order):
+    """CTC_EMU_NO_FAST switches parts of the two-region frame off (general back half everywhere / every warp computes
+    the head / no ranking of a shared histogram bin); CTC_EMU_ORDER runs the emulated threads in reversed order."""
+    monkeypatch.setenv("CTC_EMU_NO_FAST", knob)
+    monkeypatch.setenv("CTC_EMU_ORDER", order)
+    _check(cport, ctc_like_probs(2, 300, 29, seed=70).numpy(), beam=100)
+    _check(cport, ctc_like_probs(1, 150, 256, seed=71).numpy(), beam=200, cutoff_prob=0.99)
+    _check(cport, ctc_like_probs(2, 120, 64, seed=72).numpy(), beam=32, cutoff_top_n=12, nt=192)
+    _check(cport, flat_probs(2, 200, 5, seed=73, temp=1.5).numpy(), beam=24)

@@ -58,20 +58,24 @@ def test_config4_full_batch_exact_sample(cport):
     assert np.array_equal(ref["ties"] != 0, (dec.last_flags[sl].cpu().numpy() & 7) != 0)
 
 
-@pytest.mark.parametrize("knob", [None, ("CTCDEC_NO_FAST", "1"), ("CTCDEC_NO_FAST", "2"), ("CTCDEC_NT", "128"),
-                                  ("CTCDEC_NT", "512")],
-                         ids=["default", "general_back_half", "no_head_offload", "nt128", "nt512"])
+@pytest.mark.parametrize("knob", [None, ("CTCDEC_NO_FAST", "1"), ("CTCDEC_NO_FAST", "2"), ("CTCDEC_NO_FAST", "4"),
+                                  ("CTCDEC_NT", "128"), ("CTCDEC_NT", "192"), ("CTCDEC_NT", "512")],
+                         ids=["default", "general_back_half", "no_head_offload", "no_shared_bin_ranking", "nt128", "nt192",
+                              "nt512"])
 def test_frame_structure_knobs_config2_shape(cport, monkeypatch, knob):
     """The index-order beam kernel runs a frame as two regions (members | grid walk, then a barrier-free commit) and
     falls back to the general back half on rarer frames; the knobs force the general back half in every frame, switch
-    off the head hand-over, and change the block size (128: every warp owns slots AND walks the grid; 512: the
-    run-time-KP kernel).  Same bits in every case."""
+    off the head hand-over or the ranking of a shared histogram bin, and change the block size (128: every warp owns
+    slots AND walks the grid; 192: two grid-walking warps; 512: the run-time-KP kernel).  Same bits in every case,
+    index-order and cut-vocabulary kernels alike."""
     if knob:
         monkeypatch.setenv(*knob)
     for probs, kw in ((ctc_like_probs(6, 1000, 29, seed=60).numpy(), dict(beam=100)),
                       (ctc_like_probs(4, 300, 29, seed=61).numpy(), dict(beam=32)),
                       (ctc_like_probs(4, 200, 40, seed=62).numpy(), dict(beam=64, cutoff_top_n=40)),
                       (ctc_like_probs(3, 200, 29, seed=63).numpy(), dict(beam=256)),
+                      (ctc_like_probs(2, 300, 256, seed=65).numpy(), dict(beam=200, cutoff_prob=0.99)),   # cut vocabulary
+                      (ctc_like_probs(3, 200, 64, seed=66).numpy(), dict(beam=48, cutoff_top_n=12)),
                       (flat_probs(3, 300, 5, seed=64, temp=1.5).numpy(), dict(beam=24))):
         ref = cport.decode(probs, **kw)
         got = _run(probs, **kw)
