@@ -3,6 +3,39 @@
 #pragma once
 #include "beam_core.cuh"
 
+// compile-time switches of the barrier-free back half (tools/build_variants.sh builds A/B variants with -D...).
+// MEASURED (profiles/r02_variants.txt, one B200, config 2, every variant in ONE gpurun call): the frame loop is bound
+// by its INSTRUCTION FOOTPRINT.  Every one of these features -- each a win on paper, two of them also in an in-build
+// A/B with a run-time toggle -- made the kernel slower in proportion to the code it added to the loop: 6 808 -> 9 360
+// static instructions took 2.95 -> 3.74 ms.  They are OFF by default and kept, tested, for the record.  (Moving the
+// rarely taken general back half out of line with __noinline__ made it far worse still, 5.5 ms: the ABI call forces
+// the slot-array pointers and the frame's scalars through local memory.)
+#ifndef CTC_OPT_FAST2
+#define CTC_OPT_FAST2 0     // rank the keys of a shared K-th-key bin instead of taking the general back half
+#endif
+#ifndef CTC_OPT_HEADOFF
+#define CTC_OPT_HEADOFF 0   // a grid-walking warp computes the next frame's key range while the owners commit
+#endif
+#ifndef CTC_OPT_BITSCAN
+#define CTC_OPT_BITSCAN 0   // histogram suffix sums from eight ballots instead of five dependent shuffles
+#endif
+#ifndef CTC_OPT_CH
+#define CTC_OPT_CH 1        // 32-entry chunks of a list segment the barrier-free back half accepts
+#endif
+#ifndef CTC_OPT_ROWS2
+#define CTC_OPT_ROWS2 0     // grid walk: the two-rows-per-iteration / two-column-group variants of the row loop
+#endif
+#ifndef CTC_OPT_EXPECT
+#define CTC_OPT_EXPECT 0    // branch-probability hints on the rare paths
+#endif
+#if CTC_OPT_EXPECT && !defined(CTC_EMULATE)
+#define CTC_LIKELY(x) __builtin_expect(!!(x), 1)
+#define CTC_UNLIKELY(x) __builtin_expect(!!(x), 0)
+#else
+#define CTC_LIKELY(x) (x)
+#define CTC_UNLIKELY(x) (x)
+#endif
+
 namespace ctc {
 
 #if defined(CTC_EMULATE) && defined(CTC_STATS)
@@ -145,7 +178,7 @@ CTC_FN void scan_bin_all(const int *hist, int need, int &bin, int &above, int &c
   // bins), so the suffix sums are assembled from eight INDEPENDENT ballots, one per bit of tot, instead of a chain of
   // five dependent shuffles; a lane total above 255 (degenerate key distributions) takes the shuffle scan.
   int sfx;
-  if (__ballot_sync(0xffffffffu, tot > 255) == 0u) {
+  if (CTC_OPT_BITSCAN && __ballot_sync(0xffffffffu, tot > 255) == 0u) {
     const unsigned ge = 0xFFFFFFFFu << lane;
     sfx = 0;
 #pragma unroll
@@ -239,8 +272,10 @@ CTC_FN void store_node(Node *p, const Node &n) {
 #if defined(CTC_EMULATE)
   *p = n;
 #else
-  *reinterpret_cast<int4 *>(p) = make_int4(n.parent, n.chr, __float_as_int(n.lpc), n.ts);
-  p->jump = n.jump;
+  // st.global.cg: the arena is write-only here (no L1 allocation), and a GLOBAL store cannot alias the shared-memory
+  // slot arrays (a generic one could, and makes the compiler reload them after every node store)
+  __stcg(reinterpret_cast<int4 *>(p), make_int4(n.parent, n.chr, __float_as_int(n.lpc), n.ts));
+  __stcg(&p->jump, n.jump);
 #endif
 }
 // 16-byte entry of the new-node list the scorer path hands to the host (device-mapped host memory: one store)
@@ -256,7 +291,7 @@ CTC_FN void flush_lpc_ts(Node *p, float lpc, int ts) {
 #if defined(CTC_EMULATE)
   p->lpc = lpc; p->ts = ts;
 #else
-  *reinterpret_cast<int2 *>(&p->lpc) = make_int2(__float_as_int(lpc), ts);
+  __stcg(reinterpret_cast<int2 *>(&p->lpc), make_int2(__float_as_int(lpc), ts));
 #endif
 }
 
@@ -283,16 +318,19 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
   //          ballot words it keeps in registers, so the slot owners commit the new beam without another barrier.
   //          Frames that need more (dead anchors in the table, beam not full, a second radix pass, ties, list
   //          overflow) take the general back half below, unchanged.
-  constexpr bool MERGED = !LM;
+  // (cut-vocabulary kernels CAN run the two-region frame -- masks by character, rank table built a frame ahead; the
+  //  code is below and passes the same tests -- but measured on config 4 (beam 200: all eight warps own slots, so
+  //  every warp repeats the whole classification) it is 25 % SLOWER than the five-region frame: 9.17 against 7.33 ms)
+  constexpr bool MERGED = !LM && !SORTED;
   constexpr int KPW = KPT / 32;
   constexpr bool FASTB = MERGED && KPT > 0 && KPT <= NT && KPW <= 8;
   constexpr int WB0 = (MERGED && KPT > 0 && KPW < NW) ? KPW : 0;
   constexpr int NB = NW - WB0;
-  constexpr int CH = 2;  // 32-entry chunks of a list segment the barrier-free back half looks at (the second one rarely)
+  constexpr int CH = CTC_OPT_CH;  // 32-entry chunks of a list segment the barrier-free back half looks at (the second one rarely)
   // FAST2: a frame whose K-th key shares its histogram bin with other keys stays in the barrier-free back half when
   // that bin holds at most 32 keys: every warp ranks them among themselves (64 scratch words per warp: the
   // general path's selection lists, unused in such a frame)
-  constexpr bool FAST2 = FASTB && 4 * KPT >= NW * 64;
+  constexpr bool FAST2 = CTC_OPT_FAST2 && FASTB && 4 * KPT >= NW * 64;
 
   Cta<SORTED, LM> c;
 #define CTC_SLOT(type, unit) ((type *)(smem + slot_off(unit, KP)))
@@ -531,7 +569,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
   }
   CTC_BARRIER();
   int nlive = s_ctl[C_NLIVE];
-  const bool head_offload = WB0 > 0 && !(p.no_fast & 2);  // (test knob bit 1: every warp computes the head itself)
+  const bool head_offload = CTC_OPT_HEADOFF && WB0 > 0 && !(p.no_fast & 2);  // (test knob bit 1: every warp computes the head itself)
   bool head_ready = false;       // FASTB: the head block of the coming frame has been written (see the fast back half)
   int nnodes = s_ctl[C_NNODES];  // MERGED: the node count travels in a register across barrier-free commits;
   bool nn_stale = false;         // s_ctl[C_NNODES] is brought up to date before a general back half needs it
@@ -895,7 +933,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
         }
         // two rows per iteration when the grid is one group wide: two independent load -> add -> key ->
         // ballot chains in flight instead of one
-        while (!LM && G == 1 && (rows & (rows - 1u))) {
+        while (CTC_OPT_ROWS2 && !LM && G == 1 && (rows & (rows - 1u))) {
           const int rl1 = ctc_ffs(rows) - 1;
           rows &= rows - 1u;
           const int rl2 = ctc_ffs(rows) - 1;
@@ -942,7 +980,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
           cnt += n1 + ctc_popc(bal2);
           CTC_STAT(g_stats.cl_entries += n1 + ctc_popc(bal2));
         }
-        if (!LM && G == 2) {
+        if (CTC_OPT_ROWS2 && !LM && G == 2) {
           // two column groups (33..64 kept characters): both groups of a row in one go
           CTC_LV(int, colc2);
           CTC_LV(float, colv2);
@@ -1199,7 +1237,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
       // the lower edge of the K-th key's bin, any character.
       thr_hi = lo32 + ((unsigned)pre_bin << shift32);
       thr_code = 0u;
-      if (FAST2 && fastb && inbin) {
+      if (CTC_UNLIKELY(FAST2 && fastb && inbin)) {
         // ---- the bin [thr_hi, thr_hi + 2^shift32) holds pre_cnt <= 32 keys of which K - pre_above are selected: every
         //      warp gathers them (members' keys need their character, list entries the character of their column)
         //      into a scratch row of its own and ranks them by counting; the key of rank K - pre_above - 1 is the
@@ -1283,7 +1321,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
         CTC_STAT(g_stats.fast2_frames += ok2);
       }
     }
-    if (FASTB && fastb) {
+    if (CTC_LIKELY(FASTB && fastb)) {
       CTC_STAT(g_stats.passes++);
       CTC_STAT(g_stats.fast_frames++);
       // is the key (k, character ch) selected?  (the character is only looked at for a key equal to the threshold's)
@@ -2181,7 +2219,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
     const bool anchors_active = nlive > 0 || nrev > 0 || s_ctl[anyref_w] != 0;
     int nlive_next = 0;
 
-    if (anchors_active) {
+    if (CTC_UNLIKELY(anchors_active)) {
       // ---- region R5b: dead anchors nobody hangs below any more leave the trie (that IS the reference's
       //      remove()); anchors whose parent left the beam stop being anchors.
       CTC_PAR {
