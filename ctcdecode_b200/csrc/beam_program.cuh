@@ -1574,643 +1574,12 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
       head_ready = head_offload && t + 1 < Tb;
     } else {
     // ================= the general back half ===============================================================
-    if (LM && M < K) {
-      // beam not full yet: do fewer than beam_size prefixes exist?  (lo32 == 0, so the lists hold every candidate)
-      long long ncand = 0;
-      if (!fallback) {
-        for (int w = 0; w < NW; ++w) ncand += c.s_wcnt[w];
-      } else {
-        CTC_PAR {
-          int mine = 0;
-          if (n > 0) {
-            int i = tid / n, r = tid - (tid / n) * n;
-            const int di = NT / n, dr = NT - (NT / n) * n;
-            while (i < M) {
-              float sc; int ch;
-              if (c.cand(i, r, sc, ch)) ++mine;
-              r += dr; i += di;
-              if (r >= n) { r -= n; ++i; }
-            }
-          }
-          if (mine) atom_add(&s_ctl[C_NCAND], mine);
-        }
-        CTC_BARRIER();
-        ncand = s_ctl[C_NCAND];
-      }
-      total = M + ncand;
-      select_all = total <= (long long)K;
+#if defined(CTC_OPT_BLOAT) && !defined(CTC_EMULATE)
+    if (p.no_fast == 0x7fffff01) {  // (never: a measurement build carries the block twice)
+#include "beam_general_back_half.inc"
     }
-
-    uint64_t thr = 0;   // selected <=> key >= thr (no tie) / key > thr or tie-selected (tie)
-    int tie_m = 0;      // >0: exactly tie_m of the keys equal to thr are selected
-    if (!select_all && !fallback) {
-      // ---- exact radix select of the K-th largest 48-bit key over members + candidate list ---------------
-      // (replaces std::nth_element + prefix_compare, reference :149-154, decoder_utils.cpp:122-132).
-      // Pass 0 (score bits only) was histogrammed during region G.
-      CTC_STAT(g_stats.passes++);
-      int bin = pre_bin, above = pre_above, cnt = pre_cnt;
-      if (!have_scan) scan_bin_all(hist0, K, bin, above, cnt);  // every warp, redundantly: no barrier, no broadcast
-      uint64_t lo = ((uint64_t)(lo32 + ((unsigned)bin << shift32))) << 16;
-      if (!SORTED && heuristic && above + cnt < K) {
-        // the checked bound cut too deep (index-order kernels: no second walk): grid-walking select from the
-        // proven bound.  Every warp sees the same histogram, so the decision is uniform.
-        CTC_STAT(g_stats.heur_fail++);
-        CTC_BARRIER();  // the fallback clears the histograms: every warp must have scanned first
-        lo32 = lo_valid;
-        set_shift();
-        fallback = true;
-      } else if (above + cnt == K) {
-        thr = lo;
-      } else {
-        uint64_t width = 1ull << (shift32 + 16);
-        int shift = shift32 + 8;
-        int pass = 1;
-        while (true) {
-          CTC_STAT(g_stats.passes++);
-          int *const hist = c.s_hist + ((hpar + pass) & 1) * kNBins;
-          CTC_BARRIER();  // every warp is done scanning the previous histogram
-          if (pass >= 2) {
-            CTC_PAR { for (int x = tid; x < kNBins; x += NT) hist[x] = 0; }
-            CTC_BARRIER();
-          }
-          CTC_PAR {
-            for (int j = tid; j < M; j += NT) {
-              const uint64_t k = key64(c.s_snew[j], c.s_chr[j]);
-              if (k >= lo && k - lo < width) atom_add(&hist[(int)((k - lo) >> shift)], 1);
-            }
-            const int w = tid >> 5, ln = tid & 31;
-            const int cn = c.s_wcnt[w];
-            for (int e = ln; e < cn; e += 32) {
-              const int r = c.s_cli[w * SEG + e] & 0xFFFF;
-              const uint64_t k = ((uint64_t)c.s_clk[w * SEG + e] << 16) | (uint64_t)(0xFFFF - (c.chr_at(r) + 1));
-              if (k >= lo && k - lo < width) atom_add(&hist[(int)((k - lo) >> shift)], 1);
-            }
-          }
-          CTC_BARRIER();
-          int a2;
-          scan_bin_all(hist, K - above, bin, a2, cnt);
-          above += a2;
-          lo += (uint64_t)bin << shift;
-          if (above + cnt == K) { thr = lo; tie_m = 0; break; }
-          if (shift == 0) { thr = lo; tie_m = K - above; break; }
-          width = 1ull << shift;
-          shift = shift >= 8 ? shift - 8 : 0;
-          ++pass;
-        }
-        if (tie_m > 0) {
-          // comparator-equivalent prefixes straddle the cut: the reference's choice is unspecified
-          // (libstdc++ introselect); keep the lowest ids (members by slot, then candidates by (i, r)).
-          CTC_PAR {
-            for (int j = tid; j < M; j += NT)
-              if (key64(c.s_snew[j], c.s_chr[j]) == thr) c.s_tie[atom_add(&s_ctl[C_NTIE], 1)] = j;
-            const int w = tid >> 5, ln = tid & 31;
-            const int cn = c.s_wcnt[w];
-            for (int e = ln; e < cn; e += 32) {
-              const int id = c.s_cli[w * SEG + e];
-              const int r = id & 0xFFFF;
-              const uint64_t k = ((uint64_t)c.s_clk[w * SEG + e] << 16) | (uint64_t)(0xFFFF - (c.chr_at(r) + 1));
-              if (k == thr) c.s_tie[atom_add(&s_ctl[C_NTIE], 1)] = K + (id >> 16) * NP + r;
-            }
-            if (tid == 0) s_ctl[C_FLAGS] |= FLAG_TIE_PRUNE;
-          }
-          CTC_BARRIER();
-        }
-      }
-    }
-    if (!select_all && fallback) {
-      // ---- fallback: the same select with every pass walking the grid (48-bit keys from the start) -------
-      if (heuristic) {  // an overflow got here before the heuristic bound was checked: start from the proven one
-        lo32 = lo_valid;
-        set_shift();
-      }
-      CTC_PAR {
-        for (int x = tid; x < 2 * kNBins; x += NT) c.s_hist[x] = 0;
-        if (tid == 0) { s_ctl[C_ABOVE] = 0; }
-      }
-      CTC_BARRIER();
-      uint64_t lo = ((uint64_t)lo32) << 16;
-      uint64_t width = ((((uint64_t)top32) << 16) | 0xFFFFull) - lo + 1ull;
-      int shift = shift32 + 16;
-      int pass = 0;
-      while (true) {
-        CTC_STAT(g_stats.passes++);
-        int *const hist = c.s_hist + (pass & 1) * kNBins;
-        CTC_PAR {
-          int *const other = c.s_hist + ((pass + 1) & 1) * kNBins;
-          for (int x = tid; x < kNBins; x += NT) other[x] = 0;
-          for (int j = tid; j < M; j += NT) {
-            const uint64_t k = key64(c.s_snew[j], c.s_chr[j]);
-            if (k >= lo && k - lo < width) atom_add(&hist[(int)((k - lo) >> shift)], 1);
-          }
-          if (n > 0) {
-            int i = tid / n, r = tid - (tid / n) * n;
-            const int di = NT / n, dr = NT - (NT / n) * n;
-            while (i < M) {
-              float sc; int ch;
-              if (c.cand(i, r, sc, ch)) {
-                const uint64_t k = key64(sc, ch);
-                if (k >= lo && k - lo < width) atom_add(&hist[(int)((k - lo) >> shift)], 1);
-              }
-              r += dr; i += di;
-              if (r >= n) { r -= n; ++i; }
-            }
-          }
-        }
-        CTC_BARRIER();
-        const int need = K - s_ctl[C_ABOVE];
-        CTC_PAR { scan_find_bin<NT>(hist, need, s_ctl, tid); }
-        CTC_BARRIER();
-        const int bin = s_ctl[C_BIN], above = s_ctl[C_ABOVE], cnt = s_ctl[C_CNT];
-        lo += (uint64_t)bin << shift;
-        if (above + cnt == K) { thr = lo; tie_m = 0; break; }
-        if (shift == 0) { thr = lo; tie_m = K - above; break; }
-        width = 1ull << shift;
-        shift = shift >= 8 ? shift - 8 : 0;
-        ++pass;
-      }
-      if (tie_m > 0) {
-        CTC_PAR {
-          for (int j = tid; j < M; j += NT)
-            if (key64(c.s_snew[j], c.s_chr[j]) == thr) c.s_tie[atom_add(&s_ctl[C_NTIE], 1)] = j;
-          if (n > 0) {
-            int i = tid / n, r = tid - (tid / n) * n;
-            const int di = NT / n, dr = NT - (NT / n) * n;
-            while (i < M) {
-              float sc; int ch;
-              if (c.cand(i, r, sc, ch) && key64(sc, ch) == thr) c.s_tie[atom_add(&s_ctl[C_NTIE], 1)] = K + i * NP + r;
-              r += dr; i += di;
-              if (r >= n) { r -= n; ++i; }
-            }
-          }
-          if (tid == 0) s_ctl[C_FLAGS] |= FLAG_TIE_PRUNE;
-        }
-        CTC_BARRIER();
-      }
-    }
-    const int ntie = s_ctl[C_NTIE];
-    CTC_STAT(g_stats.tie_frames += tie_m > 0);
-    CTC_TICK(4);  // select
-
-    // ---- region R4a: classify members (keep / evict) and candidates (selected); compact both with
-    //      ballots so that slot assignment is deterministic without sorting
-    // FUSED (the common frame: no scorer, no dead anchors in the table, lists did not overflow): the selected
-    // candidates are turned into nodes by the owners of the slots they move into, inside region R5 -- region R4c
-    // and its barrier are skipped.  What R5 needs from members that are evicted right now (their node id / depth,
-    // as parents of new nodes) is stashed here, before the slots are overwritten.
-    const bool fused = !LM && !fallback && nlive == 0;
-    if (!fallback) {
-      CTC_WARPS {
-        if (!fused) {
-          CTC_LANES { for (int j = warp * 32 + lane; j < K; j += NT) c.s_slot2q[j] = -1; }
-        } else {
-          CTC_LANES { if (warp == 0 && lane == 0) { s_ctl[C_NLIVE] = 0; s_ctl[C_ANYREF] = 0; s_ctl[C_ANYREF_B] = 0; } }  // (R4c's resets)
-        }
-        // members, in blocks of 32 slots
-        for (int blk = warp; blk * 32 < M; blk += NW) {
-          CTC_LV(int, ev);
-          CTC_LANES {
-            const int j = blk * 32 + lane;
-            ev[LX] = 0;
-            if (j < M) {
-              const uint64_t k = key64(c.s_snew[j], c.s_chr[j]);
-              bool keep = k >= thr;
-              if (tie_m > 0 && k == thr) {
-                int lower = 0;
-                for (int x = 0; x < ntie; ++x) lower += (c.s_tie[x] < j) ? 1 : 0;
-                keep = lower < tie_m;
-              }
-              ev[LX] = keep ? 0 : 1;
-              c.s_evict[j] = ev[LX];
-            }
-          }
-          const unsigned bal = ctc_ballot(ev);
-          CTC_LANES {
-            if (ev[LX]) {
-              const int j = blk * 32 + lane, rk = ctc_popc(bal & ctc_lt_mask(lane));
-              c.s_free[blk * 32 + rk] = j;
-              if (fused) {
-                c.s_sel2[j] = rk; c.s_stash[j] = c.s_node[j]; c.s_stash[5 * KP + j] = c.s_depth[j];
-                c.s_stash[6 * KP + j] = s_jump[j];
-              }
-            }
-            if (lane == 0) c.s_evcnt[blk] = ctc_popc(bal);
-          }
-        }
-        // this warp's candidate-list segment, compacted in place
-        const int cn = c.s_wcnt[warp];
-        uint32_t *const segk = c.s_clk + warp * SEG;
-        int *const segi = c.s_cli + warp * SEG;
-        const unsigned thr_hi = (unsigned)(thr >> 16);
-        int out = 0;
-        // is list entry e selected?  (two entries per lane and iteration: two independent load -> compare chains)
-        auto classify_entry = [&](int e, int &sel, int &idv, uint32_t &kv) {
-          sel = 0; idv = 0; kv = 0u;
-          if (e < cn) {
-            const unsigned k32 = segk[e];
-            const int id = segi[e];
-            idv = id;
-            kv = k32;
-            bool s = k32 > thr_hi;
-            if (k32 == thr_hi) {
-              const int r = id & 0xFFFF;
-              const uint64_t k = ((uint64_t)k32 << 16) | (uint64_t)(0xFFFF - (c.chr_at(r) + 1));
-              s = k >= thr;
-              if (tie_m > 0 && k == thr) {
-                const int tid_id = K + (id >> 16) * NP + r;
-                int lower = 0;
-                for (int x = 0; x < ntie; ++x) lower += (c.s_tie[x] < tid_id) ? 1 : 0;
-                s = lower < tie_m;
-              }
-            }
-            sel = s ? 1 : 0;
-          }
-        };
-        for (int e0 = 0; e0 < cn; e0 += 64) {
-          CTC_LV(int, selA);
-          CTC_LV(int, selB);
-          CTC_LV(int, idA);
-          CTC_LV(int, idB);
-          CTC_LV(uint32_t, kA);
-          CTC_LV(uint32_t, kB);
-          CTC_LANES {
-            classify_entry(e0 + lane, selA[LX], idA[LX], kA[LX]);
-            classify_entry(e0 + 32 + lane, selB[LX], idB[LX], kB[LX]);
-          }
-          const unsigned balA = ctc_ballot(selA), balB = ctc_ballot(selB);
-          const int nA = ctc_popc(balA);
-          CTC_SYNCWARP();  // in-place compaction: every lane has read its entries before any lane overwrites one
-          CTC_LANES {
-            if (selA[LX]) {
-              const int pos = out + ctc_popc(balA & ctc_lt_mask(lane));
-              segi[pos] = idA[LX];
-              segk[pos] = kA[LX];  // the score key travels along: region R5 recovers the candidate's score from it
-            }
-            if (selB[LX]) {
-              const int pos = out + nA + ctc_popc(balB & ctc_lt_mask(lane));
-              segi[pos] = idB[LX];
-              segk[pos] = kB[LX];
-            }
-          }
-          out += nA + ctc_popc(balB);
-        }
-        CTC_LANES {
-          if (lane == 0) {
-            c.s_wcnt[32 + warp] = out;
-            if (out) atom_add(&s_ctl[C_NSEL], out);
-          }
-        }
-      }
-      CTC_BARRIER_T(5);
-    } else {
-      CTC_PAR {
-        for (int j = tid; j < K; j += NT) {
-          c.s_slot2q[j] = -1;
-          if (j < M) {
-            const uint64_t k = key64(c.s_snew[j], c.s_chr[j]);
-            bool keep = k >= thr;
-            if (tie_m > 0 && k == thr) {
-              int lower = 0;
-              for (int x = 0; x < ntie; ++x) lower += (c.s_tie[x] < j) ? 1 : 0;
-              keep = lower < tie_m;
-            }
-            c.s_evict[j] = keep ? 0 : 1;
-            if (!keep) c.s_sel2[atom_add(&s_ctl[C_NFREE], 1)] = j;
-          }
-        }
-        if (n > 0) {
-          int i = tid / n, r = tid - (tid / n) * n;
-          const int di = NT / n, dr = NT - (NT / n) * n;
-          while (i < M) {
-            float sc; int ch;
-            if (c.cand(i, r, sc, ch)) {
-              const uint64_t k = key64(sc, ch);
-              bool sel = k >= thr;
-              if (tie_m > 0 && k == thr) {
-                const int id = K + i * NP + r;
-                int lower = 0;
-                for (int x = 0; x < ntie; ++x) lower += (c.s_tie[x] < id) ? 1 : 0;
-                sel = lower < tie_m;
-              }
-              if (sel) c.s_sel[atom_add(&s_ctl[C_NSEL], 1)] = (i << 16) | r;
-            }
-            r += dr; i += di;
-            if (r >= n) { r -= n; ++i; }
-          }
-        }
-      }
-      CTC_BARRIER();
-      // order both lists (deterministic slot assignment); evicted slots go to s_free2, selected to s_cli[0..)
-      const int nsel_f = s_ctl[C_NSEL], nfree_f = s_ctl[C_NFREE];
-      CTC_PAR {
-        for (int q = tid; q < nsel_f; q += NT) {
-          const int v = c.s_sel[q];
-          int rk = 0;
-          for (int x = 0; x < nsel_f; ++x) rk += (c.s_sel[x] < v) ? 1 : 0;
-          c.s_free2[rk] = v;  // (s_free2 doubles as the ordered selected list in the fallback)
-        }
-        for (int q = tid; q < nfree_f; q += NT) {
-          const int v = c.s_sel2[q];
-          int rk = 0;
-          for (int x = 0; x < nfree_f; ++x) rk += (c.s_sel2[x] < v) ? 1 : 0;
-          c.s_free[rk] = v;   // ordered evicted slots, dense from 0
-        }
-      }
-      CTC_BARRIER();
-    }
-    CTC_TICK(5);  // classify
-    const int nsel = s_ctl[C_NSEL];
-
-    // q-th selected candidate / q-th free slot (evicted slots in slot order, then never-used slots)
-    auto sel_entry = [&](int q) -> int {
-      if (fallback) return c.s_free2[q];
-      int acc = 0;
-      for (int w = 0; w < NW; ++w) {
-        const int cw = c.s_wcnt[32 + w];
-        if (q < acc + cw) return c.s_cli[w * SEG + (q - acc)];
-        acc += cw;
-      }
-      return 0;
-    };
-    auto free_slot = [&](int q) -> int {
-      int acc = 0;
-      if (fallback) {
-        acc = s_ctl[C_NFREE];
-        if (q < acc) return c.s_free[q];
-      } else {
-        for (int blk = 0; blk * 32 < M; ++blk) {
-          const int cb = c.s_evcnt[blk];
-          if (q < acc + cb) return c.s_free[blk * 32 + (q - acc)];
-          acc += cb;
-        }
-      }
-      return M + (q - acc);
-    };
-
-    // ---- region R4c: selected candidates become trie nodes (or revive a dead anchor) -------------------
-    // (reference path_trie.cpp:50-56 revive, :97-105 create).  Arena stores are fire-and-forget.
-    if (!fused) {
-    CTC_PAR {
-      if (tid == 0) {
-        s_ctl[C_NLIVE] = 0; s_ctl[C_ANYREF] = 0; s_ctl[C_ANYREF_B] = 0;
-        if (LM) newlist[0] = nsel;
-      }
-      for (int q = tid; q < nsel; q += NT) {
-        const int v = sel_entry(q);
-        const int i = v >> 16, r = v & 0xFFFF;
-        float sc; int ch;
-        c.cand(i, r, sc, ch);
-        float lpc = c.lp[r];
-        int ts = t_abs, nid, rev = -1, dst = 0, jmp = -1;
-        if (nlive > 0 && ((c.s_rmask[i * W + (r >> 5)] >> (r & 31)) & 1u)) {
-          for (int a = 0; a < KP2; ++a)
-            if (c.s_dpslot[a] == i && c.s_dchr[a] == ch) rev = a;
-          nid = c.s_dnode[rev]; lpc = c.s_dlpc[rev]; ts = c.s_dts[rev];
-          dst = c.s_ddstate[rev];
-          jmp = ld_cg(&nodes[nid].jump);  // (a revived node keeps the jump pointer it was created with)
-          c.s_drev[rev] = 1;
-          atom_add(&s_ctl[C_NREV], 1);
-          CTC_STAT(g_stats.revived++);
-          if (LM) newlist[4 + 4 * q] = -1;  // the host already knows this node
-        } else {
-          nid = atom_add(&s_ctl[C_NNODES], 1);
-          CTC_STAT(g_stats.created++);
-          if (nid >= arena_cap) {  // cannot happen with capacity 1 + K * frames; never write out of bounds
-            s_ctl[C_FLAGS] |= FLAG_ERR_ARENA;
-            nid = arena_cap - 1;
-          }
-          Node nn; nn.parent = c.s_node[i]; nn.chr = ch; nn.lpc = lpc; nn.ts = ts;
-          nn.jump = jump_of_child(c.s_node[i], c.s_depth[i], s_jump[i]);
-          jmp = nn.jump;
-          store_node(&nodes[nid], nn);
-          if (LM) {
-            // dictionary state of the new node (reference path_trie.cpp:83-92); tell the host about the node: it
-            // mirrors the trie and asks the Scorer hook for the LM term the node will need when a space follows
-            const int arc = c.dict_next[(long long)c.s_dstate[i] * V + ch];
-            dst = (arc & kDictFinal) ? p.dict_start : (arc & kDictStateMask);
-            dstate_arena[nid] = dst;
-            lm_arena[nid] = 0.0f;
-            // one 16-byte store per entry: the list lives in device-mapped host memory
-            Entry16 e;
-            e.a = nid; e.b = c.s_node[i]; e.c = ch;
-            e.d = (arc & kDictSpace) ? 1 : 0;
-            store_entry16(newlist + 4 + 4 * q, e);
-          }
-        }
-        int *ni = c.s_newinfo + q * 11;
-        ni[0] = nid; ni[1] = ch; ni[2] = (int)f_bits(sc); ni[3] = free_slot(q); ni[4] = i; ni[5] = (int)f_bits(lpc);
-        ni[6] = ts; ni[7] = rev; ni[8] = c.s_depth[i] + 1; ni[9] = dst; ni[10] = jmp;
-        c.s_slot2q[ni[3]] = q;
-      }
-    }
-    CTC_BARRIER_T(6);
-    }
-    CTC_TICK(6);  // R4c
-    nrev = fused ? 0 : s_ctl[C_NREV];
-
-    if (nrev > 0) {
-      // ---- rare slow path: a dead anchor d came back to life.  Members that hung below d need the child
-      //      of d on their own path as their new nearest anchor; only here is the arena read back.
-      CTC_STAT(g_stats.rv_frames++);
-      CTC_PAR {
-        for (int y = tid; y < M; y += NT) {
-          const int a = c.s_anch[y];
-          if (c.s_pslot[y] < 0 && a >= 0 && c.s_drev[a]) {
-            const int d = c.s_dnode[a];
-            int s_new = -1;
-            for (int q = 0; q < nsel; ++q)
-              if (c.s_newinfo[q * 11 + 7] == a) s_new = c.s_newinfo[q * 11 + 3];
-            int cur = c.s_node[y];
-            while (true) {
-              CTC_STAT(g_stats.rv_hops++);
-              const int par = ld_cg(&nodes[cur].parent);
-              if (par == d) break;
-              cur = par;
-            }
-            if (cur == c.s_node[y]) {  // y is a direct child of the revived node
-              c.s_pslot[y] = s_new | kNewFlag;
-              c.s_anch[y] = -1;
-            } else {
-              const int w = atom_add(&s_ctl[C_NRVWORK], 1);
-              c.s_rvwork[3 * w] = y; c.s_rvwork[3 * w + 1] = cur; c.s_rvwork[3 * w + 2] = s_new;
-            }
-          }
-        }
-      }
-      CTC_BARRIER();
-      CTC_PAR {
-        if (tid == 0) {
-          const int nw = s_ctl[C_NRVWORK];
-          for (int w = 0; w < nw; ++w) {
-            const int y = c.s_rvwork[3 * w], cur = c.s_rvwork[3 * w + 1], tag = c.s_rvwork[3 * w + 2] | kNewFlag;
-            int e = -1;
-            for (int a = 0; a < KP2; ++a)
-              if (c.s_dpslot[a] == tag && c.s_dnode[a] == cur) e = a;
-            if (e < 0) {
-              for (int a = 0; a < KP2 && e < 0; ++a)
-                if (c.s_dpslot[a] < 0) e = a;
-              if (e < 0) { s_ctl[C_FLAGS] |= FLAG_ERR_ARENA; e = 0; }
-              const Node nd = load_node(&nodes[cur]);
-              c.s_dnode[e] = cur; c.s_dchr[e] = nd.chr; c.s_dlpc[e] = nd.lpc; c.s_dts[e] = nd.ts;
-              c.s_dpslot[e] = tag; c.s_drev[e] = 0;
-              c.s_ddstate[e] = LM ? ld_cg(&dstate_arena[cur]) : 0;
-            }
-            c.s_anch[y] = e;
-          }
-          s_ctl[C_NRVWORK] = 0;
-        }
-      }
-      CTC_BARRIER();
-    }
-    CTC_TICK(7);  // revive slow path
-
-    // ---- region R5: the new beam takes shape.  Every SLOT OWNER (thread j for slot j) either rolls its
-    //      surviving member cur -> prev (reference path_trie.cpp:129-137), or writes the evicted member's
-    //      lpc / timestep back to the arena and commits the new member that was assigned this slot.  Each
-    //      member of the new beam gets its links: parent slot if the parent is in the new beam, else its
-    //      nearest anchor -- an existing dead anchor (index a < 2KP), a member evicted right now whose own
-    //      parent stays (provisional code 2KP + slot), or nothing (-1).  This replaces the reference's removal
-    //      cascade (path_trie.cpp:144-163); the walk only crosses members evicted in this very frame.  Links
-    //      are double buffered: walks read the old beam's links while the new ones are written.
-    CTC_PAR {
-      unsigned cmin = 0xFFFFFFFFu, cmax = 0u;  // score range of the new beam (read by the next frame before its R1)
-      int npair_next = 0;
-      for (int j = tid; j < K; j += NT) {
-        int start = 0, res = -1, newp = -1;
-        bool have = false, resolved = false;
-        if (j < M && !c.s_evict[j]) {
-          c.s_bprev[j] = c.s_bnew[j];
-          c.s_nbprev[j] = c.s_nbnew[j];
-          const float sn = c.s_snew[j];
-          c.s_score[j] = sn;
-          const unsigned o = ord_f(sn);
-          cmin = o < cmin ? o : cmin;
-          cmax = o > cmax ? o : cmax;
-          have = true;
-          const int pq = c.s_pslot[j];
-          if (pq >= 0) {
-            if (CTC_PARENT_ALIVE(pq)) { newp = pq & ~kNewFlag; resolved = true; }
-            start = pq;
-          } else {
-            const int a = c.s_anch[j];
-            if (a < 0) { resolved = true; }
-            else {
-              const int q = c.s_dpslot[a];
-              if (CTC_PARENT_ALIVE(q)) { res = a; resolved = true; }
-              start = q;
-            }
-          }
-        } else {
-          int q = -1;
-          if (j < M) {  // evicted: write back, and remember what a dead anchor made of this node would need
-            CTC_STAT(g_stats.evicted++);
-            flush_lpc_ts(&nodes[c.s_node[j]], c.s_lpc[j], c.s_ts[j]);
-            if (!fused) c.s_stash[j] = c.s_node[j];  // (fused: stashed by the classification, others read it now)
-            c.s_stash[KP + j] = c.s_chr[j];
-            c.s_stash[2 * KP + j] = (int)f_bits(c.s_lpc[j]); c.s_stash[3 * KP + j] = c.s_ts[j];
-            c.s_stash[4 * KP + j] = c.s_dstate[j];
-            if (fused) {  // rank of this slot among the free slots: evicted slots in slot order ...
-              q = c.s_sel2[j];
-              for (int bb = 0; bb < (j >> 5); ++bb) q += c.s_evcnt[bb];
-            }
-          } else if (fused) {  // ... then the slots that were never used
-            q = j - M;
-            for (int bb = 0; bb * 32 < M; ++bb) q += c.s_evcnt[bb];
-          }
-          if (!fused) q = c.s_slot2q[j];
-          else if (q >= nsel) q = -1;
-          if (q >= 0) {  // a new member moves into this slot
-            int nid, ch, ts, depth, dst, par_slot, jmp;
-            float sc, lpc;
-            if (fused) {
-              // the q-th selected candidate (reference path_trie.cpp:97-105 create); its score is the list key
-              int acc = 0, w = 0;
-              for (; w < NW - 1; ++w) {
-                const int cw = c.s_wcnt[32 + w];
-                if (q < acc + cw) break;
-                acc += cw;
-              }
-              const int id = c.s_cli[w * SEG + (q - acc)];
-              sc = unord_f(c.s_clk[w * SEG + (q - acc)]);
-              par_slot = id >> 16;
-              const int r = id & 0xFFFF;
-              ch = c.chr_at(r);
-              lpc = c.lp[r];
-              ts = t_abs;
-              dst = 0;
-              const bool pe = c.s_evict[par_slot] != 0;  // the parent was evicted in this very frame
-              const int pnode = pe ? c.s_stash[par_slot] : c.s_node[par_slot];
-              depth = (pe ? c.s_stash[5 * KP + par_slot] : c.s_depth[par_slot]) + 1;
-              jmp = jump_of_child(pnode, depth - 1, pe ? c.s_stash[6 * KP + par_slot] : s_jump[par_slot]);
-              nid = atom_add(&s_ctl[C_NNODES], 1);
-              CTC_STAT(g_stats.created++);
-              if (nid >= arena_cap) {  // cannot happen with capacity 1 + K * frames; never write out of bounds
-                s_ctl[C_FLAGS] |= FLAG_ERR_ARENA;
-                nid = arena_cap - 1;
-              }
-              Node nn; nn.parent = pnode; nn.chr = ch; nn.lpc = lpc; nn.ts = ts; nn.jump = jmp;
-              store_node(&nodes[nid], nn);
-            } else {
-              const int *ni = c.s_newinfo + q * 11;
-              nid = ni[0]; ch = ni[1]; sc = bits_f((uint32_t)ni[2]); par_slot = ni[4];
-              lpc = bits_f((uint32_t)ni[5]); ts = ni[6]; depth = ni[8]; dst = ni[9]; jmp = ni[10];
-            }
-            c.s_node[j] = nid; c.s_chr[j] = ch; c.s_depth[j] = depth; s_jump[j] = jmp;
-            c.s_bprev[j] = kNInf; c.s_nbprev[j] = sc; c.s_score[j] = sc;  // score = lse(-inf, nb)
-            const unsigned o = ord_f(sc);
-            cmin = o < cmin ? o : cmin;
-            cmax = o > cmax ? o : cmax;
-            c.s_lpc[j] = lpc; c.s_ts[j] = ts;
-            c.s_dstate[j] = dst;
-            if (LM) for (int w = 0; w < L.WC; ++w) c.s_dmask[j * L.WC + w] = p.dict_mask[(long long)dst * L.WC + w];
-            c.s_lmsp[j] = 0.0f;  // supplied by the host's Scorer hook before the next launch
-            have = true;
-            start = par_slot;
-            if (c.s_evict[start] == 0) { newp = start; resolved = true; }
-          }
-        }
-        if (have) {
-          if (!resolved) {
-            int cs = start & ~kNewFlag;  // an old slot evicted in this frame
-            while (true) {
-              CTC_STAT(g_stats.walk_iters++);
-              const int pq = c.s_pslot[cs];
-              if (pq >= 0) {
-                if (CTC_PARENT_ALIVE(pq)) { res = KP2 + cs; break; }
-                cs = pq;
-                continue;
-              }
-              const int a = c.s_anch[cs];
-              if (a < 0) { res = -1; break; }
-              const int q = c.s_dpslot[a];
-              if (CTC_PARENT_ALIVE(q)) { res = a; break; }
-              cs = q;
-            }
-          }
-          if (res >= 0) { atom_add(&c.s_cnt2[res], 1); s_ctl[anyref_w] = 1; }
-          npslot[j] = newp;
-          nanch[j] = res;
-          if (MERGED && newp >= 0) {  // the "existing child" mask of the next frame
-            const int ch_mine = c.s_chr[j];
-            atom_or(&mask_next[newp * WS + (ch_mine >> 5)], 1u << (ch_mine & 31));
-            if (!SORTED) ++npair_next;
-          }
-        }
-      }
-      if (MERGED && npair_next) atom_add(&s_ctl[npairs_nx], npair_next);
-      if (!LM) warp_range_store(c.s_wcnt + 128 + 64 * (par ^ 1), cmin, cmax, tid);
-      for (int x = tid; x < KP * WS; x += NT) c.s_mask[x] = 0u;
-      for (int x = tid; x < KP * W; x += NT) c.s_rmask[x] = 0u;
-      for (int x = tid; x < 2 * kNBins; x += NT) c.s_hist[x] = 0;  // the select is over: clear both radix histograms
-      if (SORTED && !MERGED) for (int r = tid; r < n; r += NT) c.s_rank[c.idx[r]] = (int16_t)-1;
-      if (tid == 0) {  // (C_NLIVE / C_ANYREF are read below and reset in region R4c of the next frame)
-        s_ctl[C_NFREE] = 0; s_ctl[C_NTIE] = 0;
-        if (!MERGED) s_ctl[C_NPAIRS] = 0;  // (MERGED: the pair count of the next frame is being accumulated)
-        else s_ctl[C_OVF_B] = 0;
-        s_ctl[C_ABOVE] = 0; s_ctl[C_KMIN] = (int)0xFFFFFFFFu; s_ctl[C_KMAX] = 0; s_ctl[C_SMAX] = 0;
-        s_ctl[C_NEFREE] = 0; s_ctl[C_NETAKEN] = 0; s_ctl[C_OVF] = 0; s_ctl[C_SMIN] = (int)0xFFFFFFFFu;
-        s_ctl[C_NCAND] = 0;
-      }
-    }
+#endif
+#include "beam_general_back_half.inc"
     }  // general back half
     CTC_BARRIER_T(8);
     CTC_TICK(8);  // R5

@@ -17,7 +17,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-strong > /dev/null 2>&1
 # full captures of the three kernels, config 2 and config 4
 for c in c2 c4; do
-  ncu --set full --clock-control none --import-source on -c 3 -o $O/${P}_$c python tools/profile_c2.py --config $c --iters 1 > $O/ncu_$c.log 2>&1
+  ncu --set full --clock-control none --import-source on -k regex:"prune_kernel|beam_kernel|finalize_kernel" -c 3 -o $O/${P}_$c python tools/profile_c2.py --config $c --iters 1 > $O/ncu_$c.log 2>&1
   python tools/ncu_summary.py $O/${P}_$c.ncu-rep $O/${P}_${c}_ncu_full.txt "ncu --set full --clock-control none, tools/profile_c2.py --config $c (prune, beam, finalize kernel of one decode)" > /dev/null 2>&1
   python tools/ncu_traffic.py $O/${P}_$c.ncu-rep $c $O/traffic.json > /dev/null 2>&1
 done
