@@ -672,7 +672,8 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
         lo32 = (unsigned)hb[0]; top32 = (unsigned)hb[1]; lo_valid = (unsigned)hb[2]; heuristic = hb[3] != 0;
       } else {
         unsigned cmin_o, cmax_o;
-        warp_range_load<NW>(c.s_wcnt + 128 + 64 * par, cmin_o, cmax_o);
+        // (only warps that own slots leave a range: with the beam size a compile-time constant that is the first KPW)
+        warp_range_load<(KPT > 0 && KPT <= NT) ? KPW : NW>(c.s_wcnt + 128 + 64 * par, cmin_o, cmax_o);
         head_of(c.lp, cmin_o, cmax_o, M == K, lo32, top32, lo_valid, heuristic);
       }
       head_ready = false;
@@ -745,7 +746,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
           }
           const float sc = c.s_score[j];
           const int ch = c.s_chr[j];
-          if (FASTB) s_code[j] = 0xFFFF - (ch + 1);
+          if (FAST2) s_code[j] = 0xFFFF - (ch + 1);
           const float bnew = (rblank >= 0 && !c.lm_cut(c.lp[rblank], sc)) ? f_add(c.lp[rblank], sc) : kNInf;
           float rep = kNInf, ext = kNInf;
           const int rr = (ch >= 0) ? c.rank_of(ch) : -1;
@@ -908,6 +909,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
       // rows (members) are tested 32 at a time: lane l of the w-th grid-walking warp looks at row base + w + NB * l.  A row whose best
       // possible candidate (score + max non-blank log-prob) stays under lo32 contributes nothing; on config 2
       // that removes 80 % of the rows.
+#pragma unroll 1
       for (int base = 0; base < M; base += 32 * NB) {
         CTC_LV(int, rowok);
         CTC_LANES {
@@ -1326,7 +1328,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
       CTC_STAT(g_stats.fast_frames++);
       // is the key (k, character ch) selected?  (the character is only looked at for a key equal to the threshold's)
       // (thr_code != 0 only in a frame that ranked a shared bin -- uniform, so the code is not even loaded otherwise)
-      const bool two = thr_code != 0u;
+      const bool two = FAST2 && thr_code != 0u;
       CTC_TICK(14);  // fast back half: checks + histogram scan
       int nsel_f = 0;
       CTC_WARPS {
@@ -1362,7 +1364,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
         int *const scr = c.s_newinfo + (warp < KPW ? warp : 0) * 64;
         if (cnt_w > 0) {
           int acc = 0;
-#pragma unroll
+#pragma unroll 1
           for (int q = 0; q < NB; ++q) {
             const int cn = c.s_wcnt[WB0 + q];
 #pragma unroll
@@ -1564,6 +1566,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
         }
         CTC_LANES {
           if (lane == 0 && pb) atom_add(&s_ctl[npairs_nx], ctc_popc(pb));
+#pragma unroll 1
           for (int x = warp * 32 + lane; x < KP * WS; x += NT) c.s_mask[x] = 0u;  // this frame's masks: used up
           if (warp == NW - 1 && lane == 0) { s_ctl[ovf_nx] = 0; s_ctl[anyref_nx] = 0; }
         }

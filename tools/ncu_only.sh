@@ -7,3 +7,5 @@ for c in c2 c4; do
 done
 python tools/ncu_lines.py $O/${P}_c2.ncu-rep 80 > $O/${P}_c2_beam_source_lines.txt 2>&1
 ncu -i $O/${P}_c2.ncu-rep --page raw --csv > $O/${P}_c2_raw.csv 2>/dev/null
+# the reports themselves stay on the box (gpurun merges at most 64 MiB back): everything needed has been extracted
+rm -f $O/${P}_c2.ncu-rep $O/${P}_c4.ncu-rep
