@@ -268,6 +268,13 @@ struct BeamParams {
   int lm_hs_last;                   // also hand shake after the LAST frame of the launch (streaming: a next chunk follows)
   float *const *lm_arena_ptrs;      // streaming: per-stream LM / dictionary-state arrays (else lm_arena + b * stride)
   int *const *dstate_ptrs;
+  // character-based language models (reference scorer.cpp:148-161, ctc_beam_search_decoder.cpp:120-137 with
+  // is_character_based()): no dictionary, and EVERY appended character takes an LM term -- which depends on the child,
+  // so each node carries a row of V terms, float(cond_log_prob(prefix + c) * alpha), filled by the host when the node
+  // is created: lm_row[(node) * V + c].  The update block then holds (node, V floats) entries.
+  int lm_char;
+  float *lm_row;                    // [B][arena_stride][V]
+  float *const *lm_row_ptrs;        // streaming
   int *hs_abort;                    // [1] mapped host memory: host asks the kernel to stop waiting
   void (*emu_handshake)(void *ctx, int b);  // CPU emulation only: the host side of the handshake, called in place
   void *emu_ctx;
@@ -407,6 +414,8 @@ struct Cta {
   double beta;
   bool lm_full;
   float lm_cutoff;
+  bool lm_char;            // character-based model: no dictionary, an LM term per (member, character)
+  const float *lm_row;     // this utterance's [node][V] terms
 
   CTC_MFN int chr_at(int r) const { return SORTED ? (int)idx[r] : r; }
   CTC_MFN int rank_of(int c) const { return SORTED ? (int)s_rank[c] : c; }
@@ -416,6 +425,15 @@ struct Cta {
   // language model term when the appended character is the space (reference :120-137): log_p += score; log_p += beta
   CTC_MFN float lm_apply(float log_p, int i) const {
     const float a = f_add(log_p, s_lmsp[i]);
+    return (float)d_add((double)a, beta);
+  }
+  // does appending character ch to member i take a language-model term?  (reference :120: the space of a word-based
+  // model, every character of a character-based one)
+  CTC_MFN bool lm_scored(int ch) const { return ch == space_id || lm_char; }
+  // the term itself: word-based -- the member's "prefix + space" term; character-based -- the row of the member's node
+  CTC_MFN float lm_apply_c(float log_p, int i, int ch) const {
+    const float term = lm_char ? ld_cg(&lm_row[(size_t)s_node[i] * V + ch]) : s_lmsp[i];
+    const float a = f_add(log_p, term);
     return (float)d_add((double)a, beta);
   }
 
@@ -433,7 +451,7 @@ struct Cta {
       if (lm_cut(l, s_score[i])) return false;
       // a child that does not exist yet needs a dictionary arc (reference path_trie.cpp:59-70); an existing dead
       // child (rmask) is found before the dictionary is consulted (path_trie.cpp:39-57)
-      if (!((s_rmask[i * W + (r >> 5)] >> (r & 31)) & 1u) && !dict_ok(i, c)) return false;
+      if (!lm_char && !((s_rmask[i * W + (r >> 5)] >> (r & 31)) & 1u) && !dict_ok(i, c)) return false;
     }
     if (c == s_chr[i]) {
       const float b = s_bprev[i];
@@ -441,7 +459,7 @@ struct Cta {
     } else {
       sc = f_add(l, s_score[i]);
     }
-    if (LM && c == space_id) sc = lm_apply(sc, i);
+    if (LM && lm_scored(c)) sc = lm_apply_c(sc, i, c);
     return true;
   }
 };

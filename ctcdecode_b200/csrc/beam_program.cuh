@@ -373,6 +373,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
   c.WS = WS; c.mch = MERGED;
   c.s_dmask = (uint32_t *)(smem + L.dmask); c.WC = L.WC;
   c.dict_next = p.dict_next; c.space_id = p.space_id; c.beta = p.beta; c.lm_full = false; c.lm_cutoff = kNInf;
+  c.lm_char = LM && p.lm_char != 0; c.lm_row = nullptr;
   int *const s_ctl = c.s_ctl;
 #if !defined(CTC_EMULATE)
   long long *const s_tick = (long long *)(smem + H_CTL + 32 * 4);
@@ -394,16 +395,37 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
   c.nodes = nodes;
   float *const lm_arena = !LM ? nullptr : p.lm_arena_ptrs ? p.lm_arena_ptrs[b] : p.lm_arena + (long long)b * p.arena_stride;
   int *const dstate_arena = !LM ? nullptr : p.dstate_ptrs ? p.dstate_ptrs[b] : p.dstate_arena + (long long)b * p.arena_stride;
+  float *const lm_row = !(LM && p.lm_char) ? nullptr
+                        : p.lm_row_ptrs ? p.lm_row_ptrs[b] : p.lm_row + (size_t)b * (size_t)p.arena_stride * (size_t)V;
+  c.lm_row = lm_row;
   int *const newlist = LM ? p.newlist + (long long)b * p.lm_nl_stride : nullptr;
   const int *const lm_upd = LM ? p.lm_upd + (long long)b * p.lm_up_stride : nullptr;
   int *const s_upd = CTC_SLOT(int, U_NEWINFO);  // staging for the host's answer (free outside R4c..R5: 10 * KP ints)
+  // the host's answer: (node, term) pairs -- or, for a character-based model, (node, V terms) entries that are too many
+  // for the staging area and are copied from the mapped block straight into the node rows
+  auto lm_scatter_updates = [&](int tid) {
+    if (!(LM && p.lm_char)) {
+      const int nu = s_upd[1];
+      for (int q = tid; q < nu; q += NT) lm_arena[s_upd[2 + 2 * q]] = bits_f((uint32_t)s_upd[3 + 2 * q]);
+    } else {
+      const volatile int *blk = lm_upd;
+      int nu = s_upd[1];
+      if (nu > K) nu = K;
+      const int es = 1 + V;
+      for (int x = tid; x < nu * V; x += NT) {
+        const int q = x / V, cch = x - q * V;
+        const int node = blk[2 + q * es];
+        lm_row[(size_t)node * V + cch] = bits_f((uint32_t)blk[2 + q * es + 1 + cch]);
+      }
+    }
+  };
   // Fetch the host's (node, LM term) pairs into s_upd; wait_for > 0: first poll the block's go flag until it
   // reaches wait_for.  One warp, whole 128-byte lines per request: the block lives in host memory and every
   // request is a PCIe round trip (tools/micro/sysmem_pingpong.cu: ~8 us per handshake for 64..148 CTAs).
   auto lm_fetch_updates = [&](int wait_for) {
 #if defined(CTC_EMULATE)
     (void)wait_for;
-    const int words = 2 + 2 * lm_upd[1];
+    const int words = p.lm_char ? 2 : 2 + 2 * lm_upd[1];  // (the rows of a character-based model are not staged)
     for (int w = 0; w < words; ++w) s_upd[w] = lm_upd[w];
 #else
     if (threadIdx.x < 32) {
@@ -430,7 +452,8 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
       int cnt = __shfl_sync(0xffffffffu, v, 1);
       if (cnt > K) cnt = K;
       s_upd[lane] = lane == 1 ? cnt : v;
-      for (int w = 32 + lane; w < 2 + 2 * cnt; w += 32) s_upd[w] = blk[w];
+      if (!p.lm_char)
+        for (int w = 32 + lane; w < 2 + 2 * cnt; w += 32) s_upd[w] = blk[w];
     }
 #endif
   };
@@ -452,10 +475,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
     }
     lm_fetch_updates(0);
     CTC_BARRIER();
-    CTC_PAR {
-      const int nu = s_upd[1];
-      for (int q = tid; q < nu; q += NT) lm_arena[s_upd[2 + 2 * q]] = bits_f((uint32_t)s_upd[3 + 2 * q]);
-    }
+    CTC_PAR { lm_scatter_updates(tid); }
     CTC_BARRIER();
   }
   // ---- region: stage tables, load (or create) the beam state --------------------------------------
@@ -762,7 +782,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
               } else {
                 ext = f_add(l, c.s_score[i]);
               }
-              if (LM && ch == c.space_id) ext = c.lm_apply(ext, i);
+              if (LM && c.lm_scored(ch)) ext = c.lm_apply_c(ext, i, ch);
               // (MERGED: the mask bit -- and in index order the pair count -- were set when the beam was committed)
               if (!MERGED) atom_or(&c.s_mask[i * W + (rr >> 5)], 1u << (rr & 31));
               if (!MERGED || SORTED) ++npairs;
@@ -1067,8 +1087,8 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
               if (rep && !(b_i > kNInf)) sc = kNInf;
               bool okl = true;
               if (LM && ch >= 0) {  // cutoff, dictionary arc (unless the child already exists, dead), LM term
-                okl = !c.lm_cut(l, sc_i) && (((rmw >> lane) & 1u) || c.dict_ok(i, ch));
-                if (ch == c.space_id) sc = c.lm_apply(sc, i);
+                okl = !c.lm_cut(l, sc_i) && (c.lm_char || ((rmw >> lane) & 1u) || c.dict_ok(i, ch));
+                if (c.lm_scored(ch)) sc = c.lm_apply_c(sc, i, ch);
               }
               const unsigned k = ord_f(sc);
               const bool mk = MCS ? (ch >= 0 && mbit(i, ch)) : (((mw >> lane) & 1u) != 0u);
@@ -1671,10 +1691,7 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
       lm_fetch_updates(t0 + t + 1);
       CTC_BARRIER();
       CTC_TICK(12);  // handshake: fence, flag, wait for the host, fetch its answer
-      CTC_PAR {
-        const int nu = s_upd[1];
-        for (int q = tid; q < nu; q += NT) lm_arena[s_upd[2 + 2 * q]] = bits_f((uint32_t)s_upd[3 + 2 * q]);
-      }
+      CTC_PAR { lm_scatter_updates(tid); }
       CTC_BARRIER();
       CTC_PAR {
         for (int j = tid; j < M; j += NT) c.s_lmsp[j] = ld_cg(&lm_arena[c.s_node[j]]);

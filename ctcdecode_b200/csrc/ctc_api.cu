@@ -326,6 +326,7 @@ struct StreamState {
   HostScorer *sc = nullptr;
   float *lm_arena = nullptr;
   int *dstate = nullptr;
+  float *lm_row = nullptr;  // character-based model: [arena_cap][V] per-node rows of LM terms
   TrieMirror mirror;
 };
 
@@ -350,7 +351,7 @@ struct HandshakeStats { long long hooks = 0, created = 0; unsigned workers = 0; 
 static int serve_handshakes(HostScorer *sc, int B, int K, const int *need, TrieMirror *const *mirrors,
                             int *h_newlist, int *h_upd, HandshakeStats *stats) {
   int nls = 0, ups = 0;
-  exchange_strides(K, &nls, &ups);
+  exchange_strides(K, exchange_row_len(*sc), &nls, &ups);
   unsigned nt = std::thread::hardware_concurrency();
   if (const char *e = getenv("CTCDEC_LM_THREADS")) nt = (unsigned)atoi(e);
   // measured on a 128-thread host with 64 utterances (profiles/): 8, 16 and 32 workers all finish the 1000 handshakes of
@@ -759,6 +760,12 @@ int ctcdec_state_create_lm(const ctcdec_config *cfg, void *scorer, int device, v
     *state = nullptr;
     return fail(CTCDEC_E_CUDA, "cudaMalloc failed for the streaming state (scorer arrays)");
   }
+  if (sc->is_character_based &&
+      cudaMalloc(&st->lm_row, (size_t)st->arena_cap * sc->labels.size() * 4) != cudaSuccess) {
+    ctcdec_state_destroy(st);
+    *state = nullptr;
+    return fail(CTCDEC_E_CUDA, "cudaMalloc failed for the streaming state (rows of a character-based model)");
+  }
   st->sc = sc;
   st->mirror.reserve((size_t)st->arena_cap);
   return CTCDEC_OK;
@@ -772,6 +779,7 @@ int ctcdec_state_destroy(void *state) {
   cudaFree(st->state);
   if (st->lm_arena) cudaFree(st->lm_arena);
   if (st->dstate) cudaFree(st->dstate);
+  if (st->lm_row) cudaFree(st->lm_row);
   delete st;
   return CTCDEC_OK;
 }
@@ -840,6 +848,14 @@ int ctcdec_decode_stream_host(const float *probs, const int32_t *seq_lens, int B
         CU(cudaFree(sb->dstate));
         sb->lm_arena = nl;
         sb->dstate = nd;
+        if (sb->lm_row) {
+          float *nr = nullptr;
+          CU(cudaMalloc(&nr, (size_t)cap * V * 4));
+          CU(cudaMemcpyAsync(nr, sb->lm_row, (size_t)used * V * 4, cudaMemcpyDeviceToDevice, s));
+          CU(cudaStreamSynchronize(s));
+          CU(cudaFree(sb->lm_row));
+          sb->lm_row = nr;
+        }
       }
       sb->arena_cap = (int)cap;
     }
@@ -848,7 +864,7 @@ int ctcdec_decode_stream_host(const float *probs, const int32_t *seq_lens, int B
   if (any_eos && (!tokens || !timesteps || !scores || !lens)) return fail(CTCDEC_E_INVALID, "an output pointer is NULL");
   if (any_eos && out_T < 0) return fail(CTCDEC_E_INVALID, "out_T < 0");
   const size_t n_probs = (size_t)B * T * V, n_bk = (size_t)B * K, n_out = any_eos ? n_bk * (size_t)out_T : 0;
-  const size_t ptr_bytes = al256((size_t)B * 8) * 4 + al256((size_t)B * 4) + al256((size_t)B);
+  const size_t ptr_bytes = al256((size_t)B * 8) * 5 + al256((size_t)B * 4) + al256((size_t)B);
   HostScorer *const sc = s0->sc;
   if (sc && (rc = ensure_dict_on_device(sc, device))) return rc;
   if (sc) pl.L = make_layout(cfg.beam_size, cfg.vocab_size, pl.NP, pl.F, pl.sorted, pl.NT, true);  // + dictionary masks
@@ -875,10 +891,11 @@ int ctcdec_decode_stream_host(const float *probs, const int32_t *seq_lens, int B
   const size_t off_lmar = 2 * al256((size_t)B * 8) + al256((size_t)B * 4) + al256((size_t)B);
   float **h_lmar = (float **)(h_tab.get() + off_lmar);
   int **h_dst = (int **)(h_tab.get() + off_lmar + al256((size_t)B * 8));
+  float **h_rows = (float **)(h_tab.get() + off_lmar + 2 * al256((size_t)B * 8));
   for (int b = 0; b < B; ++b) {
     StreamState *sb = static_cast<StreamState *>(states[b]);
     h_arenas[b] = sb->arena; h_states[b] = sb->state; h_caps[b] = sb->arena_cap; h_fin[b] = is_eos[b] ? 1 : 0;
-    h_lmar[b] = sb->lm_arena; h_dst[b] = sb->dstate;
+    h_lmar[b] = sb->lm_arena; h_dst[b] = sb->dstate; h_rows[b] = sb->lm_row;
   }
   unsigned char *d_tab = (unsigned char *)c.buf[6];
   CU(cudaMemcpyAsync(d_tab, h_tab.get(), ptr_bytes, cudaMemcpyHostToDevice, s));
@@ -905,12 +922,20 @@ int ctcdec_decode_stream_host(const float *probs, const int32_t *seq_lens, int B
     // scorer path: one persistent launch per chunk, hand shake after EVERY frame (the frame after the chunk's last
     // one, in the next call, needs the LM terms of the nodes created now)
     int nls = 0, ups = 0;
-    exchange_strides(K, &nls, &ups);
+    exchange_strides(K, exchange_row_len(*sc), &nls, &ups);
     if ((rc = ensure_pinned(c, 0, (size_t)B * nls * 4))) return rc;
     if ((rc = ensure_pinned(c, 1, (size_t)B * ups * 4))) return rc;
     if ((rc = ensure_pinned(c, 2, 256))) return rc;
     int *h_newlist = (int *)c.pin[0], *h_upd = (int *)c.pin[1], *hs_abort = (int *)c.pin[2];
     for (int b = 0; b < B; ++b) { memset(h_newlist + (size_t)b * nls, 0, 16); memset(h_upd + (size_t)b * ups, 0, 8); }
+    if (sc->is_character_based) {  // streams that have not seen a frame yet: the root's row of LM terms first
+      std::vector<int> scratch;
+      for (int b = 0; b < B; ++b)
+        if (static_cast<StreamState *>(states[b])->frames == 0)
+          lm_char_root_entry(*sc, sc->cond_caches[0], h_upd + (size_t)b * ups, scratch);
+      bp.lm_char = 1;
+      bp.lm_row_ptrs = (float *const *)(d_tab + off_lmar + 2 * al256((size_t)B * 8));
+    }
     *hs_abort = 0;
     bp.dict_next = sc->d_next; bp.dict_mask = sc->d_mask; bp.dict_wc = sc->dict.wc; bp.dict_start = sc->dict.start;
     bp.space_id = sc->space_id; bp.beta = sc->beta;
@@ -992,14 +1017,20 @@ int ctcdec_scorer_create(const ctcdec_scorer_hooks *hooks, double alpha, double 
   if (!hooks || !hooks->cond_log_prob || !hooks->sent_log_prob) return fail(CTCDEC_E_INVALID, "scorer hooks are NULL");
   if (!labels || n_labels < 1 || (!words && n_words > 0) || n_words < 0 || !scorer)
     return fail(CTCDEC_E_INVALID, "bad labels / words / scorer argument");
-  if (is_character_based)
-    return fail(CTCDEC_E_UNSUPPORTED, "character-based language models are not built (only word-based models with a dictionary)");
+  if (max_order < 1) return fail(CTCDEC_E_INVALID, "max_order %d < 1", max_order);
   HostScorer *sc = new HostScorer();
-  sc->hooks = *hooks; sc->alpha = alpha; sc->beta = beta; sc->max_order = max_order; sc->is_character_based = 0;
+  sc->hooks = *hooks; sc->alpha = alpha; sc->beta = beta; sc->max_order = max_order;
+  sc->is_character_based = is_character_based ? 1 : 0;
   sc->space_id = -2;
   for (int i = 0; i < n_labels; ++i) {
     sc->labels.emplace_back(labels[i] ? labels[i] : "");
     if (sc->labels.back() == " ") sc->space_id = i;  // reference ctc_beam_search_decoder.cpp:34-40
+  }
+  if (sc->is_character_based) {
+    // no dictionary, every appended character is scored (reference scorer.cpp:50-53, ctc_beam_search_decoder.cpp:46, :120-137)
+    sc->dict = accept_all_dictionary(n_labels);
+    *scorer = sc;
+    return CTCDEC_OK;
   }
   if (sc->space_id < 0) {
     delete sc;
@@ -1022,7 +1053,7 @@ int ctcdec_scorer_destroy(void *scorer) {
 }
 int ctcdec_scorer_is_character_based(const void *scorer) { return scorer ? static_cast<const HostScorer *>(scorer)->is_character_based : 0; }
 int ctcdec_scorer_max_order(const void *scorer) { return scorer ? static_cast<const HostScorer *>(scorer)->max_order : 0; }
-int ctcdec_scorer_dict_size(const void *scorer) { return scorer ? static_cast<const HostScorer *>(scorer)->dict.n_words : 0; }
+int ctcdec_scorer_dict_size(const void *scorer) { return scorer ? static_cast<const HostScorer *>(scorer)->dict.n_words : 0; }  // (0 for a character-based model: reference Scorer::dict_size_ stays 0)
 int ctcdec_scorer_reset_params(void *scorer, double alpha, double beta) {
   if (!scorer) return fail(CTCDEC_E_INVALID, "scorer is NULL");
   HostScorer *sc = static_cast<HostScorer *>(scorer);
@@ -1053,8 +1084,12 @@ int ctcdec_decode_batch_lm_host(const ctcdec_config *cfg, void *scorer, const fl
   pl.L = make_layout(cfg->beam_size, cfg->vocab_size, pl.NP, pl.F, pl.sorted, pl.NT, true);  // + dictionary masks
   const size_t n_probs = (size_t)B * T * V, n_out = (size_t)B * K * T, n_bk = (size_t)B * K;
   int nls = 0, ups = 0;
-  exchange_strides(K, &nls, &ups);
+  exchange_strides(K, exchange_row_len(*sc), &nls, &ups);
   const size_t lm_bytes = al256((size_t)B * pl.arena_stride * 4) * 2;
+  const bool lm_char = sc->is_character_based != 0;
+  const size_t row_bytes = lm_char ? (size_t)B * pl.arena_stride * (size_t)V * 4 : 0;  // a row of V terms per node
+  if (row_bytes > ((size_t)64 << 30))
+    return fail(CTCDEC_E_UNSUPPORTED, "character-based model: %zu bytes of per-node rows (batch x (1 + beam x frames) x labels x 4)", row_bytes);
   if ((rc = ensure(c, 0, n_probs * 4 + 256))) return rc;
   if ((rc = ensure(c, 1, (size_t)B * 4 + 256))) return rc;
   if ((rc = ensure(c, 2, n_out * 4 + 256))) return rc;
@@ -1062,6 +1097,7 @@ int ctcdec_decode_batch_lm_host(const ctcdec_config *cfg, void *scorer, const fl
   if ((rc = ensure(c, 4, n_bk * 4 * 2 + (size_t)B * 8 + 1024))) return rc;
   if ((rc = ensure(c, 5, pl.total + 512))) return rc;
   if ((rc = ensure(c, 7, lm_bytes + 512))) return rc;
+  if (lm_char && (rc = ensure(c, 8, row_bytes + 256))) return rc;
   if ((rc = ensure_pinned(c, 0, (size_t)B * nls * 4))) return rc;
   if ((rc = ensure_pinned(c, 1, (size_t)B * ups * 4))) return rc;
   if ((rc = ensure_pinned(c, 2, 256))) return rc;
@@ -1077,6 +1113,11 @@ int ctcdec_decode_batch_lm_host(const ctcdec_config *cfg, void *scorer, const fl
   int *d_dstate = (int *)(lmb + al256((size_t)B * pl.arena_stride * 4));
   int *h_newlist = (int *)c.pin[0], *h_upd = (int *)c.pin[1], *hs_abort = (int *)c.pin[2];
   for (int b = 0; b < B; ++b) { memset(h_newlist + (size_t)b * nls, 0, 16); memset(h_upd + (size_t)b * ups, 0, 8); }
+  if (lm_char) {  // the root's row of LM terms: the first entry every CTA picks up before frame 0
+    std::vector<int> scratch;
+    lm_char_root_entry(*sc, sc->cond_caches[0], h_upd, scratch);
+    for (int b = 1; b < B; ++b) memcpy(h_upd + (size_t)b * ups, h_upd, (size_t)(3 + V) * 4);
+  }
   *hs_abort = 0;
 
   if (n_probs) CU(cudaMemcpyAsync(d_probs, probs, n_probs * 4, cudaMemcpyHostToDevice, s));
@@ -1099,6 +1140,7 @@ int ctcdec_decode_batch_lm_host(const ctcdec_config *cfg, void *scorer, const fl
   bp.force_fallback = getenv("CTCDEC_FORCE_FALLBACK") ? 1 : 0;
   bp.dict_next = sc->d_next; bp.dict_mask = sc->d_mask; bp.dict_wc = sc->dict.wc; bp.dict_start = sc->dict.start;
   bp.space_id = sc->space_id; bp.beta = sc->beta; bp.lm_arena = d_lm_arena; bp.dstate_arena = d_dstate;
+  bp.lm_char = lm_char ? 1 : 0; bp.lm_row = lm_char ? (float *)c.buf[8] : nullptr;
   bp.timing = g_prof.timing;
   // The per-frame exchange with the host goes through pinned, device-mapped host memory (unified addressing):
   // the kernel reads the few LM updates and writes the new-node list straight over PCIe, so a frame costs one
@@ -1162,6 +1204,7 @@ int ctcdec_decode_batch_lm_host(const ctcdec_config *cfg, void *scorer, const fl
       fprintf(stderr, "[ctcdec lm] frames %d: launch+copy+sync %.1f ms, host mirror+hooks %.1f ms (%lld hook calls, %lld new nodes)\n",
               tmax, t_gpu * 1e3, t_hook * 1e3, n_hook, n_new);
   }
+  const auto t_fin0 = std::chrono::steady_clock::now();
   if ((rc = launch_finalize(bp, B, s))) return rc;
   std::unique_ptr<int[]> h_nres(new int[(size_t)B * 2]);
   std::unique_ptr<float[]> h_scores(new float[n_bk]);
@@ -1184,7 +1227,12 @@ int ctcdec_decode_batch_lm_host(const ctcdec_config *cfg, void *scorer, const fl
     CU(cudaMemcpy2DAsync(timesteps, (size_t)T * 4, d_ts, (size_t)T * 4, (size_t)max_len * 4, n_bk, cudaMemcpyDeviceToHost, s));
   }
   CU(cudaStreamSynchronize(s));
+  const auto t_fin1 = std::chrono::steady_clock::now();
   lm_rescore_batch(*sc, B, K, T, h_nres.get(), tokens, lens, scores);  // reported scores: approx_ctc (reference :194-208)
+  if (lm_timing)
+    fprintf(stderr, "[ctcdec lm] finalize + copies back %.1f ms, read-out rescoring (sentence hook) %.1f ms\n",
+            std::chrono::duration<double>(t_fin1 - t_fin0).count() * 1e3,
+            std::chrono::duration<double>(std::chrono::steady_clock::now() - t_fin1).count() * 1e3);
   if (n_results) memcpy(n_results, h_nres.get(), (size_t)B * 4);
   if (flags) memcpy(flags, h_nres.get() + B, (size_t)B * 4);
   return check_error_flags(h_nres.get() + B, B);

@@ -112,6 +112,20 @@ static inline void pack_dictionary(Dictionary &d, int space_id) {
     }
 }
 
+// A character-based model has no dictionary (reference scorer.cpp:50-53, ctc_beam_search_decoder.cpp:46): the kernel
+// gets the automaton that accepts everything -- one state, every character loops back to it -- with the "tell the host
+// about this node" flag on every arc.
+static inline Dictionary accept_all_dictionary(int V) {
+  Dictionary d;
+  d.V = V;
+  d.start = d.add_state();
+  d.wc = (V + 31) / 32;
+  d.packed.assign((size_t)V, 0 | (1 << 29));
+  d.mask.assign((size_t)d.wc, 0xffffffffu);
+  for (int c = 0; c < V; ++c) d.next[c] = 0;
+  return d;
+}
+
 struct HostScorer {
   // cond_log_prob depends only on the last max_order words of the prefix, and beams share word histories: cache it
   // keyed by that tail of the label sequence (the hook is pure, so the values are the hook's own)
@@ -153,6 +167,12 @@ struct TrieMirror {
     }
     for (size_t a = 0, b = out.size(); a + 1 < b; ++a, --b) std::swap(out[a], out[b - 1]);
   }
+  // the last n labels of node nid's prefix (all of them if it is shorter)
+  void last_labels_of(int nid, int n, std::vector<int> &out) const {
+    out.clear();
+    for (int q = nid; q > 0 && (int)out.size() < n; q = parent[q]) out.push_back(chr[q]);
+    for (size_t a = 0, b = out.size(); a + 1 < b; ++a, --b) std::swap(out[a], out[b - 1]);
+  }
 };
 
 // the same tail of a label array
@@ -174,10 +194,34 @@ static inline double cached_cond(const HostScorer &sc, HostScorer::CondCache &ca
 }
 
 // The two per-utterance exchange blocks (beam_core.cuh BeamParams::newlist / lm_upd): strides in ints, each a
-// multiple of 128 bytes so that no two utterances (host workers, CTAs) share a line.
-static inline void exchange_strides(int K, int *nl_stride, int *up_stride) {
+// multiple of 128 bytes so that no two utterances (host workers, CTAs) share a line.  row_len: 0 for a word-based
+// model ((node, term) pairs), the vocabulary size for a character-based one ((node, V terms) entries).
+static inline void exchange_strides(int K, int row_len, int *nl_stride, int *up_stride) {
   *nl_stride = (4 + 4 * K + 31) / 32 * 32;
-  *up_stride = (2 + 2 * K + 31) / 32 * 32;
+  *up_stride = (2 + (row_len > 0 ? 1 + row_len : 2) * K + 31) / 32 * 32;
+}
+static inline int exchange_row_len(const struct HostScorer &sc) { return sc.is_character_based ? (int)sc.labels.size() : 0; }
+
+// Character-based model: the V terms float(cond_log_prob(prefix + c) * alpha) of one node (reference :125-133 with
+// prefix_to_score = prefix_new; Scorer::make_ngram looks at the last max_order characters only, scorer.cpp:172-174).
+// labels: the node's last min(depth, max_order - 1) labels; scratch has room for one more.
+static inline void lm_char_row(const HostScorer &sc, HostScorer::CondCache &cache, std::vector<int> &labels, int *out) {
+  const int V = (int)sc.labels.size();
+  labels.push_back(0);
+  for (int c = 0; c < V; ++c) {
+    labels.back() = c;
+    const float val = (float)(cached_cond(sc, cache, labels.data(), (int)labels.size()) * sc.alpha);
+    memcpy(&out[c], &val, 4);
+  }
+  labels.pop_back();
+}
+
+// Before the first frame of an utterance with a character-based model: the root's row, as the block's only entry.
+static inline void lm_char_root_entry(const HostScorer &sc, HostScorer::CondCache &cache, int *upd, std::vector<int> &scratch) {
+  scratch.clear();
+  upd[1] = 1;
+  upd[2] = 0;
+  lm_char_row(sc, cache, scratch, upd + 3);
 }
 
 // After a frame: register the created nodes and compute the LM term of those a space can follow.
@@ -192,7 +236,13 @@ static inline int lm_after_frame(const HostScorer &sc, HostScorer::CondCache &ca
     const int *e = newlist + 4 + 4 * q;
     if (e[0] < 0) continue;  // a revived node: already known
     mirror.add(e[0], e[1], e[2]);
-    if (e[3]) {
+    if (sc.is_character_based) {
+      const int V = (int)sc.labels.size();
+      mirror.last_labels_of(e[0], sc.max_order - 1, scratch);
+      upd[2 + (1 + V) * nu] = e[0];
+      lm_char_row(sc, cache, scratch, upd + 2 + (1 + V) * nu + 1);
+      ++nu;
+    } else if (e[3]) {
       mirror.tail_labels_of(e[0], sc.space_id, sc.max_order, scratch);
       const double cond = cached_cond(sc, cache, scratch.data(), (int)scratch.size());
       const float val = (float)(cond * sc.alpha);  // reference :133 `score = get_log_cond_prob(ngram) * alpha` (float)
@@ -205,7 +255,7 @@ static inline int lm_after_frame(const HostScorer &sc, HostScorer::CondCache &ca
   return nu;
 }
 
-// DecoderState::decode with a word-based scorer (reference ctc_beam_search_decoder.cpp:164-211): the order of the
+// DecoderState::decode with a scorer (reference ctc_beam_search_decoder.cpp:164-211): the order of the
 // results is by the raw prefix score (decoder_utils.cpp:59), the reported score is the LM-corrected approx_ctc.
 // tokens / lens / scores are one utterance's rows as written by the finalize kernel (scores = -raw score).
 // cond_rows[p] must hold cond_log_prob of row p's prefix when the row does not end in a space (computed by the
@@ -217,7 +267,7 @@ static inline void lm_rescore(const HostScorer &sc, int n_results, int row_strid
     const int len = lens[p];
     const int *tok = tokens + (size_t)p * row_stride;
     float ext = -scores[p];  // scores[prefix] = prefix->score
-    if (len > 0 && tok[len - 1] != sc.space_id) {  // :173-185 score the last (unfinished) word
+    if (!sc.is_character_based && len > 0 && tok[len - 1] != sc.space_id) {  // :173-185 score the last (unfinished) word
       float s = (float)(cond_rows[p] * sc.alpha);
       s = (float)((double)s + sc.beta);
       ext = ext + s;
@@ -242,7 +292,7 @@ static inline void lm_rescore_batch(HostScorer &sc, int B, int K, int T, const i
     for (int p = 0; p < n_results[b] && p < K; ++p) {
       const int len = lens[(size_t)b * K + p];
       const int *tok = tokens + ((size_t)b * K + p) * T;
-      if (len > 0 && tok[len - 1] != sc.space_id) {
+      if (!sc.is_character_based && len > 0 && tok[len - 1] != sc.space_id) {
         const int st = tail_start(tok, len, sc.space_id, sc.max_order);
         cond[(size_t)b * K + p] = cached_cond(sc, sc.cond_caches[0], tok + st, len - st);
       }

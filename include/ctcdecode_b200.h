@@ -127,7 +127,7 @@ int ctcdec_decode_batch_host_multi(const ctcdec_config *cfg, const float *probs,
                                    int32_t *tokens, int32_t *timesteps, float *scores, int32_t *lens,
                                    int32_t *n_results, int32_t *flags, const int *devices, int n_devices);
 
-/* ---- scorer path: word-based language model + dictionary (reference Scorer, scorer.h:41-110) --------------
+/* ---- scorer path: language model (+ dictionary for word-based models) (reference Scorer, scorer.h:41-110) ---
  *
  * The language model itself stays on the HOST behind a hook the integrator supplies -- the reference side wraps its
  * own Scorer / KenLM; this library contains no KenLM.  Both hooks take a prefix as label ids:
@@ -144,11 +144,15 @@ typedef struct ctcdec_scorer_hooks {
   double (*sent_log_prob)(void *ctx, const int32_t *labels, int n);
 } ctcdec_scorer_hooks;
 
-/* Replaces: paddle_get_scorer (binding.cpp:143-150) for word-based language models.  `labels` are the decoder's
- * labels (UTF-8), `words` the language model's vocabulary (what KenLM's EnumerateVocab reports,
- * scorer.cpp:55-72): every word spellable with the labels goes into the dictionary, followed by the space label
- * (scorer.cpp:196-230, decoder_utils.cpp:164-193).  Character-based models (is_character_based != 0) are rejected
- * with CTCDEC_E_UNSUPPORTED. */
+/* Replaces: paddle_get_scorer (binding.cpp:143-150).  `labels` are the decoder's labels (UTF-8), `words` the
+ * language model's vocabulary (what KenLM's EnumerateVocab reports, scorer.cpp:55-72): every word spellable with the
+ * labels goes into the dictionary, followed by the space label (scorer.cpp:196-230, decoder_utils.cpp:164-193).
+ * is_character_based != 0 (Scorer::is_character_based(): every word of the model is one UTF-8 character,
+ * scorer.cpp:63-71): no dictionary (`words` is ignored, ctcdec_scorer_dict_size() is 0), no " " label needed, and the
+ * hook is asked about EVERY appended character -- cond_log_prob gets the prefix's last (up to) max_order labels, the
+ * new character last (ctc_beam_search_decoder.cpp:120-137 with prefix_to_score = prefix_new, scorer.cpp:172-174); at
+ * read-out no last-word term is added (:174).  The device keeps one row of n_labels terms per trie node for such a
+ * model: batch x (1 + beam x frames) x n_labels x 4 bytes, CTCDEC_E_UNSUPPORTED beyond 64 GiB. */
 int ctcdec_scorer_create(const ctcdec_scorer_hooks *hooks, double alpha, double beta, const char *const *labels,
                          int n_labels, const char *const *words, int n_words, int max_order, int is_character_based,
                          void **scorer);

@@ -60,7 +60,7 @@ def decode(probs, seq_lens=None, beam=100, cutoff_prob=1.0, cutoff_top_n=40, bla
 
 
 def decode_lm(probs, hook_lib, scorer_ptr, labels, words, max_order, alpha, beta, seq_lens=None, beam=100,
-              cutoff_prob=1.0, cutoff_top_n=40, blank_id=0, log_input=False, nt=0):
+              cutoff_prob=1.0, cutoff_top_n=40, blank_id=0, log_input=False, nt=0, char_based=False):
     """Scorer path through the emulated CTA program.  hook_lib: the ctypes library exporting
     ref_scorer_cond_from_labels / ref_scorer_sent_from_labels (oracle/_ref); scorer_ptr: its Scorer*."""
     L = lib()
@@ -74,7 +74,7 @@ def decode_lm(probs, hook_lib, scorer_ptr, labels, words, max_order, alpha, beta
     nres = np.zeros((B,), np.int32)
     flags = np.zeros((B,), np.int32)
     lab = (ctypes.c_char_p * V)(*[x.encode() for x in labels])
-    wrd = (ctypes.c_char_p * len(words))(*[x.encode() for x in words])
+    wrd = (ctypes.c_char_p * max(1, len(words)))(*[x.encode() for x in words])
     cond = ctypes.cast(hook_lib.ref_scorer_cond_from_labels, ctypes.c_void_p)
     sent = ctypes.cast(hook_lib.ref_scorer_sent_from_labels, ctypes.c_void_p)
     f = L.emu_decode_batch_lm
@@ -82,11 +82,11 @@ def decode_lm(probs, hook_lib, scorer_ptr, labels, words, max_order, alpha, beta
     f.argtypes = [_f32p, _i32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_int,
                   ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                   ctypes.c_double, ctypes.c_double, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_char_p),
-                  ctypes.c_int, ctypes.c_int, _i32p, _i32p, _f32p, _i32p, _i32p, _i32p]
+                  ctypes.c_int, ctypes.c_int, _i32p, _i32p, _f32p, _i32p, _i32p, _i32p, ctypes.c_int]
     rc = f(probs.ctypes.data_as(_f32p), sl.ctypes.data_as(_i32p) if sl is not None else None, B, T, V, beam,
            cutoff_prob, cutoff_top_n, blank_id, int(log_input), nt, scorer_ptr, cond, sent, alpha, beta, lab, wrd,
            len(words), max_order, tok.ctypes.data_as(_i32p), ts.ctypes.data_as(_i32p), sc.ctypes.data_as(_f32p),
-           ln.ctypes.data_as(_i32p), nres.ctypes.data_as(_i32p), flags.ctypes.data_as(_i32p))
+           ln.ctypes.data_as(_i32p), nres.ctypes.data_as(_i32p), flags.ctypes.data_as(_i32p), int(char_based))
     assert rc == 0, rc
     return dict(tokens=tok, timesteps=ts, scores=sc, lens=ln, n_results=nres, ties=flags)
 

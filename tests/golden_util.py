@@ -10,7 +10,12 @@ HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 def names(lm=False):
     """Fixture names; the scorer-path fixtures (lm_*) are listed separately."""
     allf = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(HERE, "*.npz")))
-    return [n for n in allf if n.startswith("lm_") == lm]
+    return [n for n in allf if n.startswith("lm_") == lm and not n.startswith("lmchar_")]
+
+
+def names_char():
+    """Fixtures of the scorer path with a character-based model (tests/golden/make_golden_char.py)."""
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(HERE, "lmchar_*.npz")))
 
 
 def load_lm(name):

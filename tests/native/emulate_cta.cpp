@@ -213,7 +213,7 @@ int emu_decode_batch_lm(const float *probs, const int *seq_lens, int B, int T, i
                         double (*cond)(void *, const int *, int), double (*sent)(void *, const int *, int),
                         double alpha, double beta, const char *const *labels, const char *const *words, int n_words,
                         int max_order, int *tokens, int *timesteps, float *scores, int *lens, int *n_results,
-                        int *flags) {
+                        int *flags, int char_based) {
   ctcdec_config cfg;
   cfg.vocab_size = V; cfg.beam_size = K; cfg.blank_id = blank; cfg.log_input = log_input;
   cfg.cutoff_top_n = cutoff_top_n; cfg.cutoff_prob = cutoff_prob;
@@ -226,12 +226,13 @@ int emu_decode_batch_lm(const float *probs, const int *seq_lens, int B, int T, i
   pl.L = make_layout(K, V, pl.NP, pl.F, pl.sorted, NT, true);
   HostScorer sc;
   sc.hooks.ctx = hook_ctx; sc.hooks.cond_log_prob = cond; sc.hooks.sent_log_prob = sent;
-  sc.alpha = alpha; sc.beta = beta; sc.max_order = max_order; sc.is_character_based = 0; sc.space_id = -2;
+  sc.alpha = alpha; sc.beta = beta; sc.max_order = max_order; sc.is_character_based = char_based ? 1 : 0; sc.space_id = -2;
   for (int i = 0; i < V; ++i) { sc.labels.emplace_back(labels[i]); if (sc.labels.back() == " ") sc.space_id = i; }
-  if (sc.space_id < 0) return CTCDEC_E_UNSUPPORTED;
+  if (sc.space_id < 0 && !char_based) return CTCDEC_E_UNSUPPORTED;
   std::vector<std::string> w;
   for (int i = 0; i < n_words; ++i) w.emplace_back(words[i]);
-  sc.dict = build_dictionary(sc.labels, sc.space_id, w);
+  if (char_based) sc.dict = accept_all_dictionary(V);
+  else sc.dict = build_dictionary(sc.labels, sc.space_id, w);
 
   std::vector<float> lp((size_t)B * T * pl.NP + 8, 0.f);
   std::vector<uint16_t> idx(pl.sorted ? (size_t)B * T * pl.NP + 8 : 8, 0);
@@ -240,8 +241,9 @@ int emu_decode_batch_lm(const float *probs, const int *seq_lens, int B, int T, i
   std::vector<int> dstate_arena((size_t)B * pl.arena_stride, 0);
   std::vector<int> state((size_t)B * pl.state_stride, 0);
   int nls = 0, ups = 0;
-  exchange_strides(K, &nls, &ups);
+  exchange_strides(K, exchange_row_len(sc), &nls, &ups);
   std::vector<int> newlist((size_t)B * nls, 0), upd((size_t)B * ups, 0);
+  std::vector<float> lm_row(char_based ? (size_t)B * pl.arena_stride * V : 1, 0.f);
   std::vector<unsigned char> smem(pl.L.total + 64);
   for (int b = 0; b < B; ++b) flags[b] = 0;
   prune_rows(cfg, pl, probs, seq_lens, B, T, lp.data(), idx.data(), flags);
@@ -258,7 +260,7 @@ int emu_decode_batch_lm(const float *probs, const int *seq_lens, int B, int T, i
   bp.no_fast = getenv("CTC_EMU_NO_FAST") ? atoi(getenv("CTC_EMU_NO_FAST")) : 0;
   g_emu_order = getenv("CTC_EMU_ORDER") ? atoi(getenv("CTC_EMU_ORDER")) : 0;  // test knob: order of the emulated threads
   if (const char *e = getenv("CTC_EMU_HEUR_BIAS")) bp.heur_bias = (float)atof(e);  // test knob
-  pack_dictionary(sc.dict, sc.space_id);
+  if (!char_based) pack_dictionary(sc.dict, sc.space_id);
   bp.dict_next = sc.dict.packed.data(); bp.dict_mask = sc.dict.mask.data(); bp.dict_wc = sc.dict.wc;
   bp.dict_start = sc.dict.start;
   bp.space_id = sc.space_id; bp.beta = beta; bp.lm_arena = lm_arena.data(); bp.dstate_arena = dstate_arena.data();
@@ -267,6 +269,10 @@ int emu_decode_batch_lm(const float *probs, const int *seq_lens, int B, int T, i
   std::vector<TrieMirror> mirror(B);
   for (int b = 0; b < B; ++b) mirror[b].reserve(64);  // small on purpose: exercises the growth path
   std::vector<int> scratch;
+  if (char_based) {
+    bp.lm_char = 1; bp.lm_row = lm_row.data();
+    for (int b = 0; b < B; ++b) lm_char_root_entry(sc, sc.cond_caches[0], upd.data() + (size_t)b * ups, scratch);
+  }
   if (getenv("CTC_EMU_LM_PER_FRAME") == nullptr) {
     // persistent mode: one "launch" per utterance, the host side of the per-frame handshake is called in place
     struct Ctx { HostScorer *sc; std::vector<TrieMirror> *mirror; int *newlist, *upd; int nls, ups; std::vector<int> *scratch; };

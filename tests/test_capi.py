@@ -100,6 +100,10 @@ def test_scorer_abi_builds_the_dictionary(lib):
     assert lib.ctcdec_scorer_dict_size(h) == 3 and lib.ctcdec_scorer_max_order(h) == 3
     assert lib.ctcdec_scorer_is_character_based(h) == 0
     assert lib.ctcdec_scorer_destroy(h) == 0
-    assert lib.ctcdec_scorer_create(ctypes.byref(hooks), 1.0, 0.5, lab, 4, wrd, len(words), 3, 1, ctypes.byref(h)) == -2
     nospace = (ctypes.c_char_p * 3)(b"_", b"a", b"b")
+    # a character-based model has no dictionary and needs no " " label (reference scorer.cpp:50-53)
+    assert lib.ctcdec_scorer_create(ctypes.byref(hooks), 1.0, 0.5, nospace, 3, None, 0, 3, 1, ctypes.byref(h)) == 0
+    assert lib.ctcdec_scorer_is_character_based(h) == 1 and lib.ctcdec_scorer_dict_size(h) == 0
+    assert lib.ctcdec_scorer_destroy(h) == 0
+    assert lib.ctcdec_scorer_create(ctypes.byref(hooks), 1.0, 0.5, nospace, 3, None, 0, 0, 1, ctypes.byref(h)) == -1  # max_order 0
     assert lib.ctcdec_scorer_create(ctypes.byref(hooks), 1.0, 0.5, nospace, 3, wrd, len(words), 3, 0, ctypes.byref(h)) == -2

@@ -257,3 +257,107 @@ def test_cuda_config5_as_stated_matches_reference():
     got = dict(tokens=out.numpy(), timesteps=ts.numpy(), scores=scores.numpy(), lens=lens.numpy(),
                n_results=dec.last_n_results.numpy(), ties=dec.last_flags.numpy())
     compare(want, got, None, "after reset_params(0.3, 0.1)")
+
+
+# ---------------------------------------------------------------------------------------------------------------
+#  character-based language models (reference scorer.cpp:63-71 / :172-174, ctc_beam_search_decoder.cpp:46, :120-137,
+#  :174): no dictionary, an LM term for EVERY appended character, no last-word term at read-out
+# ---------------------------------------------------------------------------------------------------------------
+CHAR_LM = os.path.join(ROOT, "tests", "data", "char_lm.arpa")
+LCHAR = ["_"] + list("abcdefghijklmnop") + ["|", "'", "é", " ", "z", "qu"]   # the last three are not in the model
+
+
+@needs_ref
+@pytest.mark.parametrize("per_frame", [False, True, 5], ids=["persistent", "per_frame_launch", "chunks_of_5"])
+@pytest.mark.parametrize("name", golden_util.names_char())
+def test_emulation_char_lm_matches_reference_golden(name, per_frame, monkeypatch):
+    if per_frame is True:
+        monkeypatch.setenv("CTC_EMU_LM_PER_FRAME", "1")
+    elif per_frame:
+        monkeypatch.setenv("CTC_EMU_LM_CHUNK", str(per_frame))
+    probs, seq_lens, kw, gold, alpha, beta = golden_util.load_lm(name)
+    ref = orc.Reference(LCHAR, model_path=CHAR_LM, alpha=alpha, beta=beta)
+    assert ref.is_character_based() == 1 and ref.dict_size() == 0 and ref.max_order() == 3
+    got = emul.decode_lm(probs, ref.lib, ref.scorer, LCHAR, [], ref.max_order(), alpha, beta, seq_lens=seq_lens,
+                         char_based=True, **kw)
+    compare(gold, got, None, name)
+    live = ref.decode(probs, seq_lens, num_processes=2, **kw)
+    compare(gold, live, None, name + " (live reference)")
+
+
+@needs_ref
+@pytest.mark.parametrize("cfg", [
+    dict(alpha=1.0, beta=0.3, beam=32, T=80, seed=31),
+    dict(alpha=0.0, beta=0.0, beam=16, T=60, seed=32),
+    dict(alpha=2.5, beta=-1.0, beam=8, T=100, seed=33, log_input=True),
+    dict(alpha=0.7, beta=2.0, beam=64, T=50, seed=34, cutoff_prob=0.95),
+    dict(alpha=1.0, beta=1.0, beam=20, T=70, seed=35, blank_id=5, cutoff_top_n=6),
+    dict(alpha=1.0, beta=0.5, beam=30, T=40, seed=36, flat=True),
+    dict(alpha=1.5, beta=0.2, beam=3, T=120, seed=37, nolabels=True),
+])
+def test_emulation_char_lm_matches_reference(cfg):
+    cfg = dict(cfg)
+    alpha, beta, T, seed = cfg.pop("alpha"), cfg.pop("beta"), cfg.pop("T"), cfg.pop("seed")
+    labels = LCHAR
+    if cfg.pop("nolabels", False):
+        labels = ["_"] + list("abcdefgh")   # no " " label at all: a character-based scorer does not need one
+    V = len(labels)
+    probs = flat_probs(3, T, V, seed=seed) if cfg.pop("flat", False) else ctc_like_probs(3, T, V, seed=seed)
+    if cfg.get("log_input"):
+        probs = probs.log()
+    ref = orc.Reference(labels, model_path=CHAR_LM, alpha=alpha, beta=beta)
+    want = ref.decode(probs.numpy(), num_processes=2, **cfg)
+    got = emul.decode_lm(probs.numpy(), ref.lib, ref.scorer, labels, [], ref.max_order(), alpha, beta,
+                         char_based=True, **cfg)
+    compare(want, got, None, str(cfg))
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(PROVIDER), reason="scorer provider (providers/_build/libkenlm_provider.so) not built")
+@pytest.mark.parametrize("per_frame", [False, True], ids=["persistent", "per_frame_launch"])
+@pytest.mark.parametrize("name", golden_util.names_char())
+def test_cuda_char_lm_matches_reference_golden(name, per_frame, monkeypatch):
+    import torch
+    import ctcdecode_b200
+    if per_frame:
+        monkeypatch.setenv("CTCDEC_LM_PER_FRAME", "1")
+    probs, seq_lens, kw, gold, alpha, beta = golden_util.load_lm(name)
+    dec = ctcdecode_b200.CTCBeamDecoder(LCHAR, model_path=CHAR_LM, alpha=alpha, beta=beta, beam_width=kw["beam"],
+                                        cutoff_top_n=kw["cutoff_top_n"], cutoff_prob=kw["cutoff_prob"],
+                                        log_probs_input=kw["log_input"], scorer_provider=PROVIDER)
+    assert dec.dict_size() == 0 and dec.max_order() == 3 and dec.character_based() == 1
+    sl = None if seq_lens is None else torch.from_numpy(seq_lens)
+    out, scores, ts, lens = dec.decode(torch.from_numpy(probs), sl)
+    got = dict(tokens=out.numpy(), timesteps=ts.numpy(), scores=scores.numpy(), lens=lens.numpy(),
+               n_results=dec.last_n_results.numpy(), ties=dec.last_flags.numpy())
+    compare(gold, got, None, name)
+
+
+@pytest.mark.gpu
+@needs_ref
+@pytest.mark.skipif(not os.path.exists(PROVIDER), reason="scorer provider (providers/_build/libkenlm_provider.so) not built")
+def test_cuda_char_lm_matches_live_reference_offline_and_online():
+    """a config-5 sized batch (16 x T=300, beam 100) with the character model against the reference run on the same
+    box, then the same utterances through OnlineCTCBeamDecoder in four chunks (device-resident rows of LM terms that
+    grow with the stream)"""
+    import torch
+    import ctcdecode_b200
+    probs = ctc_like_probs(16, 300, len(LCHAR), seed=51)
+    ref = orc.Reference(LCHAR, model_path=CHAR_LM, alpha=1.3, beta=0.6)
+    want = ref.decode(probs.numpy(), beam=100)
+    dec = ctcdecode_b200.CTCBeamDecoder(LCHAR, model_path=CHAR_LM, alpha=1.3, beta=0.6, beam_width=100,
+                                        scorer_provider=PROVIDER)
+    out, scores, ts, lens = dec.decode(probs)
+    got = dict(tokens=out.numpy(), timesteps=ts.numpy(), scores=scores.numpy(), lens=lens.numpy(),
+               n_results=dec.last_n_results.numpy(), ties=dec.last_flags.numpy())
+    compare(want, got, None, "character model, 16 x 300, beam 100")
+    want = ref.decode(probs[:3].numpy(), beam=24)
+    odec = ctcdecode_b200.OnlineCTCBeamDecoder(LCHAR, model_path=CHAR_LM, alpha=1.3, beta=0.6, beam_width=24,
+                                               scorer_provider=PROVIDER)
+    st = [ctcdecode_b200.DecoderState(odec) for _ in range(3)]
+    for a, b in [(0, 1), (1, 130), (130, 131)]:
+        odec.decode(probs[:3, a:b], st, [False] * 3)
+    res, scores, ts, lens = odec.decode(probs[:3, 131:], st, [True] * 3)
+    got = dict(tokens=res.numpy(), timesteps=ts.numpy(), scores=scores.numpy(), lens=lens.numpy(),
+               n_results=odec.last_n_results.numpy(), ties=odec.last_flags.numpy())
+    compare(want, got, None, "character model, online in four calls")
