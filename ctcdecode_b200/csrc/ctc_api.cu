@@ -43,6 +43,11 @@ __global__ void __launch_bounds__(NT) finalize_kernel(const BeamParams p) {
   finalize_cta_run<NT>(p, (int)blockIdx.x, smem);
 }
 
+__global__ void selftest_math_f64_kernel(int which, const double *x, const double *x2, double *y, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    y[i] = which == 0 ? exp_glibc_nonpos(x[i]) : which == 1 ? log_glibc(x[i]) : lse_d(x[i], x2[i]);
+}
+
 __global__ void selftest_math_kernel(int which, const float *x, const float *x2, float *y, size_t n) {
   __shared__ uint64_t exptab[32];
   __shared__ double logftab[32];
@@ -311,6 +316,36 @@ static int ensure_pinned(DevCache &c, int slot, size_t bytes) {
   CU(cudaMallocHost(&c.pin[slot], bytes + bytes / 8));
   c.pcap[slot] = bytes + bytes / 8;
   return CTCDEC_OK;
+}
+
+// Result rows on their way back to the caller.  A device-to-host copy into PAGEABLE memory goes through the driver's
+// small bounce buffers and faults the caller's freshly allocated pages in from the copying thread (measured at config
+// 5: 6-15 ms for 2 x 5 MB); when the caller's arrays are not page-locked the rows are therefore copied compactly
+// ([rows][max_len]) into pinned staging memory of the library's own and spread into the caller's [rows][row_stride]
+// arrays by a few host threads.  Page-locked (or registered) destinations get the DMA directly.
+static bool host_ptr_is_pinned(const void *p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+constexpr size_t kMaxRowStaging = (size_t)512 << 20;  // beyond this the rows go straight to the caller's pages
+static void spread_rows(const int *stage_tok, const int *stage_ts, int32_t *tokens, int32_t *timesteps, size_t rows,
+                        int max_len, int row_stride) {
+  unsigned nt = std::thread::hardware_concurrency();
+  nt = nt == 0 ? 1 : (nt > 8 ? 8 : nt);
+  const size_t bytes = rows * (size_t)max_len * 8;
+  if (bytes < ((size_t)1 << 20)) nt = 1;
+  auto work = [&](unsigned w) {
+    const size_t r0 = rows * w / nt, r1 = rows * (w + 1) / nt;
+    for (size_t r = r0; r < r1; ++r) {
+      memcpy(tokens + r * row_stride, stage_tok + r * max_len, (size_t)max_len * 4);
+      memcpy(timesteps + r * row_stride, stage_ts + r * max_len, (size_t)max_len * 4);
+    }
+  };
+  std::vector<std::thread> pool;
+  for (unsigned w = 1; w < nt; ++w) pool.emplace_back(work, w);
+  work(0);
+  for (auto &th : pool) th.join();
 }
 
 // streaming state object
@@ -599,6 +634,11 @@ int ctcdec_decode_batch_host(const ctcdec_config *cfg, const float *probs, const
   int *const h_flags = h_nres + B;
   float *const h_scores = reinterpret_cast<float *>(h_flags + B);
   int *const h_lens = reinterpret_cast<int *>(h_scores + n_bk);
+  const bool staged = n_out > 0 && n_out * 8 <= kMaxRowStaging && !(host_ptr_is_pinned(tokens) && host_ptr_is_pinned(timesteps));
+  if (staged && (rc = ensure_pinned(c, 5, n_out * 8))) return rc;
+  int *const stage_tok = staged ? static_cast<int *>(c.pin[5]) : nullptr;
+  int *const stage_ts = staged ? stage_tok + n_out : nullptr;
+  int chunk_len[kHostChunks] = {};
   for (int i = 0; i < C; ++i) {
     const int b0 = i * chunk, nb = std::min(chunk, B - b0);
     cudaStream_t s = c.cs[i];
@@ -628,10 +668,13 @@ int ctcdec_decode_batch_host(const ctcdec_config *cfg, const float *probs, const
       for (int p = 0; p < nr && p < K; ++p) max_len = std::max(max_len, h_lens[(size_t)b * K + p]);
     }
     if (max_len > T) max_len = T;
+    chunk_len[i] = max_len;
     if (max_len > 0) {
       const size_t oo = (size_t)b0 * K * T;
-      CU(cudaMemcpy2DAsync(tokens + oo, (size_t)T * 4, d_tok + oo, (size_t)T * 4, (size_t)max_len * 4, (size_t)nb * K, cudaMemcpyDeviceToHost, s));
-      CU(cudaMemcpy2DAsync(timesteps + oo, (size_t)T * 4, d_ts + oo, (size_t)T * 4, (size_t)max_len * 4, (size_t)nb * K, cudaMemcpyDeviceToHost, s));
+      int32_t *const dt = staged ? stage_tok + oo : tokens + oo, *const ds = staged ? stage_ts + oo : timesteps + oo;
+      const size_t pitch = (size_t)(staged ? max_len : T) * 4;
+      CU(cudaMemcpy2DAsync(dt, pitch, d_tok + oo, (size_t)T * 4, (size_t)max_len * 4, (size_t)nb * K, cudaMemcpyDeviceToHost, s));
+      CU(cudaMemcpy2DAsync(ds, pitch, d_ts + oo, (size_t)T * 4, (size_t)max_len * 4, (size_t)nb * K, cudaMemcpyDeviceToHost, s));
     }
   }
   // rows p >= n_results[b] stay as the caller left them (the finalize kernel does not write them, and the
@@ -641,7 +684,14 @@ int ctcdec_decode_batch_host(const ctcdec_config *cfg, const float *probs, const
     memcpy(scores + (size_t)b * K, h_scores + (size_t)b * K, nr * 4);
     memcpy(lens + (size_t)b * K, h_lens + (size_t)b * K, nr * 4);
   }
-  for (int i = 0; i < C; ++i) CU(cudaStreamSynchronize(c.cs[i]));
+  for (int i = 0; i < C; ++i) {
+    CU(cudaStreamSynchronize(c.cs[i]));
+    if (staged && chunk_len[i] > 0) {  // (the later groups' rows are still on their way meanwhile)
+      const int b0 = i * chunk, nb = std::min(chunk, B - b0);
+      const size_t oo = (size_t)b0 * K * T;
+      spread_rows(stage_tok + oo, stage_ts + oo, tokens + oo, timesteps + oo, (size_t)nb * K, chunk_len[i], T);
+    }
+  }
   if (n_results) memcpy(n_results, h_nres, (size_t)B * 4);
   if (flags) memcpy(flags, h_flags, (size_t)B * 4);
   return check_error_flags(h_flags, B);
@@ -1066,6 +1116,7 @@ int ctcdec_decode_batch_lm_host(const ctcdec_config *cfg, void *scorer, const fl
                                 int B, int T, int32_t *tokens, int32_t *timesteps, float *scores, int32_t *lens,
                                 int32_t *n_results, int32_t *flags, int device) {
   if (!scorer) return fail(CTCDEC_E_INVALID, "scorer is NULL");
+  const auto t_call0 = std::chrono::steady_clock::now();
   HostScorer *sc = static_cast<HostScorer *>(scorer);
   Plan pl;
   int rc = make_plan(cfg, B, T, &pl);
@@ -1223,19 +1274,51 @@ int ctcdec_decode_batch_lm_host(const ctcdec_config *cfg, void *scorer, const fl
     for (int p = 0; p < h_nres[b] && p < K; ++p) max_len = std::max(max_len, lens[(size_t)b * K + p]);
   if (max_len > T) max_len = T;
   if (max_len > 0) {
-    CU(cudaMemcpy2DAsync(tokens, (size_t)T * 4, d_tok, (size_t)T * 4, (size_t)max_len * 4, n_bk, cudaMemcpyDeviceToHost, s));
-    CU(cudaMemcpy2DAsync(timesteps, (size_t)T * 4, d_ts, (size_t)T * 4, (size_t)max_len * 4, n_bk, cudaMemcpyDeviceToHost, s));
+    const size_t st_bytes = n_bk * (size_t)max_len * 8;
+    const bool staged = st_bytes <= kMaxRowStaging && !(host_ptr_is_pinned(tokens) && host_ptr_is_pinned(timesteps));
+    if (staged) {
+      if ((rc = ensure_pinned(c, 5, st_bytes))) return rc;
+      int *const stage_tok = static_cast<int *>(c.pin[5]), *const stage_ts = stage_tok + n_bk * (size_t)max_len;
+      CU(cudaMemcpy2DAsync(stage_tok, (size_t)max_len * 4, d_tok, (size_t)T * 4, (size_t)max_len * 4, n_bk, cudaMemcpyDeviceToHost, s));
+      CU(cudaMemcpy2DAsync(stage_ts, (size_t)max_len * 4, d_ts, (size_t)T * 4, (size_t)max_len * 4, n_bk, cudaMemcpyDeviceToHost, s));
+      CU(cudaStreamSynchronize(s));
+      spread_rows(stage_tok, stage_ts, tokens, timesteps, n_bk, max_len, T);
+    } else {
+      CU(cudaMemcpy2DAsync(tokens, (size_t)T * 4, d_tok, (size_t)T * 4, (size_t)max_len * 4, n_bk, cudaMemcpyDeviceToHost, s));
+      CU(cudaMemcpy2DAsync(timesteps, (size_t)T * 4, d_ts, (size_t)T * 4, (size_t)max_len * 4, n_bk, cudaMemcpyDeviceToHost, s));
+    }
   }
   CU(cudaStreamSynchronize(s));
   const auto t_fin1 = std::chrono::steady_clock::now();
   lm_rescore_batch(*sc, B, K, T, h_nres.get(), tokens, lens, scores);  // reported scores: approx_ctc (reference :194-208)
   if (lm_timing)
-    fprintf(stderr, "[ctcdec lm] finalize + copies back %.1f ms, read-out rescoring (sentence hook) %.1f ms\n",
+    fprintf(stderr, "[ctcdec lm] finalize + copies back %.1f ms, read-out rescoring (sentence hook) %.1f ms, whole call %.1f ms\n",
             std::chrono::duration<double>(t_fin1 - t_fin0).count() * 1e3,
-            std::chrono::duration<double>(std::chrono::steady_clock::now() - t_fin1).count() * 1e3);
+            std::chrono::duration<double>(std::chrono::steady_clock::now() - t_fin1).count() * 1e3,
+            std::chrono::duration<double>(std::chrono::steady_clock::now() - t_call0).count() * 1e3);
   if (n_results) memcpy(n_results, h_nres.get(), (size_t)B * 4);
   if (flags) memcpy(flags, h_nres.get() + B, (size_t)B * 4);
   return check_error_flags(h_nres.get() + B, B);
+}
+
+int ctcdec_selftest_math_f64(int which, const double *x, const double *x2, double *y, size_t n, int device) {
+  if (which < 0 || which > 2 || !x || !y || (which == 2 && !x2)) return fail(CTCDEC_E_INVALID, "bad selftest arguments");
+  if (cudaSetDevice(device) != cudaSuccess) return fail(CTCDEC_E_NO_DEVICE, "cudaSetDevice(%d) failed", device);
+  int rc = check_device();
+  if (rc) return rc;
+  if (n == 0) return CTCDEC_OK;
+  double *dx = nullptr, *dx2 = nullptr, *dy = nullptr;
+  CU(cudaMalloc(&dx, n * 8));
+  CU(cudaMalloc(&dy, n * 8));
+  if (which == 2) CU(cudaMalloc(&dx2, n * 8));
+  CU(cudaMemcpy(dx, x, n * 8, cudaMemcpyHostToDevice));
+  if (which == 2) CU(cudaMemcpy(dx2, x2, n * 8, cudaMemcpyHostToDevice));
+  selftest_math_f64_kernel<<<148 * 8, 256>>>(which, dx, dx2, dy, n);
+  CU(cudaGetLastError());
+  CU(cudaMemcpy(y, dy, n * 8, cudaMemcpyDeviceToHost));
+  cudaFree(dx); cudaFree(dy);
+  if (dx2) cudaFree(dx2);
+  return CTCDEC_OK;
 }
 
 int ctcdec_selftest_math(int which, const float *x, const float *x2, float *y, size_t n, int device) {

@@ -151,6 +151,29 @@ CTC_HD double log_glibc_t(double x, const double *tab) {
   return d_add(y, hi);
 }
 
+// glibc exp for x <= 0 (sysdeps/ieee754/dbl-64/e_exp.c, FMA variant), as the reference's log_sum_exp<double> calls it
+// (decoder_utils.h:47-54: exp(x - max), one of the two arguments being exactly 0).  Arguments under -40 return 0.0:
+// the true value is below 2^-57, and the only use adds it to exp(0) = 1.0, where anything under 2^-54 vanishes -- so the
+// subnormal / underflow branches of the original are not restated.  tab: kExpTab.
+CTC_HD double exp_glibc_nonpos_t(double x, const unsigned long long *tab) {
+  if (!(x < 0.0)) return d_add(1.0, x);   // x == 0 (and the tiny-|x| branch's 1.0 + x)
+  if (x < -40.0) return 0.0;
+  double kd = d_fma(CTC_EXP_INVLN2N, x, CTC_EXP_SHIFT);
+  const uint64_t ki = d_bits(kd);
+  kd = d_add(kd, -CTC_EXP_SHIFT);
+  const double r = d_fma(kd, CTC_EXP_NEGLN2LON, d_fma(kd, CTC_EXP_NEGLN2HIN, x));
+  const uint64_t idx = 2 * (ki % 128);
+  const double tail = bits_d(tab[idx]);
+  const uint64_t sbits = tab[idx + 1] + (ki << 45);
+  const double r2 = d_mul(r, r);
+  const double a = d_fma(r, CTC_EXP_C3, CTC_EXP_C2), b = d_fma(r, CTC_EXP_C5, CTC_EXP_C4);
+  const double t2 = d_fma(r2, a, d_add(tail, r));
+  const double tmp = d_fma(d_mul(r2, r2), b, t2);
+  const double scale = bits_d(sbits);
+  return d_fma(scale, tmp, scale);
+}
+CTC_HD double exp_glibc_nonpos(double x) { return exp_glibc_nonpos_t(x, (const unsigned long long *)kExpTab); }
+
 CTC_HD float expf_glibc(float x) { return expf_glibc_t(x, (const uint64_t *)kExp2fTab); }
 CTC_HD float logf_glibc(float x) { return logf_glibc_t(x, kLogfTab); }
 CTC_HD double log_glibc(double x) { return log_glibc_t(x, kLogTab); }
@@ -160,6 +183,17 @@ CTC_HD float logprob_glibc_t(float p, const double *tab) {
   return (float)log_glibc_t(d_add((double)p, (double)FLT_MIN), tab);
 }
 CTC_HD float logprob_glibc(float p) { return logprob_glibc_t(p, kLogTab); }
+
+// log_sum_exp<double>  -- reference decoder_utils.h:47-54, as decoder_utils.cpp:29 chains it over a frame's sorted
+// probabilities (cum_prob): glibc's double exp and log, operation by operation.  The sum of the two exponentials lies in
+// [1, 2], a normal double, which is all log_glibc_t handles.
+CTC_HD double lse_d(double x, double y) {
+  if (x <= -DBL_MAX) return y;
+  if (y <= -DBL_MAX) return x;
+  const double m = x > y ? x : y;
+  const double s = d_add(exp_glibc_nonpos(d_add(x, -m)), exp_glibc_nonpos(d_add(y, -m)));
+  return d_add(log_glibc(s), m);
+}
 
 // log_sum_exp<float>  -- reference decoder_utils.h:47-54
 CTC_HD float lse_f(float x, float y) {

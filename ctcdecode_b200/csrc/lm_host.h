@@ -145,13 +145,17 @@ struct HostScorer {
 
 // Per-utterance host mirror of the trie: enough to spell the prefix of any node.
 struct TrieMirror {
-  std::vector<int> parent, chr;  // sized for the arena up front: adding a node is two stores
+  // Capacity for the arena is reserved up front (address space only: a frame's worth of an utterance's nodes is a few
+  // hundred bytes, while filling 1 + beam x frames entries per utterance ahead of time cost config 5 fifty megabytes of
+  // page faults per call); node ids arrive in increasing order, so growing the used part is amortised pushes.
+  std::vector<int> parent, chr;
   void reserve(size_t nodes) {
-    parent.assign(nodes > 0 ? nodes : 1, -1);
-    chr.assign(nodes > 0 ? nodes : 1, -1);
+    parent.clear(); chr.clear();
+    parent.reserve(nodes > 0 ? nodes : 1); chr.reserve(nodes > 0 ? nodes : 1);
+    parent.push_back(-1); chr.push_back(-1);  // node 0, the root
   }
   void add(int nid, int par, int ch) {
-    if ((size_t)nid >= parent.size()) { parent.resize((size_t)nid * 2 + 1, -1); chr.resize((size_t)nid * 2 + 1, -1); }
+    if ((size_t)nid >= parent.size()) { parent.resize((size_t)nid + 1, -1); chr.resize((size_t)nid + 1, -1); }
     parent[nid] = par;
     chr[nid] = ch;
   }
@@ -298,7 +302,7 @@ static inline void lm_rescore_batch(HostScorer &sc, int B, int K, int T, const i
       }
     }
   unsigned nt = std::thread::hardware_concurrency();
-  nt = nt == 0 ? 1 : (nt > 16 ? 16 : nt);
+  nt = nt == 0 ? 1 : (nt > 32 ? 32 : nt);  // (the sentence hook of a result row costs ~15 us; config 5 has 6400 rows)
   if ((unsigned)B < nt) nt = (unsigned)B;
   std::vector<std::thread> pool;
   for (unsigned w = 0; w < nt; ++w)

@@ -386,9 +386,9 @@ __global__ void __launch_bounds__(256) prune_kernel(const PruneParams p) {
           double cum = 0.0;  // reference starts the log-domain accumulator at 0.0 (decoder_utils.cpp:26)
           for (int i = 0; i < V; ++i) {
             const double v = (double)unord_f((uint32_t)(keys[i] >> 32));
-            const double term = log_input ? v : log(v);
-            const double m = cum > term ? cum : term;
-            cum = (term <= -DBL_MAX) ? cum : log(exp(cum - m) + exp(term - m)) + m;
+            // (std::log of a float's double image: zero -> -inf, which log_sum_exp skips; the rest are normal doubles)
+            const double term = log_input ? v : (v > 0.0 ? log_glibc(v) : bits_d(v == 0.0 ? 0xfff0000000000000ull : 0x7ff8000000000000ull));
+            cum = lse_d(cum, term);
             nn += 1;
             if (cum >= p.cutoff_prob || nn >= p.top_n) break;
           }

@@ -217,6 +217,9 @@ int ctcdec_profile_region_cycles(void *device_buffer);
 /* y[i] = f(x[i]) computed ON THE DEVICE; which: 0 expf, 1 logf, 2 float(log(double(x) + FLT_MIN)),
  * 3 log_sum_exp(x[i], x2[i]).  Host pointers. */
 int ctcdec_selftest_math(int which, const float *x, const float *x2, float *y, size_t n, int device);
+/* the double chain of the vocabulary cut (reference decoder_utils.cpp:26-31): which 0 exp(x) for x <= 0 (arguments under
+ * -40 give 0.0, see glibc_math.cuh), 1 log(x) for normal positive x, 2 log_sum_exp<double>(x[i], x2[i]). */
+int ctcdec_selftest_math_f64(int which, const double *x, const double *x2, double *y, size_t n, int device);
 
 #ifdef __cplusplus
 }

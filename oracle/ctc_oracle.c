@@ -402,6 +402,10 @@ void ctc_oracle_logf_array(const float *x, float *y, long n) {
 void ctc_oracle_lse_array(const float *x, const float *y, float *z, long n) {
   for (long i = 0; i < n; ++i) z[i] = lse_f(x[i], y[i]);
 }
+/* double probes (the cum_prob chain of decoder_utils.cpp:26-31): which 0 exp(x), 1 log(x), 2 log_sum_exp<double>(x, x2) */
+void ctc_oracle_f64_array(int which, const double *x, const double *x2, double *y, long n) {
+  for (long i = 0; i < n; ++i) y[i] = which == 0 ? exp(x[i]) : which == 1 ? log(x[i]) : lse_d(x[i], x2[i]);
+}
 void ctc_oracle_logprob_array(const float *p, float *y, long n) { /* decoder_utils.cpp:40-43 */
   for (long i = 0; i < n; ++i) y[i] = (float)log((double)p[i] + NUM_FLT_MIN);
 }

@@ -70,6 +70,7 @@ class CPort:
             f = getattr(L, "ctc_oracle_%s_array" % name)
             f.argtypes = [_f32p, _f32p, ctypes.c_long]
         L.ctc_oracle_lse_array.argtypes = [_f32p, _f32p, _f32p, ctypes.c_long]
+        L.ctc_oracle_f64_array.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long]
 
     def decode(self, probs, seq_lens=None, beam=100, cutoff_prob=1.0, cutoff_top_n=40, blank_id=0,
                log_input=False):
@@ -124,6 +125,15 @@ class CPort:
         z = np.empty_like(x)
         self.lib.ctc_oracle_lse_array(_p(x, _f32p), _p(y, _f32p), _p(z, _f32p), x.size)
         return z
+
+
+    def f64(self, which, x, x2=None):
+        """host libm in double: which 0 exp(x), 1 log(x), 2 log_sum_exp<double>(x, x2)"""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        x2 = None if x2 is None else np.ascontiguousarray(x2, dtype=np.float64)
+        y = np.empty_like(x)
+        self.lib.ctc_oracle_f64_array(which, x.ctypes.data, None if x2 is None else x2.ctypes.data, y.ctypes.data, x.size)
+        return y
 
 
 def reference_available():

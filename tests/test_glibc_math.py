@@ -20,7 +20,7 @@ def test_host_sweep_strided():
                     os.path.join(ROOT, "tests", "native", "sweep_glibc_math.cpp"), "-o", out, "-lm"], check=True)
     r = subprocess.run([out, "97"], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
-    assert "expf 0/" in r.stdout and "logf 0/" in r.stdout and "logprob 0/" in r.stdout
+    assert "expf 0/" in r.stdout and "logf 0/" in r.stdout and "logprob 0/" in r.stdout and "f64chain 0/" in r.stdout
 
 
 def _device_vs_libm(cport, which, name, bits_lo, bits_hi, step=1, chunk=1 << 24):
@@ -70,3 +70,28 @@ def test_device_lse_random(cport):
     z = np.empty_like(x)
     _native.check(lib.ctcdec_selftest_math(3, x.ctypes.data, y.ctypes.data, z.ctypes.data, x.size, 0))
     assert np.array_equal(z.view(np.int32), cport.lse(x, y).view(np.int32))
+
+
+@pytest.mark.gpu
+def test_device_f64_chain_of_the_vocabulary_cut(cport):
+    """the serial replay of the reference's double cum_prob chain (decoder_utils.cpp:26-31) in the prune kernel: glibc's
+    double exp (arguments <= 0), log and log_sum_exp<double>, device against this box's libm, 2^22 random arguments
+    each over the domains the chain can produce"""
+    lib = _native.load()
+    rng = np.random.default_rng(11)
+    n = 1 << 22
+    x = np.concatenate([-40.0 * rng.random(n // 2), -rng.random(n // 4), -np.ldexp(rng.random(n // 4), -rng.integers(0, 60, n // 4))])
+    x[:4] = [0.0, -0.0, -1e-300, -40.0]
+    y = np.empty_like(x)
+    _native.check(lib.ctcdec_selftest_math_f64(0, x.ctypes.data, None, y.ctypes.data, x.size, 0))
+    assert np.array_equal(y.view(np.int64), cport.f64(0, x).view(np.int64))
+    s = 1.0 + rng.random(n)                                   # exp(0) + exp(<= 0) lies in [1, 2]
+    _native.check(lib.ctcdec_selftest_math_f64(1, s.ctypes.data, None, y.ctypes.data, s.size, 0))
+    assert np.array_equal(y.view(np.int64), cport.f64(1, s).view(np.int64))
+    cum = np.log(2.0) * rng.random(n)
+    p = rng.integers(1, 0x3F800001, n, dtype=np.int64).astype(np.uint32).view(np.float32).astype(np.float64)
+    term = cport.f64(1, p)
+    term[::7] = -0.37 * rng.integers(0, 3000, term[::7].size)  # log input: any non-positive number, far tails included
+    term[:3] = [-np.inf, -1.7976931348623157e308, 0.0]
+    _native.check(lib.ctcdec_selftest_math_f64(2, cum.ctypes.data, term.ctypes.data, y.ctypes.data, cum.size, 0))
+    assert np.array_equal(y.view(np.int64), cport.f64(2, cum, term).view(np.int64))

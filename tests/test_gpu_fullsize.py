@@ -136,3 +136,62 @@ def test_host_entry_leaves_rows_beyond_n_results_alone():
     for b in range(4):
         assert bool((lens[b, int(nres[b]):] == 0).all()), lens[b]
         assert bool((lens[b, :int(nres[b])] <= 1).all())
+
+
+def test_host_entry_pageable_and_page_locked_destinations_agree():
+    """ctcdec_decode_batch_host brings the result rows back either by DMA straight into the caller's arrays (page-locked
+    memory) or -- pageable memory -- through its own pinned staging rows and a host-side spread: same bits either way,
+    and nothing outside [:max_len] of a row is touched."""
+    import ctypes
+    from ctcdecode_b200 import _native
+    lib = _native.load()
+    B, T, V, K = 130, 90, 29, 20            # three utterance groups of the host entry point
+    probs = ctc_like_probs(B, T, V, seed=77)
+    cfg = _native.Config(V, K, 0, 0, 40, 1.0)
+    outs = []
+    for pinned in (False, True):
+        mk = (lambda *s, dt=torch.int32: torch.full(s, -7, dtype=dt).pin_memory()) if pinned else \
+             (lambda *s, dt=torch.int32: torch.full(s, -7, dtype=dt))
+        tok, ts, sc, ln = mk(B, K, T), mk(B, K, T), mk(B, K, dt=torch.float32), torch.zeros(B, K, dtype=torch.int32)
+        nres, fl = torch.zeros(B, dtype=torch.int32), torch.zeros(B, dtype=torch.int32)
+        p = probs.pin_memory() if pinned else probs
+        _native.check(lib.ctcdec_decode_batch_host(ctypes.byref(cfg), p.data_ptr(), None, B, T, tok.data_ptr(),
+                                                   ts.data_ptr(), sc.data_ptr(), ln.data_ptr(), nres.data_ptr(),
+                                                   fl.data_ptr(), 0))
+        outs.append((tok, ts, sc, ln, nres))
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.equal(a, b)
+    tok, ts, sc, ln, nres = outs[0]
+    assert bool((nres == K).all()) and int(ln.max()) > 5
+    assert bool((tok[:, :, int(ln.max()):] == -7).all())   # columns beyond the longest prefix: untouched
+
+
+@pytest.mark.parametrize("log_input", [False, True], ids=["probs", "log_probs"])
+def test_cutoff_prob_exactly_on_a_partial_sum(cport, log_input):
+    """The vocabulary cut compares the reference's double log_sum_exp chain (decoder_utils.cpp:26-31) with cutoff_prob.
+    The scan kernel decides with a prefix sum and, within 1e-9 of the threshold, replays that chain -- with the glibc
+    restatements of double exp / log (glibc_math.cuh), so the decision is the reference's own even when cutoff_prob IS
+    a partial sum of the chain, or one ulp to either side of it: every frame of this input sits on that knife edge."""
+    import ctypes
+    libm = ctypes.CDLL("libm.so.6")
+    for f in (libm.exp, libm.log):
+        f.restype, f.argtypes = ctypes.c_double, [ctypes.c_double]
+    rng = np.random.default_rng(91)
+    V, B, T, K, cut = 24, 3, 40, 12, 7
+    base = np.sort(rng.dirichlet(np.ones(V) * 0.6).astype(np.float32))[::-1].copy()
+    assert len(set(base.tolist())) == V
+    vals = np.log(base.astype(np.float64)).astype(np.float32) if log_input else base
+    cum = 0.0                                                   # the reference's chain over the sorted row
+    for i in range(cut):
+        term = float(vals[i]) if log_input else libm.log(float(vals[i]))
+        m = max(cum, term)
+        cum = libm.log(libm.exp(cum - m) + libm.exp(term - m)) + m
+    probs = np.empty((B, T, V), np.float32)
+    for b in range(B):
+        for t in range(T):
+            probs[b, t] = vals[rng.permutation(V)]
+    for cp in (cum, float(np.nextafter(cum, 2.0)), float(np.nextafter(cum, 0.0))):
+        ref = cport.decode(probs, beam=K, cutoff_prob=cp, cutoff_top_n=V, log_input=log_input)
+        for on_device in (True, False):
+            got = _run(probs, on_device=on_device, beam=K, cutoff_prob=cp, cutoff_top_n=V, log_input=log_input)
+            compare(ref, got, ref["ties"], "cutoff_prob %r on the chain's partial sum %d" % (cp, cut))
