@@ -431,12 +431,14 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
     if (threadIdx.x < 32) {
       const int lane = (int)threadIdx.x;
       const volatile int *blk = lm_upd;
+      int v = 0;
+      bool seen = false;  // the poll that saw the flag also brought the first 64-byte line of the block
       if (wait_for > 0) {
         const long long deadline = clock64() + 20000000000ll;  // ~10 s: never hang the GPU on a dead host
         unsigned it = 0;
         for (;;) {
-          const int v = blk[lane];
-          if (__shfl_sync(0xffffffffu, v, 0) >= wait_for) break;
+          v = blk[lane];
+          if (__shfl_sync(0xffffffffu, v, 0) >= wait_for) { seen = true; break; }
           if ((++it & 255u) == 0u) {
             int bad = 0;
             if (lane == 0) bad = (*(volatile int *)p.hs_abort != 0 || clock64() > deadline) ? 1 : 0;
@@ -447,9 +449,16 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
           }
         }
       }
-      if (wait_for > 0) __threadfence_system();  // acquire: the payload loads below stay behind the flag load
-      const int v = blk[lane];  // read (again) after the flag: the host writes the pairs first, the flag last
+      // The host writes the pairs first and the flag last (release), and the flag shares its 64-byte line with the
+      // count and the first seven pairs: a read of that line that shows the flag shows them too (one coherent line
+      // read; stores to a line become visible in program order).  Only a longer answer -- or a character model's
+      // rows -- costs a second PCIe round trip, behind a fence.
       int cnt = __shfl_sync(0xffffffffu, v, 1);
+      if (!(seen && !p.lm_char && cnt >= 0 && cnt <= 7)) {
+        if (wait_for > 0) __threadfence_system();  // acquire: the payload loads below stay behind the flag load
+        v = blk[lane];
+        cnt = __shfl_sync(0xffffffffu, v, 1);
+      }
       if (cnt > K) cnt = K;
       s_upd[lane] = lane == 1 ? cnt : v;
       if (!p.lm_char)
@@ -1053,6 +1062,67 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
               if (pred2[LX]) {
                 const int pos = cnt + n1 + ctc_popc(bal2 & ctc_lt_mask(lane));
                 if (pos < SEG) { segk[pos] = kk2[LX]; segi[pos] = (i << 16) | (32 + lane); }
+              }
+            }
+            cnt += n1 + ctc_popc(bal2);
+            CTC_STAT(g_stats.cl_entries += n1 + ctc_popc(bal2));
+          }
+        }
+        if (LM && G == 1) {
+          // scorer path, one column group: two rows per iteration and no divergent branch, so that the two dependent
+          // chains (shared-memory loads -> dictionary bit -> LM term in double -> key -> histogram -> ballot) overlap
+          // -- with two warps per scheduler nothing else hides their latency (the row-at-a-time loop below took 750
+          // cycles per row, 9.7 k of the scorer frame's 21 k)
+          while (rows) {
+            const int rl1 = ctc_ffs(rows) - 1;
+            rows &= rows - 1u;
+            const bool two = rows != 0u;
+            const int rl2 = two ? ctc_ffs(rows) - 1 : rl1;
+            if (two) rows &= rows - 1u;
+            const int i1 = base + (warp - WB0) + NB * rl1, i2 = base + (warp - WB0) + NB * rl2;
+            const float sc_1 = c.s_score[i1], b_1 = c.s_bprev[i1], sc_2 = c.s_score[i2], b_2 = c.s_bprev[i2];
+            const int ch_1 = c.s_chr[i1], ch_2 = c.s_chr[i2];
+            const uint32_t mw1 = c.s_mask[i1 * WS], mw2 = c.s_mask[i2 * WS];
+            const uint32_t rm1 = c.s_rmask[i1 * W], rm2 = c.s_rmask[i2 * W];
+            CTC_LV(int, pred1);
+            CTC_LV(int, pred2);
+            CTC_LV(uint32_t, kk1);
+            CTC_LV(uint32_t, kk2);
+            CTC_LANES {
+              const int ch = colc[LX];
+              const float l = colv[LX];
+              const bool valid = ch >= 0;
+              const int chs = valid ? ch : 0;
+              const bool rep1 = (ch == ch_1), rep2 = (ch == ch_2);
+              float s1 = f_add(l, rep1 ? b_1 : sc_1), s2 = f_add(l, rep2 ? b_2 : sc_2);
+              if (rep1 && !(b_1 > kNInf)) s1 = kNInf;
+              if (rep2 && !(b_2 > kNInf)) s2 = kNInf;
+              const bool okl1 = !c.lm_cut(l, sc_1) && (c.lm_char || ((rm1 >> lane) & 1u) || c.dict_ok(i1, chs));
+              const bool okl2 = !c.lm_cut(l, sc_2) && (c.lm_char || ((rm2 >> lane) & 1u) || c.dict_ok(i2, chs));
+              const float t1 = c.lm_apply_c(s1, i1, chs), t2 = c.lm_apply_c(s2, i2, chs);
+              const bool scored = c.lm_scored(ch);
+              s1 = scored ? t1 : s1;
+              s2 = scored ? t2 : s2;
+              const unsigned k1 = ord_f(s1), k2 = ord_f(s2);
+              const bool ok1 = valid && !((mw1 >> lane) & 1u) && (k1 >= lo32) && okl1;
+              const bool ok2 = two && valid && !((mw2 >> lane) & 1u) && (k2 >= lo32) && okl2;
+              pred1[LX] = ok1 ? 1 : 0; kk1[LX] = k1;
+              pred2[LX] = ok2 ? 1 : 0; kk2[LX] = k2;
+              if (!select_all) {
+                if (ok1) atom_add(&hist0[(int)((k1 - lo32) >> shift32)], 1);
+                if (ok2) atom_add(&hist0[(int)((k2 - lo32) >> shift32)], 1);
+              }
+            }
+            const unsigned bal1 = ctc_ballot(pred1), bal2 = ctc_ballot(pred2);
+            const int n1 = ctc_popc(bal1);
+            CTC_LANES {
+              if (pred1[LX]) {
+                const int pos = cnt + ctc_popc(bal1 & ctc_lt_mask(lane));
+                if (pos < SEG) { segk[pos] = kk1[LX]; segi[pos] = (i1 << 16) | lane; }
+              }
+              if (pred2[LX]) {
+                const int pos = cnt + n1 + ctc_popc(bal2 & ctc_lt_mask(lane));
+                if (pos < SEG) { segk[pos] = kk2[LX]; segi[pos] = (i2 << 16) | lane; }
               }
             }
             cnt += n1 + ctc_popc(bal2);
@@ -1691,10 +1761,18 @@ CTC_FN void beam_cta_run(const BeamParams &p, const int b, unsigned char *smem) 
       lm_fetch_updates(t0 + t + 1);
       CTC_BARRIER();
       CTC_TICK(12);  // handshake: fence, flag, wait for the host, fetch its answer
-      CTC_PAR { lm_scatter_updates(tid); }
-      CTC_BARRIER();
       CTC_PAR {
-        for (int j = tid; j < M; j += NT) c.s_lmsp[j] = ld_cg(&lm_arena[c.s_node[j]]);
+        lm_scatter_updates(tid);  // into the per-node array (read again when a node is revived or a launch starts)
+        // ... and into the slots of the members the pairs are about, straight from the staged answer: continuing members
+        // keep their term, so nothing waits for the array in global memory
+        if (!p.lm_char) {
+          const int nu = s_upd[1];
+          for (int j = tid; j < M; j += NT) {
+            const int node = c.s_node[j];
+            for (int q = 0; q < nu; ++q)
+              if (s_upd[2 + 2 * q] == node) c.s_lmsp[j] = bits_f((uint32_t)s_upd[3 + 2 * q]);
+          }
+        }
       }
       CTC_BARRIER();
       CTC_TICK(13);  // LM terms in

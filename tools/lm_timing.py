@@ -25,7 +25,7 @@ def child():
     lib = _native.load()
     for _ in range(2):
         dec.decode(probs)
-    buf = torch.zeros(B, 16, dtype=torch.int64, device="cuda")
+    buf = torch.zeros(B * 16 + B * 16 * 32, dtype=torch.int64, device="cuda")  # [B][16] + [B][16][32]
     ts = []
     for i in range(4):
         if i == 3:
@@ -35,9 +35,13 @@ def child():
         ts.append(time.perf_counter() - t0)
     lib.ctcdec_profile_region_cycles(None)
     torch.cuda.synchronize()
-    t = buf.double().mean(0).cpu() / cfg["T"]
+    t = buf[:B * 16].view(B, 16).double().mean(0).cpu() / cfg["T"]
+    wb = buf[B * 16:].view(B, 16, 32).double().mean(0).cpu() / cfg["T"]
     print("  wall ms: " + " ".join("%.1f" % (x * 1e3) for x in ts) + "  -> %.0f utt/s" % (B / min(ts[:3])))
     print("  cycles/frame: " + "  ".join(f"{n}={float(v):.0f}" for n, v in zip(NAMES, t[:14]) if float(v) > 0))
+    for rid, name in ((2, "R1"), (3, "G"), (5, "select+classify"), (6, "R4c"), (8, "R5")):
+        print("  busy cycles/frame per warp before the barrier closing %-16s " % name
+              + " ".join("%5.0f" % float(v) for v in wb[rid][:8]))
 
 
 if __name__ == "__main__":
@@ -46,6 +50,8 @@ if __name__ == "__main__":
         sys.exit(0)
     variants = [{"CTCDEC_LM_PER_FRAME": "1"}] + [{"CTCDEC_LM_THREADS": str(n)} for n in (1, 2, 4, 8)] + \
         [{"CTCDEC_LM_THREADS": "8", "LM_B": "8"}, {"CTCDEC_LM_THREADS": "1", "LM_B": "1"}]
+    if len(sys.argv) > 1 and sys.argv[1] == "quick":
+        variants = [{"CTCDEC_LM_THREADS": "8"}, {"CTCDEC_LM_THREADS": "1", "LM_B": "1"}]
     for v in variants:
         env = dict(os.environ, **v)
         print(v, flush=True)
