@@ -34,3 +34,9 @@ if os.path.exists(PROVIDER):
     os.environ["CTCDEC_LM_PER_FRAME"] = "1"
     d.decode(q)
     print("scorer path done")
+    del os.environ["CTCDEC_LM_PER_FRAME"]
+    LCH = ["_"] + list("abcdefghijklmnop") + ["|", "'", "é", " ", "z", "qu"]
+    dch = CTCBeamDecoder(LCH, model_path=os.path.join(ROOT, "tests", "data", "char_lm.arpa"), alpha=1.2, beta=0.7,
+                         beam_width=12, scorer_provider=PROVIDER)
+    dch.decode(ctc_like_probs(2, 50, len(LCH), seed=9))                                # character-based model: rows of LM terms
+    print("character model done")
