@@ -226,8 +226,11 @@ def bench_lm(args, cfg, config, rank, world, local_rank, dev, K, W, cores):
             "ms_per_step": 1e3 * float(t[0]) / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": config,
             "e2e": {"value": val, "unit": "utterances/s", "h2d_bytes_per_step": B * T * 29 * 4,
-                    "d2h_bytes_per_step": None, "note": "host-buffer API: the LM hook runs on the host between one-frame launches"},
-            "gpu_launches": K * (T + 2), "roofline": None, "sample_top1": top1}
+                    "d2h_bytes_per_step": int(2 * B * cfg["beam"] * int(out[3].max()) * 4 + 2 * B * cfg["beam"] * 4),
+                    "note": "host-buffer API: the LM hook runs on the host, once per frame, inside one persistent "
+                            "launch (per-frame handshake through mapped host memory); value == e2e"},
+            "gpu_launches": K * (T + 2 if os.environ.get("CTCDEC_LM_PER_FRAME") else 3), "roofline": None,
+            "sample_top1": top1}
     if world == 1 and not args.no_cpu_baseline:
         n = max(1, min(B, cores))
         dtr, kind = reference_cpu(probs.numpy(), cfg, n, cores)

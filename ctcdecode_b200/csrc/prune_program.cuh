@@ -107,12 +107,8 @@ __device__ __forceinline__ void lsm_row(const void *logits, int kind, long long 
 // Only if more than 64 keys share the lim-th value does the search run all 32 steps; then the keys above it and the
 // needed number of equal ones, in index order, are taken.  Returns whether an unselected element ties with the last
 // selected probability (the reference's std::sort leaves that order unspecified).
-// cap: the search stops when at most `cap` keys reach the threshold (64, or 32 for the first, cheap attempt of a
-// cumulative-probability cut: see prune_kernel); with cap == 32 the call gives up -- *nsurv_out = -1, keys untouched --
-// when more than 32 keys share the lim-th value.  *nsurv_out: how many of keys[] are the frame's largest, in order.
 template <int KPL>
-__device__ __forceinline__ bool top_select(const float *row, int V, int lim, uint64_t *keys, int lane, int cap,
-                                           int *nsurv_out) {
+__device__ __forceinline__ bool top_select(const float *row, int V, int lim, uint64_t *keys, int lane) {
   uint32_t kr[KPL];
 #pragma unroll
   for (int q = 0; q < KPL; ++q) {
@@ -122,7 +118,7 @@ __device__ __forceinline__ bool top_select(const float *row, int V, int lim, uin
   uint32_t thr = 0u;
   int cnt_thr = 32 * KPL;  // keys >= thr
 #pragma unroll 1
-  for (int bit = 31; bit >= 0 && cnt_thr > cap; --bit) {
+  for (int bit = 31; bit >= 0 && cnt_thr > 64; --bit) {
     const uint32_t cand = thr | (1u << bit);
     int cnt = 0;
 #pragma unroll
@@ -132,7 +128,6 @@ __device__ __forceinline__ bool top_select(const float *row, int V, int lim, uin
   }
   bool more_equal = false;
   int nsurv;
-  if (cap < 64 && cnt_thr > cap) { *nsurv_out = -1; return false; }
   if (cnt_thr <= 64) {
     // everything >= thr survives (thr > 0 here, so the zero keys of lanes beyond V stay out)
     int base = 0;
@@ -204,7 +199,6 @@ __device__ __forceinline__ bool top_select(const float *row, int V, int lim, uin
   }
   __syncwarp();
   if (cnt_thr <= 64) more_equal = nsurv > lim && (keys[lim - 1] >> 32) == (keys[lim] >> 32);
-  *nsurv_out = nsurv;
   return more_equal;
 }
 
@@ -325,63 +319,8 @@ __global__ void __launch_bounds__(256) prune_kernel(const PruneParams p) {
                                     : (p.top_n < V ? p.top_n : V);
     const bool partial = KPL > 0 && lim_sel > 0 && lim_sel <= 64 && lim_sel < V && V <= 32 * KPL;
     bool more_equal = false;
-    // cum_i = log(1 + sum_{k<=i} p_k) up to rounding over the first `limit` sorted entries: the first index whose
-    // prefix sum reaches the threshold (-1: none), and whether a decision on the way was within 1e-9 of it
-    auto cum_first = [&](int limit, int &first, bool &uncertain) {
-      double carry = 0.0;
-      first = -1;
-      uncertain = false;
-      for (int base = 0; base < limit && first < 0; base += 32) {
-        const int i = base + lane;
-        double pv = 0.0;
-        if (i < limit) {
-          const double v = (double)unord_f((uint32_t)(keys[i] >> 32));
-          pv = log_input ? exp(v) : v;
-        }
-        double s = pv;
-        for (int d = 1; d < 32; d <<= 1) {
-          const double o = __shfl_up_sync(0xffffffffu, s, d);
-          if (lane >= d) s += o;
-        }
-        s += carry;
-        // log(1 + s) >= cutoff_prob  <=>  s >= expm1(cutoff_prob): the thresholds (and those of the +-1e-9 band that
-        // hands the frame to the serial replay below) come from the host in double, so no log1p per element here
-        const bool in = i < limit;
-        const bool fire = in && s >= p.cp_s_fire;
-        const bool unc = in && s >= p.cp_s_lo && s <= p.cp_s_hi;
-        const unsigned fb = __ballot_sync(0xffffffffu, fire);
-        const unsigned ub = __ballot_sync(0xffffffffu, unc);
-        if (fb) {
-          const int fl = __ffs(fb) - 1;
-          first = base + fl;
-          if (ub & ((2u << fl) - 1u)) uncertain = true;
-        } else if (ub) {
-          uncertain = true;
-        }
-        carry = __shfl_sync(0xffffffffu, s, 31);
-      }
-    };
-    // A cumulative-probability cut usually falls after a handful of entries (a frame's mass sits on few characters),
-    // while the selection above it costs by the number of entries it must order: 64 sort words in two registers per
-    // lane for cutoff_top_n = 40.  So first order only the 16..32 largest (one word per lane, 15 compare-exchange
-    // steps instead of 21 double ones); if the cut falls inside them -- not within 1e-9 of the threshold, and with
-    // the entry after it in hand for the tie check -- the frame is done.  Otherwise the full selection runs as before.
-    int n = -1;
-    bool early = false;
-    if (partial && p.cp_active && lim_sel > 16) {
-      int ns = 0;
-      top_select<(KPL > 0 ? KPL : 1)>(row, V, 16, keys, lane, 32, &ns);
-      if (ns > 0) {
-        int first;
-        bool uncertain;
-        cum_first(ns, first, uncertain);
-        if (first >= 0 && !uncertain && first + 1 < ns && first + 1 <= lim_sel) { n = first + 1; early = true; }
-      }
-    }
-    if (early) {
-    } else if (partial) {
-      int ns = 0;
-      more_equal = top_select<(KPL > 0 ? KPL : 1)>(row, V, lim_sel, keys, lane, 64, &ns);
+    if (partial) {
+      more_equal = top_select<(KPL > 0 ? KPL : 1)>(row, V, lim_sel, keys, lane);
     } else {
       for (int c = lane; c < p.P; c += 32)
         keys[c] = c < V ? (((uint64_t)ord_f(row[c]) << 32) | (uint64_t)(0xFFFFFFFFu - (unsigned)c)) : 0ull;
@@ -401,17 +340,45 @@ __global__ void __launch_bounds__(256) prune_kernel(const PruneParams p) {
       }
     }
     // ---- how many entries survive (decoder_utils.cpp:25-35)
-    if (early) {
-      // decided above
-    } else if (!p.cp_active) {
+    int n;
+    if (!p.cp_active) {
       n = p.top_n < V ? p.top_n : V;
     } else {
       const int lim = V < (p.top_n > 1 ? p.top_n : 1) ? V : (p.top_n > 1 ? p.top_n : 1);
-      // decide with a prefix sum unless a decision is within 1e-9 of the threshold, in which case lane 0 replays the
-      // reference's serial chain
-      int first;
-      bool uncertain;
-      cum_first(lim, first, uncertain);
+      // cum_i = log(1 + sum_{k<=i} p_k) up to rounding; decide with a prefix sum unless a decision is
+      // within 1e-9 of the threshold, in which case lane 0 replays the reference's serial chain.
+      double carry = 0.0;
+      int first = -1;
+      bool uncertain = false;
+      for (int base = 0; base < lim && first < 0; base += 32) {
+        const int i = base + lane;
+        double pv = 0.0;
+        if (i < lim) {
+          const double v = (double)unord_f((uint32_t)(keys[i] >> 32));
+          pv = log_input ? exp(v) : v;
+        }
+        double s = pv;
+        for (int d = 1; d < 32; d <<= 1) {
+          const double o = __shfl_up_sync(0xffffffffu, s, d);
+          if (lane >= d) s += o;
+        }
+        s += carry;
+        // log(1 + s) >= cutoff_prob  <=>  s >= expm1(cutoff_prob): the thresholds (and those of the +-1e-9 band that
+        // hands the frame to the serial replay below) come from the host in double, so no log1p per element here
+        const bool in = i < lim;
+        const bool fire = in && s >= p.cp_s_fire;
+        const bool unc = in && s >= p.cp_s_lo && s <= p.cp_s_hi;
+        const unsigned fb = __ballot_sync(0xffffffffu, fire);
+        const unsigned ub = __ballot_sync(0xffffffffu, unc);
+        if (fb) {
+          const int fl = __ffs(fb) - 1;
+          first = base + fl;
+          if (ub & ((2u << fl) - 1u)) uncertain = true;
+        } else if (ub) {
+          uncertain = true;
+        }
+        carry = __shfl_sync(0xffffffffu, s, 31);
+      }
       n = first >= 0 ? first + 1 : lim;
       if (uncertain) {
         int nn = 0;
@@ -431,7 +398,7 @@ __global__ void __launch_bounds__(256) prune_kernel(const PruneParams p) {
     }
     if (lane == 0 && n > 0 && n < V) {
       // is the cut between two equal probabilities?  (with a partial sort only lim_sel entries are ordered)
-      const bool tie = (partial && !early && n == lim_sel) ? more_equal : ((keys[n - 1] >> 32) == (keys[n] >> 32));
+      const bool tie = (partial && n == lim_sel) ? more_equal : ((keys[n - 1] >> 32) == (keys[n] >> 32));
       if (tie) atomicOr(&p.flags[b], FLAG_TIE_VOCAB);
     }
     // ---- emit
