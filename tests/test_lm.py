@@ -361,3 +361,40 @@ def test_cuda_char_lm_matches_live_reference_offline_and_online():
     got = dict(tokens=res.numpy(), timesteps=ts.numpy(), scores=scores.numpy(), lens=lens.numpy(),
                n_results=odec.last_n_results.numpy(), ties=odec.last_flags.numpy())
     compare(want, got, None, "character model, online in four calls")
+
+
+@needs_ref
+def test_emulation_char_lm_random_configurations():
+    """seeded random walk over (labels, beam, T, alpha, beta, cutoffs, blank position, log input, ragged lengths, host /
+    kernel protocol) with the character model, CPU emulation of the CTA program against the reference"""
+    rng = np.random.default_rng(2024)
+    for trial in range(10):
+        nlab = int(rng.integers(4, 24))
+        pool = list("abcdefghijklmnop") + ["|", "'", "é", "z", " ", "qu"]
+        labels = [pool[i] for i in rng.permutation(len(pool))[:nlab - 1]]
+        blank = int(rng.integers(0, nlab))
+        labels.insert(blank, "_")
+        T, B = int(rng.integers(1, 70)), int(rng.integers(1, 4))
+        kw = dict(beam=int(rng.integers(1, 40)), blank_id=blank, cutoff_top_n=int(rng.integers(2, 41)),
+                  cutoff_prob=float(rng.choice([1.0, 1.0, 0.999, 0.9])), log_input=bool(rng.integers(0, 2)))
+        alpha, beta = float(np.round(rng.uniform(0, 2.5), 2)), float(np.round(rng.uniform(-1, 2), 2))
+        probs = (flat_probs(B, T, nlab, seed=int(rng.integers(1 << 30))) if rng.random() < 0.3
+                 else ctc_like_probs(B, T, nlab, seed=int(rng.integers(1 << 30)), blank_id=blank))
+        if kw["log_input"]:
+            probs = probs.log()
+        seq_lens = None if rng.random() < 0.5 else rng.integers(0, T + 1, B).astype(np.int32)
+        ref = orc.Reference(labels, model_path=CHAR_LM, alpha=alpha, beta=beta)
+        want = ref.decode(probs.numpy(), seq_lens, num_processes=2, **kw)
+        env = [{}, {"CTC_EMU_LM_PER_FRAME": "1"}, {"CTC_EMU_LM_CHUNK": "3"}][trial % 3]
+        old = {k: os.environ.get(k) for k in env}
+        os.environ.update(env)
+        try:
+            got = emul.decode_lm(probs.numpy(), ref.lib, ref.scorer, labels, [], ref.max_order(), alpha, beta,
+                                 seq_lens=seq_lens, char_based=True, **kw)
+        finally:
+            for k, v in old.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
+        compare(want, got, None, "trial %d: %r labels %d T %d B %d a %.2f b %.2f %s" % (trial, kw, nlab, T, B, alpha, beta, env))
