@@ -62,6 +62,7 @@ _SIGNATURES = {
     "ctcdec_profile_read": (ctypes.c_int, [ctypes.POINTER(ctypes.c_float)]),
     "ctcdec_profile_region_cycles": (ctypes.c_int, [_vp]),
     "ctcdec_selftest_math": (ctypes.c_int, [ctypes.c_int, _vp, _vp, _vp, ctypes.c_size_t, ctypes.c_int]),
+    "ctcdec_rows_to_host": (ctypes.c_int, [_vp, _vp, ctypes.c_longlong, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp]),
     "ctcdec_selftest_math_f64": (ctypes.c_int, [ctypes.c_int, _vp, _vp, _vp, ctypes.c_size_t, ctypes.c_int]),
 }
 EXPORTS = tuple(_SIGNATURES)

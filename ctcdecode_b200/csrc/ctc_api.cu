@@ -1301,6 +1301,19 @@ int ctcdec_decode_batch_lm_host(const ctcdec_config *cfg, void *scorer, const fl
   return check_error_flags(h_nres.get() + B, B);
 }
 
+int ctcdec_rows_to_host(const int32_t *d_tokens, const int32_t *d_timesteps, long long rows, int row_stride, int max_len,
+                        int32_t *tokens, int32_t *timesteps, void *stream) {
+  if (rows < 0 || row_stride < 0 || max_len < 0 || max_len > row_stride) return fail(CTCDEC_E_INVALID, "bad rows / row_stride / max_len");
+  if (rows == 0 || max_len == 0) return CTCDEC_OK;
+  if (!d_tokens || !d_timesteps || !tokens || !timesteps) return fail(CTCDEC_E_INVALID, "NULL pointer");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t pitch = (size_t)row_stride * 4, width = (size_t)max_len * 4;
+  CU(cudaMemcpy2DAsync(tokens, pitch, d_tokens, pitch, width, (size_t)rows, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpy2DAsync(timesteps, pitch, d_timesteps, pitch, width, (size_t)rows, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  return CTCDEC_OK;
+}
+
 int ctcdec_selftest_math_f64(int which, const double *x, const double *x2, double *y, size_t n, int device) {
   if (which < 0 || which > 2 || !x || !y || (which == 2 && !x2)) return fail(CTCDEC_E_INVALID, "bad selftest arguments");
   if (cudaSetDevice(device) != cudaSuccess) return fail(CTCDEC_E_NO_DEVICE, "cudaSetDevice(%d) failed", device);

@@ -15,15 +15,36 @@ Differences from the reference, all additive:
   * ``model_path`` (word-based KenLM models): the language model stays on the host behind a hook; the real Scorer
     comes from a provider library (``scorer_provider=`` / CTCDECODE_B200_SCORER_PROVIDER, see scorer.py and
     INTEGRATION.md; providers/ builds one from the reference's own Scorer + KenLM).  The online decoder takes a
-    scorer too (device-resident states, one persistent launch per chunk).  Character-based models are not built.
+    scorer too (device-resident states, one persistent launch per chunk).  Character-based models are detected like
+    the reference does (every word of the model is one UTF-8 character) and decoded without a dictionary.
+  * the [batch, beam, T] result tensors are PAGE-LOCKED CPU tensors (torch's caching host allocator, so a decode loop
+    reuses the same blocks) up to CTCDECODE_B200_PIN_OUTPUT_BYTES per tensor (default 1 GiB), pageable beyond: a fresh
+    pageable [256, 100, 1000] int32 pair costs ~50 ms of page faults per call, twelve times the decode itself.
   * ``device="all"`` (or no device and a CPU batch of more than 4 x 148 utterances on a multi-GPU box): the host batch
     is sharded over every visible GPU by one call (ctcdec_decode_batch_host_multi).
 """
 import ctypes
+import os
 
 import torch
 
 from . import _native
+
+_PIN_CAP = int(os.environ.get("CTCDECODE_B200_PIN_OUTPUT_BYTES", str(1 << 30)))
+
+
+def _host_empty(*shape, dtype=torch.int32):
+    """Uninitialised CPU result tensor: page-locked when it is big enough to matter and small enough to afford (the
+    rows then arrive by DMA straight from the GPU, and torch's caching host allocator recycles the block in a loop)."""
+    n = torch.empty(0, dtype=dtype).element_size()
+    for d in shape:
+        n *= int(d)
+    if (1 << 16) <= n <= _PIN_CAP and torch.cuda.is_available():
+        try:
+            return torch.empty(*shape, dtype=dtype, pin_memory=True)
+        except RuntimeError:
+            pass
+    return torch.empty(*shape, dtype=dtype)
 
 
 def convert_to_string(tokens, vocabulary, seq_len):
@@ -115,8 +136,8 @@ class CTCBeamDecoder(_Base):
         probs = probs.cpu().float().contiguous()
         if seq_lens is not None:
             seq_lens = seq_lens.cpu().int().contiguous()
-        output = torch.empty(B, K, T, dtype=torch.int32)
-        timesteps = torch.empty(B, K, T, dtype=torch.int32)
+        output = _host_empty(B, K, T)
+        timesteps = _host_empty(B, K, T)
         scores = torch.empty(B, K, dtype=torch.float32)
         out_seq_len = torch.zeros(B, K, dtype=torch.int32)
         n_results = torch.zeros(B, dtype=torch.int32)
@@ -228,11 +249,13 @@ class CTCBeamDecoder(_Base):
         # reference semantics: CPU tensors.  Only columns < max(out_lens) carry data.
         lens_cpu = out_seq_len.cpu()
         max_len = int(lens_cpu.max()) if lens_cpu.numel() else 0
-        out_cpu = torch.empty(B, K, T, dtype=torch.int32)
-        ts_cpu = torch.empty(B, K, T, dtype=torch.int32)
-        if max_len > 0:
-            out_cpu[:, :, :max_len] = output[:, :, :max_len].cpu()
-            ts_cpu[:, :, :max_len] = timesteps[:, :, :max_len].cpu()
+        out_cpu = _host_empty(B, K, T)
+        ts_cpu = _host_empty(B, K, T)
+        if max_len > 0:  # two strided DMA copies straight into the result tensors
+            with torch.cuda.device(dev):
+                _native.check(lib.ctcdec_rows_to_host(output.data_ptr(), timesteps.data_ptr(), B * K, T, max_len,
+                                                      out_cpu.data_ptr(), ts_cpu.data_ptr(),
+                                                      torch.cuda.current_stream(dev).cuda_stream))
         self.last_flags, self.last_n_results = flags.cpu(), n_results.cpu()
         return out_cpu, scores.cpu(), ts_cpu, lens_cpu
 

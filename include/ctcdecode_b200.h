@@ -213,6 +213,13 @@ int ctcdec_profile_read(float *ms3);
  * 256-thread launches with beam sizes 65..256 and for the scorer path; other shapes return CTCDEC_E_UNSUPPORTED. */
 int ctcdec_profile_region_cycles(void *device_buffer);
 
+/* The device entry points leave their results on the GPU; this brings the meaningful part of the two big tensors to the
+ * host the way ctcdec_decode_batch_host does: columns [0, max_len) of every row ([rows][row_stride] int32 on both
+ * sides, rows = batch x beam), two strided DMA copies on `stream`, synchronised before returning.  Page-locked
+ * destinations make it run at PCIe speed (reference binding.cpp:79-99 writes only [:len] of a row, too). */
+int ctcdec_rows_to_host(const int32_t *d_tokens, const int32_t *d_timesteps, long long rows, int row_stride, int max_len,
+                        int32_t *tokens, int32_t *timesteps, void *stream);
+
 /* ---- diagnostics used by the tests (device self-check of the bit-exact libm restatements) ----------- */
 /* y[i] = f(x[i]) computed ON THE DEVICE; which: 0 expf, 1 logf, 2 float(log(double(x) + FLT_MIN)),
  * 3 log_sum_exp(x[i], x2[i]).  Host pointers. */
