@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from ctcdecode_b200.sharding import decode_sharded, shard_bounds
+from ctcdecode_b200.sharding import decode_sharded, shard_bounds, shard_by_length
 
 
 def test_shard_bounds_partition():
@@ -19,6 +19,17 @@ def test_shard_bounds_partition():
             assert all(got[i][1] == got[i + 1][0] for i in range(W - 1))
             sizes = [b - a for a, b in got]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_shard_by_length_deals_longest_first():
+    lens = [40, 3, 0, 25, 40, 17, 25]
+    parts = shard_by_length(lens, 3)
+    assert sorted(i for p in parts for i in p) == list(range(7))
+    assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+    assert parts == [[0, 6, 2], [4, 5], [3, 1]]
+    frames = [sum(lens[i] for i in p) for p in parts]
+    assert max(frames) - min(frames) <= max(lens)           # contiguous thirds would give 43 / 82 / 25
+    assert shard_by_length([], 2) == [[], []]
 
 
 def _emul_decode(probs, seq_lens):
@@ -36,8 +47,9 @@ def _worker(rank, world, port, q):
     probs = ctc_like_probs(5, 40, 9, seed=3) if rank == 0 else None
     lens = torch.tensor([40, 3, 0, 25, 40], dtype=torch.int32) if rank == 0 else None
     out = decode_sharded(_emul_decode, probs, lens)
+    bal = decode_sharded(_emul_decode, probs, lens, balance="length")   # utterances dealt out by length
     if rank == 0:
-        q.put([t.numpy() for t in out])
+        q.put([t.numpy() for t in out] + [t.numpy() for t in bal])
     dist.barrier()
     dist.destroy_process_group()
 
@@ -67,3 +79,9 @@ def test_two_rank_gloo_matches_single():
             L = lens[b, p]
             assert np.array_equal(got[0][b, p, :L], full[0].numpy()[b, p, :L])
             assert np.array_equal(got[2][b, p, :L], full[2].numpy()[b, p, :L])
+    # the length-balanced partition returns the same rows in the same (original) order
+    assert np.array_equal(got[7], lens) and np.array_equal(got[5].view(np.int32), got[1].view(np.int32))
+    for b in range(5):
+        for p in range(12):
+            L = lens[b, p]
+            assert np.array_equal(got[4][b, p, :L], got[0][b, p, :L]) and np.array_equal(got[6][b, p, :L], got[2][b, p, :L])
